@@ -1,0 +1,198 @@
+"""Generate golden fixtures by running the UNMODIFIED reference in this container.
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.pt
+
+The reference (/root/reference, read-only) is imported through an empty
+namespace package so that `open_clip/__init__.py` (which needs ftfy/timm) is
+skipped - SURVEY.md §8(c).  Nothing is copied from it: only its *outputs* on
+seeded inputs are stored.  The GPU box has no /root/reference; tests read the
+fixtures only.
+"""
+import importlib
+import os
+import sys
+import types
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("COSMOS_REFERENCE", "/root/reference")
+
+
+def ref_modules():
+    pkg = types.ModuleType("open_clip")
+    pkg.__path__ = [os.path.join(REF, "src", "open_clip")]
+    sys.modules["open_clip"] = pkg
+    return importlib.import_module("open_clip.loss"), importlib.import_module("open_clip.transformer")
+
+
+def unit(g, *shape, dtype=torch.float32):
+    return torch.nn.functional.normalize(torch.randn(*shape, generator=g), dim=-1).to(dtype)
+
+
+def cosmos_inputs(g, b, d, n_img=8, n_txt=8, corr=True):
+    z = torch.randn(b, d, generator=g) if corr else None
+
+    def v():
+        x = torch.randn(b, d, generator=g)
+        if z is not None:
+            x = z + 0.5 * x
+        return torch.nn.functional.normalize(x, dim=-1)
+
+    return {"s_image": [v() for _ in range(n_img)], "s_text": [v() for _ in range(n_txt)],
+            "s_img_x": [v() for _ in range(n_img)], "s_txt_x": [v() for _ in range(n_txt)],
+            "t_image": [v() for _ in range(2)], "t_text": [v() for _ in range(2)]}
+
+
+def run_cosmos(L, inp, logit_scale, distill_scale, up=(1.0, 1.0), **ctor):
+    leaf = {k: [t.clone().requires_grad_(True) for t in v] for k, v in inp.items()}
+    ls = torch.tensor(logit_scale, requires_grad=True)
+    ds = torch.tensor(distill_scale, requires_grad=True) if distill_scale is not None else None
+    loss = L.COSMOSLoss(cache_labels=True, **ctor)
+    out = loss(leaf["s_image"], leaf["s_text"], ls, t_image_features=leaf["t_image"], t_text_features=leaf["t_text"],
+               output_dict=True, distill_logit_scale=ds, s_img_crossmodal_features=leaf["s_img_x"],
+               s_txt_crossmodal_features=leaf["s_txt_x"])
+    (up[0] * out["distill_loss"] + up[1] * out["clip_loss"]).backward()
+    grads = {k: [None if t.grad is None else t.grad.clone() for t in v] for k, v in leaf.items()}
+    return ({k: v.detach().clone() for k, v in out.items()}, grads,
+            ls.grad.clone(), None if ds is None else ds.grad.clone())
+
+
+def case_w1_small(L):
+    g = torch.Generator().manual_seed(101)
+    cases = []
+    for (b, d, ls, dsc, corr, up) in [(24, 64, 14.2857, 9.5, True, (1.0, 1.0)),
+                                      (40, 128, 100.0, None, True, (65536.0, 65536.0)),
+                                      (17, 64, 30.0, 100.0, False, (0.5, 2.0))]:
+        inp = cosmos_inputs(g, b, d, corr=corr)
+        out, grads, gls, gds = run_cosmos(L, inp, ls, dsc, up)
+        cases.append(dict(inputs=inp, logit_scale=ls, distill_logit_scale=dsc, upstream=up,
+                          out=out, grads=grads, g_logit_scale=gls, g_distill_scale=gds))
+    torch.save(cases, os.path.join(HERE, "cosmos_w1_small.pt"))
+
+
+def case_cfg1(L):
+    """BASELINE config 1 (batch 256, dim 512): inputs are re-generated from the seed by
+    the test, only summaries of the outputs are stored."""
+    g = torch.Generator().manual_seed(1234)
+    inp = cosmos_inputs(g, 256, 512)
+    out, grads, gls, gds = run_cosmos(L, inp, 14.2857, 14.2857)
+    summ = {k: [None if t is None else dict(norm=t.norm().item(), head=t[:2, :8].clone(), rowsum=t.sum(1)[:16].clone())
+                for t in v] for k, v in grads.items()}
+    torch.save(dict(seed=1234, batch=256, dim=512, logit_scale=14.2857, distill_logit_scale=14.2857,
+                    out=out, grad_summary=summ, g_logit_scale=gls, g_distill_scale=gds,
+                    # the full grads of two tensors, bf16-packed to stay small
+                    g_s_img_x0=grads["s_img_x"][0].clone(), g_s_text3=grads["s_text"][3].clone()),
+               os.path.join(HERE, "cosmos_w1_cfg1.pt"))
+
+
+def _worker(rank, world, port, payload, tmpdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L, _ = ref_modules()
+    res = {}
+    for name, (kind, shards, ls, dsc, local_loss, gwg) in payload.items():
+        mine = shards[rank]
+        if kind == "clip":
+            a = [t.clone().requires_grad_(True) for t in mine["a"]]
+            b = [t.clone().requires_grad_(True) for t in mine["b"]]
+            s = torch.tensor(ls, requires_grad=True)
+            loss = L.ClipLoss(local_loss=local_loss, gather_with_grad=gwg, cache_labels=True, rank=rank, world_size=world)
+            val = loss(a, b, s)
+            val.backward()
+            res[name] = dict(loss=val.detach().clone(), ga=[t.grad.clone() for t in a], gb=[t.grad.clone() for t in b],
+                             gscale=s.grad.clone())
+        else:
+            out, grads, gls, gds = run_cosmos(L, mine, ls, dsc, local_loss=local_loss, gather_with_grad=gwg,
+                                              rank=rank, world_size=world)
+            res[name] = dict(out=out, grads=grads, g_logit_scale=gls, g_distill_scale=gds)
+    torch.save(res, os.path.join(tmpdir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def case_multirank(world, port, fname):
+    g = torch.Generator().manual_seed(77 + world)
+    payload = {}
+    b, d = 6, 32
+    clip_shards = [dict(a=[unit(g, b, d) for _ in range(2)], b=[unit(g, b, d) for _ in range(3)]) for _ in range(world)]
+    for ll in (False, True):
+        for gwg in (False, True):
+            payload[f"clip_ll{int(ll)}_gwg{int(gwg)}"] = ("clip", clip_shards, 20.0, None, ll, gwg)
+    cos_shards = [cosmos_inputs(g, 8, 32, n_img=3, n_txt=4) for _ in range(world)]
+    for ll, gwg in ((False, False), (False, True), (True, True), (True, False)):
+        payload[f"cosmos_ll{int(ll)}_gwg{int(gwg)}"] = ("cosmos", cos_shards, 14.2857, 25.0, ll, gwg)
+    import tempfile
+    ctx = mp.get_context("spawn")
+    with tempfile.TemporaryDirectory() as tmpdir:
+        procs = [ctx.Process(target=_worker, args=(r, world, port, payload, tmpdir)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join()
+            assert p.exitcode == 0
+        got = {r: torch.load(os.path.join(tmpdir, f"rank{r}.pt")) for r in range(world)}
+    torch.save(dict(world=world, payload={k: dict(kind=v[0], shards=v[1], logit_scale=v[2], distill_logit_scale=v[3],
+                                                  local_loss=v[4], gather_with_grad=v[5]) for k, v in payload.items()},
+                    results=[got[r] for r in range(world)]), os.path.join(HERE, fname))
+
+
+def case_pooler(T):
+    """Parameters/inputs come from oracle.make_pooler_case (seeded) so the d=512 cases only
+    store outputs and gradient summaries."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle.cosmos_oracle import make_pooler_case
+    cases = []
+    for idx, (d, h, L_k, B, n) in enumerate([(64, 4, 7, 3, 2), (128, 8, 13, 2, 4), (512, 8, 77, 2, 8), (512, 8, 196, 1, 8)]):
+        params, tokens, feats, w = make_pooler_case(d, L_k, B, n, seed=50 + idx)
+        mod = T.AttentionalCrossPooler(d, d, h)
+        mod.load_state_dict(params)
+        tokens.requires_grad_(True)
+        feats.requires_grad_(True)
+        # model.py:378-380 / 382-384
+        pooled = mod(tokens[:B].repeat(n, 1, 1), feats.unsqueeze(1))
+        xmodal = torch.nn.functional.normalize(feats + pooled.squeeze(), dim=-1)
+        (xmodal * w).sum().backward()
+        gp = {k: v.grad.clone() for k, v in mod.named_parameters()}
+        rec = dict(d=d, heads=h, L=L_k, batch_size=B, n=n, seed=50 + idx, pooled=pooled.detach().clone(),
+                   xmodal=xmodal.detach().clone(), g_feats=feats.grad.clone(),
+                   g_param_norm={k: v.norm().item() for k, v in gp.items()},
+                   g_param_head={k: v.reshape(-1)[:64].clone() for k, v in gp.items()},
+                   g_tokens_norm=tokens.grad.norm().item(), g_tokens_head=tokens.grad[:, :2].clone())
+        if d <= 128:
+            rec.update(g_tokens=tokens.grad.clone(), g_params=gp)
+        cases.append(rec)
+    torch.save(cases, os.path.join(HERE, "pooler.pt"))
+
+
+def case_ema():
+    g = torch.Generator().manual_seed(9)
+    shapes = [(1,), (), (7,), (33, 5), (4096,), (1000, 3)]
+    teacher = [torch.randn(s, generator=g) * 0.02 for s in shapes]
+    student = [torch.randn(s, generator=g) * 0.02 for s in shapes]
+    t0 = [t.clone() for t in teacher]
+    outs = {}
+    for m in (0.99, 0.999, 0.5):
+        k = [t.clone() for t in t0]
+        with torch.no_grad():   # literal train.py:200-203
+            for pq, pk in zip(student, k):
+                pk.data.mul_(m).add_((1 - m) * pq.detach().data)
+        outs[m] = k
+    torch.save(dict(teacher=t0, student=student, outs=outs), os.path.join(HERE, "ema.pt"))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    L, T = ref_modules()
+    case_w1_small(L)
+    case_cfg1(L)
+    case_multirank(4, 29611, "multirank_w4.pt")
+    case_multirank(2, 29612, "multirank_w2.pt")
+    case_pooler(T)
+    case_ema()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".pt"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
