@@ -1,0 +1,228 @@
+// extern "C" surface of libcosmos_b200.so (declared in include/cosmos_b200.h).
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "infonce.h"
+#include "internal.h"
+#include "tma_host.h"
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = (prev == device) || (cudaSetDevice(device) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (ok && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+int sm_count_of(int device) {
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+  return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cosmos_abi_version(void) { return COSMOS_B200_ABI_VERSION; }
+
+const char* cosmos_status_string(int status) {
+  switch (status) {
+    case COSMOS_OK: return "ok";
+    case COSMOS_ERR_INVALID_ARGUMENT: return "invalid argument (shape, null pointer or alignment)";
+    case COSMOS_ERR_UNSUPPORTED: return "unsupported dtype or size";
+    case COSMOS_ERR_CUDA: return "CUDA runtime or launch failure";
+    case COSMOS_ERR_NO_DEVICE: return "device is not an sm_100 (B200) part";
+    case COSMOS_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown status";
+  }
+}
+
+int cosmos_device_check(int device) {
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess) {
+    cudaGetLastError();
+    return COSMOS_ERR_CUDA;
+  }
+  return major == 10 ? COSMOS_OK : COSMOS_ERR_NO_DEVICE;
+}
+
+int64_t cosmos_ema_table_entries(int64_t n_tensors, const int64_t* numel) {
+  if (n_tensors < 0 || (n_tensors > 0 && numel == nullptr)) return -1;
+  int64_t n = 0;
+  for (int64_t i = 0; i < n_tensors; ++i) {
+    if (numel[i] < 0) return -1;
+    n += (numel[i] + COSMOS_EMA_CHUNK - 1) / COSMOS_EMA_CHUNK;
+  }
+  return n;
+}
+
+int cosmos_ema_table_fill(int64_t n_tensors, const uint64_t* teacher_ptrs, const uint64_t* student_ptrs,
+                          const int64_t* numel, int elem_size, cosmos_ema_chunk* table_host) {
+  if (n_tensors < 0 || (elem_size != 2 && elem_size != 4)) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (n_tensors > 0 && (!teacher_ptrs || !student_ptrs || !numel || !table_host)) return COSMOS_ERR_INVALID_ARGUMENT;
+  int64_t e = 0;
+  for (int64_t i = 0; i < n_tensors; ++i) {
+    if (numel[i] < 0) return COSMOS_ERR_INVALID_ARGUMENT;
+    if (numel[i] > 0 && (teacher_ptrs[i] == 0 || student_ptrs[i] == 0)) return COSMOS_ERR_INVALID_ARGUMENT;
+    if ((teacher_ptrs[i] % elem_size) || (student_ptrs[i] % elem_size)) return COSMOS_ERR_INVALID_ARGUMENT;
+    for (int64_t off = 0; off < numel[i]; off += COSMOS_EMA_CHUNK) {
+      cosmos_ema_chunk& c = table_host[e++];
+      c.teacher = teacher_ptrs[i] + static_cast<uint64_t>(off) * elem_size;
+      c.student = student_ptrs[i] + static_cast<uint64_t>(off) * elem_size;
+      const int64_t left = numel[i] - off;
+      c.count = static_cast<uint32_t>(left < COSMOS_EMA_CHUNK ? left : COSMOS_EMA_CHUNK);
+      c.aligned = ((c.teacher | c.student) & 15) == 0 ? 1u : 0u;
+    }
+  }
+  return COSMOS_OK;
+}
+
+int cosmos_ema_apply(const cosmos_ema_chunk* table_dev, int64_t n_entries, double momentum, int dtype, int device,
+                     void* stream) {
+  if (n_entries < 0 || n_entries > 0x7fffffff || (n_entries > 0 && table_dev == nullptr)) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (dtype != COSMOS_DTYPE_F32 && dtype != COSMOS_DTYPE_BF16 && dtype != COSMOS_DTYPE_F16) return COSMOS_ERR_UNSUPPORTED;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  cudaError_t e = cb::launch_ema(table_dev, static_cast<int>(n_entries), momentum, dtype, sm_count_of(device),
+                                 static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? COSMOS_OK : COSMOS_ERR_CUDA;
+}
+
+}  // extern "C"
+
+namespace {
+
+struct Dims {
+  int pairs, n_row_tiles, n_col_tiles_fwd, n_col_tiles_bwd, n_slabs, ks, n_parts;
+};
+
+int check_problem(const cosmos_infonce_problem* p, Dims* d) {
+  if (p == nullptr) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (p->dtype != COSMOS_DTYPE_BF16 && p->dtype != COSMOS_DTYPE_F16) return COSMOS_ERR_UNSUPPORTED;
+  if (p->dim < 64 || p->dim > 512 || (p->dim % 64) != 0) return COSMOS_ERR_UNSUPPORTED;
+  if (p->gx <= 0 || p->gy <= 0 || p->n_rows <= 0 || p->n_cols <= 0 || p->label_offset < 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (static_cast<int64_t>(p->label_offset) + p->n_rows > p->n_cols) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (p->x == 0 || p->y == 0 || p->scale == 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if ((p->x & 15) || (p->y & 15) || (p->scale & 3)) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (static_cast<int64_t>(p->gx) * p->gy > (1 << 20)) return COSMOS_ERR_UNSUPPORTED;
+  d->pairs = p->gx * p->gy;
+  d->n_row_tiles = (p->n_rows + cb::kFwdBM - 1) / cb::kFwdBM;
+  d->n_col_tiles_fwd = (p->n_cols + cb::kFwdBN - 1) / cb::kFwdBN;
+  d->n_col_tiles_bwd = (p->n_cols + cb::kBwdBN - 1) / cb::kBwdBN;
+  d->n_slabs = d->n_row_tiles * 4;
+  d->ks = p->dim / 64;
+  d->n_parts = (p->dim + cb::kBwdDP - 1) / cb::kBwdDP;
+  return COSMOS_OK;
+}
+
+int64_t fwd_workspace(const cosmos_infonce_problem* p, const Dims& d) {
+  return static_cast<int64_t>(d.pairs) * d.n_slabs * p->n_cols * static_cast<int64_t>(sizeof(float2));
+}
+int64_t bwd_workspace(const cosmos_infonce_problem* p, const Dims& d) {
+  return static_cast<int64_t>(p->gx) * d.n_row_tiles * static_cast<int64_t>(sizeof(float));
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t cosmos_infonce_workspace_bytes(const cosmos_infonce_problem* p) {
+  Dims d;
+  if (check_problem(p, &d) != COSMOS_OK) return -1;
+  const int64_t a = fwd_workspace(p, d), b = bwd_workspace(p, d);
+  return ((a > b ? a : b) + 255) & ~static_cast<int64_t>(255);
+}
+
+int cosmos_infonce_fwd(const cosmos_infonce_problem* p, float* row_lse2, float* diag_raw, float* col_lse2, void* workspace,
+                       int64_t workspace_bytes, int device, void* stream) {
+  Dims d;
+  int st = check_problem(p, &d);
+  if (st != COSMOS_OK) return st;
+  if (!row_lse2 || !diag_raw || !col_lse2 || !workspace) return COSMOS_ERR_INVALID_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < fwd_workspace(p, d)) return COSMOS_ERR_WORKSPACE;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  CUtensorMap tmX, tmY;
+  const int bf = p->dtype == COSMOS_DTYPE_BF16;
+  if (cb::make_stack_map(&tmX, reinterpret_cast<const void*>(p->x), bf, p->dim, p->n_rows, p->gx, cb::kFwdBM) != 0 ||
+      cb::make_stack_map(&tmY, reinterpret_cast<const void*>(p->y), bf, p->dim, p->n_cols, p->gy, cb::kFwdBN) != 0)
+    return COSMOS_ERR_CUDA;
+  cb::FwdParams fp;
+  fp.gx = p->gx; fp.gy = p->gy; fp.n_rows = p->n_rows; fp.n_cols = p->n_cols; fp.ks = d.ks;
+  fp.label_offset = p->label_offset;
+  fp.n_row_tiles = d.n_row_tiles; fp.n_col_tiles = d.n_col_tiles_fwd; fp.n_slabs = d.n_slabs;
+  fp.idesc = cb::make_idesc(bf, 0, 0, cb::kFwdBM, cb::kFwdBN);
+  fp.scale = reinterpret_cast<const float*>(p->scale);
+  fp.row_lse2 = row_lse2; fp.diag_raw = diag_raw;
+  fp.col_part = reinterpret_cast<float2*>(workspace);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cb::launch_infonce_fwd(tmX, tmY, fp, s) != cudaSuccess) return COSMOS_ERR_CUDA;
+  if (cb::launch_col_combine(fp.col_part, col_lse2, d.pairs, d.n_slabs, p->n_cols, s) != cudaSuccess) return COSMOS_ERR_CUDA;
+  return COSMOS_OK;
+}
+
+int cosmos_infonce_loss_sums(const cosmos_infonce_problem* p, const float* row_lse2, const float* diag_raw,
+                             const float* col_lse2, int32_t use_rows, int32_t use_cols, float* out, void* workspace,
+                             int device, void* stream) {
+  (void)workspace;
+  Dims d;
+  int st = check_problem(p, &d);
+  if (st != COSMOS_OK) return st;
+  if (!row_lse2 || !diag_raw || !col_lse2 || !out) return COSMOS_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  if (cb::launch_loss_sums(row_lse2, diag_raw, col_lse2, reinterpret_cast<const float*>(p->scale), d.pairs, p->n_rows,
+                           p->n_cols, p->label_offset, use_rows, use_cols, out, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+    return COSMOS_ERR_CUDA;
+  return COSMOS_OK;
+}
+
+int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, const float* col_lse2, float a_row, float a_col,
+                       float s_row, float s_col, float weight, const float* upstream, void* dx, float* dscale,
+                       void* workspace, int64_t workspace_bytes, int device, void* stream) {
+  Dims d;
+  int st = check_problem(p, &d);
+  if (st != COSMOS_OK) return st;
+  if (!row_lse2 || !col_lse2 || !upstream) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (dx == nullptr && dscale == nullptr) return COSMOS_OK;
+  if (dx != nullptr && (reinterpret_cast<uintptr_t>(dx) & 15) != 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (dscale != nullptr && (workspace == nullptr || workspace_bytes < bwd_workspace(p, d))) return COSMOS_ERR_WORKSPACE;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  CUtensorMap tmX, tmY;
+  const int bf = p->dtype == COSMOS_DTYPE_BF16;
+  if (cb::make_stack_map(&tmX, reinterpret_cast<const void*>(p->x), bf, p->dim, p->n_rows, p->gx, cb::kFwdBM) != 0 ||
+      cb::make_stack_map(&tmY, reinterpret_cast<const void*>(p->y), bf, p->dim, p->n_cols, p->gy, cb::kBwdBN) != 0)
+    return COSMOS_ERR_CUDA;
+  cb::BwdParams bp;
+  bp.gx = p->gx; bp.gy = p->gy; bp.n_rows = p->n_rows; bp.n_cols = p->n_cols; bp.ks = d.ks;
+  bp.label_offset = p->label_offset;
+  bp.n_row_tiles = d.n_row_tiles; bp.n_col_tiles = d.n_col_tiles_bwd;
+  bp.n_parts = dx != nullptr ? d.n_parts : 1;
+  bp.dtype = p->dtype;
+  bp.idesc_s = cb::make_idesc(bf, 0, 0, cb::kFwdBM, cb::kBwdBN);
+  bp.idesc_g = cb::make_idesc(bf, 0, 1, cb::kFwdBM, 64);
+  bp.a_row = a_row; bp.a_col = a_col; bp.s_row = s_row; bp.s_col = s_col; bp.weight = weight;
+  bp.scale = reinterpret_cast<const float*>(p->scale);
+  bp.upstream = upstream;
+  bp.row_lse2 = row_lse2; bp.col_lse2 = col_lse2;
+  bp.dx = dx;
+  bp.dscale_part = dscale != nullptr ? reinterpret_cast<float*>(workspace) : nullptr;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cb::launch_infonce_bwd(tmX, tmY, bp, s) != cudaSuccess) return COSMOS_ERR_CUDA;
+  if (dscale != nullptr &&
+      cb::launch_dscale_reduce(bp.dscale_part, p->gx * d.n_row_tiles, weight, upstream, dscale, s) != cudaSuccess)
+    return COSMOS_ERR_CUDA;
+  return COSMOS_OK;
+}
+
+}  // extern "C"

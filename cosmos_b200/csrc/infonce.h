@@ -1,0 +1,50 @@
+// Parameter blocks and launchers of the InfoNCE kernels (shared by infonce_*.cu and api.cu).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cb {
+
+constexpr int kFwdBM = 128;  // rows per CTA tile  (= TMEM lanes)
+constexpr int kFwdBN = 256;  // columns per forward MMA tile
+constexpr int kBwdBN = 128;  // columns per backward step
+constexpr int kBwdDP = 256;  // embedding columns of dX one backward CTA accumulates (TMEM budget)
+
+struct FwdParams {
+  int gx, gy, n_rows, n_cols, ks, label_offset;
+  int n_row_tiles, n_col_tiles, n_slabs;  // n_slabs = 4 * n_row_tiles (32-row slabs)
+  uint32_t idesc;
+  const float* scale;
+  float* row_lse2;
+  float* diag_raw;
+  float2* col_part;  // [gx*gy][n_slabs][n_cols] (max2, sum)
+};
+
+struct BwdParams {
+  int gx, gy, n_rows, n_cols, ks, label_offset;
+  int n_row_tiles, n_col_tiles, n_parts;  // n_parts = ceil(dim / 256)
+  int dtype;                              // COSMOS_DTYPE_BF16 / _F16
+  uint32_t idesc_s, idesc_g;
+  float a_row, a_col, s_row, s_col, weight;
+  const float* scale;
+  const float* upstream;
+  const float* row_lse2;  // [gx*gy][n_rows]
+  const float* col_lse2;  // [gx*gy][n_cols]
+  void* dx;               // [gx][n_rows][dim] stack dtype, may be null
+  float* dscale_part;     // [items] partial sums of <dscale-mix, raw logits>, may be null
+};
+
+cudaError_t launch_infonce_fwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, cudaStream_t stream);
+cudaError_t launch_infonce_bwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const BwdParams& p, cudaStream_t stream);
+
+// infonce_aux.cu
+cudaError_t launch_col_combine(const float2* col_part, float* col_lse2, int pairs, int n_slabs, int n_cols, cudaStream_t stream);
+cudaError_t launch_loss_sums(const float* row_lse2, const float* diag_raw, const float* col_lse2, const float* scale, int pairs,
+                             int n_rows, int n_cols, int label_offset, int use_rows, int use_cols, float* out,
+                             cudaStream_t stream);
+cudaError_t launch_dscale_reduce(const float* part, int n, float weight, const float* upstream, float* dscale,
+                                 cudaStream_t stream);
+
+}  // namespace cb

@@ -1,0 +1,98 @@
+// Small HBM-bound helpers around the InfoNCE tile kernels: merge of per-slab column statistics,
+// per-pair loss sums, and the deterministic reduction of the per-CTA dscale partials.
+#include "common.cuh"
+#include "infonce.h"
+
+namespace cb {
+
+// col_part [pairs][n_slabs][n_cols] (max2, sum) -> col_lse2 [pairs][n_cols]; coalesced over columns.
+__global__ void __launch_bounds__(256)
+col_combine_kernel(const float2* __restrict__ col_part, float* __restrict__ col_lse2, int n_slabs, int n_cols) {
+  const int pair = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cols) return;
+  const float2* src = col_part + static_cast<size_t>(pair) * n_slabs * n_cols + c;
+  float m = -INFINITY, l = 0.f;
+  for (int s = 0; s < n_slabs; ++s) {
+    const float2 v = __ldcs(src + static_cast<size_t>(s) * n_cols);
+    if (v.x > m) {
+      l *= ex2(m - v.x);
+      m = v.x;
+    }
+    if (v.x != -INFINITY) l += v.y * ex2(v.x - m);
+  }
+  col_lse2[static_cast<size_t>(pair) * n_cols + c] = m + log2f(l);
+}
+
+cudaError_t launch_col_combine(const float2* col_part, float* col_lse2, int pairs, int n_slabs, int n_cols, cudaStream_t stream) {
+  dim3 grid((n_cols + 255) / 256, pairs);
+  col_combine_kernel<<<grid, 256, 0, stream>>>(col_part, col_lse2, n_slabs, n_cols);
+  return cudaGetLastError();
+}
+
+// out[pair][0] = sum_r (ln2 * row_lse2[r] - scale * diag[r])
+// out[pair][1] = sum_r (ln2 * col_lse2[label_offset + r] - scale * diag[r])      (this rank's diagonal columns)
+__global__ void __launch_bounds__(256)
+loss_sums_kernel(const float* __restrict__ row_lse2, const float* __restrict__ diag_raw, const float* __restrict__ col_lse2,
+                 const float* __restrict__ scale_ptr, int n_rows, int n_cols, int label_offset, int use_rows, int use_cols,
+                 float* __restrict__ out) {
+  const int pair = blockIdx.x;
+  const float scale = __ldg(scale_ptr);
+  double sr = 0.0, sc = 0.0;
+  for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
+    const float d = scale * diag_raw[static_cast<size_t>(pair) * n_rows + r];
+    if (use_rows) sr += static_cast<double>(kLn2 * row_lse2[static_cast<size_t>(pair) * n_rows + r] - d);
+    if (use_cols) sc += static_cast<double>(kLn2 * col_lse2[static_cast<size_t>(pair) * n_cols + label_offset + r] - d);
+  }
+  __shared__ double red[2][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    sr += __shfl_xor_sync(0xffffffffu, sr, o);
+    sc += __shfl_xor_sync(0xffffffffu, sc, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = sr;
+    red[1][threadIdx.x >> 5] = sc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) {
+      a += red[0][w];
+      b += red[1][w];
+    }
+    out[2 * pair + 0] = static_cast<float>(a);
+    out[2 * pair + 1] = static_cast<float>(b);
+  }
+}
+
+cudaError_t launch_loss_sums(const float* row_lse2, const float* diag_raw, const float* col_lse2, const float* scale, int pairs,
+                             int n_rows, int n_cols, int label_offset, int use_rows, int use_cols, float* out,
+                             cudaStream_t stream) {
+  loss_sums_kernel<<<pairs, 256, 0, stream>>>(row_lse2, diag_raw, col_lse2, scale, n_rows, n_cols, label_offset, use_rows,
+                                              use_cols, out);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+dscale_reduce_kernel(const float* __restrict__ part, int n, float weight, const float* __restrict__ upstream,
+                     float* __restrict__ dscale) {
+  double s = 0.0;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) s += static_cast<double>(part[k]);
+  __shared__ double red[8];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0;
+    for (int w = 0; w < 8; ++w) a += red[w];
+    *dscale = static_cast<float>(a * static_cast<double>(weight) * static_cast<double>(__ldg(upstream)));
+  }
+}
+
+cudaError_t launch_dscale_reduce(const float* part, int n, float weight, const float* upstream, float* dscale,
+                                 cudaStream_t stream) {
+  dscale_reduce_kernel<<<1, 256, 0, stream>>>(part, n, weight, upstream, dscale);
+  return cudaGetLastError();
+}
+
+}  // namespace cb

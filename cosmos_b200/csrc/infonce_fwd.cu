@@ -1,0 +1,240 @@
+// InfoNCE forward: flash-style log-sum-exp of S = scale * X Y^T over rows AND columns, for every
+// (row tensor i, column tensor j) block of a stack at once.  S never leaves the SM:
+//   TMA (128B-swizzled slabs) -> smem -> tcgen05.mma (M128 x N256 x K16, bf16/fp16 in, fp32 out)
+//   -> TMEM (2 x 256 columns, double buffered) -> tcgen05.ld -> online softmax statistics.
+//
+// One CTA = one work item (column tensor j, row tensor i, 128-row tile): its X tile stays in
+// shared memory (<= 8 K-slabs of 16 KB) while 256-column tiles of Y_j stream through a 3-stage ring.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue
+// (warp%4 selects the TMEM lane quarter = 32 rows, warp/4-1 the 128-column half of the tile).
+//
+// Row statistics are thread-local (one thread = one row): running max / sum in log2 units.
+// Column statistics need a reduction over rows: a 31-shuffle warp transpose-reduce per 32x32 block
+// gives lane L the (max, sum) of column L over the warp's 32 rows, written as a partial to the
+// workspace [pair][32-row slab][column]; col_combine_kernel (infonce_aux.cu) merges the slabs.
+//
+// Reference semantics: src/open_clip/loss.py:103-142 (get_logits + the two F.cross_entropy calls);
+// the positive of local row r is column label_offset + r (loss.py:90-101 with rank offset).
+#include "common.cuh"
+#include "infonce.h"
+
+namespace cb {
+
+namespace {
+
+constexpr int BM = kFwdBM, BN = kFwdBN;
+constexpr int kStages = 3;
+constexpr int kSlabX = BM * 64 * 2;    // 16 KB : 128 rows x 64 elements
+constexpr int kStageY = BN * 64 * 2;   // 32 KB : 256 cols x 64 elements
+constexpr int kSmemX = 8 * kSlabX;     // 128 KB
+constexpr int kSmemY = kStages * kStageY;
+constexpr int kSmemMisc = 2048;
+constexpr int kThreads = 384;
+constexpr int kEpiThreads = 256;
+
+struct Misc {
+  uint64_t x_full;
+  uint64_t y_full[kStages];
+  uint64_t y_empty[kStages];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_slot;
+  uint32_t pad[5];
+  float bcast[8][32];
+};
+static_assert(sizeof(Misc) <= kSmemMisc, "misc smem");
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sX = smem;
+  uint8_t* sY = smem + kSmemX;
+  Misc* misc = reinterpret_cast<Misc*>(smem + kSmemX + kSmemY);
+
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // work item
+  const int per_j = p.gx * p.n_row_tiles;
+  const int j = blockIdx.x / per_j;
+  const int rem = blockIdx.x - j * per_j;
+  const int i = rem / p.n_row_tiles;
+  const int tr = rem - i * p.n_row_tiles;
+  const int pair = i * p.gy + j;
+  const int ks = p.ks;
+  const int n_ct = p.n_col_tiles;
+
+  if (tid == 0) {
+    mbar_init(&misc->x_full, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&misc->y_full[s], 1);
+      mbar_init(&misc->y_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&misc->acc_full[s], 1);
+      mbar_init(&misc->acc_empty[s], kEpiThreads);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 2) tmem_alloc<512>(&misc->tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = misc->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      mbar_expect_tx(&misc->x_full, ks * kSlabX);
+      for (int s = 0; s < ks; ++s) tma_load_3d(sX + s * kSlabX, &tmX, &misc->x_full, s * 64, tr * BM, i);
+      uint32_t stage = 0, phase = 0;
+      for (int tc = 0; tc < n_ct; ++tc) {
+        for (int s = 0; s < ks; ++s) {
+          mbar_wait(&misc->y_empty[stage], phase ^ 1);
+          mbar_expect_tx(&misc->y_full[stage], kStageY);
+          tma_load_3d(sY + stage * kStageY, &tmY, &misc->y_full[stage], s * 64, tc * BN, j);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      mbar_wait(&misc->x_full, 0);
+      uint32_t stage = 0, phase = 0;
+      for (int tc = 0; tc < n_ct; ++tc) {
+        const uint32_t as = tc & 1;
+        mbar_wait(&misc->acc_empty[as], ((tc >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + as * BN;
+        for (int s = 0; s < ks; ++s) {
+          mbar_wait(&misc->y_full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sX + s * kSlabX);
+          const uint32_t b_base = smem_u32(sY + stage * kStageY);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_ss(d_tmem, make_smem_desc(a_base + kk * 32, 0, 1024), make_smem_desc(b_base + kk * 32, 0, 1024), p.idesc,
+                    (s | kk) != 0);
+          }
+          tc_commit(&misc->y_empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&misc->acc_full[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue: online row / column softmax statistics ----------------
+    const uint32_t ew = warp - 4;
+    const uint32_t q = warp & 3;   // TMEM lane quarter this warp may access
+    const uint32_t h = ew >> 2;    // column half of the tile
+    const int row = tr * BM + q * 32 + lane;
+    const bool row_valid = row < p.n_rows;
+    const int label = p.label_offset + row;
+    const float k2 = __ldg(p.scale) * kLog2e;
+    const float NEG_INF = -INFINITY;
+
+    float m_run = NEG_INF, l_run = 0.f, diag = 0.f;
+    float2* col_part = p.col_part + (static_cast<size_t>(pair) * p.n_slabs + tr * 4 + q) * p.n_cols;
+
+    for (int tc = 0; tc < n_ct; ++tc) {
+      const uint32_t as = tc & 1;
+      mbar_wait(&misc->acc_full[as], (tc >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        const int col0 = tc * BN + h * 128 + chunk * 32;
+        if (col0 >= p.n_cols) break;
+        uint32_t v[32];
+        tmem_ld32(tmem + ((q * 32u) << 16) + as * BN + h * 128 + chunk * 32, v);
+        tmem_ld_wait();
+        float t[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t[k] = __uint_as_float(v[k]) * k2;
+        if (col0 + 32 > p.n_cols) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) t[k] = (col0 + k < p.n_cols) ? t[k] : NEG_INF;
+        }
+        if (row_valid && label >= col0 && label < col0 + 32) {
+          const int idx = label - col0;
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (k == idx) diag = __uint_as_float(v[k]);
+        }
+        // rows: this thread's row, running (max, sum)
+        float cm = t[0];
+#pragma unroll
+        for (int k = 1; k < 32; ++k) cm = fmaxf(cm, t[k]);
+        if (cm > m_run) {
+          l_run *= ex2(m_run - cm);
+          m_run = cm;
+        }
+        if (m_run != NEG_INF) {
+          float s = 0.f;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) s += ex2(t[k] - m_run);
+          l_run += s;
+        }
+        // columns: reduce over the warp's 32 rows
+        if (!row_valid) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) t[k] = NEG_INF;
+        }
+        const float cmx = warp_transpose_reduce(t, lane, OpMax());
+        misc->bcast[ew][lane] = cmx;
+        __syncwarp();
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 o = *reinterpret_cast<const float4*>(&misc->bcast[ew][k4 * 4]);
+          t[k4 * 4 + 0] = ex2(t[k4 * 4 + 0] - (o.x == NEG_INF ? 0.f : o.x));
+          t[k4 * 4 + 1] = ex2(t[k4 * 4 + 1] - (o.y == NEG_INF ? 0.f : o.y));
+          t[k4 * 4 + 2] = ex2(t[k4 * 4 + 2] - (o.z == NEG_INF ? 0.f : o.z));
+          t[k4 * 4 + 3] = ex2(t[k4 * 4 + 3] - (o.w == NEG_INF ? 0.f : o.w));
+        }
+        __syncwarp();
+        const float csum = warp_transpose_reduce(t, lane, OpAdd());
+        if (col0 + static_cast<int>(lane) < p.n_cols) col_part[col0 + lane] = make_float2(cmx, csum);
+      }
+      tc_fence_before();
+      mbar_arrive(&misc->acc_empty[as]);
+    }
+
+    // merge the two column halves of each row; the Y ring is idle now (every MMA has completed)
+    float4* exch = reinterpret_cast<float4*>(sY);
+    if (h == 1) exch[q * 32 + lane] = make_float4(m_run, l_run, diag, 0.f);
+    named_bar_sync(1, kEpiThreads);
+    if (h == 0 && row_valid) {
+      const float4 o = exch[q * 32 + lane];
+      const float m = fmaxf(m_run, o.x);
+      float l = 0.f;
+      if (m_run != NEG_INF) l += l_run * ex2(m_run - m);
+      if (o.x != NEG_INF) l += o.y * ex2(o.x - m);
+      // the label column lives in exactly one half; the other half's diag stayed 0
+      const size_t out = static_cast<size_t>(pair) * p.n_rows + row;
+      p.row_lse2[out] = m + log2f(l);
+      p.diag_raw[out] = diag + o.z;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+cudaError_t launch_infonce_fwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, cudaStream_t stream) {
+  const int smem_bytes = kSmemX + kSmemY + kSmemMisc + 1024;
+  static_assert(kSmemX + kSmemY + kSmemMisc + 1024 <= 232448, "shared memory budget");
+  cudaError_t e = cudaFuncSetAttribute(infonce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return e;
+  const int grid = p.gy * p.gx * p.n_row_tiles;
+  infonce_fwd_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmX, tmY, p);
+  return cudaGetLastError();
+}
+
+}  // namespace cb

@@ -1,0 +1,85 @@
+"""EMA teacher update, one kernel launch for the whole parameter set.
+
+Drop-in for the inline loop of the reference's train_one_epoch
+(src/training/train.py:195-203):
+
+    with torch.no_grad():
+        for param_q, param_k in zip(student.parameters(), teacher.parameters()):
+            param_k.data.mul_(momentum).add_((1 - momentum) * param_q.detach().data)
+
+`ema_update_(student, teacher, momentum)` has the same semantics (same rounding: fp32 results
+are bit-identical), updates the SAME teacher storage in place (checkpointing keeps working,
+SURVEY.md §5) and runs after backward / before optimizer.step exactly where the loop sat.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Sequence, Union
+
+import torch
+
+from . import _lib
+
+
+def _params(x) -> List[torch.Tensor]:
+    if isinstance(x, torch.nn.Module):
+        return list(x.parameters())
+    return list(x)
+
+
+class EmaPlan:
+    """Chunk table for one (student, teacher) parameter set; rebuilt only when a pointer moves."""
+
+    def __init__(self, student: Sequence[torch.Tensor], teacher: Sequence[torch.Tensor]):
+        if len(student) != len(teacher):
+            raise RuntimeError("cosmos_b200.ema: student and teacher have different numbers of parameters")
+        self.groups = []   # one (dtype_code, device_index, table_tensor, n_entries) per (dtype, device)
+        buckets = {}
+        for q, k in zip(student, teacher):
+            _lib.require_cuda(k, "teacher parameter")
+            _lib.require_cuda(q, "student parameter")
+            if q.shape != k.shape or q.dtype != k.dtype or q.device != k.device:
+                raise RuntimeError("cosmos_b200.ema: student/teacher parameter mismatch "
+                                   f"({tuple(q.shape)} {q.dtype} {q.device} vs {tuple(k.shape)} {k.dtype} {k.device})")
+            if not (q.is_contiguous() and k.is_contiguous()):
+                raise RuntimeError("cosmos_b200.ema: parameters must be contiguous")
+            if k.numel() == 0:
+                continue
+            buckets.setdefault((k.dtype, k.device.index), []).append((k, q))
+        self.key = tuple((k.data_ptr(), q.data_ptr(), k.numel()) for q, k in zip(student, teacher))
+        lib = _lib.lib()
+        for (dtype, dev), pairs in buckets.items():
+            n = len(pairs)
+            numel = (C.c_int64 * n)(*[k.numel() for k, _ in pairs])
+            kp = (C.c_uint64 * n)(*[k.data_ptr() for k, _ in pairs])
+            qp = (C.c_uint64 * n)(*[q.data_ptr() for _, q in pairs])
+            entries = lib.cosmos_ema_table_entries(n, numel)
+            if entries < 0:
+                raise RuntimeError("cosmos_b200.ema: bad parameter sizes")
+            host = torch.empty(entries * C.sizeof(_lib.EmaChunk), dtype=torch.uint8, pin_memory=True)
+            _lib.check(lib.cosmos_ema_table_fill(n, kp, qp, numel, k.element_size(), host.data_ptr()), "ema_table_fill")
+            table = host.to(torch.device("cuda", dev), non_blocking=False)
+            self.groups.append((_lib.torch_dtype_code(dtype), dev, table, entries))
+
+    def apply(self, momentum: float) -> None:
+        lib = _lib.lib()
+        for code, dev, table, entries in self.groups:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.cosmos_ema_apply(table.data_ptr(), entries, float(momentum), code, dev, stream), "ema_apply")
+
+
+_plans = {}
+
+
+@torch.no_grad()
+def ema_update_(student: Union[torch.nn.Module, Iterable[torch.Tensor]],
+                teacher: Union[torch.nn.Module, Iterable[torch.Tensor]], momentum: float) -> None:
+    """teacher <- teacher * momentum + (1 - momentum) * student, in place, on the current stream."""
+    sp, tp = _params(student), _params(teacher)
+    key = tuple((k.data_ptr(), q.data_ptr(), k.numel()) for q, k in zip(sp, tp))
+    plan = _plans.get(id(teacher) if isinstance(teacher, torch.nn.Module) else None)
+    if plan is None or plan.key != key:
+        plan = EmaPlan(sp, tp)
+        if isinstance(teacher, torch.nn.Module):
+            _plans[id(teacher)] = plan
+    plan.apply(momentum)

@@ -1,0 +1,285 @@
+"""Host side of the block-structured InfoNCE kernels.
+
+`pairs_infonce(rows, cols, scale, ...)` is the mean, over the cartesian product of two feature
+lists, of the symmetric InfoNCE loss the reference computes pair by pair in
+`ClipLoss.forward` (src/open_clip/loss.py:121-142), including the multi-rank gather semantics of
+`gather_features` / `get_logits` (loss.py:21-65, 103-119).  All pairs of one call go through ONE
+forward kernel launch and one (row side) or two (both sides need gradients) backward launches.
+
+Partitioning: this rank owns `b` rows of every tensor.  The forward computes the
+row block  S[local rows of R_i, all N rows of C_j]  for every pair; that yields
+  * the complete row log-sum-exp of the local rows,
+  * this rank's partial column log-sum-exp for all N columns  -> combined with two all-reduces,
+  * the positives (diagonal).
+The backward recomputes the same block and needs nothing else from other ranks for the row side;
+the column side (only when it needs gradients, i.e. the CLIP term) is the same kernel run on the
+transposed block  S^T[local rows of C_j, all N rows of R_i].
+
+Mode table (probed against the reference on gloo ranks, tests/golden/multirank_w*.pt), N = W*b,
+P = number of pairs, R/C = row/column softmax, I = positives:
+
+  local_loss gather_with_grad   returned loss            d features (local)          d scale
+  False      False              global  /(2NP)           (R+C-2I)      /(2NP)        global sum (all-reduce)
+  False      True               global  /(2NP)           (R+C-2I) * W  /(2NP)        global sum (all-reduce)
+  True       True               local   /(2bP)           (R+C-2I)      /(2bP)        local rows of S and of S^T
+  True       False              local   /(2bP)           (R - I) only  /(2bP)        local rows of S and of S^T
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+LN2 = math.log(2.0)
+
+
+@dataclass(frozen=True)
+class Comm:
+    """Which ranks share the loss; mirrors the ctor arguments of the reference losses."""
+    rank: int = 0
+    world_size: int = 1
+    local_loss: bool = False
+    gather_with_grad: bool = False
+    group: Optional[object] = None
+
+    @property
+    def distributed(self) -> bool:
+        return self.world_size > 1
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel entry points (ctypes).  Tests that exercise the multi-rank host logic on CPU replace these
+# three functions with an oracle-backed emulation; the product has no other implementation.
+# ------------------------------------------------------------------------------------------------
+
+def _problem(x: torch.Tensor, y: torch.Tensor, label_offset: int, scale: torch.Tensor) -> _lib.InfoNceProblem:
+    gx, n_rows, dim = x.shape
+    gy, n_cols, dim_y = y.shape
+    if dim != dim_y or x.dtype != y.dtype:
+        raise RuntimeError("cosmos_b200: row and column stacks must share dim and dtype")
+    return _lib.InfoNceProblem(x=x.data_ptr(), y=y.data_ptr(), gx=gx, gy=gy, n_rows=n_rows, n_cols=n_cols, dim=dim,
+                               label_offset=label_offset, dtype=_lib.torch_dtype_code(x.dtype), reserved=0,
+                               scale=scale.data_ptr())
+
+
+def _workspace(prob: _lib.InfoNceProblem, device) -> torch.Tensor:
+    nbytes = _lib.lib().cosmos_infonce_workspace_bytes(C.byref(prob))
+    if nbytes < 0:
+        raise RuntimeError("cosmos_b200: unsupported InfoNCE problem "
+                           f"(dim={prob.dim} must be a multiple of 64 and <= 512, dtype bf16/fp16, n_cols >= label_offset + n_rows)")
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _k_fwd(x, y, label_offset, scale):
+    """-> row_lse2 [P, b], diag_raw [P, b], col_lse2 (this rank's rows only) [P, N]; fp32."""
+    dev = x.device
+    prob = _problem(x, y, label_offset, scale)
+    P = prob.gx * prob.gy
+    row_lse2 = torch.empty(P, prob.n_rows, dtype=torch.float32, device=dev)
+    diag_raw = torch.empty(P, prob.n_rows, dtype=torch.float32, device=dev)
+    col_lse2 = torch.empty(P, prob.n_cols, dtype=torch.float32, device=dev)
+    ws = _workspace(prob, dev)
+    st = _lib.lib().cosmos_infonce_fwd(C.byref(prob), row_lse2.data_ptr(), diag_raw.data_ptr(), col_lse2.data_ptr(),
+                                       ws.data_ptr(), ws.numel(), dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(st, "infonce_fwd")
+    return row_lse2, diag_raw, col_lse2
+
+
+def _k_loss_sums(x, y, label_offset, scale, row_lse2, diag_raw, col_lse2):
+    """-> [P, 2] fp32: natural-log row-CE sum over local rows, column-CE sum over this rank's diagonal columns."""
+    dev = x.device
+    prob = _problem(x, y, label_offset, scale)
+    out = torch.empty(prob.gx * prob.gy, 2, dtype=torch.float32, device=dev)
+    st = _lib.lib().cosmos_infonce_loss_sums(C.byref(prob), row_lse2.data_ptr(), diag_raw.data_ptr(), col_lse2.data_ptr(),
+                                             1, 1, out.data_ptr(), None, dev.index,
+                                             torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(st, "infonce_loss_sums")
+    return out
+
+
+def _k_bwd(x, y, label_offset, scale, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream, want_dx, want_dscale):
+    """-> dx [gx, b, D] in x.dtype (or None), dscale fp32 [1] (or None)."""
+    dev = x.device
+    prob = _problem(x, y, label_offset, scale)
+    dx = torch.empty_like(x) if want_dx else None
+    dscale = torch.empty(1, dtype=torch.float32, device=dev) if want_dscale else None
+    ws = _workspace(prob, dev)
+    st = _lib.lib().cosmos_infonce_bwd(C.byref(prob), row_lse2.data_ptr(), col_lse2.data_ptr(), a_row, a_col, s_row, s_col,
+                                       weight, upstream.data_ptr(), dx.data_ptr() if want_dx else None,
+                                       dscale.data_ptr() if want_dscale else None, ws.data_ptr(), ws.numel(), dev.index,
+                                       torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(st, "infonce_bwd")
+    return dx, dscale
+
+
+# ------------------------------------------------------------------------------------------------
+# layout helpers
+# ------------------------------------------------------------------------------------------------
+
+def compute_dtype(dtype: torch.dtype) -> torch.dtype:
+    """16-bit inputs are consumed as they are; fp32 features are rounded to bf16 for the tensor cores
+    (the arithmetic type of this path), accumulation and softmax stay fp32."""
+    return dtype if dtype in (torch.bfloat16, torch.float16) else torch.bfloat16
+
+
+def stack_views(tensors: Sequence[torch.Tensor], dtype: torch.dtype) -> torch.Tensor:
+    """[n, b, D] stack of same-shape 2-D tensors.  Zero-copy when they are consecutive views of one
+    buffer (the reference's `.chunk()` outputs, src/training/train.py:171-182)."""
+    t0 = tensors[0]
+    if t0.dim() != 2:
+        raise RuntimeError(f"cosmos_b200: features must be [batch, dim] matrices, got shape {tuple(t0.shape)}")
+    b, d = t0.shape
+    for t in tensors:
+        if t.shape != t0.shape or t.dtype != t0.dtype or t.device != t0.device:
+            raise RuntimeError("cosmos_b200: every feature tensor of a list must have the same shape, dtype and device")
+    step = b * d * t0.element_size()
+    if (t0.dtype == dtype and all(t.is_contiguous() for t in tensors) and t0.data_ptr() % 16 == 0
+            and all(t.data_ptr() == t0.data_ptr() + k * step for k, t in enumerate(tensors))
+            and t0.untyped_storage().data_ptr() == tensors[-1].untyped_storage().data_ptr()):
+        return torch.as_strided(t0.detach(), (len(tensors), b, d), (b * d, d, 1))
+    return torch.stack([t.detach() for t in tensors]).to(dtype)
+
+
+def gather_stack(local: torch.Tensor, comm: Comm) -> torch.Tensor:
+    """[n, b, D] on every rank -> [n, W*b, D], rows ordered rank-major as torch.cat(all_gather) does."""
+    if not comm.distributed:
+        return local
+    n, b, d = local.shape
+    out = torch.empty(comm.world_size * n, b, d, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=comm.group)
+    return out.view(comm.world_size, n, b, d).permute(1, 0, 2, 3).reshape(n, comm.world_size * b, d)
+
+
+def _allreduce_lse2(lse2: torch.Tensor, comm: Comm) -> torch.Tensor:
+    """log2-sum-exp2 over ranks of per-rank partial column statistics (max all-reduce + sum all-reduce)."""
+    if not comm.distributed:
+        return lse2
+    m = lse2.clone()
+    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=comm.group)
+    s = torch.exp2(lse2 - m)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=comm.group)
+    return m + torch.log2(s)
+
+
+def _gather_rows(t: torch.Tensor, comm: Comm) -> torch.Tensor:
+    """[P, b] per rank -> [P, W*b]."""
+    if not comm.distributed:
+        return t
+    P, b = t.shape
+    out = torch.empty(comm.world_size * P, b, dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=comm.group)
+    return out.view(comm.world_size, P, b).permute(1, 0, 2).reshape(P, comm.world_size * b)
+
+
+def _swap_pairs(t: torch.Tensor, n_r: int, n_c: int) -> torch.Tensor:
+    """[n_r * n_c, L] with pair = i * n_c + j  ->  [n_c * n_r, L] with pair = j * n_r + i."""
+    return t.view(n_r, n_c, -1).transpose(0, 1).reshape(n_c * n_r, -1).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd node
+# ------------------------------------------------------------------------------------------------
+
+class _PairsInfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scale: torch.Tensor, comm: Comm, n_r: int, *feats: torch.Tensor):
+        rows, cols = feats[:n_r], feats[n_r:]
+        n_c = len(cols)
+        dev = rows[0].device
+        dt = compute_dtype(rows[0].dtype)
+        x_r = stack_views(rows, dt)                       # [n_r, b, D]
+        x_c = stack_views(cols, dt)                       # [n_c, b, D]
+        b = x_r.shape[1]
+        if x_c.shape[1] != b:
+            raise RuntimeError("cosmos_b200: both feature lists must have the same batch size")
+        W = comm.world_size
+        N = W * b
+        off = comm.rank * b if comm.distributed else 0
+        scale_f = scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+
+        y_c = gather_stack(x_c, comm)                     # [n_c, N, D]
+        row_lse2, diag_raw, col_lse2_part = _k_fwd(x_r, y_c, off, scale_f)
+        col_lse2 = _allreduce_lse2(col_lse2_part, comm)   # global over all rows
+        sums = _k_loss_sums(x_r, y_c, off, scale_f, row_lse2, diag_raw, col_lse2)   # [P, 2]
+        P = n_r * n_c
+        total = sums.sum()
+        if comm.distributed and not comm.local_loss:
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=comm.group)
+            loss = total / (2.0 * N * P)
+        else:
+            loss = total / (2.0 * b * P)
+
+        ctx.comm, ctx.n_r, ctx.n_c, ctx.b, ctx.off = comm, n_r, n_c, b, off
+        ctx.in_dtypes = [t.dtype for t in feats]
+        ctx.scale_dtype = scale.dtype
+        ctx.save_for_backward(x_r, x_c, y_c, scale_f, row_lse2, col_lse2)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g: torch.Tensor):
+        x_r, x_c, y_c, scale_f, row_lse2, col_lse2 = ctx.saved_tensors
+        comm, n_r, n_c, b, off = ctx.comm, ctx.n_r, ctx.n_c, ctx.b, ctx.off
+        W = comm.world_size
+        N, P = W * b, n_r * n_c
+        need_scale = ctx.needs_input_grad[0]
+        need_rows = any(ctx.needs_input_grad[3:3 + n_r])
+        need_cols = any(ctx.needs_input_grad[3 + n_r:])
+        up = g.detach().to(torch.float32).reshape(1).contiguous()
+
+        local = comm.distributed and comm.local_loss
+        if local:
+            weight = 1.0 / (2.0 * b * P)
+            a = (1.0, 1.0) if comm.gather_with_grad else (1.0, 0.0)
+            s_mix = (1.0, 0.0)                      # each side reports its own rows' part of dscale
+        else:
+            boost = float(W) if (comm.distributed and comm.gather_with_grad) else 1.0
+            weight = boost / (2.0 * N * P)
+            a = (1.0, 1.0)
+            s_mix = (1.0 / boost, 1.0 / boost)
+
+        d_rows = d_scale = d_cols = None
+        if need_rows or need_scale:
+            d_rows, d_scale = _k_bwd(x_r, y_c, off, scale_f, row_lse2, col_lse2, a[0], a[1], s_mix[0], s_mix[1], weight, up,
+                                     need_rows, need_scale)
+        if need_cols or (local and need_scale):
+            # transposed block: rows = local column-side tensors, columns = all rows of the row side
+            y_r = gather_stack(x_r, comm)                                   # [n_r, N, D]
+            row_lse2_all = _gather_rows(row_lse2, comm)                     # [P, N]
+            t_row = _swap_pairs(col_lse2[:, off:off + b], n_r, n_c)         # row LSE of S^T for my rows
+            t_col = _swap_pairs(row_lse2_all, n_r, n_c)                     # column LSE of S^T (global)
+            d_cols, d_scale_t = _k_bwd(x_c, y_r, off, scale_f, t_row, t_col, a[0], a[1], s_mix[0], s_mix[1], weight, up,
+                                       need_cols, local and need_scale)
+            if d_scale_t is not None:
+                d_scale = d_scale_t if d_scale is None else d_scale + d_scale_t
+        if need_scale and comm.distributed and not comm.local_loss:
+            dist.all_reduce(d_scale, op=dist.ReduceOp.SUM, group=comm.group)
+
+        grads: List[Optional[torch.Tensor]] = []
+        for k in range(n_r):
+            grads.append(d_rows[k].to(ctx.in_dtypes[k]) if (d_rows is not None and ctx.needs_input_grad[3 + k]) else None)
+        for k in range(n_c):
+            grads.append(d_cols[k].to(ctx.in_dtypes[n_r + k])
+                         if (d_cols is not None and ctx.needs_input_grad[3 + n_r + k]) else None)
+        g_scale = d_scale.reshape(()).to(ctx.scale_dtype) if need_scale else None
+        return (g_scale, None, None, *grads)
+
+
+def pairs_infonce(rows: Sequence[torch.Tensor], cols: Sequence[torch.Tensor], scale, comm: Comm = Comm()) -> torch.Tensor:
+    """Mean symmetric InfoNCE over all (row tensor, column tensor) pairs; a 0-dim fp32 tensor.
+
+    The loss is symmetric in its two lists, so callers pass the longer / gradient-carrying list as
+    `rows` (it is never communicated) and the shorter one as `cols` (it is all-gathered)."""
+    rows, cols = list(rows), list(cols)
+    if not rows or not cols:
+        raise RuntimeError("cosmos_b200: empty feature list")
+    for t in rows + cols:
+        _lib.require_cuda(t, "feature tensor")
+    if not isinstance(scale, torch.Tensor):
+        scale = torch.tensor(float(scale), dtype=torch.float32, device=rows[0].device)
+    return _PairsInfoNCE.apply(scale, comm, len(rows), *rows, *cols)

@@ -1,0 +1,192 @@
+"""Drop-in replacement for the loss API of the reference's `open_clip.loss`
+(src/open_clip/loss.py:21-207): `gather_features`, `ClipLoss`, `COSMOSLoss` keep their constructor
+and forward signatures, argument meaning, return conventions (0-dim tensors, the
+{"distill_loss", "clip_loss"} dict) and error behaviour, but the pairwise
+logits + cross-entropy work runs in the sm_100a kernels of libcosmos_b200.so
+(cosmos_b200/infonce.py) instead of an N x N matmul + F.cross_entropy per pair.
+
+`create_loss(args)` (src/open_clip/factory.py:372-415) constructs `COSMOSLoss(local_loss=...,
+gather_with_grad=..., cache_labels=True, rank=..., world_size=..., use_horovod=...)`; the same call
+works here.  Horovod is rejected (north_star: no multi-backend dispatch).  CoCaLoss /
+DistillClipLoss / SigLipLoss are not reachable with --cosmos (factory.py:372-407) and are out of
+scope: the names exist so `from open_clip.loss import ...` keeps importing, and raise on use.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+try:
+    import torch.distributed.nn
+    from torch import distributed as dist
+
+    has_distributed = True
+except ImportError:  # pragma: no cover
+    has_distributed = False
+
+from .infonce import Comm, pairs_infonce
+
+__all__ = ["gather_features", "ClipLoss", "COSMOSLoss", "CoCaLoss", "DistillClipLoss", "SigLipLoss"]
+
+
+def gather_features(image_features, text_features, local_loss=False, gather_with_grad=False, rank=0, world_size=1,
+                    use_horovod=False):
+    """All-gather both feature tensors across ranks, rank-major row order (loss.py:21-65).
+
+    gather_with_grad -> differentiable all_gather; otherwise the remote shards are constants and the
+    local shard is spliced back in (so it keeps its graph) unless local_loss.  Pure communication:
+    uses the default process group the training script created (src/training/distributed.py:89-102)."""
+    assert has_distributed, 'torch.distributed did not import correctly, please use a PyTorch version with support.'
+    if use_horovod:
+        raise RuntimeError("cosmos_b200: Horovod is not supported (NCCL via torch.distributed only)")
+    if gather_with_grad:
+        all_image_features = torch.cat(torch.distributed.nn.all_gather(image_features), dim=0)
+        all_text_features = torch.cat(torch.distributed.nn.all_gather(text_features), dim=0)
+    else:
+        gathered_image = [torch.zeros_like(image_features) for _ in range(world_size)]
+        gathered_text = [torch.zeros_like(text_features) for _ in range(world_size)]
+        dist.all_gather(gathered_image, image_features)
+        dist.all_gather(gathered_text, text_features)
+        if not local_loss:
+            gathered_image[rank] = image_features
+            gathered_text[rank] = text_features
+        all_image_features = torch.cat(gathered_image, dim=0)
+        all_text_features = torch.cat(gathered_text, dim=0)
+    return all_image_features, all_text_features
+
+
+class ClipLoss(nn.Module):
+    """Symmetric InfoNCE, averaged over every (image tensor, text tensor) pair (loss.py:68-142)."""
+
+    def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
+                 use_horovod=False):
+        super().__init__()
+        if use_horovod:
+            raise RuntimeError("cosmos_b200: Horovod is not supported (NCCL via torch.distributed only)")
+        self.local_loss = local_loss
+        self.gather_with_grad = gather_with_grad
+        self.cache_labels = cache_labels
+        self.rank = rank
+        self.world_size = world_size
+        self.use_horovod = use_horovod
+
+        # cache state (kept for attribute compatibility; the kernels derive labels from rank * batch)
+        self.prev_num_logits = 0
+        self.labels = {}
+
+    def _comm(self) -> Comm:
+        return Comm(rank=self.rank, world_size=self.world_size, local_loss=bool(self.local_loss),
+                    gather_with_grad=bool(self.gather_with_grad))
+
+    def get_ground_truth(self, device, num_logits) -> torch.Tensor:
+        if self.prev_num_logits != num_logits or device not in self.labels:
+            labels = torch.arange(num_logits, device=device, dtype=torch.long)
+            if self.world_size > 1 and self.local_loss:
+                labels = labels + num_logits * self.rank
+            if self.cache_labels:
+                self.labels[device] = labels
+                self.prev_num_logits = num_logits
+        else:
+            labels = self.labels[device]
+        return labels
+
+    def get_logits(self, image_features, text_features, logit_scale):
+        """Materialised logits, for callers outside the COSMOS path that want them (loss.py:103-119).
+        `forward` never calls this: the kernels keep the logits in tensor memory."""
+        if self.world_size > 1:
+            all_image, all_text = gather_features(image_features, text_features, self.local_loss, self.gather_with_grad,
+                                                  self.rank, self.world_size, self.use_horovod)
+            if self.local_loss:
+                logits_per_image = logit_scale * image_features @ all_text.T
+                logits_per_text = logit_scale * text_features @ all_image.T
+            else:
+                logits_per_image = logit_scale * all_image @ all_text.T
+                logits_per_text = logits_per_image.T
+        else:
+            logits_per_image = logit_scale * image_features @ text_features.T
+            logits_per_text = logit_scale * text_features @ image_features.T
+        return logits_per_image, logits_per_text
+
+    def forward(self, image_features, text_features, logit_scale, output_dict=False):
+        if not isinstance(image_features, (list, tuple)):  # There can be multiple images from augmentation
+            image_features = [image_features]
+        if not isinstance(text_features, (list, tuple)):  # There can be multiple text from augmentation
+            text_features = [text_features]
+        # The loss is symmetric in the two lists; the shorter one becomes the all-gathered column side.
+        if len(text_features) >= len(image_features):
+            total_loss = pairs_infonce(text_features, image_features, logit_scale, self._comm())
+        else:
+            total_loss = pairs_infonce(image_features, text_features, logit_scale, self._comm())
+        return {"contrastive_loss": total_loss} if output_dict else total_loss
+
+
+class COSMOSLoss(nn.Module):
+    """COSMOS loss head (loss.py:145-207): cross-modality self-distillation (student cross-modal
+    features against detached EMA-teacher features, 4 x 16 InfoNCE pairs) + CLIP loss between the two
+    global student image crops and all student captions."""
+
+    def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
+                 use_horovod=False):
+        super().__init__()
+        self.local_loss = local_loss
+        self.gather_with_grad = gather_with_grad
+        self.cache_labels = cache_labels
+        self.rank = rank
+        self.world_size = world_size
+        self.use_horovod = use_horovod
+
+        # cache state
+        self.prev_num_logits = 0
+        self.labels = {}
+
+        self.clip_loss = ClipLoss(local_loss=self.local_loss, gather_with_grad=self.gather_with_grad,
+                                  cache_labels=self.cache_labels, rank=self.rank, world_size=self.world_size,
+                                  use_horovod=self.use_horovod)
+
+    def forward(self, s_image_features, s_text_features, logit_scale, t_image_features=None, t_text_features=None,
+                output_dict=False, distill_logit_scale=None, s_img_crossmodal_features=None,
+                s_txt_crossmodal_features=None):
+        if not isinstance(s_image_features, (list, tuple)):
+            s_image_features = [s_image_features]
+        if not isinstance(s_text_features, (list, tuple)):
+            s_text_features = [s_text_features]
+        if t_image_features is None or t_text_features is None:
+            raise RuntimeError("COSMOSLoss needs teacher image and text features")
+        if s_img_crossmodal_features is None or s_txt_crossmodal_features is None:
+            raise RuntimeError("COSMOSLoss needs the student cross-modal features")
+        assert len(t_image_features) == 2
+        assert len(t_text_features) == 2
+        # no gradient flows to teacher
+        teacher = [f.detach() for f in t_image_features] + [f.detach() for f in t_text_features]
+
+        comm = self.clip_loss._comm()
+        scale = distill_logit_scale if distill_logit_scale is not None else logit_scale
+        # mean over {img-x, txt-x} x {t_img, t_txt} of ClipLoss(8 x 2 pairs)  ==  mean of two 8 x 4 groups
+        cosmos_loss = (pairs_infonce(list(s_img_crossmodal_features), teacher, scale, comm)
+                       + pairs_infonce(list(s_txt_crossmodal_features), teacher, scale, comm)) / 2
+
+        # CLIP loss: only the two global crops on the image side (loss.py:205-206)
+        clip_loss = pairs_infonce(list(s_text_features), list(s_image_features[:2]), logit_scale, comm)
+        return {"distill_loss": cosmos_loss, "clip_loss": clip_loss} if output_dict else cosmos_loss + clip_loss
+
+
+class _OutOfScope(nn.Module):
+    _what = ""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        raise NotImplementedError(
+            f"cosmos_b200: {self._what} is not part of the COSMOS loss-head path (unreachable with --cosmos, "
+            "src/open_clip/factory.py:372-407); use the reference implementation for it")
+
+
+class CoCaLoss(_OutOfScope):
+    _what = "CoCaLoss"
+
+
+class DistillClipLoss(_OutOfScope):
+    _what = "DistillClipLoss"
+
+
+class SigLipLoss(_OutOfScope):
+    _what = "SigLipLoss"

@@ -1,0 +1,128 @@
+/*
+ * cosmos_b200 - C ABI of the B200-native COSMOS loss head.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point takes
+ * the CUDA device ordinal and stream explicitly, keeps no host-side state between calls, allocates
+ * nothing (workspaces are caller-provided device memory) and returns a status code
+ * (0 = COSMOS_OK; cosmos_status_string() names the others).  All device pointers are raw
+ * CUdeviceptr values; matrices are row-major, contiguous and 16-byte aligned.
+ *
+ * What each group replaces in the reference (paths relative to the geniusxxx/cosmos checkout):
+ *   cosmos_infonce_*   src/open_clip/loss.py:103-142  ClipLoss.get_logits + F.cross_entropy x2 per pair,
+ *                      as composed by COSMOSLoss.forward src/open_clip/loss.py:176-207
+ *   cosmos_ema_*       src/training/train.py:195-203  per-parameter mul_/add_ loop
+ *   cosmos_xpool_*     src/open_clip/transformer.py:210-230 AttentionalCrossPooler.forward and its call
+ *                      site src/open_clip/model.py:366-387
+ * The reference has no FFI of its own (pure PyTorch); INTEGRATION.md shows the ctypes binding and
+ * the two import lines a maintainer changes.
+ */
+#ifndef COSMOS_B200_H_
+#define COSMOS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COSMOS_B200_ABI_VERSION 1
+
+/* status codes */
+#define COSMOS_OK 0
+#define COSMOS_ERR_INVALID_ARGUMENT 1 /* bad shape / null pointer / misalignment */
+#define COSMOS_ERR_UNSUPPORTED 2      /* dtype or size the kernels are not built for */
+#define COSMOS_ERR_CUDA 3             /* a CUDA runtime call or launch failed */
+#define COSMOS_ERR_NO_DEVICE 4        /* device is not an sm_100 part */
+#define COSMOS_ERR_WORKSPACE 5        /* caller workspace too small */
+
+/* element types */
+#define COSMOS_DTYPE_F32 0
+#define COSMOS_DTYPE_BF16 1
+#define COSMOS_DTYPE_F16 2
+
+int cosmos_abi_version(void);
+const char* cosmos_status_string(int status);
+/* 0 when `device` can run the kernels (compute capability 10.x), else COSMOS_ERR_NO_DEVICE / _CUDA. */
+int cosmos_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * EMA teacher update           (train.py:200-203:  k.mul_(m).add_((1 - m) * q)  for every parameter)
+ * ------------------------------------------------------------------------------------------------
+ * The parameter set is described once by a chunk table (host-built, then copied to the device by
+ * the caller); each step is one kernel launch over that table.
+ */
+#define COSMOS_EMA_CHUNK 8192 /* elements per table entry */
+
+typedef struct cosmos_ema_chunk {
+  uint64_t teacher; /* device address of the first element of this chunk (updated in place) */
+  uint64_t student; /* device address of the matching student elements (read only)         */
+  uint32_t count;   /* elements in this chunk, <= COSMOS_EMA_CHUNK                          */
+  uint32_t aligned; /* 1 when both addresses are 16-byte aligned                            */
+} cosmos_ema_chunk;
+
+/* Number of table entries needed for n_tensors tensors with the given element counts. */
+int64_t cosmos_ema_table_entries(int64_t n_tensors, const int64_t* numel);
+/* Fill `table_host` (cosmos_ema_table_entries() entries). elem_size is 4 (f32) or 2 (bf16/f16). */
+int cosmos_ema_table_fill(int64_t n_tensors, const uint64_t* teacher_ptrs, const uint64_t* student_ptrs,
+                          const int64_t* numel, int elem_size, cosmos_ema_chunk* table_host);
+/* One EMA step over a device-resident table.  `momentum` is the Python double of the reference. */
+int cosmos_ema_apply(const cosmos_ema_chunk* table_dev, int64_t n_entries, double momentum, int dtype,
+                     int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Block-structured InfoNCE  (loss.py:103-142 for every (row tensor i, column tensor j) pair at once)
+ * ------------------------------------------------------------------------------------------------
+ * x is a stack of gx row-side tensors [n_rows, dim] (this rank's rows), y a stack of gy column-side
+ * tensors [n_cols, dim] (all ranks' rows, gathered by the caller).  For pair p = i*gy + j the logits
+ * are S = scale * x_i y_j^T and row r's positive is column label_offset + r.  The N x N logits are
+ * never written to memory: the kernels keep them in TMEM tiles.
+ *
+ * All log-sum-exps are exchanged in log2 units (lse2 = log2(sum_c 2^(S*log2(e)))), diagonals as raw
+ * dot products (S / scale).
+ */
+typedef struct cosmos_infonce_problem {
+  uint64_t x;           /* device address, [gx][n_rows][dim], bf16 or fp16            */
+  uint64_t y;           /* device address, [gy][n_cols][dim], same dtype              */
+  int32_t gx, gy;       /* tensors in each stack                                       */
+  int32_t n_rows;       /* rows per row-side tensor (local batch)                      */
+  int32_t n_cols;       /* rows per column-side tensor (global batch)                  */
+  int32_t dim;          /* embedding dim: multiple of 64, <= 512                       */
+  int32_t label_offset; /* rank * n_rows                                               */
+  int32_t dtype;        /* COSMOS_DTYPE_BF16 or COSMOS_DTYPE_F16                       */
+  int32_t reserved;
+  uint64_t scale;       /* device address of one fp32 (logit scale, exp already taken) */
+} cosmos_infonce_problem;
+
+/* Bytes of device workspace cosmos_infonce_fwd / _bwd need for this problem (the larger of the two). */
+int64_t cosmos_infonce_workspace_bytes(const cosmos_infonce_problem* p);
+
+/* Forward pass.  Outputs (fp32, device):
+ *   row_lse2 [gx*gy][n_rows]  log2-sum-exp of every local row over all n_cols columns
+ *   diag_raw [gx*gy][n_rows]  x_i[r] . y_j[label_offset + r]
+ *   col_lse2 [gx*gy][n_cols]  log2-sum-exp of every column over THIS rank's n_rows rows
+ *                             (the caller combines ranks with a log-sum-exp all-reduce)         */
+int cosmos_infonce_fwd(const cosmos_infonce_problem* p, float* row_lse2, float* diag_raw, float* col_lse2,
+                       void* workspace, int64_t workspace_bytes, int device, void* stream);
+
+/* Per-pair loss sums (natural-log units), out[p][0] = sum_r (LSE_row[r] - S[r, label(r)]) over local rows,
+ * out[p][1] = sum_c (LSE_col[c] - S[c - label_offset, c]) over this rank's n_rows diagonal columns, with
+ * col_lse2 the GLOBAL column log-sum-exp (already combined across ranks).  out: fp32 [gx*gy][2].          */
+int cosmos_infonce_loss_sums(const cosmos_infonce_problem* p, const float* row_lse2, const float* diag_raw,
+                             const float* col_lse2, int32_t use_rows, int32_t use_cols, float* out,
+                             void* workspace, int device, void* stream);
+
+/* Backward pass.  With R = softmax over columns of each row (from row_lse2), C = softmax over rows of each
+ * column (from the global col_lse2) and I the positives, per pair
+ *     G  = a_row * R + a_col * C - (a_row + a_col) * I
+ *     dx_i = (*upstream) * weight * scale * sum_j G_ij y_j             (written in the stack dtype)
+ *     dscale = (*upstream) * weight * sum_ij <s_row * R + s_col * C - (s_row + s_col) * I, x_i y_j^T>
+ * dx [gx][n_rows][dim] and dscale (one fp32) may be NULL to skip either output.                       */
+int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, const float* col_lse2,
+                       float a_row, float a_col, float s_row, float s_col, float weight, const float* upstream,
+                       void* dx, float* dscale, void* workspace, int64_t workspace_bytes, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COSMOS_B200_H_ */

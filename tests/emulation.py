@@ -1,0 +1,73 @@
+"""Test-only CPU emulation of the three kernel entry points of cosmos_b200.infonce.
+
+It restates exactly what include/cosmos_b200.h documents for cosmos_infonce_fwd / _loss_sums / _bwd in
+fp64 torch, so that the HOST logic (stacking, gathers, mode coefficients, LSE all-reduce, transposed
+pass) can be exercised on CPU ranks with gloo.  It lives under tests/ and is never imported by the
+package: the product path has no CPU implementation."""
+import math
+
+import torch
+
+LOG2E = math.log2(math.e)
+LN2 = math.log(2.0)
+
+
+def _raw(x, y):
+    return torch.einsum("ibd,jnd->ijbn", x.double(), y.double())       # [gx, gy, b, N]
+
+
+def emu_fwd(x, y, label_offset, scale):
+    gx, b, _ = x.shape
+    gy, N, _ = y.shape
+    raw = _raw(x, y)
+    S2 = raw * (float(scale) * LOG2E)
+    row = torch.logsumexp(S2 * LN2, dim=3) / LN2
+    col = torch.logsumexp(S2 * LN2, dim=2) / LN2
+    idx = torch.arange(b)
+    diag = raw[:, :, idx, label_offset + idx]
+    return (row.reshape(gx * gy, b).float(), diag.reshape(gx * gy, b).float(), col.reshape(gx * gy, N).float())
+
+
+def emu_loss_sums(x, y, label_offset, scale, row_lse2, diag_raw, col_lse2):
+    b = x.shape[1]
+    d = float(scale) * diag_raw.double()
+    rs = (LN2 * row_lse2.double() - d).sum(1)
+    cs = (LN2 * col_lse2.double()[:, label_offset:label_offset + b] - d).sum(1)
+    return torch.stack([rs, cs], dim=1).float()
+
+
+def emu_bwd(x, y, label_offset, scale, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream, want_dx, want_dscale):
+    gx, b, D = x.shape
+    gy, N, _ = y.shape
+    raw = _raw(x, y)
+    S2 = raw * (float(scale) * LOG2E)
+    R = torch.exp2(S2 - row_lse2.double().view(gx, gy, b, 1))
+    Cm = torch.exp2(S2 - col_lse2.double().view(gx, gy, 1, N))
+    eye = torch.zeros(b, N, dtype=torch.float64)
+    eye[torch.arange(b), label_offset + torch.arange(b)] = 1
+    G = a_row * R + a_col * Cm - (a_row + a_col) * eye
+    Gs = s_row * R + s_col * Cm - (s_row + s_col) * eye
+    up = float(upstream)
+    dx = None
+    if want_dx:
+        dx = (up * weight * float(scale)) * torch.einsum("ijbn,jnd->ibd", G, y.double())
+        dx = dx.to(x.dtype)
+    dscale = None
+    if want_dscale:
+        dscale = ((up * weight) * (Gs * raw).sum()).float().reshape(1)
+    return dx, dscale
+
+
+def install(monkeypatch=None):
+    """Patch cosmos_b200.infonce to run on CPU tensors through the emulation."""
+    from cosmos_b200 import _lib, infonce
+    if monkeypatch is not None:
+        monkeypatch.setattr(infonce, "_k_fwd", emu_fwd)
+        monkeypatch.setattr(infonce, "_k_loss_sums", emu_loss_sums)
+        monkeypatch.setattr(infonce, "_k_bwd", emu_bwd)
+        monkeypatch.setattr(_lib, "require_cuda", lambda t, what: None)
+        monkeypatch.setattr(infonce, "compute_dtype", lambda dt: dt)
+    else:
+        infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd = emu_fwd, emu_loss_sums, emu_bwd
+        _lib.require_cuda = lambda t, what: None
+        infonce.compute_dtype = lambda dt: dt

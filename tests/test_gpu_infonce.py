@@ -1,0 +1,170 @@
+"""GPU parity of the InfoNCE kernels against the CPU oracle (fp32 on the same bf16-valued inputs).
+
+Tolerances are the north_star's: loss relative error <= 1e-4, gradient cosine >= 0.9999."""
+import ctypes as C
+import math
+import os
+
+import pytest
+import torch
+
+from oracle import cosmos_oracle as O
+
+LOSS_RTOL = 1e-4
+GRAD_COS = 0.9999
+
+
+def cosine(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+def lse2_ref(S2, dim):
+    return torch.logsumexp(S2 * math.log(2.0), dim=dim) / math.log(2.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gx,gy,b,W,rank,D,scale", [
+    (1, 1, 128, 1, 0, 64, 10.0),
+    (2, 3, 300, 3, 1, 128, 20.0),
+    (3, 2, 77, 1, 0, 512, 100.0),
+    (1, 2, 256, 2, 1, 512, 14.2857),
+    (2, 1, 513, 1, 0, 192, 50.0),
+])
+def test_fwd_statistics(gx, gy, b, W, rank, D, scale):
+    """row LSE, per-rank column LSE and positives of every pair block vs a direct fp64 computation."""
+    from cosmos_b200 import infonce as K
+    g = torch.Generator().manual_seed(gx * 100 + gy * 10 + b)
+    N = W * b
+    x = torch.nn.functional.normalize(torch.randn(gx, b, D, generator=g), dim=-1).bfloat16()
+    y = torch.nn.functional.normalize(torch.randn(gy, N, D, generator=g), dim=-1).bfloat16()
+    # make positives stand out a little
+    y[:, rank * b:(rank + 1) * b] = (y[:, rank * b:(rank + 1) * b].float() * 0.6 + x[0].float() * 0.4).bfloat16()
+    sc = torch.tensor([scale], dtype=torch.float32, device="cuda")
+    row, diag, col = K._k_fwd(x.cuda(), y.cuda(), rank * b, sc)
+    torch.cuda.synchronize()
+    xd, yd = x.double(), y.double()
+    for i in range(gx):
+        for j in range(gy):
+            raw = xd[i] @ yd[j].T                                   # [b, N]
+            S2 = raw * (float(sc.item()) * math.log2(math.e))
+            p = i * gy + j
+            torch.testing.assert_close(row[p].cpu().double(), lse2_ref(S2, 1), rtol=0, atol=2e-4)
+            torch.testing.assert_close(col[p].cpu().double(), lse2_ref(S2, 0), rtol=0, atol=2e-4)
+            want_diag = raw[torch.arange(b), rank * b + torch.arange(b)]
+            torch.testing.assert_close(diag[p].cpu().double(), want_diag, rtol=0, atol=1e-5)
+
+
+def _run_ours(inp, ls, ds, up, dtype):
+    from cosmos_b200 import COSMOSLoss
+    leaf = {k: [t.to(dtype).cuda().requires_grad_(True) for t in v] for k, v in inp.items()}
+    lsd = torch.tensor(ls, device="cuda", requires_grad=True)
+    dsd = None if ds is None else torch.tensor(ds, device="cuda", requires_grad=True)
+    out = COSMOSLoss(cache_labels=True)(leaf["s_image"], leaf["s_text"], lsd, t_image_features=leaf["t_image"],
+                                        t_text_features=leaf["t_text"], output_dict=True, distill_logit_scale=dsd,
+                                        s_img_crossmodal_features=leaf["s_img_x"], s_txt_crossmodal_features=leaf["s_txt_x"])
+    assert set(out) == {"distill_loss", "clip_loss"} and out["clip_loss"].dim() == 0 and out["clip_loss"].dtype == torch.float32
+    (up[0] * out["distill_loss"] + up[1] * out["clip_loss"]).backward()
+    return out, leaf, lsd, dsd
+
+
+def _run_oracle(inp, ls, ds, up, dtype):
+    leaf = {k: [t.to(dtype).float().requires_grad_(True) for t in v] for k, v in inp.items()}
+    lsd = torch.tensor(ls, requires_grad=True)
+    dsd = None if ds is None else torch.tensor(ds, requires_grad=True)
+    out = O.cosmos_loss_single(leaf["s_image"], leaf["s_text"], lsd, leaf["t_image"], leaf["t_text"], dsd,
+                               leaf["s_img_x"], leaf["s_txt_x"])
+    (up[0] * out["distill_loss"] + up[1] * out["clip_loss"]).backward()
+    return out, leaf, lsd, dsd
+
+
+def _compare(ours, ref, up):
+    out, leaf, ls, ds = ours
+    rout, rleaf, rls, rds = ref
+    for k in ("distill_loss", "clip_loss"):
+        a, b = float(out[k]), float(rout[k])
+        assert abs(a - b) <= LOSS_RTOL * abs(b), (k, a, b)
+    for k, lst in rleaf.items():
+        for t, r in zip(leaf[k], lst):
+            if r.grad is None:
+                assert t.grad is None, k
+            else:
+                assert t.grad is not None and t.grad.dtype == t.dtype, k
+                assert cosine(t.grad.cpu().float(), r.grad) >= GRAD_COS, (k, cosine(t.grad.cpu().float(), r.grad))
+                rel = (t.grad.cpu().float().norm() / r.grad.norm()).item()
+                assert abs(rel - 1) < 5e-3, (k, rel)
+    assert abs(float(ls.grad) - float(rls.grad)) <= 2e-3 * abs(float(rls.grad)) + 1e-6 * max(up), (float(ls.grad), float(rls.grad))
+    if ds is not None:
+        assert abs(float(ds.grad) - float(rds.grad)) <= 2e-3 * abs(float(rds.grad)) + 1e-6 * max(up)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_cosmos_loss_golden_small(golden_dir, dtype):
+    """The committed reference cases (ragged batch sizes 24/40/17, dims 64/128, scales up to 100,
+    GradScaler-sized upstream gradients)."""
+    cases = torch.load(os.path.join(golden_dir, "cosmos_w1_small.pt"), weights_only=False)
+    for case in cases:
+        up = case["upstream"]
+        ours = _run_ours(case["inputs"], case["logit_scale"], case["distill_logit_scale"], up, dtype)
+        ref = _run_oracle(case["inputs"], case["logit_scale"], case["distill_logit_scale"], up, dtype)
+        _compare(ours, ref, up)
+        # and against what the reference itself produced on the un-rounded fp32 inputs (looser: input rounding)
+        for k in ("distill_loss", "clip_loss"):
+            assert abs(float(ours[0][k]) - float(case["out"][k])) <= 3e-3 * abs(float(case["out"][k]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch,dim,scale", [(256, 512, 14.2857), (384, 512, 100.0), (1000, 256, 30.0)])
+def test_cosmos_loss_vs_oracle(batch, dim, scale):
+    """BASELINE config 1 shape (batch 256, dim 512, 2 global + 6 local crops) and two more."""
+    inp = O.make_features(batch, dim, seed=1234)
+    up = (1.0, 1.0)
+    ours = _run_ours(inp, scale, scale, up, torch.bfloat16)
+    ref = _run_oracle(inp, scale, scale, up, torch.bfloat16)
+    _compare(ours, ref, up)
+
+
+@pytest.mark.gpu
+def test_config1_fp32_inputs_against_reference_golden(golden_dir):
+    """fp32 features as in BASELINE config 1: the kernels round them to bf16; the loss must still sit
+    within the north_star tolerance of what the reference produced in fp32."""
+    import importlib.util
+    rec = torch.load(os.path.join(golden_dir, "cosmos_w1_cfg1.pt"), weights_only=False)
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden_dir, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    inp = mg.cosmos_inputs(torch.Generator().manual_seed(rec["seed"]), rec["batch"], rec["dim"])
+    ours = _run_ours(inp, rec["logit_scale"], rec["distill_logit_scale"], (1.0, 1.0), torch.float32)
+    out, leaf, ls, ds = ours
+    for k in ("distill_loss", "clip_loss"):
+        assert abs(float(out[k]) - float(rec["out"][k])) <= LOSS_RTOL * abs(float(rec["out"][k])), k
+    assert leaf["s_img_x"][0].grad.dtype == torch.float32
+    assert cosine(leaf["s_img_x"][0].grad.cpu(), rec["g_s_img_x0"]) >= GRAD_COS
+    assert cosine(leaf["s_text"][3].grad.cpu(), rec["g_s_text3"]) >= GRAD_COS
+    assert leaf["s_image"][2].grad is None
+    assert abs(float(ls.grad) - float(rec["g_logit_scale"])) <= 2e-3 * abs(float(rec["g_logit_scale"]))
+    assert abs(float(ds.grad) - float(rec["g_distill_scale"])) <= 2e-3 * abs(float(rec["g_distill_scale"]))
+
+
+@pytest.mark.gpu
+def test_clip_loss_api_and_errors():
+    from cosmos_b200 import ClipLoss, COSMOSLoss
+    g = torch.Generator().manual_seed(0)
+    a = torch.nn.functional.normalize(torch.randn(64, 128, generator=g), dim=-1).bfloat16().cuda().requires_grad_(True)
+    b = torch.nn.functional.normalize(torch.randn(64, 128, generator=g), dim=-1).bfloat16().cuda().requires_grad_(True)
+    loss = ClipLoss()(a, b, torch.tensor(20.0, device="cuda"))
+    ref = O.clip_loss_single(a.detach().cpu().float(), b.detach().cpu().float(), 20.0)
+    assert abs(float(loss) - float(ref)) <= LOSS_RTOL * float(ref)
+    d = ClipLoss()(a, b, 20.0, output_dict=True)
+    assert set(d) == {"contrastive_loss"}
+    with pytest.raises(RuntimeError):
+        ClipLoss()(a.detach().cpu(), b.detach().cpu(), 20.0)         # no CPU fallback
+    with pytest.raises(RuntimeError):
+        ClipLoss(use_horovod=True)
+    with pytest.raises(AssertionError):
+        COSMOSLoss()([a], [b], 20.0, t_image_features=[a], t_text_features=[b, b], s_img_crossmodal_features=[a],
+                     s_txt_crossmodal_features=[b])
+    with pytest.raises(RuntimeError):
+        x = torch.randn(8, 100, device="cuda").bfloat16()            # dim not a multiple of 64
+        ClipLoss()(x, x, 1.0)

@@ -1,0 +1,146 @@
+"""CPU tests of the host-side logic of cosmos_b200 (no kernels): the loss API composition on one
+process and the four (local_loss, gather_with_grad) modes on gloo ranks, both against the fixtures
+the unmodified reference produced (tests/golden/make_golden.py).  Kernel entry points are replaced by
+the documented-contract emulation in tests/emulation.py."""
+import os
+import sys
+import tempfile
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _close(a, b, rtol=2e-4, atol=2e-6):
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
+
+
+def test_cosmos_api_single_process(monkeypatch):
+    from tests import emulation
+    emulation.install(monkeypatch)
+    from cosmos_b200 import COSMOSLoss
+    for case in torch.load(os.path.join(GOLDEN, "cosmos_w1_small.pt"), weights_only=False):
+        leaf = {k: [t.clone().requires_grad_(True) for t in v] for k, v in case["inputs"].items()}
+        ls = torch.tensor(case["logit_scale"], requires_grad=True)
+        ds = None if case["distill_logit_scale"] is None else torch.tensor(case["distill_logit_scale"], requires_grad=True)
+        out = COSMOSLoss(cache_labels=True)(tuple(leaf["s_image"]), tuple(leaf["s_text"]), ls, t_image_features=leaf["t_image"],
+                                            t_text_features=leaf["t_text"], output_dict=True, distill_logit_scale=ds,
+                                            s_img_crossmodal_features=leaf["s_img_x"], s_txt_crossmodal_features=leaf["s_txt_x"])
+        up = case["upstream"]
+        (up[0] * out["distill_loss"] + up[1] * out["clip_loss"]).backward()
+        for k in ("distill_loss", "clip_loss"):
+            _close(out[k].detach(), case["out"][k], rtol=2e-5)
+        for k, lst in case["grads"].items():
+            for t, g in zip(leaf[k], lst):
+                if g is None:
+                    assert t.grad is None
+                else:
+                    _close(t.grad, g, rtol=2e-4, atol=2e-6 * max(up))
+        _close(ls.grad, case["g_logit_scale"], rtol=2e-4, atol=1e-5 * max(up))
+        if ds is not None:
+            _close(ds.grad, case["g_distill_scale"], rtol=2e-4, atol=1e-5 * max(up))
+        # sum form (output_dict=False) and chunk-view inputs (zero-copy stack path)
+        total = COSMOSLoss()(leaf["s_image"], leaf["s_text"], ls, leaf["t_image"], leaf["t_text"], False, ds,
+                             leaf["s_img_x"], leaf["s_txt_x"])
+        _close(total.detach(), case["out"]["distill_loss"] + case["out"]["clip_loss"], rtol=2e-5)
+
+
+def test_stack_views_zero_copy():
+    from cosmos_b200.infonce import stack_views
+    buf = torch.randn(8 * 16, 64).bfloat16()
+    chunks = buf.chunk(8)                        # what train.py:171-182 hands the loss
+    st = stack_views(chunks, torch.bfloat16)
+    assert st.data_ptr() == buf.data_ptr() and st.shape == (8, 16, 64)
+    assert torch.equal(st[3], chunks[3])
+    st2 = stack_views(chunks[:2], torch.bfloat16)
+    assert st2.data_ptr() == buf.data_ptr() and st2.shape == (2, 16, 64)
+    sep = [c.clone() for c in chunks]
+    st3 = stack_views(sep, torch.bfloat16)
+    assert torch.equal(st3, torch.stack(sep))
+    st4 = stack_views([c.float() for c in chunks], torch.bfloat16)
+    assert st4.dtype == torch.bfloat16
+
+
+def test_out_of_scope_names_import_and_raise():
+    from cosmos_b200.loss import CoCaLoss, DistillClipLoss, SigLipLoss
+    for cls in (CoCaLoss, DistillClipLoss, SigLipLoss):
+        with pytest.raises(NotImplementedError):
+            cls()
+
+
+def test_product_rejects_cpu_tensors():
+    from cosmos_b200 import ClipLoss, ema_update_
+    a = torch.randn(8, 64)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ClipLoss()(a, a, 1.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ema_update_([a], [a.clone()], 0.9)
+
+
+def _rank_worker(rank, world, port, fname, tmpdir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests import emulation
+        emulation.install()
+        from cosmos_b200 import ClipLoss, COSMOSLoss
+        rec = torch.load(os.path.join(GOLDEN, fname), weights_only=False)
+        for name, spec in rec["payload"].items():
+            ref = rec["results"][rank][name]
+            mine = spec["shards"][rank]
+            kw = dict(local_loss=spec["local_loss"], gather_with_grad=spec["gather_with_grad"], cache_labels=True,
+                      rank=rank, world_size=world)
+            if spec["kind"] == "clip":
+                a = [t.clone().requires_grad_(True) for t in mine["a"]]
+                b = [t.clone().requires_grad_(True) for t in mine["b"]]
+                s = torch.tensor(spec["logit_scale"], requires_grad=True)
+                val = ClipLoss(**kw)(a, b, s)
+                val.backward()
+                _close(val.detach(), ref["loss"], rtol=2e-5)
+                for t, g in zip(a, ref["ga"]):
+                    _close(t.grad, g)
+                for t, g in zip(b, ref["gb"]):
+                    _close(t.grad, g)
+                _close(s.grad, ref["gscale"], rtol=2e-4, atol=2e-6)
+            else:
+                leaf = {k: [t.clone().requires_grad_(True) for t in v] for k, v in mine.items()}
+                ls = torch.tensor(spec["logit_scale"], requires_grad=True)
+                ds = torch.tensor(spec["distill_logit_scale"], requires_grad=True)
+                out = COSMOSLoss(**kw)(leaf["s_image"], leaf["s_text"], ls, t_image_features=leaf["t_image"],
+                                       t_text_features=leaf["t_text"], output_dict=True, distill_logit_scale=ds,
+                                       s_img_crossmodal_features=leaf["s_img_x"], s_txt_crossmodal_features=leaf["s_txt_x"])
+                (out["distill_loss"] + out["clip_loss"]).backward()
+                for k in ("distill_loss", "clip_loss"):
+                    _close(out[k].detach(), ref["out"][k], rtol=2e-5)
+                for k, lst in ref["grads"].items():
+                    for t, g in zip(leaf[k], lst):
+                        if g is None:
+                            assert t.grad is None, (name, k)
+                        else:
+                            _close(t.grad, g)
+                _close(ls.grad, ref["g_logit_scale"], rtol=2e-4, atol=2e-6)
+                _close(ds.grad, ref["g_distill_scale"], rtol=2e-4, atol=2e-6)
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,fname,port", [(2, "multirank_w2.pt", 29721), (4, "multirank_w4.pt", 29722)])
+def test_multirank_modes_gloo(world, fname, port):
+    ctx = mp.get_context("spawn")
+    with tempfile.TemporaryDirectory() as tmpdir:
+        procs = [ctx.Process(target=_rank_worker, args=(r, world, port, fname, tmpdir)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(300)
+        for r, p in enumerate(procs):
+            assert p.exitcode == 0, f"rank {r} failed"
+            assert os.path.exists(os.path.join(tmpdir, f"ok{r}"))
