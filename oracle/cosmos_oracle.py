@@ -247,15 +247,16 @@ def ema_update_(teacher: Sequence[torch.Tensor], student: Sequence[torch.Tensor]
 # ----------------------------------------------------------------------------
 
 def make_features(batch: int, dim: int, seed: int, n_img: int = 8, n_txt: int = 8, correlated: bool = True,
-                  dtype=torch.float32) -> dict:
+                  dtype=torch.float32, noise: float = 2.0) -> dict:
     """Unit-norm embeddings with the COSMOS list structure.  `correlated` draws a
-    shared latent per sample so positives have cosine ~0.8 (peaked softmax)."""
+    shared latent per sample; positives have cosine ~1/(1+noise^2): 0.2 by default (a
+    mid-training softmax), 0.8 with noise=0.5 (peaked softmax, loss near zero)."""
     g = torch.Generator().manual_seed(seed)
 
     def view(z):
         x = torch.randn(batch, dim, generator=g)
         if z is not None:
-            x = z + 0.5 * x
+            x = z + noise * x
         return F.normalize(x, dim=-1).to(dtype)
 
     z = torch.randn(batch, dim, generator=g) if correlated else None

@@ -32,13 +32,13 @@ def unit(g, *shape, dtype=torch.float32):
     return torch.nn.functional.normalize(torch.randn(*shape, generator=g), dim=-1).to(dtype)
 
 
-def cosmos_inputs(g, b, d, n_img=8, n_txt=8, corr=True):
+def cosmos_inputs(g, b, d, n_img=8, n_txt=8, corr=True, noise=2.0):
     z = torch.randn(b, d, generator=g) if corr else None
 
     def v():
         x = torch.randn(b, d, generator=g)
         if z is not None:
-            x = z + 0.5 * x
+            x = z + noise * x
         return torch.nn.functional.normalize(x, dim=-1)
 
     return {"s_image": [v() for _ in range(n_img)], "s_text": [v() for _ in range(n_txt)],
@@ -63,10 +63,10 @@ def run_cosmos(L, inp, logit_scale, distill_scale, up=(1.0, 1.0), **ctor):
 def case_w1_small(L):
     g = torch.Generator().manual_seed(101)
     cases = []
-    for (b, d, ls, dsc, corr, up) in [(24, 64, 14.2857, 9.5, True, (1.0, 1.0)),
-                                      (40, 128, 100.0, None, True, (65536.0, 65536.0)),
-                                      (17, 64, 30.0, 100.0, False, (0.5, 2.0))]:
-        inp = cosmos_inputs(g, b, d, corr=corr)
+    for (b, d, ls, dsc, corr, up, noise) in [(24, 64, 14.2857, 9.5, True, (1.0, 1.0), 1.0),
+                                             (40, 128, 100.0, None, True, (65536.0, 65536.0), 2.5),
+                                             (17, 64, 30.0, 100.0, False, (0.5, 2.0), 0.0)]:
+        inp = cosmos_inputs(g, b, d, corr=corr, noise=noise)
         out, grads, gls, gds = run_cosmos(L, inp, ls, dsc, up)
         cases.append(dict(inputs=inp, logit_scale=ls, distill_logit_scale=dsc, upstream=up,
                           out=out, grads=grads, g_logit_scale=gls, g_distill_scale=gds))
