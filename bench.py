@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the COSMOS loss head (BASELINE.json: loss-head fwd+bwd samples/s at global batch 32k).
+
+    python bench.py --gpus N --steps K --warmup W            # ours, one rank per GPU (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU restatement of the reference
+
+A step = COSMOSLoss.forward + backward to every student feature and both logit scales (+ the
+collectives at N > 1) on one global batch of synthetic unit-norm bf16 embeddings: 8 + 8 student
+image / text features, 8 + 8 cross-modal features, 2 + 2 teacher features per sample, dim 512.
+The global batch is fixed (strong scaling): each rank holds global_batch / N rows.
+
+Prints ONE JSON line (rank 0).  value = whole-job samples/s with inputs resident in HBM;
+e2e = the same step driven through the public API from pinned HOST buffers (H2D copy of all
+34 feature tensors and D2H read of the two loss values inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+DIM = 512
+N_IMG, N_TXT = 8, 8
+KEYS = (("s_image", N_IMG), ("s_text", N_TXT), ("s_img_x", N_IMG), ("s_txt_x", N_TXT), ("t_image", 2), ("t_text", 2))
+LOGIT_SCALE = 14.2857
+
+
+def algorithmic_flops(n_global: int, dim: int = DIM) -> float:
+    """352 * N^2 * D: 64 distill pairs x (fwd 2 + bwd 2) + 16 clip pairs x (2 + 2 + 2)."""
+    return 352.0 * n_global * n_global * dim
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return p.get("bf16_tflops", 1590.0), p.get("bf16_tflops_sustained", 1400.0), p.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs
+# ------------------------------------------------------------------------------------------------
+
+def host_inputs(b_local: int, rank: int, pinned: bool):
+    """One [n * b, D] bf16 host buffer per feature list (the layout train.py:171-182 chunks)."""
+    g = torch.Generator().manual_seed(1234 + rank)
+    z = torch.randn(b_local, DIM, generator=g)
+    out = {}
+    for key, n in KEYS:
+        views = []
+        for _ in range(n):
+            x = z + 2.0 * torch.randn(b_local, DIM, generator=g)
+            views.append(torch.nn.functional.normalize(x, dim=-1).to(torch.bfloat16))
+        buf = torch.cat(views, dim=0)
+        out[key] = buf.pin_memory() if pinned else buf
+    return out
+
+
+class Clocks:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc, self.path = None, f"/tmp/cosmos_clocks_{os.getpid()}.csv"
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons, power = [], [], set(), []
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(s for s, p in zip(sm, power) if p >= 0.5 * max(power)) or sorted(sm)
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power)}
+
+
+# ------------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------------
+
+class Instrument:
+    """Counts our kernel launches and times the InfoNCE launches with CUDA events on the launching stream."""
+
+    def __init__(self):
+        from cosmos_b200 import infonce
+        self.mod = infonce
+        self.launches = 0
+        self.events = {"fwd": [], "bwd": []}
+        self.flops = {"fwd": [], "bwd": []}
+        self.enabled = False
+        self._fwd, self._loss, self._bwd = infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd
+        infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd = self.fwd, self.loss, self.bwd
+
+    def _timed(self, kind, flops, fn, *a):
+        if not self.enabled:
+            return fn(*a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a)
+        e1.record()
+        self.events[kind].append((e0, e1))
+        self.flops[kind].append(flops)
+        return r
+
+    def fwd(self, x, y, *a):
+        self.launches += 2   # tile kernel + column-statistics merge
+        fl = 2.0 * x.shape[0] * y.shape[0] * x.shape[1] * y.shape[1] * x.shape[2]
+        return self._timed("fwd", fl, self._fwd, x, y, *a)
+
+    def loss(self, *a):
+        self.launches += 1
+        return self._loss(*a)
+
+    def bwd(self, x, y, *a):
+        want_dx, want_ds = a[-2], a[-1]
+        self.launches += 1 + (1 if want_ds else 0)
+        fl = 2.0 * x.shape[0] * y.shape[0] * x.shape[1] * y.shape[1] * x.shape[2] if want_dx else 0.0
+        return self._timed("bwd", fl, self._bwd, x, y, *a)
+
+    def summary(self):
+        out = {}
+        for kind in ("fwd", "bwd"):
+            ms = [a.elapsed_time(b) for a, b in self.events[kind]]
+            if ms:
+                out[kind] = {"launches": len(ms), "ms_total": sum(ms), "ms_avg": sum(ms) / len(ms),
+                             "flops_avg": sum(self.flops[kind]) / len(ms)}
+        return out
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from cosmos_b200 import COSMOSLoss
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    n_global = args.global_batch
+    assert n_global % world == 0
+    b = n_global // world
+    host = host_inputs(b, rank, pinned=True)
+    dev_buf = {k: torch.empty_like(v, device=dev).requires_grad_(k not in ("t_image", "t_text")) for k, v in host.items()}
+    with torch.no_grad():
+        for k in host:
+            dev_buf[k].copy_(host[k])
+    logit_scale = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
+    distill_scale = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
+    loss_mod = COSMOSLoss(local_loss=False, gather_with_grad=False, cache_labels=True, rank=rank, world_size=world)
+    inst = Instrument()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def step(from_host: bool):
+        if from_host:
+            with torch.no_grad():
+                for k in host:
+                    dev_buf[k].copy_(host[k], non_blocking=True)
+        for t in list(dev_buf.values()) + [logit_scale, distill_scale]:
+            t.grad = None
+        n = dict(KEYS)
+        out = loss_mod(dev_buf["s_image"].chunk(n["s_image"]), dev_buf["s_text"].chunk(n["s_text"]), logit_scale,
+                       t_image_features=dev_buf["t_image"].chunk(2), t_text_features=dev_buf["t_text"].chunk(2),
+                       output_dict=True, distill_logit_scale=distill_scale,
+                       s_img_crossmodal_features=dev_buf["s_img_x"].chunk(n["s_img_x"]),
+                       s_txt_crossmodal_features=dev_buf["s_txt_x"].chunk(n["s_txt_x"]))
+        total = out["distill_loss"] + out["clip_loss"]
+        total.backward()
+        if from_host:
+            return torch.stack([out["distill_loss"].detach(), out["clip_loss"].detach()]).cpu()   # 8-byte D2H
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(from_host: bool, steps: int):
+        total_ms = 0.0
+        for _ in range(steps):
+            flush.fill_(1)                       # evict L2 between timed iterations (256 MB > 126 MB L2)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step(from_host)
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    barrier()
+    clocks = Clocks(local_rank) if rank == 0 else None
+    inst.enabled = True
+    inst.launches = 0
+    dev_ms = timed(False, args.steps)
+    launches = inst.launches
+    inst.enabled = False
+    clk = clocks.stop() if clocks else None
+    if args.no_e2e:
+        e2e_ms, last = float("nan"), [float("nan")] * 2
+    else:
+        for _ in range(2):
+            step(True)
+        e2e_ms = timed(True, args.steps)
+        last = step(True)
+
+    if rank == 0:
+        burst, sustained, hbm, src = peaks()
+        ms_per_step = dev_ms / args.steps
+        value = n_global / (ms_per_step * 1e-3)
+        e2e_value = n_global / (e2e_ms / args.steps * 1e-3)
+        ksum = inst.summary()
+        dom = "bwd" if ksum.get("bwd", {}).get("ms_total", 0) >= ksum.get("fwd", {}).get("ms_total", 0) else "fwd"
+        k = ksum[dom]
+        achieved = k["flops_avg"] / (k["ms_avg"] * 1e-3) / 1e12
+        step_tflops = algorithmic_flops(n_global) / world / (ms_per_step * 1e-3) / 1e12
+        line = {
+            "metric": "loss-head fwd+bwd samples/s at global batch %d" % n_global,
+            "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "COSMOS ViT-B/16 loss head fwd+bwd, global batch %d, dim 512, 8+8 student / 8+8 "
+                                   "cross-modal / 2+2 teacher features per sample, 80 InfoNCE pairs" % n_global,
+                       "global_batch": n_global, "per_gpu_batch": b, "parallelism": "dp%d (rows sharded, columns all-gathered)" % world,
+                       "l2": "256 MB flush write between timed iterations; inputs %.0f MB per rank" % (h2d_bytes / 1e6),
+                       "loss": [float(x) for x in last]},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "infonce_%s_kernel" % dom, "achieved": achieved, "peak": sustained,
+                         "unit": "TFLOP/s", "frac": achieved / sustained, "traffic": None,
+                         "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step); burst %.1f" % (src, burst),
+                         "launch_ms_avg": k["ms_avg"], "launches_timed": k["launches"],
+                         "step_algorithmic_tflops_per_gpu": step_tflops, "step_frac": step_tflops / sustained,
+                         "kernels": ksum},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle (a restatement of the reference's PyTorch loss) on host cores
+# ------------------------------------------------------------------------------------------------
+
+def cpu_step_fn(batch: int, dtype=torch.float32):
+    from oracle import cosmos_oracle as O
+    inp = O.make_features(batch, DIM, seed=1234, dtype=dtype)
+    leaf = {k: [t.requires_grad_(k not in ("t_image", "t_text")) for t in v] for k, v in inp.items()}
+    ls = torch.tensor(LOGIT_SCALE, requires_grad=True)
+    ds = torch.tensor(LOGIT_SCALE, requires_grad=True)
+
+    def step():
+        for v in leaf.values():
+            for t in v:
+                t.grad = None
+        out = O.cosmos_loss_single(leaf["s_image"], leaf["s_text"], ls, leaf["t_image"], leaf["t_text"], ds,
+                                   leaf["s_img_x"], leaf["s_txt_x"])
+        (out["distill_loss"] + out["clip_loss"]).backward()
+        return out
+    return step
+
+
+def cpu_baseline(seconds: float, batch: int = 256):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(batch)
+    step(); step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < 3 or (time.perf_counter() - t0 < seconds and n < 2000):
+        step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": batch * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "BASELINE config 1: %d steps of batch %d, dim 512, fp32, oracle (torch CPU restatement of the reference "
+                      "loss; the reference is Python and is not present on the GPU box), %.1f s" % (n, batch, dt),
+            "ms_per_step": dt / n * 1e3, "torch_threads": cores}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = args.ref_batch
+    step = cpu_step_fn(batch)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = batch * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "loss-head fwd+bwd samples/s at global batch %d" % args.global_batch,
+        "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "COSMOS loss head fwd+bwd on host cores; each step is a bounded sample of the global-batch-%d "
+                               "workload: one batch-%d step (dim 512, 80 pairs); the full batch needs %d x %d fp32 logits "
+                               "per pair and does not fit the time budget" % (args.global_batch, batch, args.global_batch,
+                                                                              args.global_batch),
+                   "global_batch": args.global_batch, "sample_batch": batch},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps of batch %d on %d torch threads" % (args.steps, batch, cores)},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--global-batch", type=int, default=32768)
+    ap.add_argument("--ref-batch", type=int, default=1024, help="batch of one reference-arm step (bounded sample)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libcosmos_b200.so")
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 ABI_VERSION = 1
 
+_DEBUG_SYNC = os.environ.get("COSMOS_B200_DEBUG_SYNC", "0") == "1"
 _lock = threading.Lock()
 _lib = None
 
@@ -29,6 +30,10 @@ def _declare(lib):
     lib.cosmos_abi_version.argtypes = []
     lib.cosmos_status_string.restype = C.c_char_p
     lib.cosmos_status_string.argtypes = [i32]
+    lib.cosmos_last_cuda_error.restype = i32
+    lib.cosmos_last_cuda_error.argtypes = []
+    lib.cosmos_cuda_error_string.restype = C.c_char_p
+    lib.cosmos_cuda_error_string.argtypes = [i32]
     lib.cosmos_device_check.restype = i32
     lib.cosmos_device_check.argtypes = [i32]
     lib.cosmos_ema_table_entries.restype = i64
@@ -89,7 +94,13 @@ def lib():
 def check(status: int, what: str) -> None:
     if status != 0:
         msg = lib().cosmos_status_string(status).decode()
+        if status == 3:
+            code = lib().cosmos_last_cuda_error()
+            msg += f" [cuda error {code}: {lib().cosmos_cuda_error_string(code).decode()}]"
         raise RuntimeError(f"cosmos_b200: {what} failed: {msg} (status {status})")
+    if _DEBUG_SYNC:
+        import torch
+        torch.cuda.synchronize()
 
 
 def torch_dtype_code(dtype) -> int:

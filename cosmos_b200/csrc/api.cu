@@ -8,12 +8,22 @@
 
 namespace {
 
+thread_local int g_last_cuda = 0;   // diagnostic only: last CUDA error code seen by this host thread
+inline bool cu_fail(cudaError_t e) {
+  if (e == cudaSuccess) return false;
+  g_last_cuda = static_cast<int>(e);
+  cudaGetLastError();
+  return true;
+}
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = false;
   explicit DeviceGuard(int device) {
     if (cudaGetDevice(&prev) != cudaSuccess) return;
-    ok = (prev == device) || (cudaSetDevice(device) == cudaSuccess);
+    // Always (re)bind: a host thread that never touched the runtime - PyTorch's autograd worker runs our
+    // backward - has no current context yet, and cuTensorMapEncodeTiled needs one (CUDA_ERROR_INVALID_CONTEXT).
+    ok = cudaSetDevice(device) == cudaSuccess;
   }
   ~DeviceGuard() {
     int cur = -1;
@@ -32,6 +42,9 @@ int sm_count_of(int device) {
 extern "C" {
 
 int cosmos_abi_version(void) { return COSMOS_B200_ABI_VERSION; }
+
+int cosmos_last_cuda_error(void) { return g_last_cuda; }
+const char* cosmos_cuda_error_string(int code) { return cudaGetErrorString(static_cast<cudaError_t>(code)); }
 
 const char* cosmos_status_string(int status) {
   switch (status) {
@@ -93,7 +106,7 @@ int cosmos_ema_apply(const cosmos_ema_chunk* table_dev, int64_t n_entries, doubl
   if (!g.ok) return COSMOS_ERR_CUDA;
   cudaError_t e = cb::launch_ema(table_dev, static_cast<int>(n_entries), momentum, dtype, sm_count_of(device),
                                  static_cast<cudaStream_t>(stream));
-  return e == cudaSuccess ? COSMOS_OK : COSMOS_ERR_CUDA;
+  return cu_fail(e) ? COSMOS_ERR_CUDA : COSMOS_OK;
 }
 
 }  // extern "C"
@@ -153,9 +166,14 @@ int cosmos_infonce_fwd(const cosmos_infonce_problem* p, float* row_lse2, float* 
   if (!g.ok) return COSMOS_ERR_CUDA;
   CUtensorMap tmX, tmY;
   const int bf = p->dtype == COSMOS_DTYPE_BF16;
-  if (cb::make_stack_map(&tmX, reinterpret_cast<const void*>(p->x), bf, p->dim, p->n_rows, p->gx, cb::kFwdBM) != 0 ||
-      cb::make_stack_map(&tmY, reinterpret_cast<const void*>(p->y), bf, p->dim, p->n_cols, p->gy, cb::kFwdBN) != 0)
-    return COSMOS_ERR_CUDA;
+  {
+    const int m1 = cb::make_stack_map(&tmX, reinterpret_cast<const void*>(p->x), bf, p->dim, p->n_rows, p->gx, cb::kFwdBM);
+    const int m2 = cb::make_stack_map(&tmY, reinterpret_cast<const void*>(p->y), bf, p->dim, p->n_cols, p->gy, cb::kFwdBN);
+    if (m1 != 0 || m2 != 0) {
+      g_last_cuda = 100000 + (m1 != 0 ? m1 : m2);   // 100000 + CUresult of cuTensorMapEncodeTiled
+      return COSMOS_ERR_CUDA;
+    }
+  }
   cb::FwdParams fp;
   fp.gx = p->gx; fp.gy = p->gy; fp.n_rows = p->n_rows; fp.n_cols = p->n_cols; fp.ks = d.ks;
   fp.label_offset = p->label_offset;
@@ -165,8 +183,8 @@ int cosmos_infonce_fwd(const cosmos_infonce_problem* p, float* row_lse2, float* 
   fp.row_lse2 = row_lse2; fp.diag_raw = diag_raw;
   fp.col_part = reinterpret_cast<float2*>(workspace);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cb::launch_infonce_fwd(tmX, tmY, fp, s) != cudaSuccess) return COSMOS_ERR_CUDA;
-  if (cb::launch_col_combine(fp.col_part, col_lse2, d.pairs, d.n_slabs, p->n_cols, s) != cudaSuccess) return COSMOS_ERR_CUDA;
+  if (cu_fail(cb::launch_infonce_fwd(tmX, tmY, fp, s))) return COSMOS_ERR_CUDA;
+  if (cu_fail(cb::launch_col_combine(fp.col_part, col_lse2, d.pairs, d.n_slabs, p->n_cols, s))) return COSMOS_ERR_CUDA;
   return COSMOS_OK;
 }
 
@@ -180,8 +198,8 @@ int cosmos_infonce_loss_sums(const cosmos_infonce_problem* p, const float* row_l
   if (!row_lse2 || !diag_raw || !col_lse2 || !out) return COSMOS_ERR_INVALID_ARGUMENT;
   DeviceGuard g(device);
   if (!g.ok) return COSMOS_ERR_CUDA;
-  if (cb::launch_loss_sums(row_lse2, diag_raw, col_lse2, reinterpret_cast<const float*>(p->scale), d.pairs, p->n_rows,
-                           p->n_cols, p->label_offset, use_rows, use_cols, out, static_cast<cudaStream_t>(stream)) != cudaSuccess)
+  if (cu_fail(cb::launch_loss_sums(row_lse2, diag_raw, col_lse2, reinterpret_cast<const float*>(p->scale), d.pairs, p->n_rows,
+                                   p->n_cols, p->label_offset, use_rows, use_cols, out, static_cast<cudaStream_t>(stream))))
     return COSMOS_ERR_CUDA;
   return COSMOS_OK;
 }
@@ -200,9 +218,14 @@ int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, c
   if (!g.ok) return COSMOS_ERR_CUDA;
   CUtensorMap tmX, tmY;
   const int bf = p->dtype == COSMOS_DTYPE_BF16;
-  if (cb::make_stack_map(&tmX, reinterpret_cast<const void*>(p->x), bf, p->dim, p->n_rows, p->gx, cb::kFwdBM) != 0 ||
-      cb::make_stack_map(&tmY, reinterpret_cast<const void*>(p->y), bf, p->dim, p->n_cols, p->gy, cb::kBwdBN) != 0)
-    return COSMOS_ERR_CUDA;
+  {
+    const int m1 = cb::make_stack_map(&tmX, reinterpret_cast<const void*>(p->x), bf, p->dim, p->n_rows, p->gx, cb::kFwdBM);
+    const int m2 = cb::make_stack_map(&tmY, reinterpret_cast<const void*>(p->y), bf, p->dim, p->n_cols, p->gy, cb::kBwdBN);
+    if (m1 != 0 || m2 != 0) {
+      g_last_cuda = 100000 + (m1 != 0 ? m1 : m2);   // 100000 + CUresult of cuTensorMapEncodeTiled
+      return COSMOS_ERR_CUDA;
+    }
+  }
   cb::BwdParams bp;
   bp.gx = p->gx; bp.gy = p->gy; bp.n_rows = p->n_rows; bp.n_cols = p->n_cols; bp.ks = d.ks;
   bp.label_offset = p->label_offset;
@@ -218,9 +241,8 @@ int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, c
   bp.dx = dx;
   bp.dscale_part = dscale != nullptr ? reinterpret_cast<float*>(workspace) : nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cb::launch_infonce_bwd(tmX, tmY, bp, s) != cudaSuccess) return COSMOS_ERR_CUDA;
-  if (dscale != nullptr &&
-      cb::launch_dscale_reduce(bp.dscale_part, p->gx * d.n_row_tiles, weight, upstream, dscale, s) != cudaSuccess)
+  if (cu_fail(cb::launch_infonce_bwd(tmX, tmY, bp, s))) return COSMOS_ERR_CUDA;
+  if (dscale != nullptr && cu_fail(cb::launch_dscale_reduce(bp.dscale_part, p->gx * d.n_row_tiles, weight, upstream, dscale, s)))
     return COSMOS_ERR_CUDA;
   return COSMOS_OK;
 }

@@ -43,6 +43,9 @@ extern "C" {
 
 int cosmos_abi_version(void);
 const char* cosmos_status_string(int status);
+/* Diagnostics: the last CUDA error code a cosmos_* call made on THIS host thread ran into, and its name. */
+int cosmos_last_cuda_error(void);
+const char* cosmos_cuda_error_string(int code);
 /* 0 when `device` can run the kernels (compute capability 10.x), else COSMOS_ERR_NO_DEVICE / _CUDA. */
 int cosmos_device_check(int device);
 
