@@ -1,5 +1,6 @@
 // extern "C" surface of libcosmos_b200.so (declared in include/cosmos_b200.h).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "infonce.h"
@@ -30,6 +31,11 @@ struct DeviceGuard {
     if (ok && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
   }
 };
+
+int dbg_flags() {
+  const char* e = getenv("COSMOS_B200_DBG");
+  return e ? atoi(e) : 0;
+}
 
 int sm_count_of(int device) {
   int n = 0;
@@ -168,7 +174,9 @@ int cosmos_infonce_fwd(const cosmos_infonce_problem* p, float* row_lse2, float* 
   const int bf = p->dtype == COSMOS_DTYPE_BF16;
   {
     const int m1 = cb::make_stack_map(&tmX, reinterpret_cast<const void*>(p->x), bf, p->dim, p->n_rows, p->gx, cb::kFwdBM);
-    const int m2 = cb::make_stack_map(&tmY, reinterpret_cast<const void*>(p->y), bf, p->dim, p->n_cols, p->gy, cb::kFwdBN);
+    const bool pair0 = !(dbg_flags() & 4);   // COSMOS_B200_DBG=4: single-CTA forward (diagnostics)
+    const int m2 = cb::make_stack_map(&tmY, reinterpret_cast<const void*>(p->y), bf, p->dim, p->n_cols, p->gy,
+                                      pair0 ? cb::kFwdBN / 2 : cb::kFwdBN);
     if (m1 != 0 || m2 != 0) {
       g_last_cuda = 100000 + (m1 != 0 ? m1 : m2);   // 100000 + CUresult of cuTensorMapEncodeTiled
       return COSMOS_ERR_CUDA;
@@ -178,12 +186,14 @@ int cosmos_infonce_fwd(const cosmos_infonce_problem* p, float* row_lse2, float* 
   fp.gx = p->gx; fp.gy = p->gy; fp.n_rows = p->n_rows; fp.n_cols = p->n_cols; fp.ks = d.ks;
   fp.label_offset = p->label_offset;
   fp.n_row_tiles = d.n_row_tiles; fp.n_col_tiles = d.n_col_tiles_fwd; fp.n_slabs = d.n_slabs;
-  fp.idesc = cb::make_idesc(bf, 0, 0, cb::kFwdBM, cb::kFwdBN);
+  const bool pair = !(dbg_flags() & 4);
+  fp.idesc = cb::make_idesc(bf, 0, 0, pair ? 2 * cb::kFwdBM : cb::kFwdBM, cb::kFwdBN);
+  fp.dbg = dbg_flags();
   fp.scale = reinterpret_cast<const float*>(p->scale);
   fp.row_lse2 = row_lse2; fp.diag_raw = diag_raw;
   fp.col_part = reinterpret_cast<float2*>(workspace);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cu_fail(cb::launch_infonce_fwd(tmX, tmY, fp, s))) return COSMOS_ERR_CUDA;
+  if (cu_fail(cb::launch_infonce_fwd(tmX, tmY, fp, pair, s))) return COSMOS_ERR_CUDA;
   if (cu_fail(cb::launch_col_combine(fp.col_part, col_lse2, d.pairs, d.n_slabs, p->n_cols, s))) return COSMOS_ERR_CUDA;
   return COSMOS_OK;
 }
@@ -232,6 +242,7 @@ int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, c
   bp.n_row_tiles = d.n_row_tiles; bp.n_col_tiles = d.n_col_tiles_bwd;
   bp.n_parts = dx != nullptr ? d.n_parts : 1;
   bp.dtype = p->dtype;
+  bp.dbg = dbg_flags();
   bp.idesc_s = cb::make_idesc(bf, 0, 0, cb::kFwdBM, cb::kBwdBN);
   bp.idesc_g = cb::make_idesc(bf, 0, 1, cb::kFwdBM, 64);
   bp.a_row = a_row; bp.a_col = a_col; bp.s_row = s_row; bp.s_col = s_col; bp.weight = weight;

@@ -16,6 +16,7 @@ struct FwdParams {
   int gx, gy, n_rows, n_cols, ks, label_offset;
   int n_row_tiles, n_col_tiles, n_slabs;  // n_slabs = 4 * n_row_tiles (32-row slabs)
   uint32_t idesc;
+  int dbg;  // diagnostics only (COSMOS_B200_DBG): 1 = skip epilogue math, 2 = skip MMA issue
   const float* scale;
   float* row_lse2;
   float* diag_raw;
@@ -26,6 +27,7 @@ struct BwdParams {
   int gx, gy, n_rows, n_cols, ks, label_offset;
   int n_row_tiles, n_col_tiles, n_parts;  // n_parts = ceil(dim / 256)
   int dtype;                              // COSMOS_DTYPE_BF16 / _F16
+  int dbg;                                // diagnostics only (COSMOS_B200_DBG)
   uint32_t idesc_s, idesc_g;
   float a_row, a_col, s_row, s_col, weight;
   const float* scale;
@@ -36,7 +38,7 @@ struct BwdParams {
   float* dscale_part;     // [items] partial sums of <dscale-mix, raw logits>, may be null
 };
 
-cudaError_t launch_infonce_fwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, cudaStream_t stream);
+cudaError_t launch_infonce_fwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, bool pair, cudaStream_t stream);
 cudaError_t launch_infonce_bwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const BwdParams& p, cudaStream_t stream);
 
 // infonce_aux.cu

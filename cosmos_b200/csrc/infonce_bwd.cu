@@ -130,10 +130,12 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           tc_fence_after();
           const uint32_t a_base = smem_u32(sX + s * kSlab);
           const uint32_t b_base = smem_u32(sY + stage * kSlab);
+          if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ss(tmem + sb * BN, make_smem_desc(a_base + kk * 32, 0, 1024), make_smem_desc(b_base + kk * 32, 0, 1024),
-                    p.idesc_s, (s | kk) != 0);
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ss(tmem + sb * BN, make_smem_desc(a_base + kk * 32, 0, 1024), make_smem_desc(b_base + kk * 32, 0, 1024),
+                      p.idesc_s, (s | kk) != 0);
+          }
           tc_commit(&misc->y_empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -149,6 +151,7 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             mbar_wait(&misc->y_full[stage], phase);
             tc_fence_after();
             const uint32_t b_base = smem_u32(sY + stage * kSlab);
+            if (!(p.dbg & 2))
 #pragma unroll
             for (int k = 0; k < 8; ++k) {   // 128 columns of this step = K of GEMM2, 16 per MMA
               const uint32_t a_addr = smem_u32(sG) + (k >> 2) * kSlab + (k & 3) * 32;
@@ -188,8 +191,15 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       mbar_wait(&misc->s_full[sb], (t >> 1) & 1);
       tc_fence_after();
       uint32_t packed[2][16];
+      if (p.dbg & 1) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int k = 0; k < 16; ++k) packed[c][k] = 0;
+      }
 #pragma unroll
       for (int chunk = 0; chunk < 2; ++chunk) {
+        if (p.dbg & 1) break;
         const int col0 = tc * BN + h * 64 + chunk * 32;
         uint32_t v[32];
         tmem_ld32(tmem + ((q * 32u) << 16) + sb * BN + h * 64 + chunk * 32, v);

@@ -3,8 +3,13 @@
 //   TMA (128B-swizzled slabs) -> smem -> tcgen05.mma (M128 x N256 x K16, bf16/fp16 in, fp32 out)
 //   -> TMEM (2 x 256 columns, double buffered) -> tcgen05.ld -> online softmax statistics.
 //
-// One CTA = one work item (column tensor j, row tensor i, 128-row tile): its X tile stays in
-// shared memory (<= 8 K-slabs of 16 KB) while 256-column tiles of Y_j stream through a 3-stage ring.
+// One CTA = one 128-row tile of (column tensor j, row tensor i): its X tile stays in shared memory
+// (<= 8 K-slabs of 16 KB) while 256-column tiles of Y_j stream through a TMA ring.
+// kPair = true (the product path): two CTAs on neighbouring SMs form a cluster and run ONE
+// tcgen05.mma.cta_group::2 (M = 256) per K step: each CTA holds its own 128 rows of X and only HALF of
+// every Y tile (128 columns, 16 KB per stage, 6 stages), which halves the L2->SM operand traffic that
+// bounds the single-CTA version.  CTA 0 of the pair issues the MMAs; TMA loads of both CTAs complete on
+// its mbarriers; tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs.
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue
 // (warp%4 selects the TMEM lane quarter = 32 rows, warp/4-1 the 128-column half of the tile).
 //
@@ -23,19 +28,18 @@ namespace cb {
 namespace {
 
 constexpr int BM = kFwdBM, BN = kFwdBN;
-constexpr int kStages = 3;
 constexpr int kSlabX = BM * 64 * 2;    // 16 KB : 128 rows x 64 elements
-constexpr int kStageY = BN * 64 * 2;   // 32 KB : 256 cols x 64 elements
 constexpr int kSmemX = 8 * kSlabX;     // 128 KB
-constexpr int kSmemY = kStages * kStageY;
+constexpr int kSmemY = 96 * 1024;      // Y ring: 3 x 32 KB (single CTA) or 6 x 16 KB (pair)
+constexpr int kMaxStages = 6;
 constexpr int kSmemMisc = 2048;
 constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
 
 struct Misc {
   uint64_t x_full;
-  uint64_t y_full[kStages];
-  uint64_t y_empty[kStages];
+  uint64_t y_full[kMaxStages];
+  uint64_t y_empty[kMaxStages];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_slot;
@@ -46,8 +50,13 @@ static_assert(sizeof(Misc) <= kSmemMisc, "misc smem");
 
 }  // namespace
 
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, FwdParams p) {
+  constexpr int kStages = kPair ? 6 : 3;
+  constexpr int kStageY = kSmemY / kStages;                       // bytes of Y this CTA loads per K step
+  constexpr int kLoadCols = kPair ? BN / 2 : BN;                  // Y rows (= S columns) this CTA loads
+  constexpr uint32_t kCtas = kPair ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX = smem;
@@ -57,24 +66,29 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // work item
-  const int per_j = p.gx * p.n_row_tiles;
+  // (pair mode: blockIdx.x = 2 * item + cta rank; the two CTAs take consecutive row tiles)
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int tiles_padded = kPair ? 2 * ((p.n_row_tiles + 1) / 2) : p.n_row_tiles;
+  const int per_j = p.gx * tiles_padded;
   const int j = blockIdx.x / per_j;
   const int rem = blockIdx.x - j * per_j;
-  const int i = rem / p.n_row_tiles;
-  const int tr = rem - i * p.n_row_tiles;
+  const int i = rem / tiles_padded;
+  const int tr = rem - i * tiles_padded;   // may be one past the last real tile: fully masked
   const int pair = i * p.gy + j;
   const int ks = p.ks;
   const int n_ct = p.n_col_tiles;
 
+  if (kPair) cluster_sync_all();   // both CTAs are resident before any cross-CTA traffic / pair allocation
   if (tid == 0) {
-    mbar_init(&misc->x_full, 1);
+    mbar_init(&misc->x_full, kCtas);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&misc->y_full[s], 1);
-      mbar_init(&misc->y_empty[s], 1);
+      mbar_init(&misc->y_full[s], kCtas);     // one producer arrive per CTA (on the leader's barrier)
+      mbar_init(&misc->y_empty[s], 1);        // tcgen05.commit (multicast to both CTAs)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&misc->acc_full[s], 1);
-      mbar_init(&misc->acc_empty[s], kEpiThreads);
+      mbar_init(&misc->acc_empty[s], kCtas * kEpiThreads);   // epilogue threads of both CTAs (leader's barrier)
     }
     fence_mbar_init();
   }
@@ -82,30 +96,43 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmY);
   }
-  if (warp == 2) tmem_alloc<512>(&misc->tmem_slot);
+  if (warp == 2) {
+    if (kPair) tmem_alloc_pair<512>(&misc->tmem_slot);
+    else tmem_alloc<512>(&misc->tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = misc->tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
-      mbar_expect_tx(&misc->x_full, ks * kSlabX);
-      for (int s = 0; s < ks; ++s) tma_load_3d(sX + s * kSlabX, &tmX, &misc->x_full, s * 64, tr * BM, i);
+      // In pair mode every load is credited to the leader's barrier; the leader arms it with the bytes of
+      // BOTH CTAs, the other CTA adds a plain (remote) arrive.
+      auto arm = [&](uint64_t* bar, uint32_t bytes_per_cta) {
+        if (leader) mbar_expect_tx(bar, bytes_per_cta * kCtas);
+        else mbar_arrive_cluster(bar, 0);
+      };
+      auto load = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+        if (kPair) tma_load_3d_pair(dst, m, bar, c0, c1, c2);
+        else tma_load_3d(dst, m, bar, c0, c1, c2);
+      };
+      for (int s = 0; s < ks; ++s) load(sX + s * kSlabX, &tmX, &misc->x_full, s * 64, tr * BM, i);
+      arm(&misc->x_full, ks * kSlabX);
       uint32_t stage = 0, phase = 0;
       for (int tc = 0; tc < n_ct; ++tc) {
         for (int s = 0; s < ks; ++s) {
           mbar_wait(&misc->y_empty[stage], phase ^ 1);
-          mbar_expect_tx(&misc->y_full[stage], kStageY);
-          tma_load_3d(sY + stage * kStageY, &tmY, &misc->y_full[stage], s * 64, tc * BN, j);
+          load(sY + stage * kStageY, &tmY, &misc->y_full[stage], s * 64, tc * BN + cta_rank * kLoadCols, j);
+          arm(&misc->y_full[stage], kStageY);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
+    if (lane == 0 && leader) {
+      // ---------------- MMA issuer (leader CTA of the pair only) ----------------
       mbar_wait(&misc->x_full, 0);
       uint32_t stage = 0, phase = 0;
       for (int tc = 0; tc < n_ct; ++tc) {
@@ -118,15 +145,18 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           tc_fence_after();
           const uint32_t a_base = smem_u32(sX + s * kSlabX);
           const uint32_t b_base = smem_u32(sY + stage * kStageY);
+          if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            umma_ss(d_tmem, make_smem_desc(a_base + kk * 32, 0, 1024), make_smem_desc(b_base + kk * 32, 0, 1024), p.idesc,
-                    (s | kk) != 0);
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t da = make_smem_desc(a_base + kk * 32, 0, 1024), db = make_smem_desc(b_base + kk * 32, 0, 1024);
+              if (kPair) umma_ss_pair(d_tmem, da, db, p.idesc, (s | kk) != 0);
+              else umma_ss(d_tmem, da, db, p.idesc, (s | kk) != 0);
+            }
           }
-          tc_commit(&misc->y_empty[stage]);
+          if (kPair) tc_commit_pair(&misc->y_empty[stage], 3); else tc_commit(&misc->y_empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&misc->acc_full[as]);
+        if (kPair) tc_commit_pair(&misc->acc_full[as], 3); else tc_commit(&misc->acc_full[as]);
       }
     }
   } else if (warp >= 4) {
@@ -151,6 +181,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       for (int chunk = 0; chunk < 4; ++chunk) {
         const int col0 = tc * BN + h * 128 + chunk * 32;
         if (col0 >= p.n_cols) break;
+        if ((p.dbg & 1) && chunk > 0) break;
         uint32_t v[32];
         tmem_ld32(tmem + ((q * 32u) << 16) + as * BN + h * 128 + chunk * 32, v);
         tmem_ld_wait();
@@ -199,10 +230,11 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
         __syncwarp();
         const float csum = warp_transpose_reduce(t, lane, OpAdd());
-        if (col0 + static_cast<int>(lane) < p.n_cols) col_part[col0 + lane] = make_float2(cmx, csum);
+        if (tr < p.n_row_tiles && col0 + static_cast<int>(lane) < p.n_cols) col_part[col0 + lane] = make_float2(cmx, csum);
       }
       tc_fence_before();
-      mbar_arrive(&misc->acc_empty[as]);
+      if (leader) mbar_arrive(&misc->acc_empty[as]);
+      else mbar_arrive_cluster(&misc->acc_empty[as], 0);
     }
 
     // merge the two column halves of each row; the Y ring is idle now (every MMA has completed)
@@ -223,17 +255,37 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem);
+  if (kPair) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    if (kPair) tmem_dealloc_pair<512>(tmem);
+    else tmem_dealloc<512>(tmem);
+  }
 }
 
-cudaError_t launch_infonce_fwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, cudaStream_t stream) {
+cudaError_t launch_infonce_fwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, bool pair, cudaStream_t stream) {
   const int smem_bytes = kSmemX + kSmemY + kSmemMisc + 1024;
   static_assert(kSmemX + kSmemY + kSmemMisc + 1024 <= 232448, "shared memory budget");
-  cudaError_t e = cudaFuncSetAttribute(infonce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  cudaError_t e;
+  if (pair) {
+    e = cudaFuncSetAttribute(infonce_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.gy * p.gx * 2 * ((p.n_row_tiles + 1) / 2));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, infonce_fwd_kernel<true>, tmX, tmY, p);
+  }
+  e = cudaFuncSetAttribute(infonce_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return e;
-  const int grid = p.gy * p.gx * p.n_row_tiles;
-  infonce_fwd_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmX, tmY, p);
+  infonce_fwd_kernel<false><<<p.gy * p.gx * p.n_row_tiles, kThreads, smem_bytes, stream>>>(tmX, tmY, p);
   return cudaGetLastError();
 }
 
