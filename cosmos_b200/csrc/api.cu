@@ -226,13 +226,16 @@ int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, c
   if (dscale != nullptr && (workspace == nullptr || workspace_bytes < bwd_workspace(p, d))) return COSMOS_ERR_WORKSPACE;
   DeviceGuard g(device);
   if (!g.ok) return COSMOS_ERR_CUDA;
-  CUtensorMap tmX, tmY;
+  CUtensorMap tmX, tmY, tmY64;
   const int bf = p->dtype == COSMOS_DTYPE_BF16;
+  // CTA-pair kernel for dims whose 256-wide parts split evenly over two CTAs; COSMOS_B200_DBG=8 forces the 1-CTA kernel
+  const bool pair = (d.ks == 2 || d.ks == 4 || d.ks == 8) && !(dbg_flags() & 8);
   {
     const int m1 = cb::make_stack_map(&tmX, reinterpret_cast<const void*>(p->x), bf, p->dim, p->n_rows, p->gx, cb::kFwdBM);
     const int m2 = cb::make_stack_map(&tmY, reinterpret_cast<const void*>(p->y), bf, p->dim, p->n_cols, p->gy, cb::kBwdBN);
-    if (m1 != 0 || m2 != 0) {
-      g_last_cuda = 100000 + (m1 != 0 ? m1 : m2);   // 100000 + CUresult of cuTensorMapEncodeTiled
+    const int m3 = cb::make_stack_map(&tmY64, reinterpret_cast<const void*>(p->y), bf, p->dim, p->n_cols, p->gy, cb::kBwdBN / 2);
+    if (m1 != 0 || m2 != 0 || m3 != 0) {
+      g_last_cuda = 100000 + (m1 != 0 ? m1 : (m2 != 0 ? m2 : m3));   // 100000 + CUresult of cuTensorMapEncodeTiled
       return COSMOS_ERR_CUDA;
     }
   }
@@ -243,8 +246,14 @@ int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, c
   bp.n_parts = dx != nullptr ? d.n_parts : 1;
   bp.dtype = p->dtype;
   bp.dbg = dbg_flags();
-  bp.idesc_s = cb::make_idesc(bf, 0, 0, cb::kFwdBM, cb::kBwdBN);
-  bp.idesc_g = cb::make_idesc(bf, 0, 1, cb::kFwdBM, 64);
+  if (pair) {
+    const int nh = d.ks < 4 ? d.ks : 4;
+    bp.idesc_s = cb::make_idesc(bf, 0, 0, 2 * cb::kFwdBM, cb::kBwdBN);
+    bp.idesc_g = cb::make_idesc(bf, 0, 1, 2 * cb::kFwdBM, nh * 64);
+  } else {
+    bp.idesc_s = cb::make_idesc(bf, 0, 0, cb::kFwdBM, cb::kBwdBN);
+    bp.idesc_g = cb::make_idesc(bf, 0, 1, cb::kFwdBM, 64);
+  }
   bp.a_row = a_row; bp.a_col = a_col; bp.s_row = s_row; bp.s_col = s_col; bp.weight = weight;
   bp.scale = reinterpret_cast<const float*>(p->scale);
   bp.upstream = upstream;
@@ -252,7 +261,7 @@ int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, c
   bp.dx = dx;
   bp.dscale_part = dscale != nullptr ? reinterpret_cast<float*>(workspace) : nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cu_fail(cb::launch_infonce_bwd(tmX, tmY, bp, s))) return COSMOS_ERR_CUDA;
+  if (cu_fail(pair ? cb::launch_infonce_bwd_pair(tmX, tmY64, tmY, bp, s) : cb::launch_infonce_bwd(tmX, tmY, bp, s))) return COSMOS_ERR_CUDA;
   if (dscale != nullptr && cu_fail(cb::launch_dscale_reduce(bp.dscale_part, p->gx * d.n_row_tiles, weight, upstream, dscale, s)))
     return COSMOS_ERR_CUDA;
   return COSMOS_OK;

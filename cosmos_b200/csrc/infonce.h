@@ -41,6 +41,9 @@ struct BwdParams {
 cudaError_t launch_infonce_fwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, bool pair, cudaStream_t stream);
 cudaError_t launch_infonce_bwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const BwdParams& p, cudaStream_t stream);
 
+cudaError_t launch_infonce_bwd_pair(const CUtensorMap& tmX, const CUtensorMap& tmY64, const CUtensorMap& tmY128, const BwdParams& p,
+                                    cudaStream_t stream);
+
 // infonce_aux.cu
 cudaError_t launch_col_combine(const float2* col_part, float* col_lse2, int pairs, int n_slabs, int n_cols, cudaStream_t stream);
 cudaError_t launch_loss_sums(const float* row_lse2, const float* diag_raw, const float* col_lse2, const float* scale, int pairs,

@@ -88,7 +88,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&misc->acc_full[s], 1);
-      mbar_init(&misc->acc_empty[s], kCtas * kEpiThreads);   // epilogue threads of both CTAs (leader's barrier)
+      mbar_init(&misc->acc_empty[s], (p.dbg & 16) ? kCtas * kEpiThreads : kCtas * 8);   // per-warp (or per-thread) arrives of both CTAs
     }
     fence_mbar_init();
   }
@@ -233,8 +233,16 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (tr < p.n_row_tiles && col0 + static_cast<int>(lane) < p.n_cols) col_part[col0 + lane] = make_float2(cmx, csum);
       }
       tc_fence_before();
-      if (leader) mbar_arrive(&misc->acc_empty[as]);
-      else mbar_arrive_cluster(&misc->acc_empty[as], 0);
+      if (p.dbg & 16) {
+        if (leader) mbar_arrive(&misc->acc_empty[as]);
+        else mbar_arrive_cluster(&misc->acc_empty[as], 0);
+      } else {
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&misc->acc_empty[as]);
+          else mbar_arrive_cluster(&misc->acc_empty[as], 0);
+        }
+      }
     }
 
     // merge the two column halves of each row; the Y ring is idle now (every MMA has completed)
