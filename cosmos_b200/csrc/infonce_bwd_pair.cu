@@ -27,7 +27,7 @@ constexpr int kSlabX = 128 * 64 * 2;    // 16 KB: 128 rows x 64 elements
 constexpr int kSlotA = 64 * 64 * 2;     // 8 KB : 64 columns x 64 elements (this CTA's half of a GEMM1 B slab)
 constexpr int kSlotsA = 8;
 constexpr int kSlabB = 128 * 64 * 2;    // 16 KB: 128 columns x 64 embedding elements
-constexpr int kSmemMisc = 2048;
+constexpr int kSmemMisc = 3072;
 constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
 
@@ -43,6 +43,7 @@ struct Misc {
   uint32_t tmem_slot;
   uint32_t pad[3];
   float red[8];
+  float kappa[8][64];   // per epilogue warp: a_col * 2^(o - lse_col) of its 64 columns
 };
 static_assert(sizeof(Misc) <= kSmemMisc, "misc smem");
 
@@ -51,8 +52,8 @@ static_assert(sizeof(Misc) <= kSmemMisc, "misc smem");
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY64,
                         const __grid_constant__ CUtensorMap tmY128, BwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // no static shared memory in this kernel: offset 0, 1 KB aligned
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -91,7 +92,7 @@ infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       mbar_init(&misc->b_full[s], 2);
       mbar_init(&misc->b_empty[s], 1);
       mbar_init(&misc->s_full[s], 1);
-      mbar_init(&misc->g_full[s], (p.dbg & 16) ? 2 * kEpiThreads : 2 * 8);   // per-warp (or per-thread) arrives of both CTAs
+      mbar_init(&misc->g_full[s], 2 * 8);   // one arrive per epilogue warp of both CTAs
     }
     mbar_init(&misc->dx_full, 1);
     fence_mbar_init();
@@ -203,22 +204,99 @@ infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     const uint32_t lane_base = (q * 32u) << 16;
     float ds_acc = 0.f;
 
+    // dscale mix relative to the G mix: proportional (ds = ratio * <G, raw>, every shipped mode but local_loss with
+    // gather_with_grad) or rows-only (s_col == 0); anything else takes the two-exp path.
+    const bool ds_prop = fabsf(p.a_row * p.s_col - p.a_col * p.s_row) <= 1e-12f && (a_sum != 0.f);
+    const float ds_ratio = ds_prop ? s_sum / a_sum : 0.f;
+    const bool ds_rows = !ds_prop && p.s_col == 0.f;
+    const bool fast_ok = (ds_prop || ds_rows) && !(p.dbg & 32);
+    float* kbuf = misc->kappa[ew];
+
     for (int t = 0; t < T; ++t) {
       const int j = t / n_ct, tc = t - j * n_ct;
       const int pair = i * p.gy + j;
       const uint32_t buf = t & 1;
       const float lr = row_valid ? __ldg(p.row_lse2 + static_cast<size_t>(pair) * p.n_rows + row) : INFINITY;
       const float* lc_ptr = p.col_lse2 + static_cast<size_t>(pair) * p.n_cols;
+      const int colw = tc * BN + h * 64;                  // first of this warp's 64 columns
+      const bool full = colw + 64 <= p.n_cols;
+
+      // ---- one-exp path: G = 2^(S2 - o) * (a_row 2^(o - lse_row) + a_col 2^(o - lse_col)) with a per-warp offset o.
+      // Valid when the log-sum-exps this warp touches span < 200 (log2 units): then every factor stays a normal
+      // fp32 number wherever the product matters.  Otherwise (or in a ragged last tile) the two-exp path runs.
+      bool fast = fast_ok && full;
+      float o = 0.f, rho = 0.f, rho_s = 0.f;
+      if (fast) {
+        const float lc0 = __ldg(lc_ptr + colw + lane), lc1 = __ldg(lc_ptr + colw + 32 + lane);
+        float lo = fminf(lc0, lc1), hi = fmaxf(lc0, lc1);
+        if (row_valid) { lo = fminf(lo, lr); hi = fmaxf(hi, lr); }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+          lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, sft));
+          hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, sft));
+        }
+        fast = (hi - lo) <= 200.f;       // false for NaN / inf as well
+        if (fast) {
+          o = 0.5f * (hi + lo);
+          rho = p.a_row * ex2(o - lr);   // 0 for rows past the batch (lr = +inf)
+          rho_s = p.s_row * ex2(o - lr);
+          __syncwarp();
+          kbuf[lane] = p.a_col * ex2(o - lc0);
+          kbuf[32 + lane] = p.a_col * ex2(o - lc1);
+          __syncwarp();
+        }
+      }
 
       mbar_wait(&misc->s_full[buf], (t >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int chunk = 0; chunk < 2; ++chunk) {
-        const int col0 = tc * BN + h * 64 + chunk * 32;
+        const int col0 = colw + chunk * 32;
         uint32_t packed[16];
         if (p.dbg & 1) {
 #pragma unroll
           for (int k = 0; k < 16; ++k) packed[k] = 0;
+        } else if (fast) {
+          uint32_t v[32];
+          tmem_ld32(tmem + lane_base + buf * BN + h * 64 + chunk * 32, v);
+          float kap[32];
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const float4 f = *reinterpret_cast<const float4*>(kbuf + chunk * 32 + k4 * 4);
+            kap[4 * k4 + 0] = f.x; kap[4 * k4 + 1] = f.y; kap[4 * k4 + 2] = f.z; kap[4 * k4 + 3] = f.w;
+          }
+          tmem_ld_wait();
+          float g[32];
+          float acc = 0.f;
+          const float neg_o = -o;
+          if (ds_prop) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float raw = __uint_as_float(v[k]);
+              g[k] = ex2(fmaf(raw, k2, neg_o)) * (rho + kap[k]);
+              acc = fmaf(g[k], raw, acc);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float raw = __uint_as_float(v[k]);
+              const float e = ex2(fmaf(raw, k2, neg_o));
+              g[k] = e * (rho + kap[k]);
+              acc = fmaf(e, raw, acc);
+            }
+          }
+          if (label >= col0 && label < col0 + 32) {         // the positive of this row sits in this chunk
+            const int idx = label - col0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (k == idx) {
+                g[k] -= a_sum;
+                acc -= (ds_prop ? a_sum : (rho_s != 0.f ? p.s_row / rho_s : 0.f)) * __uint_as_float(v[k]);
+              }
+          }
+          if (row_valid) ds_acc += ds_prop ? ds_ratio * acc : rho_s * acc;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) packed[k] = pack2(g[2 * k], g[2 * k + 1], fmt);
         } else {
           uint32_t v[32];
           tmem_ld32(tmem + lane_base + buf * BN + h * 64 + chunk * 32, v);
@@ -260,15 +338,10 @@ infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       }
       if (want_dx) tmem_st_wait();
       tc_fence_before();
-      if (p.dbg & 16) {
+      __syncwarp();
+      if (lane == 0) {
         if (leader) mbar_arrive(&misc->g_full[buf]);
         else mbar_arrive_cluster(&misc->g_full[buf], 0);
-      } else {
-        __syncwarp();
-        if (lane == 0) {
-          if (leader) mbar_arrive(&misc->g_full[buf]);
-          else mbar_arrive_cluster(&misc->g_full[buf], 0);
-        }
       }
     }
 
@@ -318,7 +391,7 @@ cudaError_t launch_infonce_bwd_pair(const CUtensorMap& tmX, const CUtensorMap& t
                                     cudaStream_t stream) {
   const int nh_max = p.ks < 4 ? p.ks : 4;
   const int b_stages = p.ks == 8 ? 1 : 2;
-  const int smem_bytes = p.ks * kSlabX + kSlotsA * kSlotA + b_stages * (nh_max / 2) * kSlabB + kSmemMisc + 1024;
+  const int smem_bytes = p.ks * kSlabX + kSlotsA * kSlotA + b_stages * (nh_max / 2) * kSlabB + kSmemMisc;
   if (smem_bytes > 232448) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(infonce_bwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (e != cudaSuccess) return e;

@@ -169,6 +169,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const int label = p.label_offset + row;
     const float k2 = __ldg(p.scale) * kLog2e;
     const float NEG_INF = -INFINITY;
+    const bool fast_ok = k2 > 0.f && !(p.dbg & 32);
 
     float m_run = NEG_INF, l_run = 0.f, diag = 0.f;
     float2* col_part = p.col_part + (static_cast<size_t>(pair) * p.n_slabs + tr * 4 + q) * p.n_cols;
@@ -185,18 +186,61 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         uint32_t v[32];
         tmem_ld32(tmem + ((q * 32u) << 16) + as * BN + h * 128 + chunk * 32, v);
         tmem_ld_wait();
-        float t[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) t[k] = __uint_as_float(v[k]) * k2;
-        if (col0 + 32 > p.n_cols) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) t[k] = (col0 + k < p.n_cols) ? t[k] : NEG_INF;
-        }
         if (row_valid && label >= col0 && label < col0 + 32) {
           const int idx = label - col0;
 #pragma unroll
           for (int k = 0; k < 32; ++k)
             if (k == idx) diag = __uint_as_float(v[k]);
+        }
+        float t[32];
+        bool need_exact = !fast_ok || (col0 + 32 > p.n_cols);
+        if (!need_exact) {
+          // ---- one exponential per logit: rows use their own running max m_r as offset; the column sums reuse the
+          // same exponentials, re-based to the warp's largest running max M_w by one multiply with f_r = 2^(m_r - M_w).
+          float cmr = __uint_as_float(v[0]);
+#pragma unroll
+          for (int k = 1; k < 32; ++k) cmr = fmaxf(cmr, __uint_as_float(v[k]));
+          const float cm = cmr * k2;                       // k2 > 0 on this path
+          const float m_before = m_run, l_before = l_run;
+          if (cm > m_run) {
+            l_run *= ex2(m_run - cm);
+            m_run = cm;
+          }
+          float mw = row_valid ? m_run : NEG_INF;
+#pragma unroll
+          for (int sft = 16; sft > 0; sft >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, sft));
+          if (mw != NEG_INF) {                             // warp-uniform: at least one row of this warp is real
+            const float f = row_valid ? ex2(m_run - mw) : 0.f;
+            const float neg_m = -m_run;
+            float ssum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float e = ex2(fmaf(__uint_as_float(v[k]), k2, neg_m));
+              ssum += e;
+              t[k] = e * f;
+            }
+            l_run += ssum;
+            const float csum = warp_transpose_reduce(t, lane, OpAdd());
+            // Every significant term of a column is a normal fp32 number iff the column sum is not tiny relative
+            // to 2^M_w (DESIGN.md "one-exp statistics"); otherwise redo this block with true column maxima.
+            if (__all_sync(0xffffffffu, csum >= 8.0779e-28f)) {   // 2^-90
+              if (tr < p.n_row_tiles) col_part[col0 + lane] = make_float2(mw, csum);
+              continue;
+            }
+            need_exact = true;
+            // undo this block's row update: the exact path below redoes it from scratch
+            m_run = m_before;
+            l_run = l_before;
+          } else {
+            if (tr < p.n_row_tiles) col_part[col0 + lane] = make_float2(NEG_INF, 0.f);
+            continue;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t[k] = __uint_as_float(v[k]) * k2;
+        if (col0 + 32 > p.n_cols) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) t[k] = (col0 + k < p.n_cols) ? t[k] : NEG_INF;
         }
         // rows: this thread's row, running (max, sum)
         float cm = t[0];

@@ -56,6 +56,38 @@ def test_fwd_statistics(gx, gy, b, W, rank, D, scale):
             torch.testing.assert_close(diag[p].cpu().double(), want_diag, rtol=0, atol=1e-5)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale", [100.0, 30.0])
+def test_fwd_statistics_extreme_range(scale):
+    """Logits spanning [-scale, +scale] inside one 32-row block: the one-exp fast path must detect the columns whose
+    terms would underflow relative to the block's offset and redo them exactly; same for the backward's per-warp range
+    check (gradients compared with the closed form)."""
+    from cosmos_b200 import infonce as K
+    g = torch.Generator().manual_seed(5)
+    b, D = 256, 128
+    u = torch.nn.functional.normalize(torch.randn(D, generator=g), dim=0)
+    x = torch.nn.functional.normalize(torch.randn(1, b, D, generator=g), dim=-1)
+    y = torch.nn.functional.normalize(torch.randn(1, b, D, generator=g), dim=-1)
+    x[0, :64] = u                      # rows 0..63 all equal u
+    y[0, 0:8] = u                      # columns 0..7: +scale against those rows
+    y[0, 8:16] = -u                    # columns 8..15: -scale against them (2*scale below the block's row maxima)
+    y[0, 200:204] = -u
+    x, y = x.bfloat16(), y.bfloat16()
+    sc = torch.tensor([scale], dtype=torch.float32, device="cuda")
+    row, diag, col = K._k_fwd(x.cuda(), y.cuda(), 0, sc)
+    raw = x[0].double() @ y[0].double().T
+    S2 = raw * (scale * math.log2(math.e))
+    torch.testing.assert_close(row[0].cpu().double(), lse2_ref(S2, 1), rtol=0, atol=3e-4)
+    torch.testing.assert_close(col[0].cpu().double(), lse2_ref(S2, 0), rtol=0, atol=3e-4)
+    up = torch.ones(1, device="cuda")
+    w = 1.0 / (2 * b)
+    dx, dsc = K._k_bwd(x.cuda(), y.cuda(), 0, sc, row, col, 1.0, 1.0, 1.0, 1.0, w, up, True, True)
+    _, da, _, dscale = O.pair_closed_form(x[0].double(), y[0].double(), scale)
+    assert cosine(dx[0].float().cpu(), da) >= GRAD_COS
+    assert abs(float(dx[0].float().cpu().norm() / da.norm()) - 1) < 5e-3
+    assert abs(float(dsc) - float(dscale)) <= 3e-3 * abs(float(dscale)) + 1e-6
+
+
 def _run_ours(inp, ls, ds, up, dtype):
     from cosmos_b200 import COSMOSLoss
     leaf = {k: [t.to(dtype).cuda().requires_grad_(True) for t in v] for k, v in inp.items()}
