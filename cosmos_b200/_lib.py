@@ -42,6 +42,10 @@ def _declare(lib):
     lib.cosmos_ema_table_fill.argtypes = [i64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(i64), i32, vp]
     lib.cosmos_ema_apply.restype = i32
     lib.cosmos_ema_apply.argtypes = [vp, i64, f64, i32, i32, vp]
+    for name, args in _POOL_SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = i32
+        fn.argtypes = args
     for name, args in _INFONCE_SIGS.items():
         fn = getattr(lib, name)
         fn.restype = i32 if name != "cosmos_infonce_workspace_bytes" else i64
@@ -68,6 +72,18 @@ _INFONCE_SIGS = {
     "cosmos_infonce_fwd": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, vp_, i64_, i32_, vp_],
     "cosmos_infonce_loss_sums": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, i32_, i32_, vp_, vp_, i32_, vp_],
     "cosmos_infonce_bwd": [C.POINTER(InfoNceProblem), vp_, vp_, f32_, f32_, f32_, f32_, f32_, vp_, vp_, vp_, vp_, i64_, i32_, vp_],
+}
+
+
+_POOL_SIGS = {
+    "cosmos_gemm": [vp_, vp_, vp_, vp_, i32_, i32_, i32_, i64_, i64_, i64_, i32_, i32_, i32_, i32_, i32_, f32_, i32_, vp_],
+    "cosmos_layernorm_fwd": [vp_, i32_, vp_, vp_, vp_, i32_, vp_, vp_, i64_, i32_, i32_, vp_],
+    "cosmos_layernorm_bwd": [vp_, i32_, vp_, i32_, vp_, vp_, vp_, vp_, i32_, i32_, vp_, vp_, i64_, i32_, i32_, vp_],
+    "cosmos_attn_core_fwd": [vp_, vp_, vp_, vp_, i32_, i32_, i32_, i32_, i32_, i32_, i64_, i64_, i32_, vp_],
+    "cosmos_attn_core_bwd": [vp_, vp_, vp_, vp_, vp_, vp_, i32_, i32_, i32_, i32_, i32_, i32_, i64_, i64_, i32_, vp_],
+    "cosmos_addnorm_fwd": [vp_, i32_, vp_, vp_, vp_, i64_, i32_, i32_, vp_],
+    "cosmos_addnorm_bwd": [vp_, vp_, i32_, vp_, vp_, vp_, i32_, i64_, i32_, i32_, vp_],
+    "cosmos_colsum": [vp_, i32_, vp_, i64_, i32_, i64_, i32_, vp_],
 }
 
 

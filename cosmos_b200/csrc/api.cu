@@ -268,3 +268,121 @@ int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, c
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// pooler building blocks
+// ------------------------------------------------------------------------------------------------
+namespace {
+bool dtype16(int d) { return d == COSMOS_DTYPE_BF16 || d == COSMOS_DTYPE_F16; }
+bool dtype_any(int d) { return d == COSMOS_DTYPE_F32 || dtype16(d); }
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+}  // namespace
+
+extern "C" {
+
+int cosmos_gemm(const void* a, const void* b, void* d, const float* bias, int32_t M, int32_t N, int32_t K, int64_t lda,
+                int64_t ldb, int64_t ldd, int32_t a_kmajor, int32_t b_kmajor, int32_t in_dtype, int32_t out_dtype,
+                int32_t splits, float alpha, int device, void* stream) {
+  if (!a || !b || !d || M <= 0 || N <= 0 || K <= 0 || splits <= 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (!dtype16(in_dtype) || !dtype_any(out_dtype)) return COSMOS_ERR_UNSUPPORTED;
+  if ((lda & 7) || (ldb & 7) || !aligned16(a) || !aligned16(b) || !aligned16(d)) return COSMOS_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  cb::GemmArgs ga;
+  ga.a = a; ga.b = b; ga.d = d; ga.bias = bias;
+  ga.M = M; ga.N = N; ga.K = K; ga.lda = lda; ga.ldb = ldb; ga.ldd = ldd;
+  ga.a_kmajor = a_kmajor; ga.b_kmajor = b_kmajor; ga.in_dtype = in_dtype; ga.out_dtype = out_dtype;
+  ga.splits = splits; ga.alpha = alpha;
+  cudaError_t e = cudaSuccess;
+  const int r = cb::launch_gemm(ga, static_cast<cudaStream_t>(stream), &e);
+  if (r == 0) return COSMOS_OK;
+  if (r > 0) g_last_cuda = r; else cu_fail(e);
+  return COSMOS_ERR_CUDA;
+}
+
+int cosmos_layernorm_fwd(const void* x, int32_t x_dtype, const float* w, const float* b, void* y, int32_t y_dtype, float* mean,
+                         float* rstd, int64_t rows, int32_t dim, int device, void* stream) {
+  if (!x || !w || !b || !y || !mean || !rstd || rows < 0 || dim <= 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (dim > 1024 || !dtype_any(x_dtype) || !dtype_any(y_dtype)) return COSMOS_ERR_UNSUPPORTED;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  return cu_fail(cb::launch_layernorm_fwd(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim, static_cast<cudaStream_t>(stream)))
+             ? COSMOS_ERR_CUDA : COSMOS_OK;
+}
+
+int cosmos_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* w, const float* mean,
+                         const float* rstd, void* dx, int32_t dx_dtype, int32_t accumulate, float* dw, float* db, int64_t rows,
+                         int32_t dim, int device, void* stream) {
+  if (!dy || !x || !w || !mean || !rstd || !dx || rows < 0 || dim <= 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if ((dw == nullptr) != (db == nullptr)) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (dim > 1024 || !dtype_any(dy_dtype) || !dtype_any(x_dtype) || !dtype_any(dx_dtype)) return COSMOS_ERR_UNSUPPORTED;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  return cu_fail(cb::launch_layernorm_bwd(dy, dy_dtype, x, x_dtype, w, mean, rstd, dx, dx_dtype, accumulate, dw, db, rows, dim,
+                                          static_cast<cudaStream_t>(stream)))
+             ? COSMOS_ERR_CUDA : COSMOS_OK;
+}
+
+static int check_attn(int32_t dtype, int32_t n_sets, int32_t L, int32_t dim, int32_t heads, int32_t q_per_set) {
+  if (n_sets <= 0 || L <= 0 || dim <= 0 || heads <= 0 || q_per_set <= 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (!dtype16(dtype) || dim % heads != 0) return COSMOS_ERR_UNSUPPORTED;
+  const int hd = dim / heads;
+  if (!(hd == 16 || hd == 32 || hd == 64 || hd == 128) || L > 1024 || q_per_set > 64) return COSMOS_ERR_UNSUPPORTED;
+  return COSMOS_OK;
+}
+
+int cosmos_attn_core_fwd(const void* q, const void* kv, void* o, float* lse, int32_t dtype, int32_t n_sets, int32_t L, int32_t dim,
+                         int32_t heads, int32_t q_per_set, int64_t q_stride_set, int64_t q_stride_q, int device, void* stream) {
+  if (!q || !kv || !o || !lse) return COSMOS_ERR_INVALID_ARGUMENT;
+  int st = check_attn(dtype, n_sets, L, dim, heads, q_per_set);
+  if (st != COSMOS_OK) return st;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  return cu_fail(cb::launch_attn_core_fwd(q, kv, o, lse, dtype, n_sets, L, dim, heads, q_per_set, q_stride_set, q_stride_q,
+                                          static_cast<cudaStream_t>(stream)))
+             ? COSMOS_ERR_CUDA : COSMOS_OK;
+}
+
+int cosmos_attn_core_bwd(const void* q, const void* kv, const void* d_o, const float* lse, void* dq, void* dkv, int32_t dtype,
+                         int32_t n_sets, int32_t L, int32_t dim, int32_t heads, int32_t q_per_set, int64_t q_stride_set,
+                         int64_t q_stride_q, int device, void* stream) {
+  if (!q || !kv || !d_o || !lse || !dq || !dkv) return COSMOS_ERR_INVALID_ARGUMENT;
+  int st = check_attn(dtype, n_sets, L, dim, heads, q_per_set);
+  if (st != COSMOS_OK) return st;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  return cu_fail(cb::launch_attn_core_bwd(q, kv, d_o, lse, dq, dkv, dtype, n_sets, L, dim, heads, q_per_set, q_stride_set,
+                                          q_stride_q, static_cast<cudaStream_t>(stream)))
+             ? COSMOS_ERR_CUDA : COSMOS_OK;
+}
+
+int cosmos_addnorm_fwd(const void* f, int32_t f_dtype, const float* pooled, void* out, float* inv_norm, int64_t rows, int32_t dim,
+                       int device, void* stream) {
+  if (!f || !pooled || !out || !inv_norm || rows < 0 || dim <= 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (dim > 1024 || !dtype_any(f_dtype)) return COSMOS_ERR_UNSUPPORTED;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  return cu_fail(cb::launch_addnorm_fwd(f, f_dtype, pooled, out, inv_norm, rows, dim, static_cast<cudaStream_t>(stream)))
+             ? COSMOS_ERR_CUDA : COSMOS_OK;
+}
+
+int cosmos_addnorm_bwd(const void* g_out, const void* out, int32_t f_dtype, const float* inv_norm, float* g_z32, void* g_z16,
+                       int32_t g_dtype, int64_t rows, int32_t dim, int device, void* stream) {
+  if (!g_out || !out || !inv_norm || !g_z32 || !g_z16 || rows < 0 || dim <= 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (dim > 1024 || !dtype_any(f_dtype) || !dtype16(g_dtype)) return COSMOS_ERR_UNSUPPORTED;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  return cu_fail(cb::launch_addnorm_bwd(g_out, out, f_dtype, inv_norm, g_z32, g_z16, g_dtype, rows, dim,
+                                        static_cast<cudaStream_t>(stream)))
+             ? COSMOS_ERR_CUDA : COSMOS_OK;
+}
+
+int cosmos_colsum(const void* src, int32_t dtype, float* dst, int64_t rows, int32_t n, int64_t ld, int device, void* stream) {
+  if (!src || !dst || rows < 0 || n <= 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (!dtype_any(dtype)) return COSMOS_ERR_UNSUPPORTED;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  return cu_fail(cb::launch_colsum(src, dtype, dst, rows, n, ld, static_cast<cudaStream_t>(stream))) ? COSMOS_ERR_CUDA : COSMOS_OK;
+}
+
+}  // extern "C"

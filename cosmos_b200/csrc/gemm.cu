@@ -1,0 +1,210 @@
+// Generic tcgen05 GEMM used by the cross-attention pooler (linear layers, their input and weight
+// gradients):   D[M,N] (+)= alpha * opA[M,K] * opB[N,K]^T (+ bias[N])
+//   opA stored [M,K] row-major (K-major operand) or [K,M] row-major (MN-major operand); same for opB.
+//   16-bit inputs (bf16 / fp16), fp32 accumulation in TMEM, fp32 or 16-bit output.
+// Tile 128 x 128 x 64, 6-stage TMA ring, one CTA per output tile and K split (gridDim.z); K splits
+// accumulate with fp32 red.global.add into a zero-initialised D (weight gradients contract over the very
+// long row dimension, so the output has few tiles and needs the split for parallelism).
+// Warp roles as in the InfoNCE kernels: warp 0 TMA, warp 1 MMA issue, warp 2 TMEM, warps 4-7 epilogue.
+#include "common.cuh"
+#include "internal.h"
+#include "tma_host.h"
+
+namespace cb {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int kStages = 6;
+constexpr int kOpBytes = 128 * 64 * 2;   // 16 KB per operand per stage
+constexpr int kThreads = 256;
+
+struct Misc {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t acc_full;
+  uint32_t tmem_slot;
+};
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kOpBytes;
+  Misc* misc = reinterpret_cast<Misc*>(smem + 2 * kStages * kOpBytes);
+
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int k_slabs = (p.K + BK - 1) / BK;
+  const int per = (k_slabs + gridDim.z - 1) / gridDim.z;
+  const int ks0 = blockIdx.z * per;
+  const int ks1 = min(k_slabs, ks0 + per);
+  const int n_slabs = ks1 - ks0;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&misc->full[s], 1);
+      mbar_init(&misc->empty[s], 1);
+    }
+    mbar_init(&misc->acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 2) tmem_alloc<128>(&misc->tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = misc->tmem_slot;
+
+  if (n_slabs > 0) {
+    if (warp == 0 && lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int s = ks0; s < ks1; ++s) {
+        mbar_wait(&misc->empty[stage], phase ^ 1);
+        mbar_expect_tx(&misc->full[stage], 2 * kOpBytes);
+        uint8_t* a = sA + stage * kOpBytes;
+        uint8_t* b = sB + stage * kOpBytes;
+        if (p.a_kmajor) {
+          tma_load_3d(a, &tmA, &misc->full[stage], s * BK, m0, 0);            // box 64 k x 128 rows
+        } else {
+          tma_load_3d(a, &tmA, &misc->full[stage], m0, s * BK, 0);            // box 64 m x 64 k-rows, two M chunks
+          tma_load_3d(a + 8192, &tmA, &misc->full[stage], m0 + 64, s * BK, 0);
+        }
+        if (p.b_kmajor) {
+          tma_load_3d(b, &tmB, &misc->full[stage], s * BK, n0, 0);
+        } else {
+          tma_load_3d(b, &tmB, &misc->full[stage], n0, s * BK, 0);
+          tma_load_3d(b + 8192, &tmB, &misc->full[stage], n0 + 64, s * BK, 0);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp == 1 && lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int s = 0; s < n_slabs; ++s) {
+        mbar_wait(&misc->full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + stage * kOpBytes);
+        const uint32_t b_base = smem_u32(sB + stage * kOpBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t da = p.a_kmajor ? make_smem_desc(a_base + kk * 32, 0, 1024) : make_smem_desc(a_base + kk * 2048, 8192, 1024);
+          const uint64_t db = p.b_kmajor ? make_smem_desc(b_base + kk * 32, 0, 1024) : make_smem_desc(b_base + kk * 2048, 8192, 1024);
+          umma_ss(tmem, da, db, p.idesc, (s | kk) != 0);
+        }
+        tc_commit(&misc->empty[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(&misc->acc_full);
+    } else if (warp >= 4) {
+      const uint32_t q = warp & 3;
+      const int row = m0 + q * 32 + lane;
+      mbar_wait(&misc->acc_full, 0);
+      tc_fence_after();
+      const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
+      for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= p.N) break;
+        uint32_t v[32];
+        tmem_ld32(tmem + ((q * 32u) << 16) + c, v);
+        tmem_ld_wait();
+        if (row < p.M) {
+          float o[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const int col = n0 + c + k;
+            o[k] = __uint_as_float(v[k]) * p.alpha + ((add_bias && col < p.N) ? __ldg(p.bias + col) : 0.f);
+          }
+          const size_t off = static_cast<size_t>(row) * p.ldd + n0 + c;
+          if (gridDim.z > 1) {
+            float* dst = reinterpret_cast<float*>(p.d) + off;
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (n0 + c + k < p.N) atomicAdd(dst + k, o[k]);
+          } else if (p.out_dtype == COSMOS_DTYPE_F32) {
+            float* dst = reinterpret_cast<float*>(p.d) + off;
+            if (n0 + c + 32 <= p.N && (p.ldd & 3) == 0) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                reinterpret_cast<float4*>(dst)[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (n0 + c + k < p.N) dst[k] = o[k];
+            }
+          } else {
+            const int fmt = p.out_dtype == COSMOS_DTYPE_BF16 ? 1 : 0;
+            uint16_t* dst = reinterpret_cast<uint16_t*>(p.d) + off;
+            if (n0 + c + 32 <= p.N && (p.ldd & 7) == 0) {
+              uint32_t w[16];
+#pragma unroll
+              for (int k = 0; k < 16; ++k) w[k] = pack2(o[2 * k], o[2 * k + 1], fmt);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                reinterpret_cast<uint4*>(dst)[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (n0 + c + k < p.N) {
+                  const uint32_t w = pack2(o[k], 0.f, fmt);
+                  dst[k] = static_cast<uint16_t>(w & 0xffff);
+                }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<128>(tmem);
+}
+
+// 2-D operand map: K-major [rows, K] -> box {64 k, 128 rows}; MN-major [K, rows] -> box {64 rows, 64 k}.
+static int make_operand_map(CUtensorMap* map, const void* ptr, int is_bf16, int kmajor, int64_t rows, int64_t K, int64_t ld) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return -1;
+  cuuint64_t gdim[3], gstride[2];
+  cuuint32_t box[3], estr[3] = {1, 1, 1};
+  if (kmajor) {
+    gdim[0] = K; gdim[1] = rows; gdim[2] = 1;
+    box[0] = 64; box[1] = 128; box[2] = 1;
+  } else {
+    gdim[0] = rows; gdim[1] = K; gdim[2] = 1;
+    box[0] = 64; box[1] = 64; box[2] = 1;
+  }
+  gstride[0] = static_cast<cuuint64_t>(ld) * 2;
+  gstride[1] = gstride[0] * gdim[1];
+  CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), gdim,
+                  gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
+int launch_gemm(const GemmArgs& a, cudaStream_t stream, cudaError_t* err) {
+  *err = cudaSuccess;
+  CUtensorMap tmA, tmB;
+  const int bf = a.in_dtype == COSMOS_DTYPE_BF16;
+  int r1 = make_operand_map(&tmA, a.a, bf, a.a_kmajor, a.M, a.K, a.lda);
+  int r2 = make_operand_map(&tmB, a.b, bf, a.b_kmajor, a.N, a.K, a.ldb);
+  if (r1 != 0 || r2 != 0) return 100000 + (r1 != 0 ? r1 : r2);
+  GemmParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.ldd = a.ldd;
+  p.a_kmajor = a.a_kmajor; p.b_kmajor = a.b_kmajor;
+  p.out_dtype = a.splits > 1 ? COSMOS_DTYPE_F32 : a.out_dtype;
+  p.alpha = a.alpha; p.bias = a.bias; p.d = a.d;
+  p.idesc = make_idesc(bf, a.a_kmajor ? 0 : 1, a.b_kmajor ? 0 : 1, BM, BN);
+  const int smem_bytes = 2 * kStages * kOpBytes + 1024;
+  *err = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (*err != cudaSuccess) return -1;
+  dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.splits);
+  gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  *err = cudaGetLastError();
+  return *err == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace cb

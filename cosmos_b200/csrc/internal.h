@@ -12,4 +12,42 @@ typedef cosmos_ema_chunk EmaChunk;
 
 cudaError_t launch_ema(const EmaChunk* table, int n_chunks, double momentum, int dtype, int sm_count, cudaStream_t stream);
 
+
+// ---- generic tcgen05 GEMM (gemm.cu) ----
+struct GemmParams {
+  int M, N, K, ldd;
+  int a_kmajor, b_kmajor, out_dtype;
+  uint32_t idesc;
+  float alpha;
+  const float* bias;
+  void* d;
+};
+struct GemmArgs {
+  const void* a; const void* b; void* d; const float* bias;
+  int M, N, K;
+  int64_t lda, ldb, ldd;      // row strides (elements) of the stored matrices
+  int a_kmajor, b_kmajor;     // 1: stored [rows, K]; 0: stored [K, rows]
+  int in_dtype, out_dtype, splits;
+  float alpha;
+};
+// returns 0, -1 (CUDA error in *err) or 100000 + CUresult (tensor map)
+int launch_gemm(const GemmArgs& a, cudaStream_t stream, cudaError_t* err);
+
+
+// ---- pooler helpers (xpool.cu) ----
+cudaError_t launch_layernorm_fwd(const void* x, int x_dtype, const float* w, const float* b, void* y, int y_dtype, float* mean,
+                                 float* rstd, int64_t rows, int dim, cudaStream_t s);
+cudaError_t launch_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* w, const float* mean,
+                                 const float* rstd, void* dx, int dx_dtype, int accumulate, float* dw, float* db, int64_t rows,
+                                 int dim, cudaStream_t s);
+cudaError_t launch_attn_core_fwd(const void* q, const void* kv, void* o, float* lse, int dtype, int n_sets, int L, int dim, int heads,
+                                 int q_per_set, int64_t qs, int64_t qq, cudaStream_t s);
+cudaError_t launch_attn_core_bwd(const void* q, const void* kv, const void* d_o, const float* lse, void* dq, void* dkv, int dtype,
+                                 int n_sets, int L, int dim, int heads, int q_per_set, int64_t qs, int64_t qq, cudaStream_t s);
+cudaError_t launch_addnorm_fwd(const void* f, int f_dtype, const float* pooled, void* out, float* inv_norm, int64_t rows, int dim,
+                               cudaStream_t s);
+cudaError_t launch_addnorm_bwd(const void* g_out, const void* out, int f_dtype, const float* inv_norm, float* g_z32, void* g_z16,
+                               int g_dtype, int64_t rows, int dim, cudaStream_t s);
+cudaError_t launch_colsum(const void* src, int dtype, float* dst, int64_t rows, int n, int64_t ld, cudaStream_t s);
+
 }  // namespace cb

@@ -125,6 +125,53 @@ int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, c
                        float a_row, float a_col, float s_row, float s_col, float weight, const float* upstream,
                        void* dx, float* dscale, void* workspace, int64_t workspace_bytes, int device, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Cross-attention pooler building blocks
+ *   (transformer.py:210-230 AttentionalCrossPooler.forward = LayerNorm x2 + nn.MultiheadAttention with one
+ *    query per crop; model.py:378-387 residual add + F.normalize).  cosmos_b200/pooler.py composes them.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* D[M,N] (+)= alpha * opA * opB^T (+ bias[N]) on tcgen05 tensor cores, fp32 accumulation.
+ *   a_kmajor = 1: A stored [M, K] row-major with row stride lda;  0: stored [K, M] (used for weight gradients)
+ *   b_kmajor likewise for B [N, K] / [K, N].  in_dtype bf16/f16; out_dtype f32/bf16/f16.
+ *   splits > 1 splits K over gridDim.z and accumulates with fp32 atomics into D, which the caller has zeroed
+ *   (out_dtype is then forced to f32).  Strides in elements, multiples of 8; pointers 16-byte aligned.       */
+int cosmos_gemm(const void* a, const void* b, void* d, const float* bias, int32_t M, int32_t N, int32_t K,
+                int64_t lda, int64_t ldb, int64_t ldd, int32_t a_kmajor, int32_t b_kmajor, int32_t in_dtype,
+                int32_t out_dtype, int32_t splits, float alpha, int device, void* stream);
+
+/* LayerNorm over the last dim (eps = 1e-5): y = (x - mean) * rstd * w + b, one row per warp.
+ * x: [rows, dim] of x_dtype; y: [rows, dim] bf16/f16 (y_dtype); mean, rstd: fp32 [rows] (saved for backward). */
+int cosmos_layernorm_fwd(const void* x, int32_t x_dtype, const float* w, const float* b, void* y, int32_t y_dtype,
+                         float* mean, float* rstd, int64_t rows, int32_t dim, int device, void* stream);
+/* dx = LayerNorm backward of dy (dy_dtype) w.r.t. x, written as dx_dtype (added to dx when accumulate != 0);
+ * dw, db: fp32 [dim], accumulated with atomics (caller zeroes them).                                          */
+int cosmos_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* w,
+                         const float* mean, const float* rstd, void* dx, int32_t dx_dtype, int32_t accumulate,
+                         float* dw, float* db, int64_t rows, int32_t dim, int device, void* stream);
+
+/* Multi-head attention core with few queries per key/value set.  kv: [n_sets * L, 2 * dim] (keys | values,
+ * heads contiguous inside each half), q / o: [n_q, dim]; query c of set s is row s * q_stride_set + c * q_stride_q,
+ * c < q_per_set.  Softmax scale 1/sqrt(head_dim).  lse: fp32 [n_q, heads] natural-log sum-exp (saved).          */
+int cosmos_attn_core_fwd(const void* q, const void* kv, void* o, float* lse, int32_t dtype, int32_t n_sets, int32_t L,
+                         int32_t dim, int32_t heads, int32_t q_per_set, int64_t q_stride_set, int64_t q_stride_q,
+                         int device, void* stream);
+int cosmos_attn_core_bwd(const void* q, const void* kv, const void* d_o, const float* lse, void* dq, void* dkv,
+                         int32_t dtype, int32_t n_sets, int32_t L, int32_t dim, int32_t heads, int32_t q_per_set,
+                         int64_t q_stride_set, int64_t q_stride_q, int device, void* stream);
+
+/* out = normalize(f + pooled) row-wise (F.normalize, eps 1e-12): f [rows, dim] f_dtype, pooled fp32, out f_dtype,
+ * inv_norm fp32 [rows] saved.  Backward: g_z = (g_out - out * <out, g_out>) * inv_norm, written as fp32 (for the
+ * residual branch) and as 16-bit g_dtype (input of the out-projection gradient GEMMs).                          */
+int cosmos_addnorm_fwd(const void* f, int32_t f_dtype, const float* pooled, void* out, float* inv_norm, int64_t rows,
+                       int32_t dim, int device, void* stream);
+int cosmos_addnorm_bwd(const void* g_out, const void* out, int32_t f_dtype, const float* inv_norm, float* g_z32,
+                       void* g_z16, int32_t g_dtype, int64_t rows, int32_t dim, int device, void* stream);
+
+/* dst[n] += sum over rows of src[rows, n] (fp32 atomics; bias gradients).                                       */
+int cosmos_colsum(const void* src, int32_t dtype, float* dst, int64_t rows, int32_t n, int64_t ld, int device,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

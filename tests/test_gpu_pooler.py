@@ -1,0 +1,132 @@
+"""GPU parity of the cross-attention pooler: the tcgen05 GEMM against torch.matmul, the building blocks
+against their oracle formulas, and the whole module (forward + every gradient) against the fixtures the
+unmodified reference produced (tests/golden/pooler.pt)."""
+import math
+import os
+
+import pytest
+import torch
+
+from oracle import cosmos_oracle as O
+
+
+def cosine(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+def relerr(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,akm,bkm,splits,out", [
+    (256, 256, 512, True, True, 1, torch.float32),
+    (300, 200, 136, True, True, 1, torch.bfloat16),
+    (128, 1024, 512, True, True, 1, torch.bfloat16),
+    (777, 512, 1024, True, False, 1, torch.bfloat16),      # dgrad form: B stored [K, N]
+    (512, 512, 4000, False, False, 7, torch.float32),      # wgrad form: both stored [K, rows], split-K atomics
+    (64, 64, 96, False, False, 1, torch.float32),
+    (1536, 512, 200, False, True, 3, torch.float32),
+])
+def test_tcgen05_gemm(M, N, K, akm, bkm, splits, out):
+    from cosmos_b200 import pooler as P
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) / math.sqrt(K)).bfloat16()
+    B = torch.randn(N, K, generator=g).bfloat16()
+    bias = torch.randn(N, generator=g)
+    a_dev = (A if akm else A.t().contiguous()).cuda()
+    b_dev = (B if bkm else B.t().contiguous()).cuda()
+    d = (torch.zeros if splits > 1 else torch.empty)(M, N, dtype=out, device="cuda")
+    P._gemm(a_dev, b_dev, d, M, N, K, a_dev.stride(0), b_dev.stride(0), akm, bkm, bias=bias.cuda(), splits=splits, alpha=0.5)
+    want = 0.5 * (A.double() @ B.double().T) + bias.double()
+    tol = 1e-5 if out == torch.float32 else 6e-3
+    assert relerr(d, want) < tol, relerr(d, want)
+
+
+@pytest.mark.gpu
+def test_layernorm_and_addnorm_blocks():
+    from cosmos_b200 import pooler as P
+    g = torch.Generator().manual_seed(2)
+    x = (torch.randn(777, 512, generator=g) * 2 + 0.3)
+    w, b = 1 + 0.1 * torch.randn(512, generator=g), 0.1 * torch.randn(512, generator=g)
+    y, mean, rstd = P._ln_fwd(x.cuda(), w.cuda(), b.cuda(), torch.bfloat16)
+    want = O.layer_norm(x, w, b)
+    assert relerr(y.float(), want) < 5e-3
+    dy = torch.randn(777, 512, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    (O.layer_norm(xr, wr, br) * dy).sum().backward()
+    dx = torch.empty(777, 512, dtype=torch.float32, device="cuda")
+    dw, db = P._ln_bwd(dy.cuda(), x.cuda(), w.cuda(), mean, rstd, dx, False)
+    assert relerr(dx, xr.grad) < 1e-4 and relerr(dw, wr.grad) < 1e-4 and relerr(db, br.grad) < 1e-4
+
+
+def _run_case(rec, dtype, fused):
+    from cosmos_b200.pooler import AttentionalCrossPooler, crossmodal_features
+    params, tokens, feats, w = O.make_pooler_case(rec["d"], rec["L"], rec["batch_size"], rec["n"], rec["seed"])
+    B, n = rec["batch_size"], rec["n"]
+    mod = AttentionalCrossPooler(rec["d"], rec["d"], rec["heads"]).cuda()
+    mod.load_state_dict(params)
+    tok = tokens.to(dtype).cuda().requires_grad_(True)
+    f = feats.to(dtype).cuda().requires_grad_(True)
+    if fused:
+        xm = crossmodal_features(mod, tok, f, B)
+        pooled = None
+    else:
+        pooled = mod(tok[:B].repeat(n, 1, 1), f.unsqueeze(1))          # literal model.py:378 call
+        xm = torch.nn.functional.normalize(f + pooled.squeeze(1), dim=-1)
+    (xm.float() * w.cuda()).sum().backward()
+    return mod, tok, f, pooled, xm
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", [True, False])
+def test_pooler_against_reference_golden(golden_dir, fused):
+    for rec in torch.load(os.path.join(golden_dir, "pooler.pt"), weights_only=False):
+        mod, tok, f, pooled, xm = _run_case(rec, torch.float32, fused)
+        if pooled is not None:
+            assert relerr(pooled, rec["pooled"]) < 2e-2, (rec["d"], relerr(pooled, rec["pooled"]))
+        assert relerr(xm, rec["xmodal"]) < 1e-2, (rec["d"], relerr(xm, rec["xmodal"]))
+        assert cosine(f.grad, rec["g_feats"]) > 0.999, (rec["d"], cosine(f.grad, rec["g_feats"]))
+        assert abs(float(tok.grad.float().norm()) / rec["g_tokens_norm"] - 1) < 3e-2
+        assert cosine(tok.grad[:, :2], rec["g_tokens_head"]) > 0.995
+        named = dict(mod.named_parameters())
+        for k, gn in rec["g_param_norm"].items():
+            if k == "attn.in_proj_bias":
+                continue            # the key third is exactly zero in exact arithmetic (softmax shift invariance)
+            got = named[k].grad
+            assert abs(float(got.norm()) / gn - 1) < 3e-2, (rec["d"], k, float(got.norm()), gn)
+            assert cosine(got.reshape(-1)[:64], rec["g_param_head"][k]) > 0.99, (rec["d"], k)
+        if "g_params" in rec:
+            for k, gref in rec["g_params"].items():
+                if k == "attn.in_proj_bias":
+                    d = rec["d"]
+                    sel = torch.cat([torch.arange(0, d), torch.arange(2 * d, 3 * d)])
+                    assert cosine(named[k].grad[sel], gref[sel]) > 0.995, k
+                else:
+                    assert cosine(named[k].grad, gref) > 0.995, (rec["d"], k, cosine(named[k].grad, gref))
+            assert cosine(tok.grad, rec["g_tokens"]) > 0.995
+
+
+@pytest.mark.gpu
+def test_pooler_bf16_inputs_and_dedup_equivalence():
+    """bf16 tokens/features (what autocast hands the module); the fused call-site form and the literal
+    repeat() form must agree with each other and with the fp32 oracle on the same bf16-rounded values."""
+    rec = dict(d=512, heads=8, L=77, batch_size=4, n=8, seed=123)
+    modA, tokA, fA, _, xmA = _run_case(rec, torch.bfloat16, True)
+    modB, tokB, fB, _, xmB = _run_case(rec, torch.bfloat16, False)
+    assert relerr(xmA.float(), xmB.float()) < 1e-2
+    assert cosine(fA.grad.float(), fB.grad.float()) > 0.999
+    assert cosine(tokA.grad.float(), tokB.grad.float()) > 0.995
+    params, tokens, feats, w = O.make_pooler_case(512, 77, 4, 8, 123)
+    p32 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    t32 = tokens.bfloat16().float().requires_grad_(True)
+    f32 = feats.bfloat16().float().requires_grad_(True)
+    xm = O.cosmos_crossmodal(f32, t32, p32, 8, 4)
+    (xm * w).sum().backward()
+    assert relerr(xmA.float(), xm) < 1e-2
+    assert cosine(fA.grad.float(), f32.grad) > 0.999
+    assert cosine(tokA.grad.float(), t32.grad) > 0.995
+    assert cosine(dict(modA.named_parameters())["attn.out_proj.weight"].grad, p32["attn.out_proj.weight"].grad) > 0.995

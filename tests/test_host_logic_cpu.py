@@ -144,3 +144,41 @@ def test_multirank_modes_gloo(world, fname, port):
         for r, p in enumerate(procs):
             assert p.exitcode == 0, f"rank {r} failed"
             assert os.path.exists(os.path.join(tmpdir, f"ok{r}"))
+
+
+def test_pooler_module_is_checkpoint_compatible():
+    """Same parameter names/shapes as the reference AttentionalCrossPooler (transformer.py:210-230), so reference
+    state_dicts load; unsupported configurations are rejected loudly; CPU tensors are rejected (no fallback)."""
+    from cosmos_b200.pooler import AttentionalCrossPooler, crossmodal_features
+    from oracle.cosmos_oracle import make_pooler_case
+    params, tokens, feats, _ = make_pooler_case(64, 7, 3, 2, seed=1)
+    mod = AttentionalCrossPooler(64, 64, 4)
+    assert {k: tuple(v.shape) for k, v in mod.state_dict().items()} == {k: tuple(v.shape) for k, v in params.items()}
+    mod.load_state_dict(params)
+    with pytest.raises(NotImplementedError):
+        AttentionalCrossPooler(64, 64, 4, add_zero_attn=True)
+    with pytest.raises(NotImplementedError):
+        AttentionalCrossPooler(64, 32, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        crossmodal_features(mod, tokens, feats, 3)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """Every function declared in include/cosmos_b200.h is exported by libcosmos_b200.so (no compute calls)."""
+    import ctypes
+    import re
+    from cosmos_b200 import _lib
+    lib = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "cosmos_b200.h")).read()
+    names = set(re.findall(r"\b(cosmos_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.cosmos_abi_version() == 1
+    assert lib.cosmos_status_string(0) == b"ok"
+    # host-only helpers behave
+    numel = (ctypes.c_int64 * 3)(8192, 1, 8193)
+    assert lib.cosmos_ema_table_entries(3, numel) == 1 + 1 + 2
+    assert lib.cosmos_ema_table_entries(-1, numel) == -1
+    bad = _lib.InfoNceProblem(x=16, y=16, gx=1, gy=1, n_rows=8, n_cols=8, dim=100, label_offset=0, dtype=1, reserved=0, scale=4)
+    assert lib.cosmos_infonce_workspace_bytes(ctypes.byref(bad)) == -1          # dim not a multiple of 64
