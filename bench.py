@@ -283,12 +283,145 @@ def run_ours(args):
                          "step_algorithmic_tflops_per_gpu": step_tflops, "step_frac": step_tflops / sustained,
                          "kernels": ksum},
         }
+        if world == 1 and not args.no_extras:
+            del dev_buf, host
+            torch.cuda.empty_cache()
+            line["ema"] = bench_ema(dev, flush)
+            line["xattn"] = bench_xattn(dev, flush)
+            line["eager_gpu_baseline"] = bench_eager_gpu(dev)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+
+# ------------------------------------------------------------------------------------------------
+# the other rows of the hot path, timed as separate entries of the same JSON line (N = 1 only)
+# ------------------------------------------------------------------------------------------------
+
+def vitb16_cosmos_param_shapes():
+    """Parameter table of ViT-B/16 COSMOS (student == teacher): 323 tensors, 152,382,466 fp32 parameters
+    (SURVEY.md §8(a) A5), rebuilt from the architecture so that no checkpoint is needed."""
+    def block(w, mlp):
+        return [(w,), (w,), (3 * w, w), (3 * w,), (w, w), (w,), (w,), (w,), (mlp, w), (mlp,), (w, mlp), (w,)]
+    shapes = [(768, 3, 16, 16), (768,), (197, 768), (768,), (768,)]
+    for _ in range(12):
+        shapes += block(768, 3072)
+    shapes += [(768,), (768,), (768, 512), (49408, 512), (77, 512)]
+    for _ in range(12):
+        shapes += block(512, 2048)
+    shapes += [(512,), (512,), (512, 512), (), ()]
+    pool = [(1536, 512), (1536,), (512, 512), (512,), (512,), (512,), (512,), (512,)]
+    shapes += pool + pool + [(512, 768), (512,), (512, 512), (512,)]
+    return shapes
+
+
+def _event_ms(fn, reps, flush=None):
+    ms = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    ms.sort()
+    return ms[len(ms) // 2], ms[0]
+
+
+def bench_ema(dev, flush):
+    from cosmos_b200 import EmaPlan, ema_update_
+    from oracle import cosmos_oracle as O
+    shapes = vitb16_cosmos_param_shapes()
+    g = torch.Generator(device=dev).manual_seed(5)
+    student = [torch.randn(s, generator=g, device=dev) * 0.02 for s in shapes]
+    teacher = [torch.randn(s, generator=g, device=dev) * 0.02 for s in shapes]
+    n_params = sum(t.numel() for t in teacher)
+    plan = EmaPlan(student, teacher)
+    for _ in range(3):
+        plan.apply(0.99)
+        ema_update_(student, teacher, 0.99)
+    med, best = _event_ms(lambda: plan.apply(0.99), 20, flush)
+    api_med, _ = _event_ms(lambda: ema_update_(student, teacher, 0.99), 20, flush)
+    ref_med, _ = _event_ms(lambda: O.ema_update_(teacher, student, 0.99), 5, flush)      # the reference loop, eager, same GPU
+    _, _, hbm, src = peaks()
+    gbs = 12.0 * n_params / (med * 1e-3) / 1e9
+    return {"workload": "EMA teacher update, ViT-B/16 COSMOS: %d fp32 parameters in %d tensors, one launch" % (n_params, len(shapes)),
+            "ms": med, "ms_best": best, "algorithmic_bytes": 12 * n_params,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "peak_source": src},
+            "ema_update_api_ms": api_med, "eager_reference_loop_ms": ref_med}
+
+
+def bench_xattn(dev, flush):
+    """BASELINE config 4 at the reference's shapes: 8 queries per sample, 77 text / 196 image tokens, d = 512, batch 1024."""
+    from cosmos_b200.pooler import AttentionalCrossPooler, crossmodal_features
+    from oracle import cosmos_oracle as O
+    out = {}
+    B, n, d, heads = 1024, 8, 512, 8
+    for name, L in (("text_tokens_77", 77), ("image_tokens_196", 196)):
+        params, _, _, _ = O.make_pooler_case(d, 4, 1, 1, seed=3)
+        mod = AttentionalCrossPooler(d, d, heads).to(dev)
+        mod.load_state_dict(params)
+        g = torch.Generator(device=dev).manual_seed(L)
+        tokens = torch.randn(B, L, d, generator=g, device=dev).bfloat16().requires_grad_(True)
+        feats = torch.randn(n * B, d, generator=g, device=dev).bfloat16().requires_grad_(True)
+        w = torch.randn(n * B, d, generator=g, device=dev).bfloat16()
+
+        def step():
+            for t in [tokens, feats] + list(mod.parameters()):
+                t.grad = None
+            xm = crossmodal_features(mod, tokens, feats, B)
+            xm.backward(w)
+
+        for _ in range(3):
+            step()
+        med, best = _event_ms(step, 10, flush)
+        # algorithmic flops (SURVEY.md §8(d)): K/V projection once per unique sample + 8 queries, x3 for fwd+bwd
+        fwd = 2.0 * B * L * d * 2 * d + 2.0 * n * B * d * d * 2 + 4.0 * n * B * L * d
+        p16 = {k: v.to(dev) for k, v in params.items()}
+
+        def eager():
+            t32, f32 = tokens.detach().requires_grad_(True), feats.detach().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                xm = O.cosmos_crossmodal(f32, t32, {k: v.requires_grad_(True) for k, v in p16.items()}, heads, B)
+            xm.backward(w.to(xm.dtype))
+
+        eager(); eager()
+        ref_med, _ = _event_ms(eager, 3, flush)
+        burst, sustained, _, src = peaks()
+        tf = 3.0 * fwd / (med * 1e-3) / 1e12
+        out[name] = {"ms": med, "ms_best": best, "algorithmic_tflops": tf, "frac_of_bf16_peak": tf / burst,
+                     "eager_restatement_ms": ref_med, "batch": B, "queries_per_sample": n, "tokens": L, "dim": d}
+    return out
+
+
+def bench_eager_gpu(dev, n_global=4096, steps=3):
+    """The oracle (eager PyTorch restatement of the reference loss) on the same B200 under bf16 autocast:
+    the like-for-like bar, since the reference has no native kernel."""
+    from oracle import cosmos_oracle as O
+    inp = O.make_features(n_global, DIM, seed=1234)
+    leaf = {k: [t.bfloat16().to(dev).requires_grad_(k not in ("t_image", "t_text")) for t in v] for k, v in inp.items()}
+    ls = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
+    ds = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
+
+    def step():
+        for v in leaf.values():
+            for t in v:
+                t.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = O.cosmos_loss_single(leaf["s_image"], leaf["s_text"], ls, leaf["t_image"], leaf["t_text"], ds,
+                                       leaf["s_img_x"], leaf["s_txt_x"])
+        (out["distill_loss"] + out["clip_loss"]).backward()
+
+    step(); step()
+    med, _ = _event_ms(step, steps)
+    return {"workload": "oracle (eager PyTorch) loss head fwd+bwd on the same B200, bf16 autocast, global batch %d" % n_global,
+            "ms_per_step": med, "value": n_global / (med * 1e-3), "unit": "samples/s"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -372,6 +505,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=1024, help="batch of one reference-arm step (bounded sample)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the EMA / cross-attention / eager-GPU entries")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

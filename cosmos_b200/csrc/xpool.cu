@@ -183,126 +183,250 @@ __device__ __forceinline__ float block_reduce(float v, float* scratch, bool is_m
   return r;
 }
 
+constexpr int kAttnThreads = 256;
+constexpr int kQG = 8;   // queries processed together (one register accumulator each)
+
+// scores of up to kQG queries against key row l: acc[c] += sum_k A[c][k] * row[k]   (A fp32 [kQG][hd] in smem)
 template <class T>
-__global__ void __launch_bounds__(128)
-attn_core_fwd_kernel(const T* __restrict__ q, const T* __restrict__ kv, T* __restrict__ o, float* __restrict__ lse, AttnArgs a) {
-  extern __shared__ __align__(16) uint8_t sm[];
-  const int hd = a.hd, ldk = hd + 2, L = a.L;
-  T* sK = reinterpret_cast<T*>(sm);
-  T* sV = sK + L * ldk;
-  float* sQ = reinterpret_cast<float*>(sV + L * ldk);     // [hd]
-  float* sP = sQ + hd;                                    // [L]
-  float* scratch = sP + L;                                // [8]
-  float* sO = scratch + 8;                                // [128]: (128 / hd) partial sums per output
-  const int set = blockIdx.x / a.heads, h = blockIdx.x - set * a.heads;
-  load_kv(kv, sK, sV, a, set, h);
-  const float kappa = rsqrtf(static_cast<float>(hd));
-  for (int c = 0; c < a.q_per_set; ++c) {
-    const size_t qrow = static_cast<size_t>(set) * a.q_stride_set + static_cast<size_t>(c) * a.q_stride_q;
-    __syncthreads();
-    for (int k = threadIdx.x; k < hd; k += blockDim.x) sQ[k] = tof(q[qrow * a.dim + h * hd + k]) * kappa;
-    __syncthreads();
-    float mx = -INFINITY;
-    for (int l = threadIdx.x; l < L; l += blockDim.x) {
-      float s = 0.f;
-      for (int k = 0; k < hd; k += 2) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(sK + l * ldk + k);
-        T lo, hi;
-        *reinterpret_cast<uint16_t*>(&lo) = static_cast<uint16_t>(w & 0xffff);
-        *reinterpret_cast<uint16_t*>(&hi) = static_cast<uint16_t>(w >> 16);
-        s = fmaf(sQ[k], tof(lo), s);
-        s = fmaf(sQ[k + 1], tof(hi), s);
-      }
-      sP[l] = s;
-      mx = fmaxf(mx, s);
+__device__ __forceinline__ void dot_rows(const float* __restrict__ A, const T* __restrict__ row, int hd, float (&acc)[kQG]) {
+  for (int k0 = 0; k0 < hd; k0 += 8) {
+    float kv[8];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(row + k0 + 2 * w);
+      T lo, hi;
+      *reinterpret_cast<uint16_t*>(&lo) = static_cast<uint16_t>(u & 0xffff);
+      *reinterpret_cast<uint16_t*>(&hi) = static_cast<uint16_t>(u >> 16);
+      kv[2 * w] = tof(lo);
+      kv[2 * w + 1] = tof(hi);
     }
-    mx = block_reduce(mx, scratch, true);
-    float sum = 0.f;
-    for (int l = threadIdx.x; l < L; l += blockDim.x) {
-      const float e = __expf(sP[l] - mx);
-      sP[l] = e;
-      sum += e;
+#pragma unroll
+    for (int c = 0; c < kQG; ++c) {
+      const float4 a0 = *reinterpret_cast<const float4*>(A + c * hd + k0);
+      const float4 a1 = *reinterpret_cast<const float4*>(A + c * hd + k0 + 4);
+      acc[c] = fmaf(a0.x, kv[0], acc[c]); acc[c] = fmaf(a0.y, kv[1], acc[c]);
+      acc[c] = fmaf(a0.z, kv[2], acc[c]); acc[c] = fmaf(a0.w, kv[3], acc[c]);
+      acc[c] = fmaf(a1.x, kv[4], acc[c]); acc[c] = fmaf(a1.y, kv[5], acc[c]);
+      acc[c] = fmaf(a1.z, kv[6], acc[c]); acc[c] = fmaf(a1.w, kv[7], acc[c]);
     }
-    sum = block_reduce(sum, scratch, false);   // also makes sP visible
-    const float inv = 1.f / sum;
-    // O[k] = sum_l p_l V[l][k]: thread = (k, part), part strides over the keys; 128 / hd parts
-    {
-      const int parts = blockDim.x / hd;
-      const int k = threadIdx.x % hd, part = threadIdx.x / hd;
-      float acc = 0.f;
-      for (int l = part; l < L; l += parts) acc = fmaf(sP[l], tof(sV[l * ldk + k]), acc);
-      sO[part * hd + k] = acc;
-      __syncthreads();
-      if (threadIdx.x < hd) {
-        float r = 0.f;
-        for (int pp = 0; pp < parts; ++pp) r += sO[pp * hd + threadIdx.x];
-        o[qrow * a.dim + h * hd + threadIdx.x] = fromf<T>(r * inv);
-      }
-    }
-    if (threadIdx.x == 0) lse[qrow * a.heads + h] = mx + __logf(sum);
+  }
+}
+
+// out[c][k] = sum_l W[c][l] * M[l][k] for this thread's k and its share of the keys (l = part, part + parts, ...)
+template <class T>
+__device__ __forceinline__ void weighted_rows(const float* __restrict__ W, int ldw, const T* __restrict__ M, int ldk, int L, int k,
+                                              int part, int parts, float (&acc)[kQG]) {
+  for (int l = part; l < L; l += parts) {
+    const float v = tof(M[l * ldk + k]);
+#pragma unroll
+    for (int c = 0; c < kQG; ++c) acc[c] = fmaf(W[c * ldw + l], v, acc[c]);
   }
 }
 
 template <class T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kAttnThreads)
+attn_core_fwd_kernel(const T* __restrict__ q, const T* __restrict__ kv, T* __restrict__ o, float* __restrict__ lse, AttnArgs a) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int hd = a.hd, ldk = hd + 2, L = a.L;
+  const int Lp = (L + 3) & ~3;
+  T* sK = reinterpret_cast<T*>(sm);
+  T* sV = sK + L * ldk;
+  float* sQ = reinterpret_cast<float*>(sm + ((2 * static_cast<size_t>(L) * ldk * 2 + 15) & ~size_t(15)));   // [kQG][hd]
+  float* sP = sQ + kQG * hd;                              // [kQG][Lp]
+  float* sRed = sP + kQG * Lp;                            // [8 warps][kQG]
+  float* sStat = sRed + 8 * kQG;                          // [kQG] max, [kQG] 1/sum
+  float* sO = sStat + 2 * kQG;                            // [parts][kQG][hd]
+  const int set = blockIdx.x / a.heads, h = blockIdx.x - set * a.heads;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  load_kv(kv, sK, sV, a, set, h);
+  const float kappa = rsqrtf(static_cast<float>(hd));
+  for (int c0 = 0; c0 < a.q_per_set; c0 += kQG) {
+    const int nq = min(kQG, a.q_per_set - c0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kQG * hd; idx += blockDim.x) {
+      const int c = idx / hd, k = idx - c * hd;
+      const size_t qrow = static_cast<size_t>(set) * a.q_stride_set + static_cast<size_t>(c0 + c) * a.q_stride_q;
+      sQ[idx] = c < nq ? tof(q[qrow * a.dim + h * hd + k]) * kappa : 0.f;
+    }
+    __syncthreads();
+    float mx[kQG];
+#pragma unroll
+    for (int c = 0; c < kQG; ++c) mx[c] = -INFINITY;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+      float s[kQG];
+#pragma unroll
+      for (int c = 0; c < kQG; ++c) s[c] = 0.f;
+      dot_rows(sQ, sK + l * ldk, hd, s);
+#pragma unroll
+      for (int c = 0; c < kQG; ++c) {
+        sP[c * Lp + l] = s[c];
+        mx[c] = fmaxf(mx[c], s[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kQG; ++c) mx[c] = warp_max(mx[c]);
+    if (lane == 0)
+#pragma unroll
+      for (int c = 0; c < kQG; ++c) sRed[wid * kQG + c] = mx[c];
+    __syncthreads();
+    if (threadIdx.x < kQG) {
+      float m = sRed[threadIdx.x];
+      for (int w = 1; w < 8; ++w) m = fmaxf(m, sRed[w * kQG + threadIdx.x]);
+      sStat[threadIdx.x] = m;
+    }
+    __syncthreads();
+    float sum[kQG];
+#pragma unroll
+    for (int c = 0; c < kQG; ++c) sum[c] = 0.f;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+#pragma unroll
+      for (int c = 0; c < kQG; ++c) {
+        const float e = __expf(sP[c * Lp + l] - sStat[c]);
+        sP[c * Lp + l] = e;
+        sum[c] += e;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kQG; ++c) sum[c] = warp_sum(sum[c]);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+      for (int c = 0; c < kQG; ++c) sRed[wid * kQG + c] = sum[c];
+    __syncthreads();
+    if (threadIdx.x < kQG) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += sRed[w * kQG + threadIdx.x];
+      sStat[kQG + threadIdx.x] = 1.f / t;
+      if (threadIdx.x < nq) {
+        const size_t qrow = static_cast<size_t>(set) * a.q_stride_set + static_cast<size_t>(c0 + threadIdx.x) * a.q_stride_q;
+        lse[qrow * a.heads + h] = sStat[threadIdx.x] + __logf(t);
+      }
+    }
+    __syncthreads();
+    // O = P V
+    const int parts = blockDim.x / hd, k = threadIdx.x % hd, part = threadIdx.x / hd;
+    float acc[kQG];
+#pragma unroll
+    for (int c = 0; c < kQG; ++c) acc[c] = 0.f;
+    weighted_rows(sP, Lp, sV, ldk, L, k, part, parts, acc);
+#pragma unroll
+    for (int c = 0; c < kQG; ++c) sO[(part * kQG + c) * hd + k] = acc[c];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nq * hd; idx += blockDim.x) {
+      const int c = idx / hd, kk = idx - c * hd;
+      float r = 0.f;
+      for (int pp = 0; pp < parts; ++pp) r += sO[(pp * kQG + c) * hd + kk];
+      const size_t qrow = static_cast<size_t>(set) * a.q_stride_set + static_cast<size_t>(c0 + c) * a.q_stride_q;
+      o[qrow * a.dim + h * hd + kk] = fromf<T>(r * sStat[kQG + c]);
+    }
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kAttnThreads)
 attn_core_bwd_kernel(const T* __restrict__ q, const T* __restrict__ kv, const T* __restrict__ d_o, const float* __restrict__ lse,
                      T* __restrict__ dq, T* __restrict__ dkv, AttnArgs a) {
   extern __shared__ __align__(16) uint8_t sm[];
-  const int hd = a.hd, ldk = hd + 2, L = a.L, nq = a.q_per_set;
+  const int hd = a.hd, ldk = hd + 2, L = a.L;
+  const int Lp = (L + 3) & ~3;
   T* sK = reinterpret_cast<T*>(sm);
   T* sV = sK + L * ldk;
-  float* sQ = reinterpret_cast<float*>(sV + L * ldk);     // [nq][hd]  (scaled by kappa)
-  float* sDO = sQ + nq * hd;                              // [nq][hd]
-  float* sP = sDO + nq * hd;                              // [nq][L]  probabilities
-  float* sDS = sP + nq * L;                               // [nq][L]  dS
-  float* scratch = sDS + nq * L;                          // [8]
+  float* sQ = reinterpret_cast<float*>(sm + ((2 * static_cast<size_t>(L) * ldk * 2 + 15) & ~size_t(15)));   // [kQG][hd] kappa * q
+  float* sDO = sQ + kQG * hd;                             // [kQG][hd]
+  float* sP = sDO + kQG * hd;                             // [kQG][Lp]
+  float* sDS = sP + kQG * Lp;                             // [kQG][Lp]
+  float* sRed = sDS + kQG * Lp;                           // [8][kQG]
+  float* sStat = sRed + 8 * kQG;                          // [kQG] lse, [kQG] dot
+  float* sO = sStat + 2 * kQG;                            // [parts][kQG][hd]
   const int set = blockIdx.x / a.heads, h = blockIdx.x - set * a.heads;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   load_kv(kv, sK, sV, a, set, h);
   const float kappa = rsqrtf(static_cast<float>(hd));
-  for (int idx = threadIdx.x; idx < nq * hd; idx += blockDim.x) {
-    const int c = idx / hd, k = idx - c * hd;
-    const size_t qrow = static_cast<size_t>(set) * a.q_stride_set + static_cast<size_t>(c) * a.q_stride_q;
-    sQ[idx] = tof(q[qrow * a.dim + h * hd + k]) * kappa;
-    sDO[idx] = tof(d_o[qrow * a.dim + h * hd + k]);
-  }
-  __syncthreads();
-  for (int c = 0; c < nq; ++c) {
-    const size_t qrow = static_cast<size_t>(set) * a.q_stride_set + static_cast<size_t>(c) * a.q_stride_q;
-    const float l_c = lse[qrow * a.heads + h];
-    float dot = 0.f;
-    for (int l = threadIdx.x; l < L; l += blockDim.x) {
-      float s = 0.f, dp = 0.f;
-      for (int k = 0; k < hd; ++k) {
-        s = fmaf(sQ[c * hd + k], tof(sK[l * ldk + k]), s);
-        dp = fmaf(sDO[c * hd + k], tof(sV[l * ldk + k]), dp);
-      }
-      const float pr = __expf(s - l_c);
-      sP[c * L + l] = pr;
-      sDS[c * L + l] = dp;          // dP for now
-      dot = fmaf(pr, dp, dot);
-    }
-    dot = block_reduce(dot, scratch, false);
-    for (int l = threadIdx.x; l < L; l += blockDim.x) sDS[c * L + l] = sP[c * L + l] * (sDS[c * L + l] - dot);
+  const int n_groups = (a.q_per_set + kQG - 1) / kQG;
+  for (int g = 0; g < n_groups; ++g) {
+    const int c0 = g * kQG, nq = min(kQG, a.q_per_set - c0);
     __syncthreads();
-    // dQ[c][k] = kappa * sum_l dS[c][l] K[l][k]
-    for (int k = threadIdx.x; k < hd; k += blockDim.x) {
-      float acc = 0.f;
-      for (int l = 0; l < L; ++l) acc = fmaf(sDS[c * L + l], tof(sK[l * ldk + k]), acc);
-      dq[qrow * a.dim + h * hd + k] = fromf<T>(acc * kappa);
+    for (int idx = threadIdx.x; idx < kQG * hd; idx += blockDim.x) {
+      const int c = idx / hd, k = idx - c * hd;
+      const size_t qrow = static_cast<size_t>(set) * a.q_stride_set + static_cast<size_t>(c0 + c) * a.q_stride_q;
+      sQ[idx] = c < nq ? tof(q[qrow * a.dim + h * hd + k]) * kappa : 0.f;
+      sDO[idx] = c < nq ? tof(d_o[qrow * a.dim + h * hd + k]) : 0.f;
     }
-  }
-  __syncthreads();
-  // dK[l][k] = sum_c dS[c][l] * (kappa q[c][k]);  dV[l][k] = sum_c P[c][l] dO[c][k]
-  for (int idx = threadIdx.x; idx < L * hd; idx += blockDim.x) {
-    const int l = idx / hd, k = idx - l * hd;
-    float dk = 0.f, dv = 0.f;
-    for (int c = 0; c < nq; ++c) {
-      dk = fmaf(sDS[c * L + l], sQ[c * hd + k], dk);
-      dv = fmaf(sP[c * L + l], sDO[c * hd + k], dv);
+    if (threadIdx.x < kQG) {
+      const size_t qrow = static_cast<size_t>(set) * a.q_stride_set + static_cast<size_t>(c0 + threadIdx.x) * a.q_stride_q;
+      sStat[threadIdx.x] = threadIdx.x < nq ? lse[qrow * a.heads + h] : INFINITY;
     }
-    T* rowp = dkv + (static_cast<size_t>(set) * L + l) * (2 * a.dim) + h * hd + k;
-    rowp[0] = fromf<T>(dk);
-    rowp[a.dim] = fromf<T>(dv);
+    __syncthreads();
+    float dot[kQG];
+#pragma unroll
+    for (int c = 0; c < kQG; ++c) dot[c] = 0.f;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+      float s[kQG], dp[kQG];
+#pragma unroll
+      for (int c = 0; c < kQG; ++c) s[c] = dp[c] = 0.f;
+      dot_rows(sQ, sK + l * ldk, hd, s);
+      dot_rows(sDO, sV + l * ldk, hd, dp);
+#pragma unroll
+      for (int c = 0; c < kQG; ++c) {
+        const float pr = __expf(s[c] - sStat[c]);     // 0 for padded queries (lse = +inf)
+        sP[c * Lp + l] = pr;
+        sDS[c * Lp + l] = dp[c];
+        dot[c] = fmaf(pr, dp[c], dot[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kQG; ++c) dot[c] = warp_sum(dot[c]);
+    if (lane == 0)
+#pragma unroll
+      for (int c = 0; c < kQG; ++c) sRed[wid * kQG + c] = dot[c];
+    __syncthreads();
+    if (threadIdx.x < kQG) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += sRed[w * kQG + threadIdx.x];
+      sStat[kQG + threadIdx.x] = t;
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < L; l += blockDim.x)
+#pragma unroll
+      for (int c = 0; c < kQG; ++c) sDS[c * Lp + l] = sP[c * Lp + l] * (sDS[c * Lp + l] - sStat[kQG + c]);
+    __syncthreads();
+    // dQ = kappa * dS K
+    {
+      const int parts = blockDim.x / hd, k = threadIdx.x % hd, part = threadIdx.x / hd;
+      float acc[kQG];
+#pragma unroll
+      for (int c = 0; c < kQG; ++c) acc[c] = 0.f;
+      weighted_rows(sDS, Lp, sK, ldk, L, k, part, parts, acc);
+#pragma unroll
+      for (int c = 0; c < kQG; ++c) sO[(part * kQG + c) * hd + k] = acc[c];
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < nq * hd; idx += blockDim.x) {
+        const int c = idx / hd, kk = idx - c * hd;
+        float r = 0.f;
+        for (int pp = 0; pp < parts; ++pp) r += sO[(pp * kQG + c) * hd + kk];
+        const size_t qrow = static_cast<size_t>(set) * a.q_stride_set + static_cast<size_t>(c0 + c) * a.q_stride_q;
+        dq[qrow * a.dim + h * hd + kk] = fromf<T>(r * kappa);
+      }
+    }
+    // dK[l][k] (+)= sum_c dS[c][l] * (kappa q[c][k]);  dV[l][k] (+)= sum_c P[c][l] dO[c][k]   (two k per thread)
+    for (int idx = threadIdx.x; idx < L * (hd / 2); idx += blockDim.x) {
+      const int l = idx / (hd / 2), k = (idx - l * (hd / 2)) * 2;
+      float dk0 = 0.f, dk1 = 0.f, dv0 = 0.f, dv1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < kQG; ++c) {
+        const float ds = sDS[c * Lp + l], pr = sP[c * Lp + l];
+        const float2 qq = *reinterpret_cast<const float2*>(sQ + c * hd + k);
+        const float2 oo = *reinterpret_cast<const float2*>(sDO + c * hd + k);
+        dk0 = fmaf(ds, qq.x, dk0); dk1 = fmaf(ds, qq.y, dk1);
+        dv0 = fmaf(pr, oo.x, dv0); dv1 = fmaf(pr, oo.y, dv1);
+      }
+      T* rowp = dkv + (static_cast<size_t>(set) * L + l) * (2 * a.dim) + h * hd + k;
+      if (g > 0) {   // more than kQG queries per set: accumulate over the groups
+        dk0 += tof(rowp[0]); dk1 += tof(rowp[1]); dv0 += tof(rowp[a.dim]); dv1 += tof(rowp[a.dim + 1]);
+      }
+      rowp[0] = fromf<T>(dk0); rowp[1] = fromf<T>(dk1);
+      rowp[a.dim] = fromf<T>(dv0); rowp[a.dim + 1] = fromf<T>(dv1);
+    }
   }
 }
 
@@ -388,7 +512,10 @@ cudaError_t launch_layernorm_bwd(const void* dy, int dy_dtype, const void* x, in
                                  const float* rstd, void* dx, int dx_dtype, int accumulate, float* dw, float* db, int64_t rows,
                                  int dim, cudaStream_t s) {
   if (rows == 0) return cudaSuccess;
-  const int rows_per_block = 64;
+  // few, long-running blocks: the dw/db partials of a block end in 2*dim global atomics
+  int64_t blocks = (rows + 63) / 64;
+  if (blocks > 592) blocks = 592;
+  const int rows_per_block = static_cast<int>(((rows + blocks - 1) / blocks + 7) / 8 * 8);
   layernorm_bwd_kernel<<<static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block), 256, 2 * dim * sizeof(float), s>>>(
       dy, dy_dtype, x, x_dtype, w, mean, rstd, dx, dx_dtype, accumulate, dw, db, rows, dim, rows_per_block);
   return cudaGetLastError();
@@ -404,17 +531,20 @@ static AttnArgs make_attn_args(int n_sets, int L, int dim, int heads, int q_per_
 cudaError_t launch_attn_core_fwd(const void* q, const void* kv, void* o, float* lse, int dtype, int n_sets, int L, int dim, int heads,
                                  int q_per_set, int64_t qs, int64_t qq, cudaStream_t s) {
   const AttnArgs a = make_attn_args(n_sets, L, dim, heads, q_per_set, qs, qq);
-  const size_t smem = 2 * static_cast<size_t>(L) * (a.hd + 2) * 2 + (a.hd + L + 8 + 128) * sizeof(float);
+  const size_t Lp = (L + 3) & ~3;
+  const size_t smem = ((2 * static_cast<size_t>(L) * (a.hd + 2) * 2 + 15) & ~size_t(15)) +
+                      (kQG * a.hd + kQG * Lp + 8 * kQG + 2 * kQG + kAttnThreads * kQG) * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e;
   if (dtype == COSMOS_DTYPE_BF16) {
     e = cudaFuncSetAttribute(attn_core_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attn_core_fwd_kernel<__nv_bfloat16><<<n_sets * heads, 128, smem, s>>>(
+    attn_core_fwd_kernel<__nv_bfloat16><<<n_sets * heads, kAttnThreads, smem, s>>>(
         static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kv), static_cast<__nv_bfloat16*>(o), lse, a);
   } else {
     e = cudaFuncSetAttribute(attn_core_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attn_core_fwd_kernel<__half><<<n_sets * heads, 128, smem, s>>>(static_cast<const __half*>(q), static_cast<const __half*>(kv),
+    attn_core_fwd_kernel<__half><<<n_sets * heads, kAttnThreads, smem, s>>>(static_cast<const __half*>(q), static_cast<const __half*>(kv),
                                                                      static_cast<__half*>(o), lse, a);
   }
   return cudaGetLastError();
@@ -423,20 +553,21 @@ cudaError_t launch_attn_core_fwd(const void* q, const void* kv, void* o, float* 
 cudaError_t launch_attn_core_bwd(const void* q, const void* kv, const void* d_o, const float* lse, void* dq, void* dkv, int dtype,
                                  int n_sets, int L, int dim, int heads, int q_per_set, int64_t qs, int64_t qq, cudaStream_t s) {
   const AttnArgs a = make_attn_args(n_sets, L, dim, heads, q_per_set, qs, qq);
-  const size_t smem = 2 * static_cast<size_t>(L) * (a.hd + 2) * 2 +
-                      (2 * static_cast<size_t>(q_per_set) * a.hd + 2 * static_cast<size_t>(q_per_set) * L + 8) * sizeof(float);
+  const size_t Lp = (L + 3) & ~3;
+  const size_t smem = ((2 * static_cast<size_t>(L) * (a.hd + 2) * 2 + 15) & ~size_t(15)) +
+                      (2 * kQG * a.hd + 2 * kQG * Lp + 8 * kQG + 2 * kQG + kAttnThreads * kQG) * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
   cudaError_t e;
   if (dtype == COSMOS_DTYPE_BF16) {
     e = cudaFuncSetAttribute(attn_core_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attn_core_bwd_kernel<__nv_bfloat16><<<n_sets * heads, 128, smem, s>>>(
+    attn_core_bwd_kernel<__nv_bfloat16><<<n_sets * heads, kAttnThreads, smem, s>>>(
         static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kv), static_cast<const __nv_bfloat16*>(d_o), lse,
         static_cast<__nv_bfloat16*>(dq), static_cast<__nv_bfloat16*>(dkv), a);
   } else {
     e = cudaFuncSetAttribute(attn_core_bwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attn_core_bwd_kernel<__half><<<n_sets * heads, 128, smem, s>>>(static_cast<const __half*>(q), static_cast<const __half*>(kv),
+    attn_core_bwd_kernel<__half><<<n_sets * heads, kAttnThreads, smem, s>>>(static_cast<const __half*>(q), static_cast<const __half*>(kv),
                                                                      static_cast<const __half*>(d_o), lse, static_cast<__half*>(dq),
                                                                      static_cast<__half*>(dkv), a);
   }

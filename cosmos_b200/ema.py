@@ -47,6 +47,7 @@ class EmaPlan:
                 continue
             buckets.setdefault((k.dtype, k.device.index), []).append((k, q))
         self.key = tuple((k.data_ptr(), q.data_ptr(), k.numel()) for q, k in zip(student, teacher))
+        self._keep = (list(student), list(teacher))   # keeps the ids used as cache key alive
         lib = _lib.lib()
         for (dtype, dev), pairs in buckets.items():
             n = len(pairs)
@@ -71,15 +72,33 @@ class EmaPlan:
 _plans = {}
 
 
+def _full_key(sp, tp):
+    return tuple((k.data_ptr(), q.data_ptr(), k.numel()) for q, k in zip(sp, tp))
+
+
 @torch.no_grad()
 def ema_update_(student: Union[torch.nn.Module, Iterable[torch.Tensor]],
                 teacher: Union[torch.nn.Module, Iterable[torch.Tensor]], momentum: float) -> None:
-    """teacher <- teacher * momentum + (1 - momentum) * student, in place, on the current stream."""
+    """teacher <- teacher * momentum + (1 - momentum) * student, in place, on the current stream.
+
+    The chunk table is cached per parameter set (keyed by the identity of the parameter objects); a few
+    storage pointers are re-checked on every call and all of them every 64th call, so a re-allocated
+    parameter rebuilds the table instead of updating stale memory.  Hold an `EmaPlan` yourself to skip
+    even that bookkeeping."""
     sp, tp = _params(student), _params(teacher)
-    key = tuple((k.data_ptr(), q.data_ptr(), k.numel()) for q, k in zip(sp, tp))
-    plan = _plans.get(id(teacher) if isinstance(teacher, torch.nn.Module) else None)
-    if plan is None or plan.key != key:
-        plan = EmaPlan(sp, tp)
-        if isinstance(teacher, torch.nn.Module):
-            _plans[id(teacher)] = plan
+    ident = (tuple(map(id, tp)), tuple(map(id, sp)))
+    entry = _plans.get(ident)
+    if entry is not None:
+        plan, calls = entry
+        probe = (0, len(tp) // 2, len(tp) - 1) if tp else ()
+        ok = all(plan.key[i] == (tp[i].data_ptr(), sp[i].data_ptr(), tp[i].numel()) for i in probe)
+        if ok and calls % 64 == 63:
+            ok = plan.key == _full_key(sp, tp)
+        if not ok:
+            entry = None
+    if entry is None:
+        if len(_plans) > 16:
+            _plans.clear()
+        plan, calls = EmaPlan(sp, tp), 0
+    _plans[ident] = (plan, calls + 1)
     plan.apply(momentum)
