@@ -34,41 +34,86 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-constexpr int kLnMaxPerLane = 32;   // dim <= 1024
+
+// One row in registers, element c = k * 32 + lane.  The dtype switch sits OUTSIDE the unrolled loops so that the
+// loads of a row are independent instructions the memory system can overlap.
+template <class T>
+__device__ __forceinline__ float cvt_in(T v);
+template <>
+__device__ __forceinline__ float cvt_in<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float cvt_in<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float cvt_in<__half>(__half v) { return __half2float(v); }
+template <class T>
+__device__ __forceinline__ T cvt_out(float v);
+template <>
+__device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
+
+template <class T, int V>
+__device__ __forceinline__ void load_row_t(const T* __restrict__ p, int dim, int lane, float (&v)[V]) {
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int c = k * 32 + lane;
+    v[k] = c < dim ? cvt_in<T>(p[c]) : 0.f;
+  }
+}
+template <int V>
+__device__ __forceinline__ void load_row(const void* base, int dtype, int64_t row, int dim, int lane, float (&v)[V]) {
+  if (dtype == COSMOS_DTYPE_F32) load_row_t(reinterpret_cast<const float*>(base) + row * dim, dim, lane, v);
+  else if (dtype == COSMOS_DTYPE_BF16) load_row_t(reinterpret_cast<const __nv_bfloat16*>(base) + row * dim, dim, lane, v);
+  else load_row_t(reinterpret_cast<const __half*>(base) + row * dim, dim, lane, v);
+}
+template <class T, int V>
+__device__ __forceinline__ void store_row_t(T* __restrict__ p, int dim, int lane, const float (&v)[V]) {
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int c = k * 32 + lane;
+    if (c < dim) p[c] = cvt_out<T>(v[k]);
+  }
+}
+template <int V>
+__device__ __forceinline__ void store_row(void* base, int dtype, int64_t row, int dim, int lane, const float (&v)[V]) {
+  if (dtype == COSMOS_DTYPE_F32) store_row_t(reinterpret_cast<float*>(base) + row * dim, dim, lane, v);
+  else if (dtype == COSMOS_DTYPE_BF16) store_row_t(reinterpret_cast<__nv_bfloat16*>(base) + row * dim, dim, lane, v);
+  else store_row_t(reinterpret_cast<__half*>(base) + row * dim, dim, lane, v);
+}
 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the row lives in registers (dim <= 1024)
 // ------------------------------------------------------------------------------------------------
+template <int V>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ w, const float* __restrict__ b,
                      void* __restrict__ y, int y_dtype, float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int dim) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
-  float v[kLnMaxPerLane];
+  float v[V], wv[V], bv[V];
+  load_row(x, x_dtype, row, dim, lane, v);
+  load_row_t(w, dim, lane, wv);
+  load_row_t(b, dim, lane, bv);
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnMaxPerLane; ++k) {
-    const int c = k * 32 + lane;
-    v[k] = c < dim ? ld_elem(x, x_dtype, row * dim + c) : 0.f;
-    s += v[k];
-  }
+  for (int k = 0; k < V; ++k) s += v[k];
   const float mu = warp_sum(s) / dim;
   float q = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnMaxPerLane; ++k) {
+  for (int k = 0; k < V; ++k) {
     const int c = k * 32 + lane;
     const float d = c < dim ? v[k] - mu : 0.f;
     q += d * d;
   }
   const float rs = rsqrtf(warp_sum(q) / dim + 1e-5f);
 #pragma unroll
-  for (int k = 0; k < kLnMaxPerLane; ++k) {
-    const int c = k * 32 + lane;
-    if (c < dim) st_elem(y, y_dtype, row * dim + c, (v[k] - mu) * rs * w[c] + b[c]);
-  }
+  for (int k = 0; k < V; ++k) v[k] = (v[k] - mu) * rs * wv[k] + bv[k];
+  store_row(y, y_dtype, row, dim, lane, v);
   if (lane == 0) {
     mean[row] = mu;
     rstd[row] = rs;
@@ -76,6 +121,7 @@ layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __res
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w;  dw += dy * xhat, db += dy (block partials -> atomics)
+template <int V>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x, int x_dtype,
                      const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -85,44 +131,38 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
   for (int c = threadIdx.x; c < 2 * dim; c += blockDim.x) red[c] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float aw[kLnMaxPerLane], ab[kLnMaxPerLane];
+  float aw[V], ab[V], wv[V];
 #pragma unroll
-  for (int k = 0; k < kLnMaxPerLane; ++k) aw[k] = ab[k] = 0.f;
+  for (int k = 0; k < V; ++k) aw[k] = ab[k] = 0.f;
+  load_row_t(w, dim, lane, wv);
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
   for (int64_t row = r0 + wid; row < min(rows, r0 + rows_per_block); row += 8) {
     const float mu = mean[row], rs = rstd[row];
-    float g[kLnMaxPerLane], xh[kLnMaxPerLane];
+    float g[V], xh[V];
+    load_row(dy, dy_dtype, row, dim, lane, g);
+    load_row(x, x_dtype, row, dim, lane, xh);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxPerLane; ++k) {
+    for (int k = 0; k < V; ++k) {
       const int c = k * 32 + lane;
-      if (c < dim) {
-        const float d = ld_elem(dy, dy_dtype, row * dim + c);
-        xh[k] = (ld_elem(x, x_dtype, row * dim + c) - mu) * rs;
-        g[k] = d * w[c];
-        aw[k] += d * xh[k];
-        ab[k] += d;
-        s1 += g[k];
-        s2 += g[k] * xh[k];
-      } else {
-        g[k] = xh[k] = 0.f;
-      }
+      xh[k] = c < dim ? (xh[k] - mu) * rs : 0.f;
+      aw[k] = fmaf(g[k], xh[k], aw[k]);
+      ab[k] += g[k];
+      g[k] *= wv[k];
+      s1 += g[k];
+      s2 = fmaf(g[k], xh[k], s2);
     }
     s1 = warp_sum(s1) / dim;
     s2 = warp_sum(s2) / dim;
+    float o[V];
+    if (accumulate) load_row(dx, dx_dtype, row, dim, lane, o);
 #pragma unroll
-    for (int k = 0; k < kLnMaxPerLane; ++k) {
-      const int c = k * 32 + lane;
-      if (c < dim) {
-        float o = rs * (g[k] - s1 - xh[k] * s2);
-        if (accumulate) o += ld_elem(dx, dx_dtype, row * dim + c);
-        st_elem(dx, dx_dtype, row * dim + c, o);
-      }
-    }
+    for (int k = 0; k < V; ++k) o[k] = (accumulate ? o[k] : 0.f) + rs * (g[k] - s1 - xh[k] * s2);
+    store_row(dx, dx_dtype, row, dim, lane, o);
   }
   if (dw != nullptr) {
 #pragma unroll
-    for (int k = 0; k < kLnMaxPerLane; ++k) {
+    for (int k = 0; k < V; ++k) {
       const int c = k * 32 + lane;
       if (c < dim) {
         atomicAdd(&red[c], aw[k]);
@@ -433,19 +473,21 @@ attn_core_bwd_kernel(const T* __restrict__ q, const T* __restrict__ kv, const T*
 // ------------------------------------------------------------------------------------------------
 // residual add + L2 normalise (one warp per row)
 // ------------------------------------------------------------------------------------------------
+template <int V>
 __global__ void __launch_bounds__(256)
 addnorm_fwd_kernel(const void* __restrict__ f, int f_dtype, const float* __restrict__ pooled, void* __restrict__ out,
                    float* __restrict__ inv_norm, int64_t rows, int dim) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
-  float v[kLnMaxPerLane];
+  float v[V], pv[V];
+  load_row(f, f_dtype, row, dim, lane, v);
+  load_row_t(pooled + row * dim, dim, lane, pv);
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnMaxPerLane; ++k) {
-    const int c = k * 32 + lane;
+  for (int k = 0; k < V; ++k) {
     // the reference adds in the feature dtype (model.py:379): round the sum to it before normalising
-    float z = c < dim ? ld_elem(f, f_dtype, row * dim + c) + pooled[row * dim + c] : 0.f;
+    float z = v[k] + pv[k];
     if (f_dtype == COSMOS_DTYPE_BF16) z = __bfloat162float(__float2bfloat16_rn(z));
     else if (f_dtype == COSMOS_DTYPE_F16) z = __half2float(__float2half_rn(z));
     v[k] = z;
@@ -453,39 +495,30 @@ addnorm_fwd_kernel(const void* __restrict__ f, int f_dtype, const float* __restr
   }
   const float inv = 1.f / fmaxf(sqrtf(warp_sum(s)), 1e-12f);
 #pragma unroll
-  for (int k = 0; k < kLnMaxPerLane; ++k) {
-    const int c = k * 32 + lane;
-    if (c < dim) st_elem(out, f_dtype, row * dim + c, v[k] * inv);
-  }
+  for (int k = 0; k < V; ++k) v[k] *= inv;
+  store_row(out, f_dtype, row, dim, lane, v);
   if (lane == 0) inv_norm[row] = inv;
 }
 
+template <int V>
 __global__ void __launch_bounds__(256)
 addnorm_bwd_kernel(const void* __restrict__ g_out, const void* __restrict__ out, int f_dtype, const float* __restrict__ inv_norm,
                    float* __restrict__ g_z32, void* __restrict__ g_z16, int g_dtype, int64_t rows, int dim) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
-  float g[kLnMaxPerLane], y[kLnMaxPerLane];
+  float g[V], y[V];
+  load_row(g_out, f_dtype, row, dim, lane, g);
+  load_row(out, f_dtype, row, dim, lane, y);
   float s = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLnMaxPerLane; ++k) {
-    const int c = k * 32 + lane;
-    g[k] = c < dim ? ld_elem(g_out, f_dtype, row * dim + c) : 0.f;
-    y[k] = c < dim ? ld_elem(out, f_dtype, row * dim + c) : 0.f;
-    s += g[k] * y[k];
-  }
+  for (int k = 0; k < V; ++k) s = fmaf(g[k], y[k], s);
   s = warp_sum(s);
   const float inv = inv_norm[row];
 #pragma unroll
-  for (int k = 0; k < kLnMaxPerLane; ++k) {
-    const int c = k * 32 + lane;
-    if (c < dim) {
-      const float gz = (g[k] - y[k] * s) * inv;
-      g_z32[row * dim + c] = gz;
-      st_elem(g_z16, g_dtype, row * dim + c, gz);
-    }
-  }
+  for (int k = 0; k < V; ++k) g[k] = (g[k] - y[k] * s) * inv;
+  store_row_t(g_z32 + row * dim, dim, lane, g);
+  store_row(g_z16, g_dtype, row, dim, lane, g);
 }
 
 __global__ void __launch_bounds__(256)
@@ -504,7 +537,10 @@ colsum_kernel(const void* __restrict__ src, int dtype, float* __restrict__ dst, 
 cudaError_t launch_layernorm_fwd(const void* x, int x_dtype, const float* w, const float* b, void* y, int y_dtype, float* mean,
                                  float* rstd, int64_t rows, int dim, cudaStream_t s) {
   if (rows == 0) return cudaSuccess;
-  layernorm_fwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim);
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  if (dim <= 256) layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim);
+  else if (dim <= 512) layernorm_fwd_kernel<16><<<grid, 256, 0, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim);
+  else layernorm_fwd_kernel<32><<<grid, 256, 0, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim);
   return cudaGetLastError();
 }
 
@@ -516,8 +552,14 @@ cudaError_t launch_layernorm_bwd(const void* dy, int dy_dtype, const void* x, in
   int64_t blocks = (rows + 63) / 64;
   if (blocks > 592) blocks = 592;
   const int rows_per_block = static_cast<int>(((rows + blocks - 1) / blocks + 7) / 8 * 8);
-  layernorm_bwd_kernel<<<static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block), 256, 2 * dim * sizeof(float), s>>>(
-      dy, dy_dtype, x, x_dtype, w, mean, rstd, dx, dx_dtype, accumulate, dw, db, rows, dim, rows_per_block);
+  const unsigned grid = static_cast<unsigned>((rows + rows_per_block - 1) / rows_per_block);
+  const size_t sm = 2 * dim * sizeof(float);
+  if (dim <= 256)
+    layernorm_bwd_kernel<8><<<grid, 256, sm, s>>>(dy, dy_dtype, x, x_dtype, w, mean, rstd, dx, dx_dtype, accumulate, dw, db, rows, dim, rows_per_block);
+  else if (dim <= 512)
+    layernorm_bwd_kernel<16><<<grid, 256, sm, s>>>(dy, dy_dtype, x, x_dtype, w, mean, rstd, dx, dx_dtype, accumulate, dw, db, rows, dim, rows_per_block);
+  else
+    layernorm_bwd_kernel<32><<<grid, 256, sm, s>>>(dy, dy_dtype, x, x_dtype, w, mean, rstd, dx, dx_dtype, accumulate, dw, db, rows, dim, rows_per_block);
   return cudaGetLastError();
 }
 
@@ -577,15 +619,20 @@ cudaError_t launch_attn_core_bwd(const void* q, const void* kv, const void* d_o,
 cudaError_t launch_addnorm_fwd(const void* f, int f_dtype, const float* pooled, void* out, float* inv_norm, int64_t rows, int dim,
                                cudaStream_t s) {
   if (rows == 0) return cudaSuccess;
-  addnorm_fwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(f, f_dtype, pooled, out, inv_norm, rows, dim);
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  if (dim <= 256) addnorm_fwd_kernel<8><<<grid, 256, 0, s>>>(f, f_dtype, pooled, out, inv_norm, rows, dim);
+  else if (dim <= 512) addnorm_fwd_kernel<16><<<grid, 256, 0, s>>>(f, f_dtype, pooled, out, inv_norm, rows, dim);
+  else addnorm_fwd_kernel<32><<<grid, 256, 0, s>>>(f, f_dtype, pooled, out, inv_norm, rows, dim);
   return cudaGetLastError();
 }
 
 cudaError_t launch_addnorm_bwd(const void* g_out, const void* out, int f_dtype, const float* inv_norm, float* g_z32, void* g_z16,
                                int g_dtype, int64_t rows, int dim, cudaStream_t s) {
   if (rows == 0) return cudaSuccess;
-  addnorm_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(g_out, out, f_dtype, inv_norm, g_z32, g_z16, g_dtype, rows,
-                                                                          dim);
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  if (dim <= 256) addnorm_bwd_kernel<8><<<grid, 256, 0, s>>>(g_out, out, f_dtype, inv_norm, g_z32, g_z16, g_dtype, rows, dim);
+  else if (dim <= 512) addnorm_bwd_kernel<16><<<grid, 256, 0, s>>>(g_out, out, f_dtype, inv_norm, g_z32, g_z16, g_dtype, rows, dim);
+  else addnorm_bwd_kernel<32><<<grid, 256, 0, s>>>(g_out, out, f_dtype, inv_norm, g_z32, g_z16, g_dtype, rows, dim);
   return cudaGetLastError();
 }
 
