@@ -145,8 +145,23 @@ int check_problem(const cosmos_infonce_problem* p, Dims* d) {
 int64_t fwd_workspace(const cosmos_infonce_problem* p, const Dims& d) {
   return static_cast<int64_t>(d.pairs) * d.n_slabs * p->n_cols * static_cast<int64_t>(sizeof(float2));
 }
-int64_t bwd_workspace(const cosmos_infonce_problem* p, const Dims& d) {
-  return static_cast<int64_t>(p->gx) * d.n_row_tiles * static_cast<int64_t>(sizeof(float));
+constexpr int kMaxTSplits = 4;
+int64_t bwd_partials_bytes(const cosmos_infonce_problem* p, const Dims& d) {   // dscale partials, 256-byte aligned
+  return ((static_cast<int64_t>(p->gx) * d.n_row_tiles * kMaxTSplits * static_cast<int64_t>(sizeof(float))) + 255) & ~int64_t(255);
+}
+int64_t bwd_workspace(const cosmos_infonce_problem* p, const Dims& d) {       // + fp32 dX accumulation buffer (split column sweeps)
+  return bwd_partials_bytes(p, d) + static_cast<int64_t>(p->gx) * p->n_rows * p->dim * static_cast<int64_t>(sizeof(float));
+}
+// Column-sweep split of the pair kernel: the fewest slices for which the clusters fill whole waves of SM pairs.
+int choose_t_splits(int clusters, int slots, int T_all) {
+  int best = 1;
+  double best_eff = 0.0;
+  for (int ts = 1; ts <= kMaxTSplits && 2 * ts <= T_all; ++ts) {
+    const int c = clusters * ts;
+    const double eff = static_cast<double>(c) / (static_cast<double>((c + slots - 1) / slots) * slots) - 0.01 * (ts - 1);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = ts; }
+  }
+  return best;
 }
 
 }  // namespace
@@ -223,7 +238,7 @@ int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, c
   if (!row_lse2 || !col_lse2 || !upstream) return COSMOS_ERR_INVALID_ARGUMENT;
   if (dx == nullptr && dscale == nullptr) return COSMOS_OK;
   if (dx != nullptr && (reinterpret_cast<uintptr_t>(dx) & 15) != 0) return COSMOS_ERR_INVALID_ARGUMENT;
-  if (dscale != nullptr && (workspace == nullptr || workspace_bytes < bwd_workspace(p, d))) return COSMOS_ERR_WORKSPACE;
+  if (workspace == nullptr || workspace_bytes < bwd_workspace(p, d)) return COSMOS_ERR_WORKSPACE;
   DeviceGuard g(device);
   if (!g.ok) return COSMOS_ERR_CUDA;
   CUtensorMap tmX, tmY, tmY64;
@@ -260,9 +275,34 @@ int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, c
   bp.row_lse2 = row_lse2; bp.col_lse2 = col_lse2;
   bp.dx = dx;
   bp.dscale_part = dscale != nullptr ? reinterpret_cast<float*>(workspace) : nullptr;
+  bp.t_splits = 1;
+  bp.dx32 = nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cu_fail(pair ? cb::launch_infonce_bwd_pair(tmX, tmY64, tmY, bp, s) : cb::launch_infonce_bwd(tmX, tmY, bp, s))) return COSMOS_ERR_CUDA;
-  if (dscale != nullptr && cu_fail(cb::launch_dscale_reduce(bp.dscale_part, p->gx * d.n_row_tiles, weight, upstream, dscale, s)))
+  if (pair && dx != nullptr && !(dbg_flags() & 64)) {
+    const int clusters = p->gx * ((d.n_row_tiles + 1) / 2) * bp.n_parts;
+    (void)clusters;   // measured: splitting the sweep does not pay (per-item prologue + atomics eat the wave-tail gain)
+    bp.t_splits = 1;
+    if (const char* e = getenv("COSMOS_B200_TSPLIT")) bp.t_splits = atoi(e);   // diagnostics
+    if (bp.t_splits > 1) {
+      bp.dx32 = reinterpret_cast<float*>(static_cast<char*>(workspace) + bwd_partials_bytes(p, d));
+      if (cu_fail(cudaMemsetAsync(bp.dx32, 0, static_cast<size_t>(p->gx) * p->n_rows * p->dim * sizeof(float), s))) return COSMOS_ERR_CUDA;
+    }
+  }
+  // dim 512 with dX wanted: 4-CTA clusters that share the softmax-gradient tiles between the two embedding parts
+  const bool quad = pair && d.ks == 8 && dx != nullptr && !(dbg_flags() & 128);   // COSMOS_B200_DBG=128: pair kernel (diagnostics)
+  int ds_slots = bp.t_splits;
+  if (quad) {
+    bp.n_parts = 2;
+    ds_slots = 2;
+    if (cu_fail(cb::launch_infonce_bwd_quad(tmX, tmY64, bp, s))) return COSMOS_ERR_CUDA;
+  } else if (cu_fail(pair ? cb::launch_infonce_bwd_pair(tmX, tmY64, tmY, bp, s) : cb::launch_infonce_bwd(tmX, tmY, bp, s))) {
+    return COSMOS_ERR_CUDA;
+  }
+  if (bp.t_splits > 1 &&
+      cu_fail(cb::launch_convert_dx(bp.dx32, dx, p->dtype, static_cast<size_t>(p->gx) * p->n_rows * p->dim, s)))
+    return COSMOS_ERR_CUDA;
+  if (dscale != nullptr &&
+      cu_fail(cb::launch_dscale_reduce(bp.dscale_part, p->gx * d.n_row_tiles * ds_slots, weight, upstream, dscale, s)))
     return COSMOS_ERR_CUDA;
   return COSMOS_OK;
 }
@@ -327,7 +367,7 @@ static int check_attn(int32_t dtype, int32_t n_sets, int32_t L, int32_t dim, int
   if (n_sets <= 0 || L <= 0 || dim <= 0 || heads <= 0 || q_per_set <= 0) return COSMOS_ERR_INVALID_ARGUMENT;
   if (!dtype16(dtype) || dim % heads != 0) return COSMOS_ERR_UNSUPPORTED;
   const int hd = dim / heads;
-  if (!(hd == 16 || hd == 32 || hd == 64 || hd == 128) || L > 1024 || q_per_set > 64) return COSMOS_ERR_UNSUPPORTED;
+  if (!(hd == 16 || hd == 32 || hd == 64 || hd == 128) || L > 1024 || q_per_set > 4096) return COSMOS_ERR_UNSUPPORTED;
   return COSMOS_OK;
 }
 

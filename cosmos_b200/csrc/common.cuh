@@ -169,6 +169,50 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
+// ---- distributed shared memory (cluster) ----
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta) {   // same offset in CTA `cta`'s smem
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t remote_addr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(remote_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+// asynchronous 16-byte store into another CTA's shared memory; its bytes are credited (complete_tx) to an mbarrier that
+// lives in the SAME destination CTA, so the sender never waits for the transfer
+__device__ __forceinline__ void st_async_cluster_v4(uint32_t remote_addr, uint4 v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// arrive (release at cluster scope) on an mbarrier given by its shared::cluster address
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t remote_bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// wait for a phase whose arrivals come from other CTAs of the cluster (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_try_wait_cluster(addr, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+#pragma unroll 1
+  for (uint32_t spin = 1;; ++spin) {
+    if (mbar_try_wait_cluster(addr, parity)) return;
+    if ((spin & 0x3FF) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
+  }
+}
 __device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"

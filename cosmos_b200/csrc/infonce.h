@@ -36,6 +36,8 @@ struct BwdParams {
   const float* col_lse2;  // [gx*gy][n_cols]
   void* dx;               // [gx][n_rows][dim] stack dtype, may be null
   float* dscale_part;     // [items] partial sums of <dscale-mix, raw logits>, may be null
+  int t_splits;           // pair kernel: the column sweep of one row block is split over this many clusters
+  float* dx32;            // fp32 [gx][n_rows][dim] accumulation buffer (zeroed), used when t_splits > 1
 };
 
 cudaError_t launch_infonce_fwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, bool pair, cudaStream_t stream);
@@ -44,11 +46,14 @@ cudaError_t launch_infonce_bwd(const CUtensorMap& tmX, const CUtensorMap& tmY, c
 cudaError_t launch_infonce_bwd_pair(const CUtensorMap& tmX, const CUtensorMap& tmY64, const CUtensorMap& tmY128, const BwdParams& p,
                                     cudaStream_t stream);
 
+cudaError_t launch_infonce_bwd_quad(const CUtensorMap& tmX, const CUtensorMap& tmY64, const BwdParams& p, cudaStream_t stream);
+
 // infonce_aux.cu
 cudaError_t launch_col_combine(const float2* col_part, float* col_lse2, int pairs, int n_slabs, int n_cols, cudaStream_t stream);
 cudaError_t launch_loss_sums(const float* row_lse2, const float* diag_raw, const float* col_lse2, const float* scale, int pairs,
                              int n_rows, int n_cols, int label_offset, int use_rows, int use_cols, float* out,
                              cudaStream_t stream);
+cudaError_t launch_convert_dx(const float* src, void* dst, int dtype, size_t n, cudaStream_t stream);
 cudaError_t launch_dscale_reduce(const float* part, int n, float weight, const float* upstream, float* dscale,
                                  cudaStream_t stream);
 

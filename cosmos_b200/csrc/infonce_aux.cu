@@ -95,4 +95,20 @@ cudaError_t launch_dscale_reduce(const float* part, int n, float weight, const f
   return cudaGetLastError();
 }
 
+
+__global__ void __launch_bounds__(256)
+convert_dx_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int fmt, size_t n4) {
+  for (size_t k = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; k < n4; k += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldcs(src + k);
+    dst[k] = make_uint2(pack2(v.x, v.y, fmt), pack2(v.z, v.w, fmt));
+  }
+}
+
+cudaError_t launch_convert_dx(const float* src, void* dst, int dtype, size_t n, cudaStream_t stream) {
+  const size_t n4 = n / 4;   // n is a multiple of 64
+  convert_dx_kernel<<<148 * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst),
+                                                 dtype == 1 ? 1 : 0, n4);
+  return cudaGetLastError();
+}
+
 }  // namespace cb

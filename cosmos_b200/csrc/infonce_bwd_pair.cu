@@ -26,7 +26,7 @@ constexpr int BM = kFwdBM, BN = kBwdBN;
 constexpr int kSlabX = 128 * 64 * 2;    // 16 KB: 128 rows x 64 elements
 constexpr int kSlotA = 64 * 64 * 2;     // 8 KB : 64 columns x 64 elements (this CTA's half of a GEMM1 B slab)
 constexpr int kSlotsA = 8;
-constexpr int kSlabB = 128 * 64 * 2;    // 16 KB: 128 columns x 64 embedding elements
+constexpr int kSlabB = 64 * 64 * 2;     // 8 KB : 64 columns (half a step) x 64 embedding elements
 constexpr int kSmemMisc = 3072;
 constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
@@ -43,7 +43,7 @@ struct Misc {
   uint32_t tmem_slot;
   uint32_t pad[3];
   float red[8];
-  float kappa[8][64];   // per epilogue warp: a_col * 2^(o - lse_col) of its 64 columns
+  alignas(16) float kappa[8][64];   // per epilogue warp: a_col * 2^(o - lse_col) of its 64 columns
 };
 static_assert(sizeof(Misc) <= kSmemMisc, "misc smem");
 
@@ -62,18 +62,22 @@ infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const int ks = p.ks;
   // work item: (row tensor i, pair of row tiles, embedding part); the two CTAs take consecutive row tiles
   const int tiles_padded = 2 * ((p.n_row_tiles + 1) / 2);
-  const int part = (blockIdx.x >> 1) % p.n_parts;
-  const int rt = ((blockIdx.x >> 1) / p.n_parts) * 2 + cta_rank;       // padded row-tile index over all tensors
+  const int split = (blockIdx.x >> 1) % p.t_splits;                    // which slice of the column sweep
+  const int part = ((blockIdx.x >> 1) / p.t_splits) % p.n_parts;
+  const int rt = ((blockIdx.x >> 1) / (p.t_splits * p.n_parts)) * 2 + cta_rank;   // padded row-tile index over all tensors
   const int i = rt / tiles_padded;
   const int tr = rt - i * tiles_padded;
   const bool tile_valid = tr < p.n_row_tiles;
   const int slab0 = part * 4;
   const int nh = (ks - slab0) < 4 ? (ks - slab0) : 4;                  // 64-wide embedding slabs in this part (even)
   const int nb = nh >> 1;                                              // slabs this CTA loads for GEMM2
-  const int b_stages = ks == 8 ? 1 : 2;
+  const int b_stages = 2;                                              // one per 64-column half of a step
   const int b_stage_bytes = nb * kSlabB;
   const int n_ct = p.n_col_tiles;
-  const int T = p.gy * n_ct;
+  const int T_all = p.gy * n_ct;
+  const int T_per = (T_all + p.t_splits - 1) / p.t_splits;
+  const int t_begin = split * T_per;
+  const int T = min(T_all, t_begin + T_per) - t_begin;                 // >= 1: the host keeps t_splits <= T_all / 2
   const bool want_dx = p.dx != nullptr;
 
   uint8_t* sX = smem;
@@ -119,7 +123,7 @@ infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       arm(&misc->x_full, ks * kSlabX);
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       auto load_g1 = [&](int t) {
-        const int j = t / n_ct, tc = t - j * n_ct;
+        const int j = (t_begin + t) / n_ct, tc = (t_begin + t) - j * n_ct;
         for (int s = 0; s < ks; ++s) {
           mbar_wait(&misc->a_empty[sa], pa ^ 1);
           tma_load_3d_pair(sA + sa * kSlotA, &tmY64, &misc->a_full[sa], s * 64, tc * BN + cta_rank * 64, j);
@@ -127,14 +131,17 @@ infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           if (++sa == kSlotsA) { sa = 0; pa ^= 1; }
         }
       };
-      auto load_g2 = [&](int t) {
-        const int j = t / n_ct, tc = t - j * n_ct;
-        mbar_wait(&misc->b_empty[sb], pb ^ 1);
-        for (int s = 0; s < nb; ++s)
-          tma_load_3d_pair(sB + sb * b_stage_bytes + s * kSlabB, &tmY128, &misc->b_full[sb],
-                           (slab0 + cta_rank * nb + s) * 64, tc * BN, j);
-        arm(&misc->b_full[sb], b_stage_bytes);
-        if (++sb == static_cast<uint32_t>(b_stages)) { sb = 0; pb ^= 1; }
+      auto load_g2 = [&](int t) {     // GEMM2 operand in two 64-column halves: the first half's stage refills while the second runs
+        const int j = (t_begin + t) / n_ct, tc = (t_begin + t) - j * n_ct;
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(&misc->b_empty[sb], pb ^ 1);
+          for (int s = 0; s < nb; ++s)
+            tma_load_3d_pair(sB + sb * b_stage_bytes + s * kSlabB, &tmY64, &misc->b_full[sb],
+                             (slab0 + cta_rank * nb + s) * 64, tc * BN + half * 64, j);
+          arm(&misc->b_full[sb], b_stage_bytes);
+          sb ^= 1;
+          if (sb == 0) pb ^= 1;
+        }
       };
       load_g1(0);
       for (int t = 0; t < T; ++t) {
@@ -172,18 +179,21 @@ infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         const uint32_t buf = t & 1;
         mbar_wait(&misc->g_full[buf], (t >> 1) & 1);
         if (want_dx) {
-          mbar_wait(&misc->b_full[sb], pb);
-          tc_fence_after();
-          const uint32_t b_base = smem_u32(sB + sb * b_stage_bytes);
-          if (!(p.dbg & 2)) {
+          for (int half = 0; half < 2; ++half) {
+            mbar_wait(&misc->b_full[sb], pb);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(sB + sb * b_stage_bytes);
+            if (!(p.dbg & 2)) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {   // K = the 128 columns of this step, 16 per MMA = 8 packed TMEM columns of G
-              const uint32_t a_tmem = tmem + buf * BN + (k >> 2) * 64 + (k & 3) * 8;
-              umma_ts_pair(tmem + 256, a_tmem, make_smem_desc(b_base + k * 2048, kSlabB, 1024), p.idesc_g, (t | k) != 0);
+              for (int k = 0; k < 4; ++k) {   // K = 64 columns of this half, 16 per MMA = 8 packed TMEM columns of G
+                const uint32_t a_tmem = tmem + buf * BN + half * 64 + k * 8;
+                umma_ts_pair(tmem + 256, a_tmem, make_smem_desc(b_base + k * 2048, kSlabB, 1024), p.idesc_g, (t | half | k) != 0);
+              }
             }
+            tc_commit_pair(&misc->b_empty[sb], 3);
+            sb ^= 1;
+            if (sb == 0) pb ^= 1;
           }
-          tc_commit_pair(&misc->b_empty[sb], 3);
-          if (++sb == static_cast<uint32_t>(b_stages)) { sb = 0; pb ^= 1; }
         }
       }
       tc_commit_pair(&misc->dx_full, 3);
@@ -213,7 +223,7 @@ infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     float* kbuf = misc->kappa[ew];
 
     for (int t = 0; t < T; ++t) {
-      const int j = t / n_ct, tc = t - j * n_ct;
+      const int j = (t_begin + t) / n_ct, tc = (t_begin + t) - j * n_ct;
       const int pair = i * p.gy + j;
       const uint32_t buf = t & 1;
       const float lr = row_valid ? __ldg(p.row_lse2 + static_cast<size_t>(pair) * p.n_rows + row) : INFINITY;
@@ -353,7 +363,7 @@ infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       if (ew == 0 && lane == 0 && tile_valid) {
         float s = 0.f;
         for (int w = 0; w < 8; ++w) s += misc->red[w];
-        p.dscale_part[i * p.n_row_tiles + tr] = s;
+        p.dscale_part[(i * p.n_row_tiles + tr) * p.t_splits + split] = s;
       }
     }
 
@@ -369,14 +379,20 @@ infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         tmem_ld32(tmem + lane_base + 256 + c, v);
         tmem_ld_wait();
         if (row_valid) {
-          uint32_t o[16];
+          const size_t off = (static_cast<size_t>(i) * p.n_rows + row) * dim + slab0 * 64 + c;
+          if (p.t_splits > 1) {
+            float* dst = p.dx32 + off;       // several clusters sweep different column ranges of this row block
 #pragma unroll
-          for (int k = 0; k < 16; ++k)
-            o[k] = pack2(__uint_as_float(v[2 * k]) * coef, __uint_as_float(v[2 * k + 1]) * coef, fmt);
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dx) +
-                                                (static_cast<size_t>(i) * p.n_rows + row) * dim + slab0 * 64 + c);
+            for (int k = 0; k < 32; ++k) atomicAdd(dst + k, __uint_as_float(v[k]) * coef);
+          } else {
+            uint32_t o[16];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+            for (int k = 0; k < 16; ++k)
+              o[k] = pack2(__uint_as_float(v[2 * k]) * coef, __uint_as_float(v[2 * k + 1]) * coef, fmt);
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dx) + off);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+          }
         }
       }
     }
@@ -390,13 +406,13 @@ infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
 cudaError_t launch_infonce_bwd_pair(const CUtensorMap& tmX, const CUtensorMap& tmY64, const CUtensorMap& tmY128, const BwdParams& p,
                                     cudaStream_t stream) {
   const int nh_max = p.ks < 4 ? p.ks : 4;
-  const int b_stages = p.ks == 8 ? 1 : 2;
+  const int b_stages = 2;
   const int smem_bytes = p.ks * kSlabX + kSlotsA * kSlotA + b_stages * (nh_max / 2) * kSlabB + kSmemMisc;
   if (smem_bytes > 232448) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(infonce_bwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(p.gx * ((p.n_row_tiles + 1) / 2) * p.n_parts * 2);
+  cfg.gridDim = dim3(p.gx * ((p.n_row_tiles + 1) / 2) * p.n_parts * p.t_splits * 2);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
