@@ -161,9 +161,14 @@ class COSMOSLoss(nn.Module):
 
         comm = self.clip_loss._comm()
         scale = distill_logit_scale if distill_logit_scale is not None else logit_scale
-        # mean over {img-x, txt-x} x {t_img, t_txt} of ClipLoss(8 x 2 pairs)  ==  mean of two 8 x 4 groups
-        cosmos_loss = (pairs_infonce(list(s_img_crossmodal_features), teacher, scale, comm)
-                       + pairs_infonce(list(s_txt_crossmodal_features), teacher, scale, comm)) / 2
+        # mean over {img-x, txt-x} x {t_img, t_txt} of ClipLoss(n x 2 pairs)  ==  mean of the two n x 4 groups; with equally
+        # long lists (the COSMOS recipes: 8 + 8) that is the plain mean over all 16 x 4 pairs -> ONE grouped launch, which
+        # fills whole waves of SM clusters where two half-sized launches would each leave a partial wave.
+        img_x, txt_x = list(s_img_crossmodal_features), list(s_txt_crossmodal_features)
+        if len(img_x) == len(txt_x):
+            cosmos_loss = pairs_infonce(img_x + txt_x, teacher, scale, comm)
+        else:
+            cosmos_loss = (pairs_infonce(img_x, teacher, scale, comm) + pairs_infonce(txt_x, teacher, scale, comm)) / 2
 
         # CLIP loss: only the two global crops on the image side (loss.py:205-206)
         clip_loss = pairs_infonce(list(s_text_features), list(s_image_features[:2]), logit_scale, comm)
