@@ -159,6 +159,17 @@ def test_cosmos_loss_vs_oracle(batch, dim, scale):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("batch,scale", [(200, 14.2857), (130, 60.0)])
+def test_cosmos_loss_fp16_dim512(batch, scale):
+    """fp16 features (the reference's `--precision amp`) through the dim-512 cluster kernels, ragged batch."""
+    inp = O.make_features(batch, 512, seed=77)
+    up = (65536.0, 65536.0)          # GradScaler's initial scale
+    ours = _run_ours(inp, scale, scale * 0.7, up, torch.float16)
+    ref = _run_oracle(inp, scale, scale * 0.7, up, torch.float16)
+    _compare(ours, ref, up)
+
+
+@pytest.mark.gpu
 def test_config1_fp32_inputs_against_reference_golden(golden_dir):
     """fp32 features as in BASELINE config 1: the kernels round them to bf16; the loss must still sit
     within the north_star tolerance of what the reference produced in fp32."""

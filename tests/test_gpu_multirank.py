@@ -21,9 +21,11 @@ def _worker(rank, world, port, tmpdir):
     try:
         from cosmos_b200 import COSMOSLoss
         from oracle import cosmos_oracle as O
-        b, D = 160, 128
-        shards_cpu = [O.make_features(b, D, seed=900 + r, n_img=3, n_txt=4) for r in range(world)]
-        for ll, gwg in ((False, False), (False, True), (True, True), (True, False)):
+        # (b, D, n_img, n_txt): dim 128 runs the CTA-pair backward, dim 512 the 4-CTA-cluster backward
+        configs = ((160, 128, 3, 4), (192, 512, 4, 4))
+        cases = [(cfg, ll, gwg) for cfg in configs for ll, gwg in ((False, False), (False, True), (True, True), (True, False))]
+        for (b, D, n_img, n_txt), ll, gwg in cases:
+            shards_cpu = [O.make_features(b, D, seed=900 + r, n_img=n_img, n_txt=n_txt) for r in range(world)]
             # ours, on this rank's shard
             mine = {k: [t.bfloat16().cuda().requires_grad_(True) for t in v] for k, v in shards_cpu[rank].items()}
             ls = torch.tensor(14.2857, device="cuda", requires_grad=True)
