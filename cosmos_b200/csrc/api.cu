@@ -334,7 +334,7 @@ int cosmos_gemm(const void* a, const void* b, void* d, const float* bias, int32_
   ga.a_kmajor = a_kmajor; ga.b_kmajor = b_kmajor; ga.in_dtype = in_dtype; ga.out_dtype = out_dtype;
   ga.splits = splits; ga.alpha = alpha;
   cudaError_t e = cudaSuccess;
-  const int r = cb::launch_gemm(ga, static_cast<cudaStream_t>(stream), &e);
+  const int r = cb::launch_gemm(ga, sm_count_of(device), static_cast<cudaStream_t>(stream), &e);
   if (r == 0) return COSMOS_OK;
   if (r > 0) g_last_cuda = r; else cu_fail(e);
   return COSMOS_ERR_CUDA;

@@ -14,113 +14,148 @@ namespace cb {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kStages = 6;
-constexpr int kOpBytes = 128 * 64 * 2;   // 16 KB per operand per stage
+constexpr int BM = 128, BK = 64;
+constexpr int kABytes = 128 * 64 * 2;    // 16 KB of A per stage
 constexpr int kThreads = 256;
+constexpr int kMaxStages = 6;
 
 struct Misc {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
-  uint64_t acc_full;
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
   uint32_t tmem_slot;
 };
 
 }  // namespace
 
+// Persistent: CTA c works on items c, c + gridDim.x, ...; item = (output tile, K split).  Two accumulator stages in
+// TMEM let the epilogue of one tile overlap the MMAs of the next.
+template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  constexpr int kStages = BN == 256 ? 4 : 6;
+  constexpr int kBBytes = BN * 64 * 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * kOpBytes;
-  Misc* misc = reinterpret_cast<Misc*>(smem + 2 * kStages * kOpBytes);
+  uint8_t* sB = smem + kStages * kABytes;
+  Misc* misc = reinterpret_cast<Misc*>(smem + kStages * (kABytes + kBBytes));
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + BM - 1) / BM;
   const int k_slabs = (p.K + BK - 1) / BK;
-  const int per = (k_slabs + gridDim.z - 1) / gridDim.z;
-  const int ks0 = blockIdx.z * per;
-  const int ks1 = min(k_slabs, ks0 + per);
-  const int n_slabs = ks1 - ks0;
+  const int per_split = (k_slabs + p.splits - 1) / p.splits;
+  const int n_items = tiles_m * tiles_n * p.splits;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&misc->full[s], 1);
       mbar_init(&misc->empty[s], 1);
     }
-    mbar_init(&misc->acc_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&misc->acc_full[s], 1);
+      mbar_init(&misc->acc_empty[s], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 2) tmem_alloc<128>(&misc->tmem_slot);
+  if (warp == 2) tmem_alloc<2 * BN>(&misc->tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = misc->tmem_slot;
 
-  if (n_slabs > 0) {
-    if (warp == 0 && lane == 0) {
-      uint32_t stage = 0, phase = 0;
+  auto decode = [&](int item, int& m0, int& n0, int& ks0, int& ks1) {
+    const int split = item % p.splits;
+    const int tile = item / p.splits;
+    n0 = (tile % tiles_n) * BN;     // n fastest: CTAs running together share the A rows
+    m0 = (tile / tiles_n) * BM;
+    ks0 = split * per_split;
+    ks1 = min(k_slabs, ks0 + per_split);
+  };
+
+  if (warp == 0 && lane == 0) {
+    uint32_t stage = 0, phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int m0, n0, ks0, ks1;
+      decode(item, m0, n0, ks0, ks1);
       for (int s = ks0; s < ks1; ++s) {
         mbar_wait(&misc->empty[stage], phase ^ 1);
-        mbar_expect_tx(&misc->full[stage], 2 * kOpBytes);
-        uint8_t* a = sA + stage * kOpBytes;
-        uint8_t* b = sB + stage * kOpBytes;
+        mbar_expect_tx(&misc->full[stage], kABytes + kBBytes);
+        uint8_t* a = sA + stage * kABytes;
+        uint8_t* b = sB + stage * kBBytes;
         if (p.a_kmajor) {
           tma_load_3d(a, &tmA, &misc->full[stage], s * BK, m0, 0);            // box 64 k x 128 rows
         } else {
-          tma_load_3d(a, &tmA, &misc->full[stage], m0, s * BK, 0);            // box 64 m x 64 k-rows, two M chunks
+          tma_load_3d(a, &tmA, &misc->full[stage], m0, s * BK, 0);            // box 64 m x 64 k-rows per 64-wide chunk
           tma_load_3d(a + 8192, &tmA, &misc->full[stage], m0 + 64, s * BK, 0);
         }
         if (p.b_kmajor) {
-          tma_load_3d(b, &tmB, &misc->full[stage], s * BK, n0, 0);
+#pragma unroll
+          for (int c = 0; c < BN / 128; ++c) tma_load_3d(b + c * 16384, &tmB, &misc->full[stage], s * BK, n0 + c * 128, 0);
         } else {
-          tma_load_3d(b, &tmB, &misc->full[stage], n0, s * BK, 0);
-          tma_load_3d(b + 8192, &tmB, &misc->full[stage], n0 + 64, s * BK, 0);
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) tma_load_3d(b + c * 8192, &tmB, &misc->full[stage], n0 + c * 64, s * BK, 0);
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-    } else if (warp == 1 && lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int s = 0; s < n_slabs; ++s) {
+    }
+  } else if (warp == 1 && lane == 0) {
+    uint32_t stage = 0, phase = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      int m0, n0, ks0, ks1;
+      decode(item, m0, n0, ks0, ks1);
+      const uint32_t as = it & 1;
+      mbar_wait(&misc->acc_empty[as], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int s = ks0; s < ks1; ++s) {
         mbar_wait(&misc->full[stage], phase);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(sA + stage * kOpBytes);
-        const uint32_t b_base = smem_u32(sB + stage * kOpBytes);
+        const uint32_t a_base = smem_u32(sA + stage * kABytes);
+        const uint32_t b_base = smem_u32(sB + stage * kBBytes);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t da = p.a_kmajor ? make_smem_desc(a_base + kk * 32, 0, 1024) : make_smem_desc(a_base + kk * 2048, 8192, 1024);
           const uint64_t db = p.b_kmajor ? make_smem_desc(b_base + kk * 32, 0, 1024) : make_smem_desc(b_base + kk * 2048, 8192, 1024);
-          umma_ss(tmem, da, db, p.idesc, (s | kk) != 0);
+          umma_ss(tmem + as * BN, da, db, p.idesc, (s > ks0 || kk > 0) ? 1u : 0u);
         }
         tc_commit(&misc->empty[stage]);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      tc_commit(&misc->acc_full);
-    } else if (warp >= 4) {
-      const uint32_t q = warp & 3;
+      tc_commit(&misc->acc_full[as]);     // also fires for an empty K range: the epilogue then sees no valid data, see below
+    }
+  } else if (warp >= 4) {
+    const uint32_t q = warp & 3;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      int m0, n0, ks0, ks1;
+      decode(item, m0, n0, ks0, ks1);
+      const uint32_t as = it & 1;
       const int row = m0 + q * 32 + lane;
-      mbar_wait(&misc->acc_full, 0);
+      mbar_wait(&misc->acc_full[as], (it >> 1) & 1);
       tc_fence_after();
-      const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
+      const bool add_bias = p.bias != nullptr && (item % p.splits) == 0;
+      const bool has_k = ks1 > ks0;
       for (int c = 0; c < BN; c += 32) {
         if (n0 + c >= p.N) break;
         uint32_t v[32];
-        tmem_ld32(tmem + ((q * 32u) << 16) + c, v);
+        tmem_ld32(tmem + ((q * 32u) << 16) + as * BN + c, v);
         tmem_ld_wait();
         if (row < p.M) {
           float o[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const int col = n0 + c + k;
-            o[k] = __uint_as_float(v[k]) * p.alpha + ((add_bias && col < p.N) ? __ldg(p.bias + col) : 0.f);
+            o[k] = (has_k ? __uint_as_float(v[k]) * p.alpha : 0.f) + ((add_bias && col < p.N) ? __ldg(p.bias + col) : 0.f);
           }
           const size_t off = static_cast<size_t>(row) * p.ldd + n0 + c;
-          if (gridDim.z > 1) {
+          if (p.splits > 1) {
             float* dst = reinterpret_cast<float*>(p.d) + off;
 #pragma unroll
             for (int k = 0; k < 32; ++k)
@@ -157,11 +192,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&misc->acc_empty[as]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<128>(tmem);
+  if (warp == 2) tmem_dealloc<2 * BN>(tmem);
 }
 
 // 2-D operand map: K-major [rows, K] -> box {64 k, 128 rows}; MN-major [K, rows] -> box {64 rows, 64 k}.
@@ -185,25 +223,34 @@ static int make_operand_map(CUtensorMap* map, const void* ptr, int is_bf16, int 
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
-int launch_gemm(const GemmArgs& a, cudaStream_t stream, cudaError_t* err) {
+template <int BN>
+static cudaError_t launch_gemm_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, int bf, int sm_count, cudaStream_t stream) {
+  constexpr int kStages = BN == 256 ? 4 : 6;
+  p.idesc = make_idesc(bf, p.a_kmajor ? 0 : 1, p.b_kmajor ? 0 : 1, BM, BN);
+  const int smem_bytes = kStages * (kABytes + BN * 64 * 2) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return e;
+  const int items = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.splits;
+  const int grid = items < sm_count ? items : sm_count;
+  gemm_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  return cudaGetLastError();
+}
+
+int launch_gemm(const GemmArgs& a, int sm_count, cudaStream_t stream, cudaError_t* err) {
   *err = cudaSuccess;
   CUtensorMap tmA, tmB;
   const int bf = a.in_dtype == COSMOS_DTYPE_BF16;
+  const bool wide = a.N >= 256;       // 128 x 256 tiles when the output is wide enough
   int r1 = make_operand_map(&tmA, a.a, bf, a.a_kmajor, a.M, a.K, a.lda);
   int r2 = make_operand_map(&tmB, a.b, bf, a.b_kmajor, a.N, a.K, a.ldb);
   if (r1 != 0 || r2 != 0) return 100000 + (r1 != 0 ? r1 : r2);
   GemmParams p;
-  p.M = a.M; p.N = a.N; p.K = a.K; p.ldd = a.ldd;
-  p.a_kmajor = a.a_kmajor; p.b_kmajor = a.b_kmajor;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.ldd = static_cast<int>(a.ldd);
+  p.a_kmajor = a.a_kmajor; p.b_kmajor = a.b_kmajor; p.splits = a.splits;
   p.out_dtype = a.splits > 1 ? COSMOS_DTYPE_F32 : a.out_dtype;
   p.alpha = a.alpha; p.bias = a.bias; p.d = a.d;
-  p.idesc = make_idesc(bf, a.a_kmajor ? 0 : 1, a.b_kmajor ? 0 : 1, BM, BN);
-  const int smem_bytes = 2 * kStages * kOpBytes + 1024;
-  *err = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-  if (*err != cudaSuccess) return -1;
-  dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.splits);
-  gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
-  *err = cudaGetLastError();
+  p.idesc = 0;
+  *err = wide ? launch_gemm_bn<256>(tmA, tmB, p, bf, sm_count, stream) : launch_gemm_bn<128>(tmA, tmB, p, bf, sm_count, stream);
   return *err == cudaSuccess ? 0 : -1;
 }
 

@@ -16,7 +16,7 @@ cudaError_t launch_ema(const EmaChunk* table, int n_chunks, double momentum, int
 // ---- generic tcgen05 GEMM (gemm.cu) ----
 struct GemmParams {
   int M, N, K, ldd;
-  int a_kmajor, b_kmajor, out_dtype;
+  int a_kmajor, b_kmajor, out_dtype, splits;
   uint32_t idesc;
   float alpha;
   const float* bias;
@@ -31,7 +31,7 @@ struct GemmArgs {
   float alpha;
 };
 // returns 0, -1 (CUDA error in *err) or 100000 + CUresult (tensor map)
-int launch_gemm(const GemmArgs& a, cudaStream_t stream, cudaError_t* err);
+int launch_gemm(const GemmArgs& a, int sm_count, cudaStream_t stream, cudaError_t* err);
 
 
 // ---- pooler helpers (xpool.cu) ----

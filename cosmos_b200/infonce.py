@@ -162,9 +162,9 @@ def _allreduce_lse2(lse2: torch.Tensor, comm: Comm) -> torch.Tensor:
         return lse2
     m = lse2.clone()
     dist.all_reduce(m, op=dist.ReduceOp.MAX, group=comm.group)
-    s = torch.exp2(lse2 - m)
+    s = torch.exp((lse2 - m) * LN2)          # exp / log instead of exp2 / log2: the latter are NVRTC-jitted by torch
     dist.all_reduce(s, op=dist.ReduceOp.SUM, group=comm.group)
-    return m + torch.log2(s)
+    return m + torch.log(s) / LN2
 
 
 def _gather_rows(t: torch.Tensor, comm: Comm) -> torch.Tensor:

@@ -66,8 +66,9 @@ def _wgrad(g, x):
     R, N = g.shape
     K = x.shape[1]
     out = torch.zeros(N, K, dtype=torch.float32, device=g.device)
-    tiles = ((N + 127) // 128) * ((K + 127) // 128)
-    splits = max(1, min((R + 511) // 512, (296 + tiles - 1) // tiles))
+    bn = 256 if K >= 256 else 128                      # output tile of the GEMM kernel (csrc/gemm.cu)
+    tiles = ((N + 127) // 128) * ((K + bn - 1) // bn)
+    splits = max(1, min((R + 1023) // 1024, 148 // tiles if tiles <= 148 else 1))    # one wave of persistent CTAs
     return _gemm(g, x, out, N, K, R, g.stride(0), x.stride(0), False, False, splits=splits)
 
 
