@@ -86,6 +86,7 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const int n_own = (T - static_cast<int>(pr) + 1) / 2;          // steps t = pr, pr + 2, ...
   const int n_rem = (T - static_cast<int>(1 - pr) + 1) / 2;      // steps of the other pair
   const int n_round = n_own > n_rem ? n_own : n_rem;
+  const uint32_t n_slots_a = (p.dbg & 512) ? 2u : static_cast<uint32_t>(kSlotsA);   // diagnostics: ring-depth sensitivity
 
   uint8_t* sX = smem;
   uint8_t* sA = sX + kKs * kSlabX;
@@ -140,7 +141,7 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           mbar_wait(&misc->a_empty[sa], pa ^ 1);
           tma_load_3d_pair(sA + sa * kSlotA, &tmY64, &misc->a_full[sa], s * 64, tc * BN + r * 64, j);
           arm(&misc->a_full[sa], kSlotA);
-          if (++sa == kSlotsA) { sa = 0; pa ^= 1; }
+          if (++sa == n_slots_a) { sa = 0; pa ^= 1; }
         }
       }
     }
@@ -170,7 +171,9 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       // ---------------- receive side of the G exchange: arm the byte count, wait for the tile, tell the pair leader ----------------
       for (int k = 0; k < n_rem; ++k) {
         mbar_expect_tx(&misc->gr_full, kSmemG);
-        mbar_wait_cluster(&misc->gr_full, k & 1);
+        // plain (CTA-scope) wait: a cluster-scope acquire compiles to an L1 invalidate (CCTL.IVALL) per poll, which this
+        // spinning thread would inflict on the epilogue warps' global loads; the consumer fences once, below
+        mbar_wait(&misc->gr_full, k & 1);
         if (leader) mbar_arrive(&misc->gr_ready);
         else mbar_arrive_remote_release(mapa_u32(smem_u32(&misc->gr_ready), L));
       }
@@ -193,7 +196,7 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             umma_ss_pair(tmem + buf * BN, make_smem_desc(a_base + kk * 32, 0, 1024), make_smem_desc(b_base + kk * 32, 0, 1024),
                          p.idesc_s, (s | kk) != 0);
           tc_commit_pair(&misc->a_empty[sa], my_pair_mask);
-          if (++sa == kSlotsA) { sa = 0; pa ^= 1; }
+          if (++sa == n_slots_a) { sa = 0; pa ^= 1; }
         }
         if (hlf == 1) tc_commit_pair(&misc->s_full[buf], my_pair_mask);
       };
@@ -202,8 +205,8 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         if (own) {
           mbar_wait(&misc->g_full[buf], (k >> 1) & 1);
         } else {
-          mbar_wait_cluster(&misc->gr_ready, k & 1);   // G tile written by the sibling pair through DSMEM, in both CTAs
-          fence_proxy_async_all();
+          mbar_wait(&misc->gr_ready, k & 1);           // G tile written by the sibling pair through DSMEM, in both CTAs
+          fence_proxy_async_all();                     // st.async data (complete_tx observed through the barrier chain) -> UMMA
         }
         for (int half = 0; half < 2; ++half) {
           mbar_wait(&misc->b_full[sb], pb);
@@ -381,7 +384,7 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       }
       // other pair: K-major, 128B-swizzled rows in the sibling CTA's shared memory, once it has consumed the tile
       // we sent one own-step ago
-      mbar_wait_cluster(&misc->gr_empty, (k & 1) ^ 1);
+      mbar_wait(&misc->gr_empty, (k & 1) ^ 1);      // write-after-read only: no data is acquired, a CTA-scope wait suffices
 #pragma unroll
       for (int chunk = 0; chunk < 2; ++chunk) {
 #pragma unroll

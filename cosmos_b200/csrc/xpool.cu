@@ -122,7 +122,7 @@ layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __res
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w;  dw += dy * xhat, db += dy (block partials -> atomics)
 template <int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, V <= 16 ? 2 : 1)
 layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x, int x_dtype,
                      const float* __restrict__ w, const float* __restrict__ mean, const float* __restrict__ rstd,
                      void* __restrict__ dx, int dx_dtype, int accumulate, float* __restrict__ dw, float* __restrict__ db,
@@ -464,8 +464,9 @@ attn_core_bwd_kernel(const T* __restrict__ q, const T* __restrict__ kv, const T*
       if (g > 0) {   // more than kQG queries per set: accumulate over the groups
         dk0 += tof(rowp[0]); dk1 += tof(rowp[1]); dv0 += tof(rowp[a.dim]); dv1 += tof(rowp[a.dim + 1]);
       }
-      rowp[0] = fromf<T>(dk0); rowp[1] = fromf<T>(dk1);
-      rowp[a.dim] = fromf<T>(dv0); rowp[a.dim + 1] = fromf<T>(dv1);
+      T pk[2] = {fromf<T>(dk0), fromf<T>(dk1)}, pv[2] = {fromf<T>(dv0), fromf<T>(dv1)};
+      *reinterpret_cast<uint32_t*>(rowp) = *reinterpret_cast<const uint32_t*>(pk);            // k is even: 4-byte aligned
+      *reinterpret_cast<uint32_t*>(rowp + a.dim) = *reinterpret_cast<const uint32_t*>(pv);
     }
   }
 }
