@@ -397,6 +397,29 @@ def bench_xattn(dev, flush):
         tf = 3.0 * fwd / (med * 1e-3) / 1e12
         out[name] = {"ms": med, "ms_best": best, "algorithmic_tflops": tf, "frac_of_bf16_peak": tf / burst,
                      "eager_restatement_ms": ref_med, "batch": B, "queries_per_sample": n, "tokens": L, "dim": d}
+    # BASELINE config 4 as literally written (token sequences as queries: 77 x 197 and 197 x 77, width 768, 12 heads),
+    # through the module's forward(x, q); SURVEY §0 D2 explains why the reference never runs this shape.
+    for name, (Lq, Lk) in (("literal_77q_x_197kv_w768", (77, 197)), ("literal_197q_x_77kv_w768", (197, 77))):
+        d2, h2, B2 = 768, 12, 256
+        params, _, _, _ = O.make_pooler_case(d2, 4, 1, 1, seed=4)
+        mod = AttentionalCrossPooler(d2, d2, h2).to(dev)
+        mod.load_state_dict(params)
+        g = torch.Generator(device=dev).manual_seed(Lq)
+        x = torch.randn(B2, Lk, d2, generator=g, device=dev).bfloat16().requires_grad_(True)
+        q = torch.randn(B2, Lq, d2, generator=g, device=dev).bfloat16().requires_grad_(True)
+        w = torch.randn(B2, Lq, d2, generator=g, device=dev).bfloat16()
+
+        def step2():
+            for t in [x, q] + list(mod.parameters()):
+                t.grad = None
+            mod(x, q).backward(w)
+
+        for _ in range(3):
+            step2()
+        med, best = _event_ms(step2, 5, flush)
+        fwd = 2.0 * B2 * (Lq + 2 * Lk) * d2 * d2 + 4.0 * B2 * Lq * Lk * d2 + 2.0 * B2 * Lq * d2 * d2
+        out[name] = {"ms": med, "ms_best": best, "algorithmic_tflops": 3.0 * fwd / (med * 1e-3) / 1e12, "batch": B2,
+                     "queries": Lq, "tokens": Lk, "dim": d2, "heads": h2}
     return out
 
 

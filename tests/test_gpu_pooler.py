@@ -130,3 +130,29 @@ def test_pooler_bf16_inputs_and_dedup_equivalence():
     assert cosine(fA.grad.float(), f32.grad) > 0.999
     assert cosine(tokA.grad.float(), t32.grad) > 0.995
     assert cosine(dict(modA.named_parameters())["attn.out_proj.weight"].grad, p32["attn.out_proj.weight"].grad) > 0.995
+
+
+@pytest.mark.gpu
+def test_pooler_module_many_queries():
+    """forward(x, q) with more queries per sample than one kernel pass handles (20 > 8) and width 768 / 12 heads
+    (the literal BASELINE config-4 geometry, scaled down), against the oracle."""
+    from cosmos_b200.pooler import AttentionalCrossPooler
+    d, h, L, B, Lq = 768, 12, 37, 3, 20
+    params, tokens, _, _ = O.make_pooler_case(d, L, B, 1, seed=11)
+    g = torch.Generator().manual_seed(12)
+    q = torch.randn(B, Lq, d, generator=g)
+    w = torch.randn(B, Lq, d, generator=g)
+    mod = AttentionalCrossPooler(d, d, h).cuda()
+    mod.load_state_dict(params)
+    x_d = tokens.cuda().requires_grad_(True)
+    q_d = q.cuda().requires_grad_(True)
+    out = mod(x_d, q_d)
+    (out * w.cuda()).sum().backward()
+    p32 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    x_c, q_c = tokens.clone().requires_grad_(True), q.clone().requires_grad_(True)
+    ref = O.cross_pool(x_c, q_c, p32, h)
+    (ref * w).sum().backward()
+    assert relerr(out, ref) < 2e-2
+    assert cosine(q_d.grad, q_c.grad) > 0.999
+    assert cosine(x_d.grad, x_c.grad) > 0.99
+    assert cosine(mod.attn.in_proj_weight.grad, p32["attn.in_proj_weight"].grad) > 0.99
