@@ -156,6 +156,47 @@ def gather_stack(local: torch.Tensor, comm: Comm) -> torch.Tensor:
     return out.view(comm.world_size, n, b, d).permute(1, 0, 2, 3).reshape(n, comm.world_size * b, d)
 
 
+class GatherHandle:
+    """An all-gather of one [n, b, D] stack started with async_op=True: the transfer runs on NCCL's stream while the
+    caller keeps launching kernels; `get()` makes the current stream wait for it and returns the [n, W*b, D] layout."""
+
+    def __init__(self, local: torch.Tensor, comm: Comm):
+        self.comm, self.shape = comm, tuple(local.shape)
+        if comm.distributed:
+            n, b, d = local.shape
+            self.out = torch.empty(comm.world_size * n, b, d, dtype=local.dtype, device=local.device)
+            self.work = dist.all_gather_into_tensor(self.out, local.contiguous(), group=comm.group, async_op=True)
+        else:
+            self.out, self.work = local, None
+        self._result = None
+
+    def get(self) -> torch.Tensor:
+        if self._result is None:
+            if self.work is not None:
+                self.work.wait()
+                n, b, d = self.shape
+                W = self.comm.world_size
+                self._result = self.out.view(W, n, b, d).permute(1, 0, 2, 3).reshape(n, W * b, d)
+            else:
+                self._result = self.out
+        return self._result
+
+
+class Prefetch:
+    """Gathers started ahead of time by the caller (COSMOSLoss starts every list's all-gather before the first kernel,
+    so only the first one is exposed); keyed by the data pointer of the local stack."""
+
+    def __init__(self):
+        self.handles = {}
+
+    def start(self, tensors: Sequence[torch.Tensor], comm: Comm) -> None:
+        if not comm.distributed:
+            return
+        tensors = list(tensors)
+        st = stack_views(tensors, compute_dtype(tensors[0].dtype))
+        self.handles[tuple(id(t) for t in tensors)] = (st, GatherHandle(st, comm), tensors)   # keeps the ids alive
+
+
 def _allreduce_lse2(lse2: torch.Tensor, comm: Comm) -> torch.Tensor:
     """log2-sum-exp2 over ranks of per-rank partial column statistics (max all-reduce + sum all-reduce)."""
     if not comm.distributed:
@@ -188,13 +229,19 @@ def _swap_pairs(t: torch.Tensor, n_r: int, n_c: int) -> torch.Tensor:
 
 class _PairsInfoNCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, scale: torch.Tensor, comm: Comm, n_r: int, *feats: torch.Tensor):
+    def forward(ctx, scale: torch.Tensor, comm: Comm, n_r: int, prefetch, *feats: torch.Tensor):
         rows, cols = feats[:n_r], feats[n_r:]
         n_c = len(cols)
         dev = rows[0].device
         dt = compute_dtype(rows[0].dtype)
         x_r = stack_views(rows, dt)                       # [n_r, b, D]
-        x_c = stack_views(cols, dt)                       # [n_c, b, D]
+        pre_c = pre_r = None
+        if prefetch is not None and comm.distributed:
+            pre_c = prefetch.handles.get(tuple(id(t) for t in cols))
+            pre_r = prefetch.handles.get(tuple(id(t) for t in rows))
+        x_c = pre_c[0] if pre_c is not None else stack_views(cols, dt)   # [n_c, b, D]
+        if pre_r is not None:
+            x_r = pre_r[0]
         b = x_r.shape[1]
         if x_c.shape[1] != b:
             raise RuntimeError("cosmos_b200: both feature lists must have the same batch size")
@@ -203,7 +250,7 @@ class _PairsInfoNCE(torch.autograd.Function):
         off = comm.rank * b if comm.distributed else 0
         scale_f = scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
 
-        y_c = gather_stack(x_c, comm)                     # [n_c, N, D]
+        y_c = pre_c[1].get() if pre_c is not None else gather_stack(x_c, comm)     # [n_c, N, D]
         row_lse2, diag_raw, col_lse2_part = _k_fwd(x_r, y_c, off, scale_f)
         col_lse2 = _allreduce_lse2(col_lse2_part, comm)   # global over all rows
         sums = _k_loss_sums(x_r, y_c, off, scale_f, row_lse2, diag_raw, col_lse2)   # [P, 2]
@@ -216,6 +263,7 @@ class _PairsInfoNCE(torch.autograd.Function):
             loss = total / (2.0 * b * P)
 
         ctx.comm, ctx.n_r, ctx.n_c, ctx.b, ctx.off = comm, n_r, n_c, b, off
+        ctx.pre_r = pre_r[1] if pre_r is not None else None
         ctx.in_dtypes = [t.dtype for t in feats]
         ctx.scale_dtype = scale.dtype
         ctx.save_for_backward(x_r, x_c, y_c, scale_f, row_lse2, col_lse2)
@@ -228,8 +276,8 @@ class _PairsInfoNCE(torch.autograd.Function):
         W = comm.world_size
         N, P = W * b, n_r * n_c
         need_scale = ctx.needs_input_grad[0]
-        need_rows = any(ctx.needs_input_grad[3:3 + n_r])
-        need_cols = any(ctx.needs_input_grad[3 + n_r:])
+        need_rows = any(ctx.needs_input_grad[4:4 + n_r])
+        need_cols = any(ctx.needs_input_grad[4 + n_r:])
         up = g.detach().to(torch.float32).reshape(1).contiguous()
 
         local = comm.distributed and comm.local_loss
@@ -249,7 +297,7 @@ class _PairsInfoNCE(torch.autograd.Function):
                                      need_rows, need_scale)
         if need_cols or (local and need_scale):
             # transposed block: rows = local column-side tensors, columns = all rows of the row side
-            y_r = gather_stack(x_r, comm)                                   # [n_r, N, D]
+            y_r = ctx.pre_r.get() if ctx.pre_r is not None else gather_stack(x_r, comm)     # [n_r, N, D]
             row_lse2_all = _gather_rows(row_lse2, comm)                     # [P, N]
             t_row = _swap_pairs(col_lse2[:, off:off + b], n_r, n_c)         # row LSE of S^T for my rows
             t_col = _swap_pairs(row_lse2_all, n_r, n_c)                     # column LSE of S^T (global)
@@ -262,15 +310,16 @@ class _PairsInfoNCE(torch.autograd.Function):
 
         grads: List[Optional[torch.Tensor]] = []
         for k in range(n_r):
-            grads.append(d_rows[k].to(ctx.in_dtypes[k]) if (d_rows is not None and ctx.needs_input_grad[3 + k]) else None)
+            grads.append(d_rows[k].to(ctx.in_dtypes[k]) if (d_rows is not None and ctx.needs_input_grad[4 + k]) else None)
         for k in range(n_c):
             grads.append(d_cols[k].to(ctx.in_dtypes[n_r + k])
-                         if (d_cols is not None and ctx.needs_input_grad[3 + n_r + k]) else None)
+                         if (d_cols is not None and ctx.needs_input_grad[4 + n_r + k]) else None)
         g_scale = d_scale.reshape(()).to(ctx.scale_dtype) if need_scale else None
-        return (g_scale, None, None, *grads)
+        return (g_scale, None, None, None, *grads)
 
 
-def pairs_infonce(rows: Sequence[torch.Tensor], cols: Sequence[torch.Tensor], scale, comm: Comm = Comm()) -> torch.Tensor:
+def pairs_infonce(rows: Sequence[torch.Tensor], cols: Sequence[torch.Tensor], scale, comm: Comm = Comm(),
+                  prefetch: Optional["Prefetch"] = None) -> torch.Tensor:
     """Mean symmetric InfoNCE over all (row tensor, column tensor) pairs; a 0-dim fp32 tensor.
 
     The loss is symmetric in its two lists, so callers pass the longer / gradient-carrying list as
@@ -282,4 +331,4 @@ def pairs_infonce(rows: Sequence[torch.Tensor], cols: Sequence[torch.Tensor], sc
         _lib.require_cuda(t, "feature tensor")
     if not isinstance(scale, torch.Tensor):
         scale = torch.tensor(float(scale), dtype=torch.float32, device=rows[0].device)
-    return _PairsInfoNCE.apply(scale, comm, len(rows), *rows, *cols)
+    return _PairsInfoNCE.apply(scale, comm, len(rows), prefetch, *rows, *cols)

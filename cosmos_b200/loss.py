@@ -24,7 +24,7 @@ try:
 except ImportError:  # pragma: no cover
     has_distributed = False
 
-from .infonce import Comm, pairs_infonce
+from .infonce import Comm, Prefetch, pairs_infonce
 
 __all__ = ["gather_features", "ClipLoss", "COSMOSLoss", "CoCaLoss", "DistillClipLoss", "SigLipLoss"]
 
@@ -161,17 +161,26 @@ class COSMOSLoss(nn.Module):
 
         comm = self.clip_loss._comm()
         scale = distill_logit_scale if distill_logit_scale is not None else logit_scale
+        # Start every all-gather now (NCCL stream): the teacher stack is needed first, the student image stack by the
+        # CLIP forward, the student text stack only by the CLIP backward - all but the first hide behind kernels.
+        images2, texts = list(s_image_features[:2]), list(s_text_features)
+        prefetch = Prefetch()
+        prefetch.start(teacher, comm)
+        prefetch.start(images2, comm)
+        if any(t.requires_grad for t in images2):
+            prefetch.start(texts, comm)
         # mean over {img-x, txt-x} x {t_img, t_txt} of ClipLoss(n x 2 pairs)  ==  mean of the two n x 4 groups; with equally
         # long lists (the COSMOS recipes: 8 + 8) that is the plain mean over all 16 x 4 pairs -> ONE grouped launch, which
         # fills whole waves of SM clusters where two half-sized launches would each leave a partial wave.
         img_x, txt_x = list(s_img_crossmodal_features), list(s_txt_crossmodal_features)
         if len(img_x) == len(txt_x):
-            cosmos_loss = pairs_infonce(img_x + txt_x, teacher, scale, comm)
+            cosmos_loss = pairs_infonce(img_x + txt_x, teacher, scale, comm, prefetch)
         else:
-            cosmos_loss = (pairs_infonce(img_x, teacher, scale, comm) + pairs_infonce(txt_x, teacher, scale, comm)) / 2
+            cosmos_loss = (pairs_infonce(img_x, teacher, scale, comm, prefetch)
+                           + pairs_infonce(txt_x, teacher, scale, comm, prefetch)) / 2
 
         # CLIP loss: only the two global crops on the image side (loss.py:205-206)
-        clip_loss = pairs_infonce(list(s_text_features), list(s_image_features[:2]), logit_scale, comm)
+        clip_loss = pairs_infonce(texts, images2, logit_scale, comm, prefetch)
         return {"distill_loss": cosmos_loss, "clip_loss": clip_loss} if output_dict else cosmos_loss + clip_loss
 
 
