@@ -39,6 +39,20 @@ def algorithmic_flops(n_global: int, dim: int = DIM) -> float:
     return 352.0 * n_global * n_global * dim
 
 
+def ncu_traffic(kind):
+    """DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full summary (global batch 4096)."""
+    path = os.path.join(ROOT, "profiles", "ncu_%s_r01.txt" % kind)
+    try:
+        tot = 0.0
+        for line in open(path):
+            f = line.split()
+            if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+        return tot or None
+    except OSError:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -276,8 +290,12 @@ def run_ours(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "infonce_%s_kernel" % dom, "achieved": achieved, "peak": sustained,
-                         "unit": "TFLOP/s", "frac": achieved / sustained, "traffic": None,
+            "roofline": {"bound": "tensor",
+                         "kernel": "infonce_bwd_quad_kernel (+ dscale reduce)" if dom == "bwd" else "infonce_fwd_kernel<pair> (+ column merge)",
+                         "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+                         "traffic": ncu_traffic(dom) if n_global == 4096 else None,
+                         "traffic_note": "dram__bytes_read+write of one launch from profiles/ncu_*_r01.txt (captured at global batch 4096)",
+                         "executed_tflops": achieved * (2.0 if dom == "bwd" else 1.0),
                          "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step); burst %.1f" % (src, burst),
                          "launch_ms_avg": k["ms_avg"], "launches_timed": k["launches"],
                          "step_algorithmic_tflops_per_gpu": step_tflops, "step_frac": step_tflops / sustained,
