@@ -202,13 +202,19 @@ struct AttnArgs {
 
 template <class T>
 __device__ __forceinline__ void load_kv(const T* __restrict__ kv, T* sK, T* sV, const AttnArgs& a, int set, int h) {
+  // 16-byte global loads (hd is a power of two >= 16), 4-byte stores into the padded rows
   const int hd = a.hd, ldk = hd + 2;
-  const int per_row = hd / 2;      // 32-bit words per row
+  const int per_row = hd >> 3;                       // uint4 per row
+  const int shift = 31 - __clz(per_row);
   for (int idx = threadIdx.x; idx < a.L * per_row; idx += blockDim.x) {
-    const int l = idx / per_row, w = idx - l * per_row;
-    const T* rowp = kv + (static_cast<size_t>(set) * a.L + l) * (2 * a.dim) + h * hd;
-    reinterpret_cast<uint32_t*>(sK + l * ldk)[w] = reinterpret_cast<const uint32_t*>(rowp)[w];
-    reinterpret_cast<uint32_t*>(sV + l * ldk)[w] = reinterpret_cast<const uint32_t*>(rowp + a.dim)[w];
+    const int l = idx >> shift, j = idx & (per_row - 1);
+    const T* rowp = kv + (static_cast<size_t>(set) * a.L + l) * (2 * a.dim) + h * hd + j * 8;
+    const uint4 k4 = __ldg(reinterpret_cast<const uint4*>(rowp));
+    const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(rowp + a.dim));
+    uint32_t* dk = reinterpret_cast<uint32_t*>(sK + l * ldk + j * 8);
+    uint32_t* dv = reinterpret_cast<uint32_t*>(sV + l * ldk + j * 8);
+    dk[0] = k4.x; dk[1] = k4.y; dk[2] = k4.z; dk[3] = k4.w;
+    dv[0] = v4.x; dv[1] = v4.y; dv[2] = v4.z; dv[3] = v4.w;
   }
 }
 
@@ -252,14 +258,23 @@ __device__ __forceinline__ void dot_rows(const float* __restrict__ A, const T* _
   }
 }
 
-// out[c][k] = sum_l W[c][l] * M[l][k] for this thread's k and its share of the keys (l = part, part + parts, ...)
+// out[c][k] = sum_l W[c][l] * M[l][k] for this thread's k and its share of the keys: groups of 4 consecutive keys
+// (one LDS.128 of W per query and group).  W rows are padded to a multiple of 4 with zeros.
 template <class T>
 __device__ __forceinline__ void weighted_rows(const float* __restrict__ W, int ldw, const T* __restrict__ M, int ldk, int L, int k,
                                               int part, int parts, float (&acc)[kQG]) {
-  for (int l = part; l < L; l += parts) {
-    const float v = tof(M[l * ldk + k]);
+  for (int l0 = part * 4; l0 < L; l0 += parts * 4) {
+    float v[4];
 #pragma unroll
-    for (int c = 0; c < kQG; ++c) acc[c] = fmaf(W[c * ldw + l], v, acc[c]);
+    for (int u = 0; u < 4; ++u) v[u] = (l0 + u < L) ? tof(M[(l0 + u) * ldk + k]) : 0.f;
+#pragma unroll
+    for (int c = 0; c < kQG; ++c) {
+      const float4 w = *reinterpret_cast<const float4*>(W + c * ldw + l0);
+      acc[c] = fmaf(w.x, v[0], acc[c]);
+      acc[c] = fmaf(w.y, v[1], acc[c]);
+      acc[c] = fmaf(w.z, v[2], acc[c]);
+      acc[c] = fmaf(w.w, v[3], acc[c]);
+    }
   }
 }
 
@@ -318,10 +333,10 @@ attn_core_fwd_kernel(const T* __restrict__ q, const T* __restrict__ kv, T* __res
     float sum[kQG];
 #pragma unroll
     for (int c = 0; c < kQG; ++c) sum[c] = 0.f;
-    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    for (int l = threadIdx.x; l < Lp; l += blockDim.x) {
 #pragma unroll
       for (int c = 0; c < kQG; ++c) {
-        const float e = __expf(sP[c * Lp + l] - sStat[c]);
+        const float e = l < L ? __expf(sP[c * Lp + l] - sStat[c]) : 0.f;      // pad columns stay zero for the P V product
         sP[c * Lp + l] = e;
         sum[c] += e;
       }
@@ -426,9 +441,9 @@ attn_core_bwd_kernel(const T* __restrict__ q, const T* __restrict__ kv, const T*
       sStat[kQG + threadIdx.x] = t;
     }
     __syncthreads();
-    for (int l = threadIdx.x; l < L; l += blockDim.x)
+    for (int l = threadIdx.x; l < Lp; l += blockDim.x)
 #pragma unroll
-      for (int c = 0; c < kQG; ++c) sDS[c * Lp + l] = sP[c * Lp + l] * (sDS[c * Lp + l] - sStat[kQG + c]);
+      for (int c = 0; c < kQG; ++c) sDS[c * Lp + l] = l < L ? sP[c * Lp + l] * (sDS[c * Lp + l] - sStat[kQG + c]) : 0.f;
     __syncthreads();
     // dQ = kappa * dS K
     {
