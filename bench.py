@@ -248,10 +248,10 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    clocks = Clocks(local_rank) if rank == 0 else None     # sampled from the warm-up on: short timed regions still get samples
     for _ in range(max(args.warmup, 3)):
         step(False)
     barrier()
-    clocks = Clocks(local_rank) if rank == 0 else None
     inst.enabled = True
     inst.launches = 0
     dev_ms = timed(False, args.steps)
