@@ -202,7 +202,7 @@ int cosmos_infonce_fwd(const cosmos_infonce_problem* p, float* row_lse2, float* 
   fp.label_offset = p->label_offset;
   fp.n_row_tiles = d.n_row_tiles; fp.n_col_tiles = d.n_col_tiles_fwd; fp.n_slabs = d.n_slabs;
   const bool pair = !(dbg_flags() & 4);
-  fp.idesc = cb::make_idesc(bf, 0, 0, pair ? 2 * cb::kFwdBM : cb::kFwdBM, cb::kFwdBN);
+  fp.idesc = cb::make_idesc(bf, 0, 0, pair ? 2 * cb::kFwdBM : cb::kFwdBM, (dbg_flags() & 8192) ? 16 : cb::kFwdBN);   // 8192: issue-rate diagnostics (wrong results)
   fp.dbg = dbg_flags();
   fp.scale = reinterpret_cast<const float*>(p->scale);
   fp.row_lse2 = row_lse2; fp.diag_raw = diag_raw;
@@ -263,8 +263,8 @@ int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, c
   bp.dbg = dbg_flags();
   if (pair) {
     const int nh = d.ks < 4 ? d.ks : 4;
-    bp.idesc_s = cb::make_idesc(bf, 0, 0, 2 * cb::kFwdBM, cb::kBwdBN);
-    bp.idesc_g = cb::make_idesc(bf, 0, 1, 2 * cb::kFwdBM, nh * 64);
+    bp.idesc_s = cb::make_idesc(bf, 0, 0, 2 * cb::kFwdBM, (dbg_flags() & 8192) ? 16 : cb::kBwdBN);
+    bp.idesc_g = cb::make_idesc(bf, 0, 1, 2 * cb::kFwdBM, (dbg_flags() & 8192) ? 16 : nh * 64);
   } else {
     bp.idesc_s = cb::make_idesc(bf, 0, 0, cb::kFwdBM, cb::kBwdBN);
     bp.idesc_g = cb::make_idesc(bf, 0, 1, cb::kFwdBM, 64);

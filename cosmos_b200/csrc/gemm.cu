@@ -79,16 +79,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     ks1 = min(k_slabs, ks0 + per_split);
   };
 
-  if (warp == 0 && lane == 0) {
+  // Single-thread roles: whole warp converged, elect.sync around the asynchronous instructions (a divergent `lane == 0`
+  // branch makes the compiler wrap every UTMALDG / UTCHMMA / UTCBAR in an elect-and-branch loop).
+  if (warp == 0) {
     uint32_t stage = 0, phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int m0, n0, ks0, ks1;
       decode(item, m0, n0, ks0, ks1);
       for (int s = ks0; s < ks1; ++s) {
         mbar_wait(&misc->empty[stage], phase ^ 1);
-        mbar_expect_tx(&misc->full[stage], kABytes + kBBytes);
         uint8_t* a = sA + stage * kABytes;
         uint8_t* b = sB + stage * kBBytes;
+        if (elect_one()) {
+        mbar_expect_tx(&misc->full[stage], kABytes + kBBytes);
         if (p.a_kmajor) {
           tma_load_3d(a, &tmA, &misc->full[stage], s * BK, m0, 0);            // box 64 k x 128 rows
         } else {
@@ -102,10 +105,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int c = 0; c < BN / 64; ++c) tma_load_3d(b + c * 8192, &tmB, &misc->full[stage], n0 + c * 64, s * BK, 0);
         }
+        }
+        __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     uint32_t stage = 0, phase = 0;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -119,16 +124,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA + stage * kABytes);
         const uint32_t b_base = smem_u32(sB + stage * kBBytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t da = p.a_kmajor ? make_smem_desc(a_base + kk * 32, 0, 1024) : make_smem_desc(a_base + kk * 2048, 8192, 1024);
-          const uint64_t db = p.b_kmajor ? make_smem_desc(b_base + kk * 32, 0, 1024) : make_smem_desc(b_base + kk * 2048, 8192, 1024);
-          umma_ss(tmem + as * BN, da, db, p.idesc, (s > ks0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t da = p.a_kmajor ? make_smem_desc(a_base + kk * 32, 0, 1024) : make_smem_desc(a_base + kk * 2048, 8192, 1024);
+            const uint64_t db = p.b_kmajor ? make_smem_desc(b_base + kk * 32, 0, 1024) : make_smem_desc(b_base + kk * 2048, 8192, 1024);
+            umma_ss(tmem + as * BN, da, db, p.idesc, (s > ks0 || kk > 0) ? 1u : 0u);
+          }
+          tc_commit(&misc->empty[stage]);
         }
-        tc_commit(&misc->empty[stage]);
+        __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      tc_commit(&misc->acc_full[as]);     // also fires for an empty K range: the epilogue then sees no valid data, see below
+      if (elect_one()) tc_commit(&misc->acc_full[as]);     // also fires for an empty K range: the epilogue then sees no valid data, see below
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const uint32_t q = warp & 3;

@@ -95,41 +95,47 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = misc->tmem_slot;
 
+  // Single-thread roles: whole warp converged, elect.sync around the asynchronous instructions (a divergent `lane == 0`
+  // branch makes the compiler wrap every UTMALDG / UTCHMMA / UTCBAR in an elect-and-branch loop).
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer: slabs in the order the MMA warp consumes them ----------------
+    // ---------------- TMA producer: slabs in the order the MMA warp consumes them ----------------
+    if (elect_one()) {
       mbar_expect_tx(&misc->x_full, ks * kSlab);
       for (int s = 0; s < ks; ++s) tma_load_3d(sX + s * kSlab, &tmX, &misc->x_full, s * 64, tr * BM, i);
-      uint32_t stage = 0, phase = 0;
-      auto load = [&](int t, int s) {
-        const int j = t / n_ct, tc = t - j * n_ct;
-        mbar_wait(&misc->y_empty[stage], phase ^ 1);
+    }
+    __syncwarp();
+    uint32_t stage = 0, phase = 0;
+    auto load = [&](int t, int s) {
+      const int j = t / n_ct, tc = t - j * n_ct;
+      mbar_wait(&misc->y_empty[stage], phase ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&misc->y_full[stage], kSlab);
         tma_load_3d(sY + stage * kSlab, &tmY, &misc->y_full[stage], s * 64, tc * BN, j);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-      };
-      for (int s = 0; s < ks; ++s) load(0, s);
-      for (int t = 0; t < T; ++t) {
-        if (t + 1 < T)
-          for (int s = 0; s < ks; ++s) load(t + 1, s);
-        if (want_dx)
-          for (int s = 0; s < nh; ++s) load(t, slab0 + s);
       }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    };
+    for (int s = 0; s < ks; ++s) load(0, s);
+    for (int t = 0; t < T; ++t) {
+      if (t + 1 < T)
+        for (int s = 0; s < ks; ++s) load(t + 1, s);
+      if (want_dx)
+        for (int s = 0; s < nh; ++s) load(t, slab0 + s);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      mbar_wait(&misc->x_full, 0);
-      uint32_t stage = 0, phase = 0;
-      auto gemm1 = [&](int t) {
-        const uint32_t sb = t & 1;
-        mbar_wait(&misc->s_empty[sb], ((t >> 1) & 1) ^ 1);
+    // ---------------- MMA issuer (whole warp waits, one elected lane issues) ----------------
+    mbar_wait(&misc->x_full, 0);
+    uint32_t stage = 0, phase = 0;
+    auto gemm1 = [&](int t) {
+      const uint32_t sb = t & 1;
+      mbar_wait(&misc->s_empty[sb], ((t >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int s = 0; s < ks; ++s) {
+        mbar_wait(&misc->y_full[stage], phase);
         tc_fence_after();
-        for (int s = 0; s < ks; ++s) {
-          mbar_wait(&misc->y_full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sX + s * kSlab);
-          const uint32_t b_base = smem_u32(sY + stage * kSlab);
+        const uint32_t a_base = smem_u32(sX + s * kSlab);
+        const uint32_t b_base = smem_u32(sY + stage * kSlab);
+        if (elect_one()) {
           if (!(p.dbg & 2)) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
@@ -137,35 +143,41 @@ infonce_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                       p.idesc_s, (s | kk) != 0);
           }
           tc_commit(&misc->y_empty[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (s == ks - 1) tc_commit(&misc->s_full[sb]);
         }
-        tc_commit(&misc->s_full[sb]);
-      };
-      gemm1(0);
-      for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) gemm1(t + 1);
-        if (want_dx) {
-          mbar_wait(&misc->g_full, t & 1);
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    };
+    gemm1(0);
+    for (int t = 0; t < T; ++t) {
+      if (t + 1 < T) gemm1(t + 1);
+      if (want_dx) {
+        mbar_wait(&misc->g_full, t & 1);
+        tc_fence_after();
+        for (int s = 0; s < nh; ++s) {
+          mbar_wait(&misc->y_full[stage], phase);
           tc_fence_after();
-          for (int s = 0; s < nh; ++s) {
-            mbar_wait(&misc->y_full[stage], phase);
-            tc_fence_after();
-            const uint32_t b_base = smem_u32(sY + stage * kSlab);
-            if (!(p.dbg & 2))
+          const uint32_t b_base = smem_u32(sY + stage * kSlab);
+          if (elect_one()) {
+            if (!(p.dbg & 2)) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {   // 128 columns of this step = K of GEMM2, 16 per MMA
-              const uint32_t a_addr = smem_u32(sG) + (k >> 2) * kSlab + (k & 3) * 32;
-              umma_ss(tmem + 256 + s * 64, make_smem_desc(a_addr, 0, 1024), make_smem_desc(b_base + k * 2048, kSlab, 1024),
-                      p.idesc_g, (t | k) != 0);
+              for (int k = 0; k < 8; ++k) {   // 128 columns of this step = K of GEMM2, 16 per MMA
+                const uint32_t a_addr = smem_u32(sG) + (k >> 2) * kSlab + (k & 3) * 32;
+                umma_ss(tmem + 256 + s * 64, make_smem_desc(a_addr, 0, 1024), make_smem_desc(b_base + k * 2048, kSlab, 1024),
+                        p.idesc_g, (t | k) != 0);
+              }
             }
             tc_commit(&misc->y_empty[stage]);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (s == nh - 1) tc_commit(&misc->g_empty);
           }
-          tc_commit(&misc->g_empty);
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
-      tc_commit(&misc->dx_full);
     }
+    if (elect_one()) tc_commit(&misc->dx_full);
+    __syncwarp();
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------
     const uint32_t ew = warp - 4;

@@ -112,46 +112,55 @@ infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   tc_fence_after();
   const uint32_t tmem = misc->tmem_slot;
 
+  // Single-thread roles: whole warp converged, elect.sync around the asynchronous instructions (a divergent `lane == 0`
+  // branch makes the compiler wrap every UTMALDG / UTCHMMA / UTCBAR in an elect-and-branch loop).
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      auto arm = [&](uint64_t* bar, uint32_t bytes_per_cta) {
-        if (leader) mbar_expect_tx(bar, 2 * bytes_per_cta);
-        else mbar_arrive_cluster(bar, 0);
-      };
+    // ---------------- TMA producer ----------------
+    auto arm = [&](uint64_t* bar, uint32_t bytes_per_cta) {
+      if (leader) mbar_expect_tx(bar, 2 * bytes_per_cta);
+      else mbar_arrive_cluster(bar, 0);
+    };
+    if (elect_one()) {
       for (int s = 0; s < ks; ++s) tma_load_3d_pair(sX + s * kSlabX, &tmX, &misc->x_full, s * 64, tr * BM, i);
       arm(&misc->x_full, ks * kSlabX);
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-      auto load_g1 = [&](int t) {
-        const int j = (t_begin + t) / n_ct, tc = (t_begin + t) - j * n_ct;
-        for (int s = 0; s < ks; ++s) {
-          mbar_wait(&misc->a_empty[sa], pa ^ 1);
+    }
+    __syncwarp();
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+    auto load_g1 = [&](int t) {
+      const int j = (t_begin + t) / n_ct, tc = (t_begin + t) - j * n_ct;
+      for (int s = 0; s < ks; ++s) {
+        mbar_wait(&misc->a_empty[sa], pa ^ 1);
+        if (elect_one()) {
           tma_load_3d_pair(sA + sa * kSlotA, &tmY64, &misc->a_full[sa], s * 64, tc * BN + cta_rank * 64, j);
           arm(&misc->a_full[sa], kSlotA);
-          if (++sa == kSlotsA) { sa = 0; pa ^= 1; }
         }
-      };
-      auto load_g2 = [&](int t) {     // GEMM2 operand in two 64-column halves: the first half's stage refills while the second runs
-        const int j = (t_begin + t) / n_ct, tc = (t_begin + t) - j * n_ct;
-        for (int half = 0; half < 2; ++half) {
-          mbar_wait(&misc->b_empty[sb], pb ^ 1);
+        __syncwarp();
+        if (++sa == kSlotsA) { sa = 0; pa ^= 1; }
+      }
+    };
+    auto load_g2 = [&](int t) {     // GEMM2 operand in two 64-column halves: the first half's stage refills while the second runs
+      const int j = (t_begin + t) / n_ct, tc = (t_begin + t) - j * n_ct;
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(&misc->b_empty[sb], pb ^ 1);
+        if (elect_one()) {
           for (int s = 0; s < nb; ++s)
             tma_load_3d_pair(sB + sb * b_stage_bytes + s * kSlabB, &tmY64, &misc->b_full[sb],
                              (slab0 + cta_rank * nb + s) * 64, tc * BN + half * 64, j);
           arm(&misc->b_full[sb], b_stage_bytes);
-          sb ^= 1;
-          if (sb == 0) pb ^= 1;
         }
-      };
-      load_g1(0);
-      for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) load_g1(t + 1);
-        if (want_dx) load_g2(t);
+        __syncwarp();
+        sb ^= 1;
+        if (sb == 0) pb ^= 1;
       }
+    };
+    load_g1(0);
+    for (int t = 0; t < T; ++t) {
+      if (t + 1 < T) load_g1(t + 1);
+      if (want_dx) load_g2(t);
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ---------------- MMA issuer (leader CTA only) ----------------
+    if (leader) {
+      // ---------------- MMA issuer (leader CTA only; whole warp waits, one elected lane issues) ----------------
       mbar_wait(&misc->x_full, 0);
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       auto gemm1 = [&](int t) {
@@ -161,16 +170,19 @@ infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           tc_fence_after();
           const uint32_t a_base = smem_u32(sX + s * kSlabX);
           const uint32_t b_base = smem_u32(sA + sa * kSlotA);
-          if (!(p.dbg & 2)) {
+          if (elect_one()) {
+            if (!(p.dbg & 2)) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_ss_pair(tmem + buf * BN, make_smem_desc(a_base + kk * 32, 0, 1024), make_smem_desc(b_base + kk * 32, 0, 1024),
-                           p.idesc_s, (s | kk) != 0);
+              for (int kk = 0; kk < 4; ++kk)
+                umma_ss_pair(tmem + buf * BN, make_smem_desc(a_base + kk * 32, 0, 1024), make_smem_desc(b_base + kk * 32, 0, 1024),
+                             p.idesc_s, (s | kk) != 0);
+            }
+            tc_commit_pair(&misc->a_empty[sa], 3);
+            if (s == ks - 1) tc_commit_pair(&misc->s_full[buf], 3);
           }
-          tc_commit_pair(&misc->a_empty[sa], 3);
+          __syncwarp();
           if (++sa == kSlotsA) { sa = 0; pa ^= 1; }
         }
-        tc_commit_pair(&misc->s_full[buf], 3);
       };
       gemm1(0);
       for (int t = 0; t < T; ++t) {
@@ -183,20 +195,24 @@ infonce_bwd_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             mbar_wait(&misc->b_full[sb], pb);
             tc_fence_after();
             const uint32_t b_base = smem_u32(sB + sb * b_stage_bytes);
-            if (!(p.dbg & 2)) {
+            if (elect_one()) {
+              if (!(p.dbg & 2)) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {   // K = 64 columns of this half, 16 per MMA = 8 packed TMEM columns of G
-                const uint32_t a_tmem = tmem + buf * BN + half * 64 + k * 8;
-                umma_ts_pair(tmem + 256, a_tmem, make_smem_desc(b_base + k * 2048, kSlabB, 1024), p.idesc_g, (t | half | k) != 0);
+                for (int k = 0; k < 4; ++k) {   // K = 64 columns of this half, 16 per MMA = 8 packed TMEM columns of G
+                  const uint32_t a_tmem = tmem + buf * BN + half * 64 + k * 8;
+                  umma_ts_pair(tmem + 256, a_tmem, make_smem_desc(b_base + k * 2048, kSlabB, 1024), p.idesc_g, (t | half | k) != 0);
+                }
               }
+              tc_commit_pair(&misc->b_empty[sb], 3);
             }
-            tc_commit_pair(&misc->b_empty[sb], 3);
+            __syncwarp();
             sb ^= 1;
             if (sb == 0) pb ^= 1;
           }
         }
       }
-      tc_commit_pair(&misc->dx_full, 3);
+      if (elect_one()) tc_commit_pair(&misc->dx_full, 3);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------

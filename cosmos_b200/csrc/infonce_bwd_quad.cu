@@ -18,6 +18,7 @@
 // buffer G2(o_{k-1}) reads.  Barriers: *_full on the pair leader (TMA bytes of both CTAs / arrivals of both
 // epilogues), *_empty by multicast tcgen05.commit; gr_full lives on the CONSUMING pair's leader and is armed by
 // remote release-arrives of the producing pair's epilogue warps; gr_empty is committed back to the producers.
+#include <cstdio>
 #include "common.cuh"
 #include "infonce.h"
 #include "internal.h"
@@ -128,49 +129,57 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     else mbar_arrive_cluster(bar, L);
   };
 
+  // Single-thread roles run with the WHOLE warp converged and an elect.sync predicate around the asynchronous instructions:
+  // inside a divergent `lane == 0` branch the compiler wraps every UTMALDG / UTCHMMA / UTCBAR in an elect-and-branch
+  // loop (~14 instructions and a branch per MMA), which made the issuing thread, not the tensor pipe, the bottleneck.
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer, ring A: this CTA's 64-column halves of the S-tile operands of OWN steps ----------------
+    // ---------------- TMA producer, ring A: this CTA's 64-column halves of the S-tile operands of OWN steps ----------------
+    if (elect_one()) {
       for (int s = 0; s < kKs; ++s) tma_load_3d_pair(sX + s * kSlabX, &tmX, &misc->x_full, s * 64, tr * BM, i);
       arm(&misc->x_full, kKs * kSlabX);
-      uint32_t sa = 0, pa = 0;
-      for (int k = 0; k < n_own; ++k) {
-        const int t = 2 * k + pr;
-        const int j = t / n_ct, tc = t - j * n_ct;
-        for (int s = 0; s < kKs; ++s) {
-          mbar_wait(&misc->a_empty[sa], pa ^ 1);
+    }
+    __syncwarp();
+    uint32_t sa = 0, pa = 0;
+    for (int k = 0; k < n_own; ++k) {
+      const int t = 2 * k + pr;
+      const int j = t / n_ct, tc = t - j * n_ct;
+      for (int s = 0; s < kKs; ++s) {
+        mbar_wait(&misc->a_empty[sa], pa ^ 1);
+        if (elect_one()) {
           tma_load_3d_pair(sA + sa * kSlotA, &tmY64, &misc->a_full[sa], s * 64, tc * BN + r * 64, j);
           arm(&misc->a_full[sa], kSlotA);
-          if (++sa == n_slots_a) { sa = 0; pa ^= 1; }
         }
+        __syncwarp();
+        if (++sa == n_slots_a) { sa = 0; pa ^= 1; }
       }
     }
   } else if (warp == 3) {
-    if (lane == 0) {
-      // ---------------- TMA producer, ring B: GEMM2 operands of EVERY step, in the order the MMA warp uses them ----------------
-      uint32_t sb = 0, pb = 0;
-      auto load_b = [&](int t) {
-        const int j = t / n_ct, tc = t - j * n_ct;
-        for (int half = 0; half < 2; ++half) {
-          mbar_wait(&misc->b_empty[sb], pb ^ 1);
+    // ---------------- TMA producer, ring B: GEMM2 operands of EVERY step, in the order the MMA warp uses them ----------------
+    uint32_t sb = 0, pb = 0;
+    auto load_b = [&](int t) {
+      const int j = t / n_ct, tc = t - j * n_ct;
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(&misc->b_empty[sb], pb ^ 1);
+        if (elect_one()) {
           for (int s = 0; s < 2; ++s)
             tma_load_3d_pair(sB + sb * kStageB + s * kSlabB, &tmY64, &misc->b_full[sb], (slab0 + r * 2 + s) * 64,
                              tc * BN + half * 64, j);
           arm(&misc->b_full[sb], kStageB);
-          sb ^= 1;
-          if (sb == 0) pb ^= 1;
         }
-      };
-      for (int k = 0; k < n_round; ++k) {
-        if (k < n_own) load_b(2 * k + pr);
-        if (k < n_rem) load_b(2 * k + (1 - pr));
+        __syncwarp();
+        sb ^= 1;
+        if (sb == 0) pb ^= 1;
       }
+    };
+    for (int k = 0; k < n_round; ++k) {
+      if (k < n_own) load_b(2 * k + pr);
+      if (k < n_rem) load_b(2 * k + (1 - pr));
     }
   } else if (warp == 2) {
     if (lane == 0) {
       // ---------------- receive side of the G exchange: arm the byte count, wait for the tile, tell the pair leader ----------------
       for (int k = 0; k < n_rem; ++k) {
-        mbar_expect_tx(&misc->gr_full, kSmemG);
+        mbar_expect_tx(&misc->gr_full, (p.dbg & 4096) ? kSmemG / 8 : kSmemG);
         // plain (CTA-scope) wait: a cluster-scope acquire compiles to an L1 invalidate (CCTL.IVALL) per poll, which this
         // spinning thread would inflict on the epilogue warps' global loads; the consumer fences once, below
         mbar_wait(&misc->gr_full, k & 1);
@@ -179,55 +188,74 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ---------------- MMA issuer (leader of each pair) ----------------
+    if (leader) {
+      // ---------------- MMA issuer (leader of each pair; whole warp waits, one elected lane issues) ----------------
+      const bool prof = (p.dbg & 1024) != 0;
+      long long w_a = 0, w_g = 0, w_gr = 0, w_b = 0;
+      const long long t_begin = clock64();
+      auto wait_t = [&](uint64_t* bar, uint32_t ph, long long& acc) {
+        if (prof) {
+          const long long c0 = clock64();
+          mbar_wait(bar, ph);
+          acc += clock64() - c0;
+        } else {
+          mbar_wait(bar, ph);
+        }
+      };
       mbar_wait(&misc->x_full, 0);
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
       bool dx_started = false;
       auto gemm1_half = [&](int k, int hlf) {          // own step index k, K slabs [4*hlf, 4*hlf + 4)
         const uint32_t buf = k & 1;
         for (int s = 4 * hlf; s < 4 * hlf + 4; ++s) {
-          mbar_wait(&misc->a_full[sa], pa);
+          wait_t(&misc->a_full[sa], pa, w_a);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sX + s * kSlabX);
           const uint32_t b_base = smem_u32(sA + sa * kSlotA);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_ss_pair(tmem + buf * BN, make_smem_desc(a_base + kk * 32, 0, 1024), make_smem_desc(b_base + kk * 32, 0, 1024),
-                         p.idesc_s, (s | kk) != 0);
-          tc_commit_pair(&misc->a_empty[sa], my_pair_mask);
+            for (int kk = 0; kk < 4; ++kk)
+              umma_ss_pair(tmem + buf * BN, make_smem_desc(a_base + kk * 32, 0, 1024), make_smem_desc(b_base + kk * 32, 0, 1024),
+                           p.idesc_s, (s | kk) != 0);
+            tc_commit_pair(&misc->a_empty[sa], my_pair_mask);
+            if (hlf == 1 && s == 7) tc_commit_pair(&misc->s_full[buf], my_pair_mask);
+          }
+          __syncwarp();
           if (++sa == n_slots_a) { sa = 0; pa ^= 1; }
         }
-        if (hlf == 1) tc_commit_pair(&misc->s_full[buf], my_pair_mask);
       };
       auto gemm2 = [&](bool own, int k) {
         const uint32_t buf = k & 1;
         if (own) {
-          mbar_wait(&misc->g_full[buf], (k >> 1) & 1);
+          wait_t(&misc->g_full[buf], (k >> 1) & 1, w_g);
         } else {
-          mbar_wait(&misc->gr_ready, k & 1);           // G tile written by the sibling pair through DSMEM, in both CTAs
+          wait_t(&misc->gr_ready, k & 1, w_gr);           // G tile written by the sibling pair through DSMEM, in both CTAs
           fence_proxy_async_all();                     // st.async data (complete_tx observed through the barrier chain) -> UMMA
         }
         for (int half = 0; half < 2; ++half) {
-          mbar_wait(&misc->b_full[sb], pb);
+          wait_t(&misc->b_full[sb], pb, w_b);
           tc_fence_after();
           const uint32_t b_base = smem_u32(sB + sb * kStageB);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t db = make_smem_desc(b_base + kk * 2048, kSlabB, 1024);
-            if (own) {
-              umma_ts_pair(tmem + 256, tmem + buf * BN + half * 64 + kk * 8, db, p.idesc_g, dx_started ? 1u : 0u);
-            } else {
-              const uint64_t da = make_smem_desc(smem_u32(sG) + half * kSlabX + kk * 32, 0, 1024);
-              umma_ss_pair(tmem + 256, da, db, p.idesc_g, dx_started ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t db = make_smem_desc(b_base + kk * 2048, kSlabB, 1024);
+              const uint32_t acc = (dx_started || kk > 0) ? 1u : 0u;
+              if (own) {
+                umma_ts_pair(tmem + 256, tmem + buf * BN + half * 64 + kk * 8, db, p.idesc_g, acc);
+              } else {
+                const uint64_t da = make_smem_desc(smem_u32(sG) + half * kSlabX + kk * 32, 0, 1024);
+                umma_ss_pair(tmem + 256, da, db, p.idesc_g, acc);
+              }
             }
-            dx_started = true;
+            tc_commit_pair(&misc->b_empty[sb], my_pair_mask);
+            if (!own && half == 1) tc_commit_pair(&misc->gr_empty, other_pair_mask);   // the producers may overwrite our G buffer
           }
-          tc_commit_pair(&misc->b_empty[sb], my_pair_mask);
+          __syncwarp();
+          dx_started = true;
           sb ^= 1;
           if (sb == 0) pb ^= 1;
         }
-        if (!own) tc_commit_pair(&misc->gr_empty, other_pair_mask);   // the producers may overwrite our G buffer
       };
       if (n_own > 0) {
         gemm1_half(0, 0);
@@ -239,7 +267,11 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         if (k + 1 < n_own) gemm1_half(k + 1, 1);
         if (k < n_rem) gemm2(false, k);
       }
-      tc_commit_pair(&misc->dx_full, my_pair_mask);
+      if (elect_one()) tc_commit_pair(&misc->dx_full, my_pair_mask);
+      __syncwarp();
+      if (prof && lane == 0 && ((blockIdx.x >> 2) % 97) == 5)
+        printf("quad prof cluster %d pair %u: issue thread total %lld clk, waits a_full %lld g_full %lld gr_ready %lld b_full %lld (rounds %d)\n",
+               blockIdx.x >> 2, pr, clock64() - t_begin, w_a, w_g, w_gr, w_b, n_round);
     }
   } else if (warp >= 4) {
     // ---------------- epilogue: softmax gradient of OWN steps, kept in TMEM and sent to the sibling CTA ----------------
@@ -264,6 +296,8 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     const uint32_t g_remote_row = mapa_u32(smem_u32(sG) + h * kSlabX + r_t * 128, sibling);
     const uint32_t gr_full_remote = mapa_u32(smem_u32(&misc->gr_full), sibling);
 
+    const bool eprof = (p.dbg & 1024) != 0 && ((blockIdx.x >> 2) % 97) == 5 && lane == 0 && (ew == 0 || ew == 7);
+    long long e_wait = 0, e_work = 0, e_gre = 0, e_send = 0;
     for (int k = 0; k < n_own; ++k) {
       const int t = 2 * k + pr;
       const int j = t / n_ct, tc = t - j * n_ct;
@@ -297,8 +331,11 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         }
       }
 
+      long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+      if (eprof) c0 = clock64();
       mbar_wait(&misc->s_full[buf], (k >> 1) & 1);
       tc_fence_after();
+      if (eprof) c1 = clock64();
       uint32_t packed_all[2][16];
 #pragma unroll
       for (int chunk = 0; chunk < 2; ++chunk) {
@@ -306,7 +343,11 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         uint32_t (&packed)[16] = packed_all[chunk];
         uint32_t v[32];
         tmem_ld32(tmem + lane_base + buf * BN + h * 64 + chunk * 32, v);
-        if (fast) {
+        if (p.dbg & 2048) {          // diagnostics: no softmax math (wrong results)
+          tmem_ld_wait();
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk) packed[kk] = v[2 * kk] ^ v[2 * kk + 1];
+        } else if (fast) {
           float kap[32];
 #pragma unroll
           for (int k4 = 0; k4 < 8; ++k4) {
@@ -384,19 +425,31 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       }
       // other pair: K-major, 128B-swizzled rows in the sibling CTA's shared memory, once it has consumed the tile
       // we sent one own-step ago
+      if (eprof) c2 = clock64();
       mbar_wait(&misc->gr_empty, (k & 1) ^ 1);      // write-after-read only: no data is acquired, a CTA-scope wait suffices
+      if (eprof) c3 = clock64();
 #pragma unroll
       for (int chunk = 0; chunk < 2; ++chunk) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int jj = chunk * 4 + c;
+          if ((p.dbg & 4096) && jj > 0) continue;   // diagnostics: 1/8 of the exchange (wrong results)
           st_async_cluster_v4(g_remote_row + ((jj ^ (r_t & 7)) << 4),
                               make_uint4(packed_all[chunk][c * 4 + 0], packed_all[chunk][c * 4 + 1], packed_all[chunk][c * 4 + 2],
                                          packed_all[chunk][c * 4 + 3]),
                               gr_full_remote);
         }
       }
+      if (eprof) {
+        e_wait += c1 - c0;
+        e_work += c2 - c1;
+        e_gre += c3 - c2;
+        e_send += clock64() - c3;
+      }
     }
+    if (eprof)
+      printf("quad prof cluster %d rank %u warp %u: epilogue s_full wait %lld, softmax+publish %lld, gr_empty wait %lld, send %lld (own steps %d)\n",
+             blockIdx.x >> 2, rank, ew, e_wait, e_work, e_gre, e_send, n_own);
 
     if (p.dscale_part != nullptr) {
 #pragma unroll

@@ -105,34 +105,41 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = misc->tmem_slot;
 
+  // Single-thread roles run with the whole warp converged and an elect.sync predicate around the asynchronous
+  // instructions: inside a divergent `lane == 0` branch the compiler wraps every UTMALDG / UTCHMMA / UTCBAR in an
+  // elect-and-branch loop, several times the instruction count per MMA.
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      // In pair mode every load is credited to the leader's barrier; the leader arms it with the bytes of
-      // BOTH CTAs, the other CTA adds a plain (remote) arrive.
-      auto arm = [&](uint64_t* bar, uint32_t bytes_per_cta) {
-        if (leader) mbar_expect_tx(bar, bytes_per_cta * kCtas);
-        else mbar_arrive_cluster(bar, 0);
-      };
-      auto load = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
-        if (kPair) tma_load_3d_pair(dst, m, bar, c0, c1, c2);
-        else tma_load_3d(dst, m, bar, c0, c1, c2);
-      };
+    // ---------------- TMA producer ----------------
+    // In pair mode every load is credited to the leader's barrier; the leader arms it with the bytes of
+    // BOTH CTAs, the other CTA adds a plain (remote) arrive.
+    auto arm = [&](uint64_t* bar, uint32_t bytes_per_cta) {
+      if (leader) mbar_expect_tx(bar, bytes_per_cta * kCtas);
+      else mbar_arrive_cluster(bar, 0);
+    };
+    auto load = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+      if (kPair) tma_load_3d_pair(dst, m, bar, c0, c1, c2);
+      else tma_load_3d(dst, m, bar, c0, c1, c2);
+    };
+    if (elect_one()) {
       for (int s = 0; s < ks; ++s) load(sX + s * kSlabX, &tmX, &misc->x_full, s * 64, tr * BM, i);
       arm(&misc->x_full, ks * kSlabX);
-      uint32_t stage = 0, phase = 0;
-      for (int tc = 0; tc < n_ct; ++tc) {
-        for (int s = 0; s < ks; ++s) {
-          mbar_wait(&misc->y_empty[stage], phase ^ 1);
+    }
+    __syncwarp();
+    uint32_t stage = 0, phase = 0;
+    for (int tc = 0; tc < n_ct; ++tc) {
+      for (int s = 0; s < ks; ++s) {
+        mbar_wait(&misc->y_empty[stage], phase ^ 1);
+        if (elect_one()) {
           load(sY + stage * kStageY, &tmY, &misc->y_full[stage], s * 64, tc * BN + cta_rank * kLoadCols, j);
           arm(&misc->y_full[stage], kStageY);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ---------------- MMA issuer (leader CTA of the pair only) ----------------
+    if (leader) {
+      // ---------------- MMA issuer (leader CTA of the pair only; whole warp waits, one elected lane issues) ----------------
       mbar_wait(&misc->x_full, 0);
       uint32_t stage = 0, phase = 0;
       for (int tc = 0; tc < n_ct; ++tc) {
@@ -145,18 +152,23 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           tc_fence_after();
           const uint32_t a_base = smem_u32(sX + s * kSlabX);
           const uint32_t b_base = smem_u32(sY + stage * kStageY);
-          if (!(p.dbg & 2)) {
+          if (elect_one()) {
+            if (!(p.dbg & 2)) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t da = make_smem_desc(a_base + kk * 32, 0, 1024), db = make_smem_desc(b_base + kk * 32, 0, 1024);
-              if (kPair) umma_ss_pair(d_tmem, da, db, p.idesc, (s | kk) != 0);
-              else umma_ss(d_tmem, da, db, p.idesc, (s | kk) != 0);
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t da = make_smem_desc(a_base + kk * 32, 0, 1024), db = make_smem_desc(b_base + kk * 32, 0, 1024);
+                if (kPair) umma_ss_pair(d_tmem, da, db, p.idesc, (s | kk) != 0);
+                else umma_ss(d_tmem, da, db, p.idesc, (s | kk) != 0);
+              }
+            }
+            if (kPair) tc_commit_pair(&misc->y_empty[stage], 3); else tc_commit(&misc->y_empty[stage]);
+            if (s == ks - 1) {
+              if (kPair) tc_commit_pair(&misc->acc_full[as], 3); else tc_commit(&misc->acc_full[as]);
             }
           }
-          if (kPair) tc_commit_pair(&misc->y_empty[stage], 3); else tc_commit(&misc->y_empty[stage]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (kPair) tc_commit_pair(&misc->acc_full[as], 3); else tc_commit(&misc->acc_full[as]);
       }
     }
   } else if (warp >= 4) {

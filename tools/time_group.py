@@ -23,4 +23,4 @@ def run(b, D, gx=8, gy=4, reps=5):
     print(f"DBG={os.environ.get('COSMOS_B200_DBG','0')} b={b}: fwd {tf/reps:.3f} ms ({fl/(tf/reps)*1e-9:.0f} TF/s)  "
           f"bwd {tb/reps:.3f} ms (exec {3*fl/(tb/reps)*1e-9:.0f} TF/s)", flush=True)
 
-run(int(sys.argv[1]) if len(sys.argv) > 1 else 4096, 512)
+run(int(sys.argv[1]) if len(sys.argv) > 1 else 4096, 512, reps=int(sys.argv[2]) if len(sys.argv) > 2 else 5)
