@@ -10,8 +10,8 @@
 // every Y tile (128 columns, 16 KB per stage, 6 stages), which halves the L2->SM operand traffic that
 // bounds the single-CTA version.  CTA 0 of the pair issues the MMAs; TMA loads of both CTAs complete on
 // its mbarriers; tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs.
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue
-// (warp%4 selects the TMEM lane quarter = 32 rows, warp/4-1 the 128-column half of the tile).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-19 epilogue
+// (warp%4 selects the TMEM lane quarter = 32 rows, warp/4-1 the 64-column group of the tile).
 //
 // Row statistics are thread-local (one thread = one row): running max / sum in log2 units.
 // Column statistics need a reduction over rows: a 31-shuffle warp transpose-reduce per 32x32 block
@@ -20,6 +20,7 @@
 //
 // Reference semantics: src/open_clip/loss.py:103-142 (get_logits + the two F.cross_entropy calls);
 // the positive of local row r is column label_offset + r (loss.py:90-101 with rank offset).
+#include <cstdio>
 #include "common.cuh"
 #include "infonce.h"
 
@@ -32,9 +33,10 @@ constexpr int kSlabX = BM * 64 * 2;    // 16 KB : 128 rows x 64 elements
 constexpr int kSmemX = 8 * kSlabX;     // 128 KB
 constexpr int kSmemY = 96 * 1024;      // Y ring: 3 x 32 KB (single CTA) or 6 x 16 KB (pair)
 constexpr int kMaxStages = 6;
-constexpr int kSmemMisc = 2048;
-constexpr int kThreads = 384;
-constexpr int kEpiThreads = 256;
+constexpr int kSmemMisc = 3072;
+constexpr int kEpiWarps = 16;            // 4 TMEM lane quarters x 4 column groups of 64: the statistics loop is latency-bound,
+constexpr int kThreads = 128 + 32 * kEpiWarps;   // 4 warps per scheduler hide what 2 could not
+constexpr int kEpiThreads = 32 * kEpiWarps;
 
 struct Misc {
   uint64_t x_full;
@@ -44,7 +46,7 @@ struct Misc {
   uint64_t acc_empty[2];
   uint32_t tmem_slot;
   uint32_t pad[5];
-  float bcast[8][32];
+  float bcast[kEpiWarps][32];
 };
 static_assert(sizeof(Misc) <= kSmemMisc, "misc smem");
 
@@ -57,8 +59,8 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   constexpr int kStageY = kSmemY / kStages;                       // bytes of Y this CTA loads per K step
   constexpr int kLoadCols = kPair ? BN / 2 : BN;                  // Y rows (= S columns) this CTA loads
   constexpr uint32_t kCtas = kPair ? 2 : 1;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sX = smem;
   uint8_t* sY = smem + kSmemX;
   Misc* misc = reinterpret_cast<Misc*>(smem + kSmemX + kSmemY);
@@ -88,7 +90,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&misc->acc_full[s], 1);
-      mbar_init(&misc->acc_empty[s], (p.dbg & 16) ? kCtas * kEpiThreads : kCtas * 8);   // per-warp (or per-thread) arrives of both CTAs
+      mbar_init(&misc->acc_empty[s], (p.dbg & 16) ? kCtas * kEpiThreads : kCtas * kEpiWarps);   // per-warp (or per-thread) arrives of both CTAs
     }
     fence_mbar_init();
   }
@@ -140,15 +142,27 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   } else if (warp == 1) {
     if (leader) {
       // ---------------- MMA issuer (leader CTA of the pair only; whole warp waits, one elected lane issues) ----------------
+      const bool prof = (p.dbg & 1024) != 0;          // diagnostics: where the issuing warp waits
+      long long w_acc = 0, w_y = 0;
+      const long long t_begin = clock64();
+      auto wait_t = [&](uint64_t* bar, uint32_t ph, long long& acc) {
+        if (prof) {
+          const long long c0 = clock64();
+          mbar_wait(bar, ph);
+          acc += clock64() - c0;
+        } else {
+          mbar_wait(bar, ph);
+        }
+      };
       mbar_wait(&misc->x_full, 0);
       uint32_t stage = 0, phase = 0;
       for (int tc = 0; tc < n_ct; ++tc) {
         const uint32_t as = tc & 1;
-        mbar_wait(&misc->acc_empty[as], ((tc >> 1) & 1) ^ 1);
+        wait_t(&misc->acc_empty[as], ((tc >> 1) & 1) ^ 1, w_acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem + as * BN;
         for (int s = 0; s < ks; ++s) {
-          mbar_wait(&misc->y_full[stage], phase);
+          wait_t(&misc->y_full[stage], phase, w_y);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sX + s * kSlabX);
           const uint32_t b_base = smem_u32(sY + stage * kStageY);
@@ -170,12 +184,15 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      if (prof && lane == 0 && (blockIdx.x % 194) == 10)
+        printf("fwd prof cta %d: issue warp total %lld clk, waits acc_empty %lld y_full %lld (col tiles %d)\n", blockIdx.x,
+               clock64() - t_begin, w_acc, w_y, n_ct);
     }
   } else if (warp >= 4) {
     // ---------------- epilogue: online row / column softmax statistics ----------------
     const uint32_t ew = warp - 4;
     const uint32_t q = warp & 3;   // TMEM lane quarter this warp may access
-    const uint32_t h = ew >> 2;    // column half of the tile
+    const uint32_t h = ew >> 2;    // 64-column group of the tile
     const int row = tr * BM + q * 32 + lane;
     const bool row_valid = row < p.n_rows;
     const int label = p.label_offset + row;
@@ -186,17 +203,26 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     float m_run = NEG_INF, l_run = 0.f, diag = 0.f;
     float2* col_part = p.col_part + (static_cast<size_t>(pair) * p.n_slabs + tr * 4 + q) * p.n_cols;
 
+    const bool eprof = (p.dbg & 1024) != 0 && (blockIdx.x % 194) == 10 && lane == 0 && (ew == 0 || ew == 7);
+    long long e_wait = 0;
+    const long long e_begin = clock64();
     for (int tc = 0; tc < n_ct; ++tc) {
       const uint32_t as = tc & 1;
-      mbar_wait(&misc->acc_full[as], (tc >> 1) & 1);
+      if (eprof) {
+        const long long c0 = clock64();
+        mbar_wait(&misc->acc_full[as], (tc >> 1) & 1);
+        e_wait += clock64() - c0;
+      } else {
+        mbar_wait(&misc->acc_full[as], (tc >> 1) & 1);
+      }
       tc_fence_after();
 #pragma unroll 1   // measured: unrolling by 2 lowers throughput (register pressure in the 8 epilogue warps)
-      for (int chunk = 0; chunk < 4; ++chunk) {
-        const int col0 = tc * BN + h * 128 + chunk * 32;
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        const int col0 = tc * BN + h * 64 + chunk * 32;
         if (col0 >= p.n_cols) break;
         if ((p.dbg & 1) && chunk > 0) break;
         uint32_t v[32];
-        tmem_ld32(tmem + ((q * 32u) << 16) + as * BN + h * 128 + chunk * 32, v);
+        tmem_ld32(tmem + ((q * 32u) << 16) + as * BN + h * 64 + chunk * 32, v);
         tmem_ld_wait();
         if (row_valid && label >= col0 && label < col0 + 32) {
           const int idx = label - col0;
@@ -301,20 +327,29 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
     }
 
-    // merge the two column halves of each row; the Y ring is idle now (every MMA has completed)
+    if (eprof)
+      printf("fwd prof cta %d warp %u: epilogue total %lld clk, acc_full wait %lld\n", blockIdx.x, ew, clock64() - e_begin, e_wait);
+    // merge the four column groups of each row; the Y ring is idle now (every MMA has completed)
     float4* exch = reinterpret_cast<float4*>(sY);
-    if (h == 1) exch[q * 32 + lane] = make_float4(m_run, l_run, diag, 0.f);
+    if (h != 0) exch[(h - 1) * 128 + q * 32 + lane] = make_float4(m_run, l_run, diag, 0.f);
     named_bar_sync(1, kEpiThreads);
     if (h == 0 && row_valid) {
-      const float4 o = exch[q * 32 + lane];
-      const float m = fmaxf(m_run, o.x);
+      float m = m_run, dg = diag;
+      float4 o[3];
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        o[g] = exch[g * 128 + q * 32 + lane];
+        m = fmaxf(m, o[g].x);
+        dg += o[g].z;            // the label column lives in exactly one group; the others' diag stayed 0
+      }
       float l = 0.f;
       if (m_run != NEG_INF) l += l_run * ex2(m_run - m);
-      if (o.x != NEG_INF) l += o.y * ex2(o.x - m);
-      // the label column lives in exactly one half; the other half's diag stayed 0
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+        if (o[g].x != NEG_INF) l += o[g].y * ex2(o[g].x - m);
       const size_t out = static_cast<size_t>(pair) * p.n_rows + row;
       p.row_lse2[out] = m + log2f(l);
-      p.diag_raw[out] = diag + o.z;
+      p.diag_raw[out] = dg;
     }
   }
 
@@ -327,8 +362,8 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 }
 
 cudaError_t launch_infonce_fwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, bool pair, cudaStream_t stream) {
-  const int smem_bytes = kSmemX + kSmemY + kSmemMisc + 1024;
-  static_assert(kSmemX + kSmemY + kSmemMisc + 1024 <= 232448, "shared memory budget");
+  const int smem_bytes = kSmemX + kSmemY + kSmemMisc;
+  static_assert(kSmemX + kSmemY + kSmemMisc <= 232448, "shared memory budget");
   cudaError_t e;
   if (pair) {
     e = cudaFuncSetAttribute(infonce_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
