@@ -186,6 +186,25 @@ __device__ __forceinline__ void st_async_cluster_v4(uint32_t remote_addr, uint4 
                ::"r"(remote_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar)
                : "memory");
 }
+// 4 x 4 transpose of 16-byte elements inside each aligned group of four lanes: on entry lane j of a group holds
+// a[c] = element (row j, column c); on return a[i] = element (row i, column j).  Two butterfly stages (lane ^ 1, lane ^ 2),
+// 16 shuffles; all register indices are compile-time (the lane only picks between two registers).
+__device__ __forceinline__ void quad_transpose_u4(uint4 (&a)[4], uint32_t lane) {
+  const bool b0 = (lane & 1) != 0, b1 = (lane & 2) != 0;
+  auto xchg = [](uint4& keep_if_set, uint4& keep_if_clear, bool set, int mask) {
+    // a lane with `set` sends keep_if_clear and overwrites it with what arrives; a lane without sends / overwrites the other
+    uint4 x = set ? keep_if_clear : keep_if_set, y;
+    y.x = __shfl_xor_sync(0xffffffffu, x.x, mask);
+    y.y = __shfl_xor_sync(0xffffffffu, x.y, mask);
+    y.z = __shfl_xor_sync(0xffffffffu, x.z, mask);
+    y.w = __shfl_xor_sync(0xffffffffu, x.w, mask);
+    if (set) keep_if_clear = y; else keep_if_set = y;
+  };
+  xchg(a[1], a[0], b0, 1);
+  xchg(a[3], a[2], b0, 1);
+  xchg(a[2], a[0], b1, 2);
+  xchg(a[3], a[1], b1, 2);
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // arrive (release at cluster scope) on an mbarrier given by its shared::cluster address
 __device__ __forceinline__ void mbar_arrive_remote_release(uint32_t remote_bar_addr) {

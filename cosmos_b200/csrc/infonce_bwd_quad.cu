@@ -293,7 +293,7 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     const bool ds_rows = !ds_prop && p.s_col == 0.f;
     const bool fast_ok = (ds_prop || ds_rows) && !(p.dbg & 32);
     float* kbuf = misc->kappa[ew];
-    const uint32_t g_remote_row = mapa_u32(smem_u32(sG) + h * kSlabX + r_t * 128, sibling);
+    const uint32_t g_remote_slab = mapa_u32(smem_u32(sG) + h * kSlabX, sibling);
     const uint32_t gr_full_remote = mapa_u32(smem_u32(&misc->gr_full), sibling);
 
     const bool eprof = (p.dbg & 1024) != 0 && ((blockIdx.x >> 2) % 97) == 5 && lane == 0 && (ew == 0 || ew == 7);
@@ -428,16 +428,23 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       if (eprof) c2 = clock64();
       mbar_wait(&misc->gr_empty, (k & 1) ^ 1);      // write-after-read only: no data is acquired, a CTA-scope wait suffices
       if (eprof) c3 = clock64();
+      // A warp store that touches 32 different rows moves ~10 B/clk per SM through DSMEM, one whose lanes cover 64 contiguous
+      // bytes of 8 rows ~19.7 B/clk (tools/dsmem_bw.cu).  So the four lanes that own rows 4g..4g+3 first transpose their
+      // 4 x 4 blocks of 16-byte pieces (16 shuffles per block): afterwards lane j holds piece j of each of the four rows.
 #pragma unroll
       for (int chunk = 0; chunk < 2; ++chunk) {
+        uint4 a[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          a[c] = make_uint4(packed_all[chunk][c * 4 + 0], packed_all[chunk][c * 4 + 1], packed_all[chunk][c * 4 + 2],
+                            packed_all[chunk][c * 4 + 3]);
+        quad_transpose_u4(a, lane);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int jj = chunk * 4 + c;
-          if ((p.dbg & 4096) && jj > 0) continue;   // diagnostics: 1/8 of the exchange (wrong results)
-          st_async_cluster_v4(g_remote_row + ((jj ^ (r_t & 7)) << 4),
-                              make_uint4(packed_all[chunk][c * 4 + 0], packed_all[chunk][c * 4 + 1], packed_all[chunk][c * 4 + 2],
-                                         packed_all[chunk][c * 4 + 3]),
-                              gr_full_remote);
+          if ((p.dbg & 4096) && (chunk | c) != 0) continue;   // diagnostics: 1/8 of the exchange (wrong results)
+          const uint32_t rr = (static_cast<uint32_t>(r_t) & ~3u) + c;             // row of the tile this piece belongs to
+          const uint32_t pos = (chunk * 4 + (lane & 3)) ^ (rr & 7);                 // 128B swizzle of the K-major slab
+          st_async_cluster_v4(g_remote_slab + rr * 128 + (pos << 4), a[c], gr_full_remote);
         }
       }
       if (eprof) {
