@@ -16,7 +16,7 @@ struct FwdParams {
   int gx, gy, n_rows, n_cols, ks, label_offset;
   int n_row_tiles, n_col_tiles, n_slabs;  // n_slabs = 4 * n_row_tiles (32-row slabs)
   uint32_t idesc;
-  int dbg;  // diagnostics only (COSMOS_B200_DBG): 1 = skip epilogue math, 2 = skip MMA issue
+  int dbg;  // diagnostics only (COSMOS_B200_DBG): 1 = skip epilogue math, 2 = skip MMA issue, 1024 = print stall counters
   const float* scale;
   float* row_lse2;
   float* diag_raw;

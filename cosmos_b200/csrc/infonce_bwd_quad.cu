@@ -6,8 +6,10 @@
 // the two parts of the SAME 256 rows sit in one cluster and SHARE the softmax-gradient tiles:
 //   pair p (cluster ranks 2p, 2p+1; tcgen05 cta_group::2, M = 256) computes S_t and G_t only for steps t = p mod 2,
 //   keeps G_t in its own tensor memory (A operand of its GEMM2, tcgen05.mma [d],[a_tmem],b_desc) and ALSO stores it,
-//   128B-swizzled, into the shared memory of the sibling CTA of the other pair through DSMEM
-//   (st.shared::cluster), which uses it as the shared-memory A operand of ITS GEMM2 for that step.
+//   128B-swizzled, into the shared memory of the sibling CTA of the other pair through DSMEM (st.async, completion
+//   counted in bytes on an mbarrier of the destination CTA), which uses it as the shared-memory A operand of ITS GEMM2
+//   for that step.  The stores are shaped for the DSMEM path (8 rows x 64 contiguous bytes per warp store, see the
+//   lane-quad transpose in the epilogue): 2x the bandwidth of the natural lane = row shape (tools/dsmem_bw.cu).
 // Executed work per pair of steps and SM: one S tile (2048 MMA cycles) + two dX updates (2 x 1024) instead of
 // two S tiles + two updates: 1.5x fewer tensor-core cycles, half the softmax work, 2/3 of the operand traffic.
 //
@@ -15,9 +17,13 @@
 //   G1(o_0) | G1a(o_{k+1})  G2(o_k)  G1b(o_{k+1})  G2(q_k) | ...
 // so the softmax of an own step has two MMA slots (2048 cycles) of cover, every GEMM2 is followed by half a GEMM1
 // while its next operand half streams in, and the in-order tensor pipe keeps G1(o_{k+1}) from overwriting the
-// buffer G2(o_{k-1}) reads.  Barriers: *_full on the pair leader (TMA bytes of both CTAs / arrivals of both
-// epilogues), *_empty by multicast tcgen05.commit; gr_full lives on the CONSUMING pair's leader and is armed by
-// remote release-arrives of the producing pair's epilogue warps; gr_empty is committed back to the producers.
+// buffer G2(o_{k-1}) reads.  (Consuming the remote tile earlier in the round serialises the two pairs: G2(q_k) then
+// blocks the in-order issue of G1b(o_{k+1}), whose softmax produces the tile the other pair is waiting for.)
+// Barriers: *_full on the pair leader (TMA bytes of both CTAs / arrivals of both epilogues), *_empty by multicast
+// tcgen05.commit; gr_full lives in every CONSUMING CTA (complete_tx bytes of the sibling's st.async), a helper thread
+// relays it to its pair leader's gr_ready; gr_empty is committed back to the producing CTAs.
+// COSMOS_B200_DBG (diagnostics, wrong results unless noted): 512 two-slot operand ring, 1024 print stall counters
+// (results unchanged), 2048 no softmax math, 4096 one eighth of the exchange.
 #include <cstdio>
 #include "common.cuh"
 #include "infonce.h"
