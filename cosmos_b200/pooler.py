@@ -104,6 +104,46 @@ def _ln_bwd(dy, x2d, w, mean, rstd, dx, accumulate):
     return dw, db
 
 
+class _MapTokens(torch.autograd.Function):
+    """y = x @ w^T + b on the tcgen05 GEMM, x [R, K] 16-bit, w [N, K], b [N] (or None)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        w16 = w.detach().to(x.dtype)
+        y = _linear(x, w16, b.detach().float() if b is not None else None, x.dtype)
+        ctx.save_for_backward(x, w16)
+        ctx.has_bias = b is not None
+        ctx.w_dtype = w.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w16 = ctx.saved_tensors
+        g = g.contiguous()
+        dx = _dgrad(g, w16, x.dtype) if ctx.needs_input_grad[0] else None
+        dw = _wgrad(g, x).to(ctx.w_dtype) if ctx.needs_input_grad[1] else None
+        db = _colsum(g, g.shape[1]).to(ctx.w_dtype) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+def map_tokens(tokens: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], batch_size: int) -> torch.Tensor:
+    """`text_token_mapping` / `image_token_mapping` (nn.Linear, src/open_clip/model.py:285-287, 306, 331) applied ONLY to
+    the tokens the cross-attention poolers read: the first `batch_size` samples (model.py:370, 372 take `[:B]` of the mapped
+    tokens; the reference maps all 2B global crops / 8B captions first).  tokens [n, L, K] 16-bit -> [batch_size, L, N]
+    (SURVEY.md §8(f) N3).  Differentiable w.r.t. tokens, weight and bias; rows past `batch_size` get zero gradient, as in the
+    reference, because they never reach the loss."""
+    if tokens.dim() != 3 or tokens.shape[0] < batch_size or weight.dim() != 2 or weight.shape[1] != tokens.shape[2]:
+        raise RuntimeError("cosmos_b200.pooler.map_tokens: tokens [n >= batch_size, L, K], weight [N, K]")
+    if not tokens.is_cuda:
+        raise RuntimeError("cosmos_b200.pooler.map_tokens: CUDA tensors only (no CPU fallback)")
+    if tokens.dtype not in (torch.bfloat16, torch.float16):
+        raise RuntimeError("cosmos_b200.pooler.map_tokens: 16-bit tokens only (run under autocast or cast the tokens)")
+    x = tokens[:batch_size]
+    L, K = x.shape[1], x.shape[2]
+    y = _MapTokens.apply(x.reshape(batch_size * L, K), weight, bias)
+    return y.view(batch_size, L, weight.shape[0])
+
+
 class _CrossPool(torch.autograd.Function):
     """tokens [n_sets, L, C], queries [n_q, d]; query c of set s is row s * qs + c * qq.
     fuse_norm: return normalize(queries + pooled) (model.py:379-380) instead of pooled."""

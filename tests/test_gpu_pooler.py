@@ -156,3 +156,37 @@ def test_pooler_module_many_queries():
     assert cosine(q_d.grad, q_c.grad) > 0.999
     assert cosine(x_d.grad, x_c.grad) > 0.99
     assert cosine(mod.attn.in_proj_weight.grad, p32["attn.in_proj_weight"].grad) > 0.99
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,N,L,n,B,bias", [(768, 512, 196, 6, 3, True), (512, 512, 77, 8, 5, True), (512, 512, 50, 2, 2, False)])
+def test_map_tokens_matches_linear_on_the_tokens_the_pooler_reads(K, N, L, n, B, bias):
+    """`map_tokens` == `nn.Linear(tokens)[:B]` (model.py:370, 372: the pooler only ever reads the first B mapped samples),
+    forward and every gradient, on bf16-rounded values; samples past B get no gradient (None -> treated as zero)."""
+    from cosmos_b200.pooler import map_tokens
+    g = torch.Generator().manual_seed(K + L)
+    tok = torch.randn(n, L, K, generator=g)
+    w = torch.randn(N, K, generator=g) / math.sqrt(K)
+    b = torch.randn(N, generator=g) * 0.1 if bias else None
+    up = torch.randn(B, L, N, generator=g)
+
+    t32 = tok.bfloat16().float().requires_grad_(True)
+    w32 = w.bfloat16().float().requires_grad_(True)          # the GEMM consumes the 16-bit rounded weight (autocast does too)
+    b32 = b.clone().requires_grad_(True) if bias else None
+    ref = torch.nn.functional.linear(t32, w32, b32)[:B]
+    (ref * up).sum().backward()
+
+    tc = tok.bfloat16().cuda().requires_grad_(True)
+    wc = w.cuda().requires_grad_(True)                        # fp32 master weight, as in the reference model
+    bc = b.cuda().requires_grad_(True) if bias else None
+    out = map_tokens(tc, wc, bc, B)
+    assert out.shape == (B, L, N) and out.dtype == torch.bfloat16
+    (out.float() * up.cuda()).sum().backward()
+    assert relerr(out.float(), ref.detach()) < 6e-3           # bf16 output rounding
+    assert cosine(tc.grad.float(), t32.grad) > 0.9995
+    assert float(tc.grad[B:].abs().sum()) == 0.0
+    assert wc.grad.dtype == torch.float32 and cosine(wc.grad, w32.grad) > 0.9995
+    if bias:
+        assert cosine(bc.grad, b32.grad) > 0.9999
+    with pytest.raises(RuntimeError):
+        map_tokens(tok, w, b, B)                               # CPU tensors: no fallback
