@@ -135,11 +135,11 @@ class Instrument:
         from cosmos_b200 import infonce
         self.mod = infonce
         self.launches = 0
-        self.events = {"fwd": [], "bwd": []}
-        self.flops = {"fwd": [], "bwd": []}
+        self.events = {"fwd": [], "bwd": [], "colgrad": []}
+        self.flops = {"fwd": [], "bwd": [], "colgrad": []}
         self.enabled = False
-        self._fwd, self._loss, self._bwd = infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd
-        infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd = self.fwd, self.loss, self.bwd
+        self._fwd, self._loss, self._bwd, self._colgrad = infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd, infonce._k_colgrad
+        infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd, infonce._k_colgrad = self.fwd, self.loss, self.bwd, self.colgrad
 
     def _timed(self, kind, flops, fn, *a):
         if not self.enabled:
@@ -162,14 +162,18 @@ class Instrument:
         return self._loss(*a)
 
     def bwd(self, x, y, *a):
-        want_dx, want_ds = a[-2], a[-1]
+        want_dx, want_ds = a[10], a[11]          # (..., weight, upstream, want_dx, want_dscale[, g_out])
         self.launches += 1 + (1 if want_ds else 0)
         fl = 2.0 * x.shape[0] * y.shape[0] * x.shape[1] * y.shape[1] * x.shape[2] if want_dx else 0.0
         return self._timed("bwd", fl, self._bwd, x, y, *a)
 
+    def colgrad(self, g, x2d, n_c, n_cols):
+        self.launches += 1                       # the column-side gradient GEMM (G^T x) on the stored tiles
+        return self._timed("colgrad", 2.0 * x2d.shape[0] * n_c * n_cols * x2d.shape[1], self._colgrad, g, x2d, n_c, n_cols)
+
     def summary(self):
         out = {}
-        for kind in ("fwd", "bwd"):
+        for kind in ("fwd", "bwd", "colgrad"):
             ms = [a.elapsed_time(b) for a, b in self.events[kind]]
             if ms:
                 out[kind] = {"launches": len(ms), "ms_total": sum(ms), "ms_avg": sum(ms) / len(ms),

@@ -72,6 +72,8 @@ _INFONCE_SIGS = {
     "cosmos_infonce_fwd": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, vp_, i64_, i32_, vp_],
     "cosmos_infonce_loss_sums": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, i32_, i32_, vp_, vp_, i32_, vp_],
     "cosmos_infonce_bwd": [C.POINTER(InfoNceProblem), vp_, vp_, f32_, f32_, f32_, f32_, f32_, vp_, vp_, vp_, vp_, i64_, i32_, vp_],
+    "cosmos_infonce_bwd_g": [C.POINTER(InfoNceProblem), vp_, vp_, f32_, f32_, f32_, f32_, f32_, vp_, vp_, vp_, vp_, i64_, vp_, i64_,
+                             i32_, vp_],
 }
 
 

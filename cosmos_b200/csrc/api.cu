@@ -232,6 +232,13 @@ int cosmos_infonce_loss_sums(const cosmos_infonce_problem* p, const float* row_l
 int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, const float* col_lse2, float a_row, float a_col,
                        float s_row, float s_col, float weight, const float* upstream, void* dx, float* dscale,
                        void* workspace, int64_t workspace_bytes, int device, void* stream) {
+  return cosmos_infonce_bwd_g(p, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream, dx, dscale, nullptr, 0, workspace,
+                              workspace_bytes, device, stream);
+}
+
+int cosmos_infonce_bwd_g(const cosmos_infonce_problem* p, const float* row_lse2, const float* col_lse2, float a_row, float a_col,
+                         float s_row, float s_col, float weight, const float* upstream, void* dx, float* dscale, void* g_out,
+                         int64_t g_ld, void* workspace, int64_t workspace_bytes, int device, void* stream) {
   Dims d;
   int st = check_problem(p, &d);
   if (st != COSMOS_OK) return st;
@@ -239,6 +246,13 @@ int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, c
   if (dx == nullptr && dscale == nullptr) return COSMOS_OK;
   if (dx != nullptr && (reinterpret_cast<uintptr_t>(dx) & 15) != 0) return COSMOS_ERR_INVALID_ARGUMENT;
   if (workspace == nullptr || workspace_bytes < bwd_workspace(p, d)) return COSMOS_ERR_WORKSPACE;
+  if (g_out != nullptr) {
+    // only the dim-512 cluster kernel keeps the tiles in a shape that can be stored cheaply; 16-byte pieces must not straddle
+    if (d.ks != 8 || dx == nullptr || (dbg_flags() & (8 | 128))) return COSMOS_ERR_UNSUPPORTED;
+    if ((p->n_cols & 7) != 0 || (g_ld & 7) != 0 || g_ld < static_cast<int64_t>(p->gy) * p->n_cols ||
+        (reinterpret_cast<uintptr_t>(g_out) & 15) != 0)
+      return COSMOS_ERR_INVALID_ARGUMENT;
+  }
   DeviceGuard g(device);
   if (!g.ok) return COSMOS_ERR_CUDA;
   CUtensorMap tmX, tmY, tmY64;
@@ -277,6 +291,8 @@ int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, c
   bp.dscale_part = dscale != nullptr ? reinterpret_cast<float*>(workspace) : nullptr;
   bp.t_splits = 1;
   bp.dx32 = nullptr;
+  bp.g_out = g_out;
+  bp.g_ld = g_ld;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (pair && dx != nullptr && !(dbg_flags() & 64)) {
     const int clusters = p->gx * ((d.n_row_tiles + 1) / 2) * bp.n_parts;

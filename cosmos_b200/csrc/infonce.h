@@ -38,6 +38,8 @@ struct BwdParams {
   float* dscale_part;     // [items] partial sums of <dscale-mix, raw logits>, may be null
   int t_splits;           // pair kernel: the column sweep of one row block is split over this many clusters
   float* dx32;            // fp32 [gx][n_rows][dim] accumulation buffer (zeroed), used when t_splits > 1
+  void* g_out;            // quad kernel: optional copy of every G tile, [gx * n_rows][g_ld] stack dtype, column j * n_cols + c
+  long long g_ld;         // row stride of g_out in elements (multiple of 8)
 };
 
 cudaError_t launch_infonce_fwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, bool pair, cudaStream_t stream);

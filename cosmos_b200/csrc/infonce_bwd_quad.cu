@@ -451,6 +451,16 @@ infonce_bwd_quad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           const uint32_t rr = (static_cast<uint32_t>(r_t) & ~3u) + c;             // row of the tile this piece belongs to
           const uint32_t pos = (chunk * 4 + (lane & 3)) ^ (rr & 7);                 // 128B swizzle of the K-major slab
           st_async_cluster_v4(g_remote_slab + rr * 128 + (pos << 4), a[c], gr_full_remote);
+          if (p.g_out != nullptr) {
+            // optional copy of the tile for the column-side gradient GEMM (api.cu: cosmos_infonce_bwd_g); the transposed
+            // layout also makes these 8 rows x 64 contiguous bytes per warp store
+            const int grow = tr * BM + static_cast<int>(rr);
+            const int gcol = tc * BN + static_cast<int>(h) * 64 + (chunk * 4 + static_cast<int>(lane & 3)) * 8;
+            if (tile_valid && grow < p.n_rows && gcol < p.n_cols)
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.g_out) +
+                                        (static_cast<size_t>(i) * p.n_rows + grow) * static_cast<size_t>(p.g_ld) +
+                                        static_cast<size_t>(j) * p.n_cols + gcol) = a[c];
+          }
         }
       }
       if (eprof) {

@@ -26,6 +26,8 @@ P = number of pairs, R/C = row/column softmax, I = positives:
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import math
 from dataclasses import dataclass
@@ -103,19 +105,35 @@ def _k_loss_sums(x, y, label_offset, scale, row_lse2, diag_raw, col_lse2):
     return out
 
 
-def _k_bwd(x, y, label_offset, scale, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream, want_dx, want_dscale):
-    """-> dx [gx, b, D] in x.dtype (or None), dscale fp32 [1] (or None)."""
+def _k_bwd(x, y, label_offset, scale, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream, want_dx, want_dscale,
+           g_out=None):
+    """-> dx [gx, b, D] in x.dtype (or None), dscale fp32 [1] (or None).
+    g_out [gx * b, >= gy * N] (x.dtype): also receives G itself, block (i, j) at rows i * b, columns j * N."""
     dev = x.device
     prob = _problem(x, y, label_offset, scale)
     dx = torch.empty_like(x) if want_dx else None
     dscale = torch.empty(1, dtype=torch.float32, device=dev) if want_dscale else None
     ws = _workspace(prob, dev)
-    st = _lib.lib().cosmos_infonce_bwd(C.byref(prob), row_lse2.data_ptr(), col_lse2.data_ptr(), a_row, a_col, s_row, s_col,
-                                       weight, upstream.data_ptr(), dx.data_ptr() if want_dx else None,
-                                       dscale.data_ptr() if want_dscale else None, ws.data_ptr(), ws.numel(), dev.index,
-                                       torch.cuda.current_stream(dev).cuda_stream)
+    common = (C.byref(prob), row_lse2.data_ptr(), col_lse2.data_ptr(), a_row, a_col, s_row, s_col, weight, upstream.data_ptr(),
+              dx.data_ptr() if want_dx else None, dscale.data_ptr() if want_dscale else None)
+    tail = (ws.data_ptr(), ws.numel(), dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    if g_out is None:
+        st = _lib.lib().cosmos_infonce_bwd(*common, *tail)
+    else:
+        st = _lib.lib().cosmos_infonce_bwd_g(*common, g_out.data_ptr(), g_out.stride(0), *tail)
     _lib.check(st, "infonce_bwd")
     return dx, dscale
+
+
+def _k_colgrad(g: torch.Tensor, x2d: torch.Tensor, n_c: int, n_cols: int) -> torch.Tensor:
+    """sum over rows of G^T x: g [R, >= n_c * n_cols] (block j at columns j * n_cols), x2d [R, D] -> fp32 [n_c, n_cols, D].
+    A tcgen05 GEMM with both operands read in their stored layout (contraction over the rows, like a weight gradient)."""
+    from .pooler import _gemm
+    R, D = x2d.shape
+    out = torch.empty(n_c, n_cols, D, dtype=torch.float32, device=g.device)
+    # the column blocks are adjacent in g, so [n_c * n_cols, D] = g^T x2d is ONE GEMM (more tiles per wave than n_c small ones)
+    _gemm(g, x2d, out.view(n_c * n_cols, D), n_c * n_cols, D, R, g.stride(0), x2d.stride(0), False, False)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -227,6 +245,45 @@ def _swap_pairs(t: torch.Tensor, n_r: int, n_c: int) -> torch.Tensor:
 # autograd node
 # ------------------------------------------------------------------------------------------------
 
+_G_STORE_MAX_BYTES = int(float(os.environ.get("COSMOS_B200_GSTORE_MAX_GB", "48")) * (1 << 30))
+# below ~1 GB of tiles the second sweep is short and the extra launches cost what they save (measured at N = 4096 on one
+# GPU: 4.67 ms with the GEMM route, 4.54 ms with the second sweep; at N = 32768: 265 vs 283 ms)
+_G_STORE_MIN_BYTES = int(float(os.environ.get("COSMOS_B200_GSTORE_MIN_GB", "1")) * (1 << 30))
+
+
+def _g_store_ok(x_r: torch.Tensor, y_c: torch.Tensor) -> bool:
+    """Can the row pass keep its G tiles for the column-side GEMM?  dim 512 (the cluster kernel), 16-byte pieces that do
+    not straddle the last column, and a buffer that fits comfortably (n_r * b x n_c * N 16-bit values)."""
+    n_r, b, dim = x_r.shape
+    n_c, n_all, _ = y_c.shape
+    if dim != 512 or (n_all & 7) != 0 or _G_STORE_MAX_BYTES <= 0:
+        return False
+    nbytes = n_r * b * n_c * n_all * x_r.element_size()
+    if nbytes > _G_STORE_MAX_BYTES or nbytes < _G_STORE_MIN_BYTES:
+        return False
+    if x_r.is_cuda:
+        free, _total = torch.cuda.mem_get_info(x_r.device)
+        free += torch.cuda.memory_reserved(x_r.device) - torch.cuda.memory_allocated(x_r.device)   # cached blocks are reusable
+        if 2 * nbytes > free:
+            return False
+    return True
+
+
+def _reduce_scatter_rows(d_all: torch.Tensor, comm: Comm, b: int) -> torch.Tensor:
+    """[n_c, W * b, D] per-rank partial sums -> [n_c, b, D]: the sum over ranks of this rank's rows."""
+    if not comm.distributed:
+        return d_all
+    W, rank = comm.world_size, comm.rank
+    n_c, _, D = d_all.shape
+    if dist.get_backend(comm.group) == "nccl":
+        send = d_all.view(n_c, W, b, D).transpose(0, 1).contiguous()          # rank-major chunks
+        out = torch.empty(n_c, b, D, dtype=d_all.dtype, device=d_all.device)
+        dist.reduce_scatter_tensor(out, send, op=dist.ReduceOp.SUM, group=comm.group)
+        return out
+    dist.all_reduce(d_all, op=dist.ReduceOp.SUM, group=comm.group)           # backends without reduce-scatter (gloo, CPU tests)
+    return d_all[:, rank * b:(rank + 1) * b].contiguous()
+
+
 class _PairsInfoNCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, scale: torch.Tensor, comm: Comm, n_r: int, prefetch, *feats: torch.Tensor):
@@ -292,10 +349,21 @@ class _PairsInfoNCE(torch.autograd.Function):
             s_mix = (1.0 / boost, 1.0 / boost)
 
         d_rows = d_scale = d_cols = None
+        g_tiles = None
+        if need_rows and need_cols and not local and _g_store_ok(x_r, y_c):
+            # non-local modes weigh the row and the column softmax equally, so the gradient matrix of the transposed block is
+            # G^T: keep G from the row pass (bf16, the operand precision of both passes anyway) and turn the column side
+            # into one GEMM instead of a second sweep that recomputes every logit
+            g_tiles = torch.empty(n_r * b, n_c * N, dtype=x_r.dtype, device=x_r.device)
         if need_rows or need_scale:
             d_rows, d_scale = _k_bwd(x_r, y_c, off, scale_f, row_lse2, col_lse2, a[0], a[1], s_mix[0], s_mix[1], weight, up,
-                                     need_rows, need_scale)
-        if need_cols or (local and need_scale):
+                                     need_rows, need_scale, g_tiles)
+        if g_tiles is not None:
+            d_all = _k_colgrad(g_tiles, x_r.reshape(n_r * b, x_r.shape[2]), n_c, N)        # [n_c, N, D] fp32, this rank's rows
+            del g_tiles
+            d_loc = _reduce_scatter_rows(d_all, comm, b)                                     # [n_c, b, D], all ranks' rows
+            d_cols = (d_loc * (up * scale_f.reshape(1) * weight)).to(x_c.dtype)
+        elif need_cols or (local and need_scale):
             # transposed block: rows = local column-side tensors, columns = all rows of the row side
             y_r = ctx.pre_r.get() if ctx.pre_r is not None else gather_stack(x_r, comm)     # [n_r, N, D]
             row_lse2_all = _gather_rows(row_lse2, comm)                     # [P, N]

@@ -162,13 +162,14 @@ class COSMOSLoss(nn.Module):
         comm = self.clip_loss._comm()
         scale = distill_logit_scale if distill_logit_scale is not None else logit_scale
         # Start every all-gather now (NCCL stream): the teacher stack is needed first, the student image stack by the
-        # CLIP forward, the student text stack only by the CLIP backward - all but the first hide behind kernels.
+        # CLIP forward, the student text stack only by the CLIP backward of the local-loss modes - all but the first hide
+        # behind kernels.
         images2, texts = list(s_image_features[:2]), list(s_text_features)
         prefetch = Prefetch()
         prefetch.start(teacher, comm)
         prefetch.start(images2, comm)
-        if any(t.requires_grad for t in images2):
-            prefetch.start(texts, comm)
+        if any(t.requires_grad for t in images2) and comm.local_loss:
+            prefetch.start(texts, comm)      # only the local-loss modes sweep the transposed block (infonce.py backward)
         # mean over {img-x, txt-x} x {t_img, t_txt} of ClipLoss(n x 2 pairs)  ==  mean of the two n x 4 groups; with equally
         # long lists (the COSMOS recipes: 8 + 8) that is the plain mean over all 16 x 4 pairs -> ONE grouped launch, which
         # fills whole waves of SM clusters where two half-sized launches would each leave a partial wave.

@@ -125,6 +125,17 @@ int cosmos_infonce_bwd(const cosmos_infonce_problem* p, const float* row_lse2, c
                        float a_row, float a_col, float s_row, float s_col, float weight, const float* upstream,
                        void* dx, float* dscale, void* workspace, int64_t workspace_bytes, int device, void* stream);
 
+/* Same, and additionally stores G itself (stack dtype, without the upstream * weight * scale factor):
+ *     g_out[(i * n_rows + r) * g_ld + j * n_cols + c] = G_ij[r][c]
+ * so that the gradient of the COLUMN side, dy_j = (*upstream) * weight * scale * sum_i G_ij^T x_i (loss.py:103-119: both
+ * logits_per_image and logits_per_text back-propagate into both feature lists), becomes one plain GEMM per column tensor
+ * (cosmos_gemm with a_kmajor = b_kmajor = 0) instead of a second sweep that recomputes every logit.  dim 512 and dx != NULL
+ * only (COSMOS_ERR_UNSUPPORTED otherwise); n_cols and g_ld multiples of 8, g_ld >= gy * n_cols, g_out 16-byte aligned. */
+int cosmos_infonce_bwd_g(const cosmos_infonce_problem* p, const float* row_lse2, const float* col_lse2,
+                         float a_row, float a_col, float s_row, float s_col, float weight, const float* upstream,
+                         void* dx, float* dscale, void* g_out, int64_t g_ld, void* workspace, int64_t workspace_bytes,
+                         int device, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Cross-attention pooler building blocks
  *   (transformer.py:210-230 AttentionalCrossPooler.forward = LayerNorm x2 + nn.MultiheadAttention with one

@@ -36,7 +36,8 @@ def emu_loss_sums(x, y, label_offset, scale, row_lse2, diag_raw, col_lse2):
     return torch.stack([rs, cs], dim=1).float()
 
 
-def emu_bwd(x, y, label_offset, scale, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream, want_dx, want_dscale):
+def emu_bwd(x, y, label_offset, scale, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream, want_dx, want_dscale,
+            g_out=None):
     gx, b, D = x.shape
     gy, N, _ = y.shape
     raw = _raw(x, y)
@@ -47,6 +48,8 @@ def emu_bwd(x, y, label_offset, scale, row_lse2, col_lse2, a_row, a_col, s_row, 
     eye[torch.arange(b), label_offset + torch.arange(b)] = 1
     G = a_row * R + a_col * Cm - (a_row + a_col) * eye
     Gs = s_row * R + s_col * Cm - (s_row + s_col) * eye
+    if g_out is not None:        # cosmos_infonce_bwd_g: block (i, j) of G at rows i * b, columns j * N, in the stack dtype
+        g_out[:, :gy * N] = G.permute(0, 2, 1, 3).reshape(gx * b, gy * N).to(g_out.dtype)
     up = float(upstream)
     dx = None
     if want_dx:
@@ -58,6 +61,12 @@ def emu_bwd(x, y, label_offset, scale, row_lse2, col_lse2, a_row, a_col, s_row, 
     return dx, dscale
 
 
+def emu_colgrad(g, x2d, n_c, n_cols):
+    """infonce._k_colgrad: fp32 [n_c, n_cols, D] = sum over rows of G^T x."""
+    D = x2d.shape[1]
+    return (g[:, :n_c * n_cols].double().T @ x2d.double()).reshape(n_c, n_cols, D).float()
+
+
 def install(monkeypatch=None):
     """Patch cosmos_b200.infonce to run on CPU tensors through the emulation."""
     from cosmos_b200 import _lib, infonce
@@ -65,9 +74,11 @@ def install(monkeypatch=None):
         monkeypatch.setattr(infonce, "_k_fwd", emu_fwd)
         monkeypatch.setattr(infonce, "_k_loss_sums", emu_loss_sums)
         monkeypatch.setattr(infonce, "_k_bwd", emu_bwd)
+        monkeypatch.setattr(infonce, "_k_colgrad", emu_colgrad)
         monkeypatch.setattr(_lib, "require_cuda", lambda t, what: None)
         monkeypatch.setattr(infonce, "compute_dtype", lambda dt: dt)
     else:
         infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd = emu_fwd, emu_loss_sums, emu_bwd
+        infonce._k_colgrad = emu_colgrad
         _lib.require_cuda = lambda t, what: None
         infonce.compute_dtype = lambda dt: dt

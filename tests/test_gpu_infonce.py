@@ -148,20 +148,33 @@ def test_cosmos_loss_golden_small(golden_dir, dtype):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("batch,dim,scale", [(256, 512, 14.2857), (384, 512, 100.0), (1000, 256, 30.0)])
-def test_cosmos_loss_vs_oracle(batch, dim, scale):
-    """BASELINE config 1 shape (batch 256, dim 512, 2 global + 6 local crops) and two more."""
+@pytest.mark.parametrize("batch,dim,scale,keep_g", [(256, 512, 14.2857, False), (384, 512, 100.0, False), (1000, 256, 30.0, False),
+                                                    (256, 512, 14.2857, True), (392, 512, 100.0, True)])
+def test_cosmos_loss_vs_oracle(batch, dim, scale, keep_g, monkeypatch):
+    """BASELINE config 1 shape (batch 256, dim 512, 2 global + 6 local crops) and two more.  keep_g: the image-side CLIP
+    gradient through the stored G tiles + GEMM (cosmos_infonce_bwd_g), the route large batches take, forced at this size."""
+    if keep_g:
+        from cosmos_b200 import infonce
+        monkeypatch.setattr(infonce, "_G_STORE_MIN_BYTES", 0)
+        calls = []
+        real = infonce._k_colgrad
+        monkeypatch.setattr(infonce, "_k_colgrad", lambda *a: calls.append(1) or real(*a))
     inp = O.make_features(batch, dim, seed=1234)
     up = (1.0, 1.0)
     ours = _run_ours(inp, scale, scale, up, torch.bfloat16)
     ref = _run_oracle(inp, scale, scale, up, torch.bfloat16)
     _compare(ours, ref, up)
+    if keep_g:
+        assert calls, "the stored-G route was not taken"
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("batch,scale", [(200, 14.2857), (130, 60.0)])
-def test_cosmos_loss_fp16_dim512(batch, scale):
-    """fp16 features (the reference's `--precision amp`) through the dim-512 cluster kernels, ragged batch."""
+def test_cosmos_loss_fp16_dim512(batch, scale, monkeypatch):
+    """fp16 features (the reference's `--precision amp`) through the dim-512 cluster kernels, ragged batch; batch 200 also
+    takes the stored-G route for the image-side CLIP gradient (130 is not a multiple of 8 and falls back to the second sweep)."""
+    from cosmos_b200 import infonce
+    monkeypatch.setattr(infonce, "_G_STORE_MIN_BYTES", 0)
     inp = O.make_features(batch, 512, seed=77)
     up = (65536.0, 65536.0)          # GradScaler's initial scale
     ours = _run_ours(inp, scale, scale * 0.7, up, torch.float16)

@@ -12,17 +12,20 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, tmpdir):
+def _worker(rank, world, port, tmpdir, keep_g=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        from cosmos_b200 import COSMOSLoss
+        from cosmos_b200 import COSMOSLoss, infonce
         from oracle import cosmos_oracle as O
         # (b, D, n_img, n_txt): dim 128 runs the CTA-pair backward, dim 512 the 4-CTA-cluster backward
         configs = ((160, 128, 3, 4), (192, 512, 4, 4))
+        if keep_g:      # non-local modes at dim 512: image-side CLIP gradient = NCCL reduce-scatter of G^T x over the stored tiles
+            infonce._G_STORE_MIN_BYTES = 0
+            configs = ((192, 512, 4, 4),)
         cases = [(cfg, ll, gwg) for cfg in configs for ll, gwg in ((False, False), (False, True), (True, True), (True, False))]
         for (b, D, n_img, n_txt), ll, gwg in cases:
             shards_cpu = [O.make_features(b, D, seed=900 + r, n_img=n_img, n_txt=n_txt) for r in range(world)]
@@ -67,12 +70,13 @@ def _worker(rank, world, port, tmpdir):
 
 
 @pytest.mark.gpu
-def test_two_rank_nccl_all_modes():
+@pytest.mark.parametrize("keep_g,port", [(False, 29731), (True, 29732)])
+def test_two_rank_nccl_all_modes(keep_g, port):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
     with tempfile.TemporaryDirectory() as tmpdir:
-        procs = [ctx.Process(target=_worker, args=(r, 2, 29731, tmpdir)) for r in range(2)]
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, tmpdir, keep_g)) for r in range(2)]
         for p in procs:
             p.start()
         for p in procs:

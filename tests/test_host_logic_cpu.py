@@ -19,10 +19,14 @@ def _close(a, b, rtol=2e-4, atol=2e-6):
     torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
 
 
-def test_cosmos_api_single_process(monkeypatch):
+@pytest.mark.parametrize("keep_g", [False, True])
+def test_cosmos_api_single_process(monkeypatch, keep_g):
     from tests import emulation
     emulation.install(monkeypatch)
-    from cosmos_b200 import COSMOSLoss
+    from cosmos_b200 import COSMOSLoss, infonce
+    used = []
+    if keep_g:      # column-side gradient through the stored G tiles + GEMM (the dim-512 route of the GPU path)
+        monkeypatch.setattr(infonce, "_g_store_ok", lambda x_r, y_c: used.append(1) or True)
     for case in torch.load(os.path.join(GOLDEN, "cosmos_w1_small.pt"), weights_only=False):
         leaf = {k: [t.clone().requires_grad_(True) for t in v] for k, v in case["inputs"].items()}
         ls = torch.tensor(case["logit_scale"], requires_grad=True)
@@ -47,6 +51,7 @@ def test_cosmos_api_single_process(monkeypatch):
         total = COSMOSLoss()(leaf["s_image"], leaf["s_text"], ls, leaf["t_image"], leaf["t_text"], False, ds,
                              leaf["s_img_x"], leaf["s_txt_x"])
         _close(total.detach(), case["out"]["distill_loss"] + case["out"]["clip_loss"], rtol=2e-5)
+    assert bool(used) == keep_g
 
 
 def test_stack_views_zero_copy():
@@ -81,7 +86,7 @@ def test_product_rejects_cpu_tensors():
         ema_update_([a], [a.clone()], 0.9)
 
 
-def _rank_worker(rank, world, port, fname, tmpdir):
+def _rank_worker(rank, world, port, fname, tmpdir, keep_g=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -89,7 +94,9 @@ def _rank_worker(rank, world, port, fname, tmpdir):
     try:
         from tests import emulation
         emulation.install()
-        from cosmos_b200 import ClipLoss, COSMOSLoss
+        from cosmos_b200 import ClipLoss, COSMOSLoss, infonce
+        if keep_g:      # non-local modes: column-side gradient = reduce-scatter of G^T x (stored G tiles) instead of a second sweep
+            infonce._g_store_ok = lambda x_r, y_c: True
         rec = torch.load(os.path.join(GOLDEN, fname), weights_only=False)
         for name, spec in rec["payload"].items():
             ref = rec["results"][rank][name]
@@ -132,11 +139,12 @@ def _rank_worker(rank, world, port, fname, tmpdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,fname,port", [(2, "multirank_w2.pt", 29721), (4, "multirank_w4.pt", 29722)])
-def test_multirank_modes_gloo(world, fname, port):
+@pytest.mark.parametrize("world,fname,port,keep_g", [(2, "multirank_w2.pt", 29721, False), (4, "multirank_w4.pt", 29722, False),
+                                                     (2, "multirank_w2.pt", 29723, True), (4, "multirank_w4.pt", 29724, True)])
+def test_multirank_modes_gloo(world, fname, port, keep_g):
     ctx = mp.get_context("spawn")
     with tempfile.TemporaryDirectory() as tmpdir:
-        procs = [ctx.Process(target=_rank_worker, args=(r, world, port, fname, tmpdir)) for r in range(world)]
+        procs = [ctx.Process(target=_rank_worker, args=(r, world, port, fname, tmpdir, keep_g)) for r in range(world)]
         for p in procs:
             p.start()
         for p in procs:
