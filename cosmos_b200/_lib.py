@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libcosmos_b200.so")
 
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 ABI_VERSION = 1
+CLAMP_MAX = 8   # COSMOS_CLAMP_MAX
 
 _DEBUG_SYNC = os.environ.get("COSMOS_B200_DEBUG_SYNC", "0") == "1"
 _lock = threading.Lock()
@@ -42,6 +43,8 @@ def _declare(lib):
     lib.cosmos_ema_table_fill.argtypes = [i64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(i64), i32, vp]
     lib.cosmos_ema_apply.restype = i32
     lib.cosmos_ema_apply.argtypes = [vp, i64, f64, i32, i32, vp]
+    lib.cosmos_clamp_scalars.restype = i32
+    lib.cosmos_clamp_scalars.argtypes = [C.POINTER(C.c_uint64), i32, f64, f64, i32, i32, vp]
     for name, args in _POOL_SIGS.items():
         fn = getattr(lib, name)
         fn.restype = i32

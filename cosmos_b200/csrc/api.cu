@@ -115,6 +115,22 @@ int cosmos_ema_apply(const cosmos_ema_chunk* table_dev, int64_t n_entries, doubl
   return cu_fail(e) ? COSMOS_ERR_CUDA : COSMOS_OK;
 }
 
+int cosmos_clamp_scalars(const uint64_t* ptrs, int32_t n, double lo, double hi, int dtype, int device, void* stream) {
+  if (n < 0 || n > COSMOS_CLAMP_MAX || (n > 0 && ptrs == nullptr) || !(lo <= hi)) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (dtype != COSMOS_DTYPE_F32 && dtype != COSMOS_DTYPE_BF16 && dtype != COSMOS_DTYPE_F16) return COSMOS_ERR_UNSUPPORTED;
+  cb::ClampTable t = {};
+  t.n = n;
+  const uintptr_t align = dtype == COSMOS_DTYPE_F32 ? 3 : 1;
+  for (int i = 0; i < n; ++i) {
+    if (ptrs[i] == 0 || (ptrs[i] & align) != 0) return COSMOS_ERR_INVALID_ARGUMENT;
+    t.ptr[i] = ptrs[i];
+  }
+  if (n == 0) return COSMOS_OK;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  return cu_fail(cb::launch_clamp_scalars(t, lo, hi, dtype, static_cast<cudaStream_t>(stream))) ? COSMOS_ERR_CUDA : COSMOS_OK;
+}
+
 }  // extern "C"
 
 namespace {

@@ -117,6 +117,27 @@ ema_16_kernel(const EmaChunk* __restrict__ table, int n_chunks, float m, float o
   }
 }
 
+// Clamp of the logit-scale scalars (src/training/train.py:237-243: four 1-element clamp_ launches) in one launch.
+// torch.clamp_ semantics: min(max(x, lo), hi) with the bounds rounded to fp32, NaN kept.
+template <class T>
+__global__ void clamp_scalars_kernel(ClampTable t, float lo, float hi) {
+  const int i = threadIdx.x;
+  if (i >= t.n) return;
+  T* ptr = reinterpret_cast<T*>(t.ptr[i]);
+  const float x = static_cast<float>(*ptr);
+  if (x != x) return;
+  *ptr = static_cast<T>(fminf(fmaxf(x, lo), hi));   // the expression ATen's CUDA clamp evaluates (in fp32 for 16-bit types)
+}
+
+cudaError_t launch_clamp_scalars(const ClampTable& t, double lo, double hi, int dtype, cudaStream_t stream) {
+  if (t.n <= 0) return cudaSuccess;
+  const float flo = static_cast<float>(lo), fhi = static_cast<float>(hi);
+  if (dtype == COSMOS_DTYPE_F32) clamp_scalars_kernel<float><<<1, 32, 0, stream>>>(t, flo, fhi);
+  else if (dtype == COSMOS_DTYPE_BF16) clamp_scalars_kernel<__nv_bfloat16><<<1, 32, 0, stream>>>(t, flo, fhi);
+  else clamp_scalars_kernel<__half><<<1, 32, 0, stream>>>(t, flo, fhi);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_ema(const EmaChunk* table, int n_chunks, double momentum, int dtype, int sm_count, cudaStream_t stream) {
   if (n_chunks <= 0) return cudaSuccess;
   const float m = static_cast<float>(momentum);

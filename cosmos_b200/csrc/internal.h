@@ -12,6 +12,12 @@ typedef cosmos_ema_chunk EmaChunk;
 
 cudaError_t launch_ema(const EmaChunk* table, int n_chunks, double momentum, int dtype, int sm_count, cudaStream_t stream);
 
+struct ClampTable {
+  uint64_t ptr[COSMOS_CLAMP_MAX];
+  int n;
+};
+cudaError_t launch_clamp_scalars(const ClampTable& t, double lo, double hi, int dtype, cudaStream_t stream);
+
 
 // ---- generic tcgen05 GEMM (gemm.cu) ----
 struct GemmParams {

@@ -14,6 +14,7 @@ SURVEY.md §5) and runs after backward / before optimizer.step exactly where the
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Iterable, List, Sequence, Union
 
 import torch
@@ -102,3 +103,46 @@ def ema_update_(student: Union[torch.nn.Module, Iterable[torch.Tensor]],
         plan, calls = EmaPlan(sp, tp), 0
     _plans[ident] = (plan, calls + 1)
     plan.apply(momentum)
+
+
+def _unwrap(model):
+    """DistributedDataParallel / DataParallel wrappers keep the model in `.module` (train.py: unwrap_model)."""
+    return model.module if hasattr(model, "module") else model
+
+
+@torch.no_grad()
+def clamp_logit_scales_(student, teacher=None, lo: float = 0.0, hi: float = math.log(100)) -> None:
+    """Drop-in for the clamps at the end of the reference's training step (src/training/train.py:237-243):
+
+        unwrap_model(student).logit_scale.clamp_(0, math.log(100))
+        unwrap_model(teacher).logit_scale.clamp_(0, math.log(100))
+        # and, when the model has one, the same for distill_logit_scale
+
+    One launch for all (up to four) scalars instead of four; same results bit for bit (torch.clamp_ semantics).
+    `student` / `teacher` may be modules (wrapped or not) or iterables of 1-element tensors."""
+    scalars: List[torch.Tensor] = []
+    for m in (student, teacher):
+        if m is None:
+            continue
+        if isinstance(m, torch.nn.Module):
+            m = _unwrap(m)
+            for name in ("logit_scale", "distill_logit_scale"):
+                t = getattr(m, name, None)
+                if isinstance(t, torch.Tensor):
+                    scalars.append(t)
+        else:
+            scalars.extend(m)
+    groups = {}
+    for t in scalars:
+        _lib.require_cuda(t, "logit scale")
+        if t.numel() != 1:
+            raise RuntimeError(f"cosmos_b200.ema: clamp_logit_scales_ expects 1-element tensors, got {tuple(t.shape)}")
+        groups.setdefault((t.dtype, t.device.index), []).append(t)
+    lib = _lib.lib()
+    for (dtype, dev), ts in groups.items():
+        code = _lib.torch_dtype_code(dtype)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        for first in range(0, len(ts), _lib.CLAMP_MAX):
+            part = ts[first:first + _lib.CLAMP_MAX]
+            ptrs = (C.c_uint64 * len(part))(*[t.data_ptr() for t in part])
+            _lib.check(lib.cosmos_clamp_scalars(ptrs, len(part), float(lo), float(hi), code, dev, stream), "clamp_scalars")

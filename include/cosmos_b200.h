@@ -11,6 +11,7 @@
  *   cosmos_infonce_*   src/open_clip/loss.py:103-142  ClipLoss.get_logits + F.cross_entropy x2 per pair,
  *                      as composed by COSMOSLoss.forward src/open_clip/loss.py:176-207
  *   cosmos_ema_*       src/training/train.py:195-203  per-parameter mul_/add_ loop
+ *   cosmos_clamp_scalars  src/training/train.py:237-243  logit-scale clamps of student and teacher
  *   cosmos_xpool_*     src/open_clip/transformer.py:210-230 AttentionalCrossPooler.forward and its call
  *                      site src/open_clip/model.py:366-387
  * The reference has no FFI of its own (pure PyTorch); INTEGRATION.md shows the ctypes binding and
@@ -72,6 +73,13 @@ int cosmos_ema_table_fill(int64_t n_tensors, const uint64_t* teacher_ptrs, const
 /* One EMA step over a device-resident table.  `momentum` is the Python double of the reference. */
 int cosmos_ema_apply(const cosmos_ema_chunk* table_dev, int64_t n_entries, double momentum, int dtype,
                      int device, void* stream);
+
+/* Logit-scale clamp (train.py:237-243: logit_scale.clamp_(0, ln 100) on student and teacher, and the same for
+ * distill_logit_scale - four 1-element launches in the reference).  `ptrs` is a HOST array of n <= COSMOS_CLAMP_MAX
+ * device addresses of scalars of type `dtype`; all are clamped in place to [lo, hi] by one launch, with
+ * torch.clamp_ semantics (bounds rounded to fp32, NaN kept). */
+#define COSMOS_CLAMP_MAX 8
+int cosmos_clamp_scalars(const uint64_t* ptrs, int32_t n, double lo, double hi, int dtype, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Block-structured InfoNCE  (loss.py:103-142 for every (row tensor i, column tensor j) pair at once)

@@ -77,3 +77,40 @@ def test_ema_module_api():
         ema_update_(student, teacher, 0.99)
     for a, b in zip(teacher.parameters(), ref.parameters()):
         assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_clamp_logit_scales_bit_exact(dtype):
+    """The clamps of src/training/train.py:237-243 in one launch: bit-identical to four clamp_ calls, NaN kept."""
+    import math
+    from cosmos_b200 import clamp_logit_scales_
+
+    class M(torch.nn.Module):
+        def __init__(self, a, b):
+            super().__init__()
+            self.logit_scale = torch.nn.Parameter(torch.tensor(a, dtype=dtype))
+            self.distill_logit_scale = torch.nn.Parameter(torch.tensor(b, dtype=dtype))
+
+    class Wrapped(torch.nn.Module):      # stands in for DistributedDataParallel (train.py: unwrap_model)
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+
+    for vals in ((4.7, -0.3, 2.6593, 4.60517), (float("nan"), 100.0, 0.0, -0.0), (math.log(100), 4.6051702, 4.605171, 1e-30)):
+        student, teacher = M(vals[0], vals[1]).cuda(), M(vals[2], vals[3]).cuda()
+        want = [p.detach().clone() for m in (student, teacher) for p in (m.logit_scale, m.distill_logit_scale)]
+        for w in want:
+            w.clamp_(0, math.log(100))
+        clamp_logit_scales_(Wrapped(student), teacher)
+        torch.cuda.synchronize()
+        got = [p.detach() for m in (student, teacher) for p in (m.logit_scale, m.distill_logit_scale)]
+        for g, w in zip(got, want):
+            assert torch.equal(g.view(torch.int16 if dtype != torch.float32 else torch.int32),
+                               w.view(torch.int16 if dtype != torch.float32 else torch.int32)), (vals, g, w)
+    # plain tensors, more than one launch's worth, model without a distill scale
+    ts = [torch.tensor(float(i) - 3.0, device="cuda") for i in range(11)]
+    clamp_logit_scales_(ts, None, 0.0, 4.0)
+    assert [float(t) for t in ts] == [min(max(float(i) - 3.0, 0.0), 4.0) for i in range(11)]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        clamp_logit_scales_([torch.tensor(1.0)])

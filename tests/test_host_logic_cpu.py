@@ -188,5 +188,12 @@ def test_c_abi_exports_every_declared_symbol():
     numel = (ctypes.c_int64 * 3)(8192, 1, 8193)
     assert lib.cosmos_ema_table_entries(3, numel) == 1 + 1 + 2
     assert lib.cosmos_ema_table_entries(-1, numel) == -1
+    # clamp launch: argument validation happens before any device call
+    two = (ctypes.c_uint64 * 2)(256, 258)
+    assert lib.cosmos_clamp_scalars(two, 9, 0.0, 1.0, 0, 0, None) == 1          # more than COSMOS_CLAMP_MAX
+    assert lib.cosmos_clamp_scalars(two, 2, 0.0, 1.0, 0, 0, None) == 1          # fp32 scalar at a 2-byte-aligned address
+    assert lib.cosmos_clamp_scalars(two, 2, 1.0, 0.0, 1, 0, None) == 1          # lo > hi
+    assert lib.cosmos_clamp_scalars(two, 2, 0.0, 1.0, 7, 0, None) == 2          # unknown dtype
+    assert lib.cosmos_clamp_scalars(None, 0, 0.0, 1.0, 0, 0, None) == 0         # nothing to do
     bad = _lib.InfoNceProblem(x=16, y=16, gx=1, gy=1, n_rows=8, n_cols=8, dim=100, label_offset=0, dtype=1, reserved=0, scale=4)
     assert lib.cosmos_infonce_workspace_bytes(ctypes.byref(bad)) == -1          # dim not a multiple of 64
