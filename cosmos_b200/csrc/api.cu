@@ -457,4 +457,18 @@ int cosmos_colsum(const void* src, int32_t dtype, float* dst, int64_t rows, int3
   return cu_fail(cb::launch_colsum(src, dtype, dst, rows, n, ld, static_cast<cudaStream_t>(stream))) ? COSMOS_ERR_CUDA : COSMOS_OK;
 }
 
+int cosmos_retrieval_ranks(const void* q, const void* gal, int dtype, int32_t M, int32_t N, int32_t D, int64_t ldq, int64_t ldg,
+                           const int32_t* gt_offsets, const int32_t* gt_index, float* best, int32_t* ranks, int device,
+                           void* stream) {
+  if (!q || !gal || !best || !ranks || M <= 0 || N <= 0 || D <= 0 || ldq < D || ldg < D) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (gt_index != nullptr && gt_offsets == nullptr) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (!dtype_any(dtype)) return COSMOS_ERR_UNSUPPORTED;
+  if (M > 65535 * 128) return COSMOS_ERR_UNSUPPORTED;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  return cu_fail(cb::launch_retrieval_ranks(q, gal, dtype, M, N, D, ldq, ldg, gt_offsets, gt_index, best, ranks,
+                                            static_cast<cudaStream_t>(stream)))
+             ? COSMOS_ERR_CUDA : COSMOS_OK;
+}
+
 }  // extern "C"

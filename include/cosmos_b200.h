@@ -12,6 +12,7 @@
  *                      as composed by COSMOSLoss.forward src/open_clip/loss.py:176-207
  *   cosmos_ema_*       src/training/train.py:195-203  per-parameter mul_/add_ loop
  *   cosmos_clamp_scalars  src/training/train.py:237-243  logit-scale clamps of student and teacher
+ *   cosmos_retrieval_ranks  src/training/train.py:712-785  eval similarity + argsort + rank search (outside the step)
  *   cosmos_xpool_*     src/open_clip/transformer.py:210-230 AttentionalCrossPooler.forward and its call
  *                      site src/open_clip/model.py:366-387
  * The reference has no FFI of its own (pure PyTorch); INTEGRATION.md shows the ctypes binding and
@@ -190,6 +191,21 @@ int cosmos_addnorm_bwd(const void* g_out, const void* out, int32_t f_dtype, cons
 /* dst[n] += sum over rows of src[rows, n] (fp32 atomics; bias gradients).                                       */
 int cosmos_colsum(const void* src, int32_t dtype, float* dst, int64_t rows, int32_t n, int64_t ld, int device,
                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Retrieval ranks for the evaluation metrics  (src/training/train.py:766-785 get_clip_metrics and
+ * 712-763 compute_retrieval: similarity matrix on the CPU + argsort of every row + position search)
+ * ------------------------------------------------------------------------------------------------
+ * ranks[r] = number of gallery items whose fp32 dot product with query r is larger than the best dot
+ * product of r's ground-truth items = the 0-based position of the best ground-truth item in a descending
+ * sort of row r.  q is [M][D] with row stride ldq, g is [N][D] with row stride ldg (elements; dtype f32,
+ * bf16 or f16, products and sums in fp32).  Ground truth in CSR form: items gt_index[gt_offsets[r] ..
+ * gt_offsets[r+1]) (device int32 arrays); both null = item r for query r (get_clip_metrics); gt_index
+ * null = the contiguous range [gt_offsets[r], gt_offsets[r+1]).  best [M] fp32 receives the threshold
+ * scores (raw dot products), ranks [M] int32 the result.  No similarity matrix is written to memory. */
+int cosmos_retrieval_ranks(const void* q, const void* g, int dtype, int32_t M, int32_t N, int32_t D, int64_t ldq, int64_t ldg,
+                           const int32_t* gt_offsets, const int32_t* gt_index, float* best, int32_t* ranks, int device,
+                           void* stream);
 
 #ifdef __cplusplus
 }

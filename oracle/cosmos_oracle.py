@@ -20,6 +20,8 @@ Reference anchors (paths relative to /root/reference):
   * cross-attention pooler    src/open_clip/transformer.py:210-230 and the call
                               site src/open_clip/model.py:366-387
   * EMA teacher update        src/training/train.py:195-203
+  * logit-scale clamps        src/training/train.py:237-243
+  * eval retrieval metrics    src/training/train.py:712-763, 766-785
 """
 from __future__ import annotations
 
@@ -245,6 +247,75 @@ def ema_update_(teacher: Sequence[torch.Tensor], student: Sequence[torch.Tensor]
 # Synthetic inputs (shared by tests, smoke and bench so that every leg sees the
 # same tensors; SURVEY.md §8(d) "Synthetic inputs")
 # ----------------------------------------------------------------------------
+
+def clamp_logit_scales_(scalars: Sequence[torch.Tensor], lo: float = 0.0, hi: float = math.log(100)) -> None:
+    """train.py:237-243: every logit scale (student and teacher, clip and distill) is clamped in place to [0, ln 100]."""
+    with torch.no_grad():
+        for t in scalars:
+            t.clamp_(lo, hi)
+
+
+# ----------------------------------------------------------------------------
+# Retrieval metrics of the evaluation (outside the training step)
+# ----------------------------------------------------------------------------
+
+def ranks_from_scores(scores: torch.Tensor, gt: Sequence[Sequence[int]]) -> torch.Tensor:
+    """0-based position of the best ground-truth item of every row in a descending sort of that row
+    (train.py:722-731 for several items per row, 745-748 / 776-777 for one)."""
+    out = torch.zeros(scores.shape[0], dtype=torch.long)
+    for r, row in enumerate(scores):
+        order = torch.argsort(row, descending=True)
+        pos = torch.empty_like(order)
+        pos[order] = torch.arange(order.numel())
+        out[r] = min(int(pos[t]) for t in gt[r])
+    return out
+
+
+def _report(ranks: torch.Tensor, name: str, float32_mean: bool) -> Dict[str, float]:
+    import numpy as np
+    r = ranks.numpy()
+    mean = float(ranks.float().mean().item()) if float32_mean else float(r.mean())
+    d = {f"{name}_mean_rank": mean + 1, f"{name}_median_rank": float(np.floor(np.median(r)) + 1)}
+    for k in (1, 5, 10):
+        d[f"{name}_R@{k}"] = float(np.mean(r < k))
+    return d
+
+
+def get_clip_metrics(image_features: torch.Tensor, text_features: torch.Tensor, logit_scale) -> Dict[str, float]:
+    """train.py:766-785: paired features, item r of one side matches item r of the other."""
+    per_image = (logit_scale * image_features @ text_features.t()).detach().cpu()
+    n = per_image.shape[0]
+    gt = [[r] for r in range(n)]
+    out = {}
+    out.update(_report(ranks_from_scores(per_image, gt), "image_to_text", False))
+    out.update(_report(ranks_from_scores(per_image.t(), gt), "text_to_image", False))
+    return out
+
+
+def compute_retrieval(similarity: torch.Tensor, txt2img: Dict[int, int], img2txt: Dict[int, Sequence[int]]) -> Dict[str, float]:
+    """train.py:712-763: similarity is [images, captions]; an image has several captions (best one counts),
+    a caption one image.  Ranks are held in a float32 tensor there, so the mean is a float32 mean."""
+    n_img, n_txt = similarity.shape
+    out = {}
+    out.update(_report(ranks_from_scores(similarity.t(), [[txt2img[c]] for c in range(n_txt)]), "text_to_image", True))
+    out.update(_report(ranks_from_scores(similarity, [list(img2txt[i]) for i in range(n_img)]), "image_to_text", True))
+    return out
+
+
+def make_retrieval_case(n_img: int, caps_per_img: int, dim: int, seed: int, noise: float = 1.5, shuffle: bool = True):
+    """Seeded eval-like features: every image has `caps_per_img` captions scattered over the caption list."""
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(n_img, dim, generator=g)
+    img = F.normalize(z + noise * torch.randn(n_img, dim, generator=g), dim=-1)
+    n_txt = n_img * caps_per_img
+    owner = torch.arange(n_img).repeat_interleave(caps_per_img)
+    if shuffle:
+        owner = owner[torch.randperm(n_txt, generator=g)]
+    txt = F.normalize(z[owner] + noise * torch.randn(n_txt, dim, generator=g), dim=-1)
+    txt2img = {c: int(owner[c]) for c in range(n_txt)}
+    img2txt = {i: [c for c in range(n_txt) if txt2img[c] == i] for i in range(n_img)}
+    return img, txt, txt2img, img2txt
+
 
 def make_features(batch: int, dim: int, seed: int, n_img: int = 8, n_txt: int = 8, correlated: bool = True,
                   dtype=torch.float32, noise: float = 2.0) -> dict:

@@ -184,6 +184,38 @@ def case_ema():
     torch.save(dict(teacher=t0, student=student, outs=outs), os.path.join(HERE, "ema.pt"))
 
 
+def ref_train_functions(*names):
+    """The named top-level functions of the reference's src/training/train.py, compiled from the file where it lies
+    (the module itself cannot be imported here: it needs open_clip's package __init__, PIL, tqdm, ...)."""
+    import ast
+    import numpy as np
+    path = os.path.join(REF, "src", "training", "train.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    tree.body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    ns = {"torch": torch, "np": np}
+    exec(compile(tree, path, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def case_retrieval():
+    """Eval metrics (train.py:712-763, 766-785) on seeded features from oracle.make_retrieval_case; only the metric
+    dictionaries are stored, the tests regenerate the inputs."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle.cosmos_oracle import make_retrieval_case
+    get_clip_metrics, compute_retrieval = ref_train_functions("get_clip_metrics", "compute_retrieval")
+    cases = []
+    for (n_img, caps, dim, seed, noise) in [(60, 5, 64, 301, 1.5), (131, 3, 96, 302, 2.5), (257, 1, 512, 303, 3.0)]:
+        img, txt, txt2img, img2txt = make_retrieval_case(n_img, caps, dim, seed, noise)
+        sim = 14.2857 * img @ txt.t()
+        rec = dict(n_img=n_img, caps=caps, dim=dim, seed=seed, noise=noise,
+                   compute_retrieval={k: float(v) for k, v in compute_retrieval(sim, txt2img, img2txt).items()})
+        if caps == 1:
+            img_p, txt_p, _, _ = make_retrieval_case(n_img, 1, dim, seed, noise, shuffle=False)
+            rec["get_clip_metrics"] = {k: float(v) for k, v in get_clip_metrics(img_p, txt_p, torch.tensor(14.2857)).items()}
+        cases.append(rec)
+    torch.save(cases, os.path.join(HERE, "retrieval.pt"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     L, T = ref_modules()
@@ -193,6 +225,7 @@ if __name__ == "__main__":
     case_multirank(2, 29612, "multirank_w2.pt")
     case_pooler(T)
     case_ema()
+    case_retrieval()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

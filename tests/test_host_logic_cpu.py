@@ -197,3 +197,44 @@ def test_c_abi_exports_every_declared_symbol():
     assert lib.cosmos_clamp_scalars(None, 0, 0.0, 1.0, 0, 0, None) == 0         # nothing to do
     bad = _lib.InfoNceProblem(x=16, y=16, gx=1, gy=1, n_rows=8, n_cols=8, dim=100, label_offset=0, dtype=1, reserved=0, scale=4)
     assert lib.cosmos_infonce_workspace_bytes(ctypes.byref(bad)) == -1          # dim not a multiple of 64
+
+
+def test_retrieval_host_logic_against_reference_fixture(monkeypatch):
+    """compute_retrieval / get_clip_metrics of cosmos_b200.retrieval (CSR ground truth, metric expressions, key names)
+    with the rank kernel replaced by its documented contract: ranks[r] = #{c : <q_r, g_c> > max_t <q_r, g_t>}."""
+    from cosmos_b200 import retrieval
+    from oracle import cosmos_oracle as O
+
+    def ranks_contract(q, g, gt_offsets=None, gt_index=None):
+        s = q.double() @ g.double().t()
+        out = torch.empty(q.shape[0], dtype=torch.int32)
+        for r in range(q.shape[0]):
+            if gt_offsets is None:
+                items = [r]
+            else:
+                span = range(int(gt_offsets[r]), int(gt_offsets[r + 1]))
+                items = [int(gt_index[e]) for e in span] if gt_index is not None else list(span)
+            out[r] = int((s[r] > s[r, items].max()).sum())
+        return out
+
+    monkeypatch.setattr(retrieval, "retrieval_ranks", ranks_contract)
+    for rec in torch.load(os.path.join(GOLDEN, "retrieval.pt"), weights_only=False):
+        img, txt, txt2img, img2txt = O.make_retrieval_case(rec["n_img"], rec["caps"], rec["dim"], rec["seed"], rec["noise"])
+        got = retrieval.compute_retrieval(img, txt, txt2img, img2txt)
+        assert list(got.keys()) == list(rec["compute_retrieval"].keys())
+        for k, v in rec["compute_retrieval"].items():
+            assert float(got[k]) == pytest.approx(v, rel=1e-6, abs=0), k
+        if "get_clip_metrics" in rec:
+            img_p, txt_p, _, _ = O.make_retrieval_case(rec["n_img"], 1, rec["dim"], rec["seed"], rec["noise"], shuffle=False)
+            got = retrieval.get_clip_metrics(img_p, txt_p, torch.tensor(14.2857))
+            assert list(got.keys()) == list(rec["get_clip_metrics"].keys())
+            for k, v in rec["get_clip_metrics"].items():
+                assert float(got[k]) == pytest.approx(v, rel=1e-12, abs=0), k
+    with pytest.raises(RuntimeError, match="outside the gallery"):
+        retrieval.compute_retrieval(img, txt, {c: 10 ** 6 for c in txt2img}, img2txt)
+
+
+def test_retrieval_rejects_cpu_tensors():
+    from cosmos_b200 import retrieval_ranks
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        retrieval_ranks(torch.randn(4, 8), torch.randn(5, 8))

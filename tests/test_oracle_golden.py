@@ -154,3 +154,19 @@ def test_ema_matches_reference(golden_dir):
         O.ema_update_(k, rec["student"], m)
         for a, b in zip(k, want):
             assert torch.equal(a, b)
+
+
+def test_retrieval_metrics_match_reference(golden_dir):
+    """oracle.get_clip_metrics / compute_retrieval against the reference's own functions (train.py:712-785)."""
+    for rec in _load(golden_dir, "retrieval.pt"):
+        img, txt, txt2img, img2txt = O.make_retrieval_case(rec["n_img"], rec["caps"], rec["dim"], rec["seed"], rec["noise"])
+        got = O.compute_retrieval(14.2857 * img @ txt.t(), txt2img, img2txt)
+        assert got.keys() == rec["compute_retrieval"].keys()
+        for k, v in rec["compute_retrieval"].items():
+            assert got[k] == pytest.approx(v, rel=1e-6, abs=0), k
+        if "get_clip_metrics" in rec:
+            img_p, txt_p, _, _ = O.make_retrieval_case(rec["n_img"], 1, rec["dim"], rec["seed"], rec["noise"], shuffle=False)
+            got = O.get_clip_metrics(img_p, txt_p, torch.tensor(14.2857))
+            assert got.keys() == rec["get_clip_metrics"].keys()
+            for k, v in rec["get_clip_metrics"].items():
+                assert got[k] == pytest.approx(v, rel=1e-12, abs=0), k
