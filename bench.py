@@ -311,6 +311,7 @@ def run_ours(args):
             torch.cuda.empty_cache()
             line["ema"] = bench_ema(dev, flush)
             line["xattn"] = bench_xattn(dev, flush)
+            line["retrieval"] = bench_retrieval(dev, flush)
             line["eager_gpu_baseline"] = bench_eager_gpu(dev)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
@@ -444,6 +445,32 @@ def bench_xattn(dev, flush):
         out[name] = {"ms": med, "ms_best": best, "algorithmic_tflops": 3.0 * fwd / (med * 1e-3) / 1e12, "batch": B2,
                      "queries": Lq, "tokens": Lk, "dim": d2, "heads": h2}
     return out
+
+
+def bench_retrieval(dev, flush, n=32768, n_cpu=2048):
+    """Eval metrics: paired retrieval ranks at the headline batch, fp32 on the CUDA cores, next to the
+    reference's CPU path (similarity matrix + argsort + position search, the oracle restatement) on a bounded sample."""
+    from cosmos_b200.retrieval import get_clip_metrics, retrieval_ranks
+    from oracle import cosmos_oracle as O
+    g = torch.Generator(device=dev).manual_seed(21)
+    z = torch.randn(n, DIM, generator=g, device=dev)
+    img = torch.nn.functional.normalize(z + 2.0 * torch.randn(n, DIM, generator=g, device=dev), dim=-1)
+    txt = torch.nn.functional.normalize(z + 2.0 * torch.randn(n, DIM, generator=g, device=dev), dim=-1)
+    for _ in range(2):
+        retrieval_ranks(img, txt)
+    med, best = _event_ms(lambda: retrieval_ranks(img, txt), 5, flush)
+    t0 = time.perf_counter()
+    m = get_clip_metrics(img, txt, LOGIT_SCALE)                      # both directions + D2H of the ranks + numpy metrics
+    api_ms = (time.perf_counter() - t0) * 1e3
+    img_c, txt_c = img[:n_cpu].cpu(), txt[:n_cpu].cpu()
+    t0 = time.perf_counter()
+    O.get_clip_metrics(img_c, txt_c, torch.tensor(LOGIT_SCALE))
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    tf = 2.0 * n * n * DIM / (med * 1e-3) / 1e12
+    return {"workload": "paired retrieval ranks, %d x %d items, dim %d, fp32 (one direction per launch)" % (n, n, DIM),
+            "ms": med, "ms_best": best, "fp32_tflops": tf, "frac_of_fp32_fma_peak": tf / (148 * 128 * 2 * 1.965e9 / 1e12),
+            "get_clip_metrics_api_ms": api_ms, "R@1": float(m["image_to_text_R@1"]),
+            "cpu_reference_path": {"items": n_cpu, "ms": cpu_ms, "note": "oracle restatement of train.py:766-785 on host cores"}}
 
 
 def bench_eager_gpu(dev, n_global=4096, steps=3):
