@@ -130,16 +130,21 @@ class Clocks:
 
 class Instrument:
     """Counts our kernel launches and times the InfoNCE launches with CUDA events on the launching stream."""
+    KINDS = ("fwd", "bwd", "bwd_e", "colgrad")
+    NAMES = {"fwd": "infonce_fwd_kernel<pair> (+ column merge)", "bwd": "infonce_bwd_quad_kernel (+ dscale reduce)",
+             "bwd_e": "infonce_bwd_e_kernel (+ dscale reduce)", "colgrad": "gemm_kernel<256> (column-side gradient)"}
 
     def __init__(self):
         from cosmos_b200 import infonce
         self.mod = infonce
         self.launches = 0
-        self.events = {"fwd": [], "bwd": [], "colgrad": []}
-        self.flops = {"fwd": [], "bwd": [], "colgrad": []}
+        self.events = {k: [] for k in self.KINDS}
+        self.flops = {k: [] for k in self.KINDS}
         self.enabled = False
         self._fwd, self._loss, self._bwd, self._colgrad = infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd, infonce._k_colgrad
+        self._bwd_e = infonce._k_bwd_e
         infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd, infonce._k_colgrad = self.fwd, self.loss, self.bwd, self.colgrad
+        infonce._k_bwd_e = self.bwd_e
 
     def _timed(self, kind, flops, fn, *a):
         if not self.enabled:
@@ -167,13 +172,19 @@ class Instrument:
         fl = 2.0 * x.shape[0] * y.shape[0] * x.shape[1] * y.shape[1] * x.shape[2] if want_dx else 0.0
         return self._timed("bwd", fl, self._bwd, x, y, *a)
 
+    def bwd_e(self, x, y, *a):
+        want_ds = a[12]          # (label_offset, scale, e, off, row, col, a_row, a_col, s_row, s_col, weight, upstream, want_dscale[, g_out])
+        self.launches += 1 + (1 if want_ds else 0)
+        fl = 2.0 * x.shape[0] * y.shape[0] * x.shape[1] * y.shape[1] * x.shape[2]
+        return self._timed("bwd_e", fl, self._bwd_e, x, y, *a)
+
     def colgrad(self, g, x2d, n_c, n_cols):
         self.launches += 1                       # the column-side gradient GEMM (G^T x) on the stored tiles
         return self._timed("colgrad", 2.0 * x2d.shape[0] * n_c * n_cols * x2d.shape[1], self._colgrad, g, x2d, n_c, n_cols)
 
     def summary(self):
         out = {}
-        for kind in ("fwd", "bwd", "colgrad"):
+        for kind in self.KINDS:
             ms = [a.elapsed_time(b) for a, b in self.events[kind]]
             if ms:
                 out[kind] = {"launches": len(ms), "ms_total": sum(ms), "ms_avg": sum(ms) / len(ms),
@@ -277,7 +288,7 @@ def run_ours(args):
         value = n_global / (ms_per_step * 1e-3)
         e2e_value = n_global / (e2e_ms / args.steps * 1e-3)
         ksum = inst.summary()
-        dom = "bwd" if ksum.get("bwd", {}).get("ms_total", 0) >= ksum.get("fwd", {}).get("ms_total", 0) else "fwd"
+        dom = max(ksum, key=lambda kind: ksum[kind]["ms_total"])
         k = ksum[dom]
         achieved = k["flops_avg"] / (k["ms_avg"] * 1e-3) / 1e12
         step_tflops = algorithmic_flops(n_global) / world / (ms_per_step * 1e-3) / 1e12
@@ -296,11 +307,11 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "tensor",
-                         "kernel": "infonce_bwd_quad_kernel (+ dscale reduce)" if dom == "bwd" else "infonce_fwd_kernel<pair> (+ column merge)",
+                         "kernel": Instrument.NAMES[dom],
                          "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-                         "traffic": ncu_traffic(dom) if n_global == 4096 else None,
+                         "traffic": ncu_traffic(dom) if (n_global == 4096 and dom in ("fwd", "bwd")) else None,
                          "traffic_note": "dram__bytes_read+write of one launch from profiles/ncu_*_r01.txt (captured at global batch 4096)",
-                         "executed_tflops": achieved * (2.0 if dom == "bwd" else 1.0),
+                         "executed_tflops": achieved * (2.0 if dom == "bwd" else 1.0),   # the recompute backward runs S and dX
                          "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step); burst %.1f" % (src, burst),
                          "launch_ms_avg": k["ms_avg"], "launches_timed": k["launches"],
                          "step_algorithmic_tflops_per_gpu": step_tflops, "step_frac": step_tflops / sustained,

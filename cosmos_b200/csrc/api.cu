@@ -1,5 +1,6 @@
 // extern "C" surface of libcosmos_b200.so (declared in include/cosmos_b200.h).
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -193,12 +194,26 @@ int64_t cosmos_infonce_workspace_bytes(const cosmos_infonce_problem* p) {
 
 int cosmos_infonce_fwd(const cosmos_infonce_problem* p, float* row_lse2, float* diag_raw, float* col_lse2, void* workspace,
                        int64_t workspace_bytes, int device, void* stream) {
+  return cosmos_infonce_fwd_e(p, row_lse2, diag_raw, col_lse2, nullptr, nullptr, workspace, workspace_bytes, device, stream);
+}
+
+int64_t cosmos_infonce_e_bytes(const cosmos_infonce_problem* p) {
+  Dims d;
+  if (check_problem(p, &d) != COSMOS_OK) return -1;
+  return static_cast<int64_t>(d.pairs) * d.n_row_tiles * d.n_col_tiles_bwd * 32768;
+}
+
+int cosmos_infonce_fwd_e(const cosmos_infonce_problem* p, float* row_lse2, float* diag_raw, float* col_lse2, void* e_out,
+                         float* off_out, void* workspace, int64_t workspace_bytes, int device, void* stream) {
   Dims d;
   int st = check_problem(p, &d);
   if (st != COSMOS_OK) return st;
   if (!row_lse2 || !diag_raw || !col_lse2 || !workspace) return COSMOS_ERR_INVALID_ARGUMENT;
   if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return COSMOS_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < fwd_workspace(p, d)) return COSMOS_ERR_WORKSPACE;
+  if (e_out != nullptr) {
+    if (off_out == nullptr || (reinterpret_cast<uintptr_t>(e_out) & 15) != 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  }
   DeviceGuard g(device);
   if (!g.ok) return COSMOS_ERR_CUDA;
   CUtensorMap tmX, tmY;
@@ -223,6 +238,10 @@ int cosmos_infonce_fwd(const cosmos_infonce_problem* p, float* row_lse2, float* 
   fp.scale = reinterpret_cast<const float*>(p->scale);
   fp.row_lse2 = row_lse2; fp.diag_raw = diag_raw;
   fp.col_part = reinterpret_cast<float2*>(workspace);
+  fp.e_out = static_cast<uint16_t*>(e_out);
+  fp.off_out = off_out;
+  fp.n_steps = d.n_col_tiles_bwd;
+  fp.n_chunks = (p->n_cols + 31) / 32;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (cu_fail(cb::launch_infonce_fwd(tmX, tmY, fp, pair, s))) return COSMOS_ERR_CUDA;
   if (cu_fail(cb::launch_col_combine(fp.col_part, col_lse2, d.pairs, d.n_slabs, p->n_cols, s))) return COSMOS_ERR_CUDA;
@@ -339,6 +358,60 @@ int cosmos_infonce_bwd_g(const cosmos_infonce_problem* p, const float* row_lse2,
   return COSMOS_OK;
 }
 
+int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const float* off, const float* row_lse2,
+                         const float* col_lse2, float a_row, float a_col, float s_row, float s_col,
+                         float weight, const float* upstream, void* dx, float* dscale, void* g_out, int64_t g_ld, void* workspace,
+                         int64_t workspace_bytes, int device, void* stream) {
+  Dims d;
+  int st = check_problem(p, &d);
+  if (st != COSMOS_OK) return st;
+  if (!e || !off || !row_lse2 || !col_lse2 || !upstream || !dx) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (p->dim != 512) return COSMOS_ERR_UNSUPPORTED;     // the dX accumulator of 128 rows x 512 columns is the whole tensor memory
+  // d(scale) is read off the dX accumulators, which weigh the two softmax terms like G: the mixes must be proportional
+  if (dscale != nullptr && (fabsf(a_row * s_col - a_col * s_row) > 1e-12f || a_row + a_col == 0.f)) return COSMOS_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(e) & 15) != 0 || (reinterpret_cast<uintptr_t>(dx) & 15) != 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (g_out != nullptr && ((p->n_cols & 7) != 0 || (g_ld & 7) != 0 || g_ld < static_cast<int64_t>(p->gy) * p->n_cols ||
+                           (reinterpret_cast<uintptr_t>(g_out) & 15) != 0))
+    return COSMOS_ERR_INVALID_ARGUMENT;
+  if (workspace == nullptr || workspace_bytes < bwd_partials_bytes(p, d)) return COSMOS_ERR_WORKSPACE;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  CUtensorMap tmE, tmY64;
+  const int bf = p->dtype == COSMOS_DTYPE_BF16;
+  {
+    // E is bf16 whatever the stack dtype is (fp16 has no range for 2^(s2 - max)); the kernel converts in shared memory
+    const int m1 = cb::make_piece_map(&tmE, e, static_cast<uint64_t>(d.pairs) * d.n_row_tiles * d.n_col_tiles_bwd * 16);
+    const int m2 = cb::make_stack_map(&tmY64, reinterpret_cast<const void*>(p->y), bf, p->dim, p->n_cols, p->gy, 64);
+    if (m1 != 0 || m2 != 0) {
+      g_last_cuda = 100000 + (m1 != 0 ? m1 : m2);
+      return COSMOS_ERR_CUDA;
+    }
+  }
+  cb::BwdEParams bp;
+  bp.gx = p->gx; bp.gy = p->gy; bp.n_rows = p->n_rows; bp.n_cols = p->n_cols; bp.label_offset = p->label_offset;
+  bp.n_row_tiles = d.n_row_tiles; bp.n_col_tiles = d.n_col_tiles_bwd;
+  bp.n_chunks = (p->n_cols + 31) / 32;
+  bp.dtype = p->dtype;
+  bp.dbg = dbg_flags();
+  bp.idesc_g = cb::make_idesc(bf, 0, 1, 2 * cb::kFwdBM, 256);
+  bp.a_row = a_row; bp.a_col = a_col; bp.s_row = s_row; bp.s_col = s_col; bp.weight = weight;
+  bp.scale = reinterpret_cast<const float*>(p->scale);
+  bp.upstream = upstream;
+  bp.e = e; bp.off = off; bp.row_lse2 = row_lse2; bp.col_lse2 = col_lse2;
+  bp.x = reinterpret_cast<const void*>(p->x);
+  bp.dx = dx;
+  bp.dscale_part = dscale != nullptr ? reinterpret_cast<float*>(workspace) : nullptr;
+  bp.g_out = g_out;
+  bp.g_ld = g_ld;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cu_fail(cb::launch_infonce_bwd_e(tmE, tmY64, bp, s))) return COSMOS_ERR_CUDA;
+  // partial sums hold <G, raw> with G's mix; (s_row + s_col) / (a_row + a_col) turns it into the requested one
+  if (dscale != nullptr && cu_fail(cb::launch_dscale_reduce(bp.dscale_part, p->gx * d.n_row_tiles,
+                                                            weight * (s_row + s_col) / (a_row + a_col), upstream, dscale, s)))
+    return COSMOS_ERR_CUDA;
+  return COSMOS_OK;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------
@@ -366,7 +439,12 @@ int cosmos_gemm(const void* a, const void* b, void* d, const float* bias, int32_
   ga.a_kmajor = a_kmajor; ga.b_kmajor = b_kmajor; ga.in_dtype = in_dtype; ga.out_dtype = out_dtype;
   ga.splits = splits; ga.alpha = alpha;
   cudaError_t e = cudaSuccess;
-  const int r = cb::launch_gemm(ga, sm_count_of(device), static_cast<cudaStream_t>(stream), &e);
+  int ctas = sm_count_of(device);
+  if (const char* cap = getenv("COSMOS_B200_GEMM_CTAS")) {   // diagnostics (tools/overlap_probe.py): persistent CTAs of this launch
+    const int c = atoi(cap);
+    if (c > 0 && c < ctas) ctas = c;
+  }
+  const int r = cb::launch_gemm(ga, ctas, static_cast<cudaStream_t>(stream), &e);
   if (r == 0) return COSMOS_OK;
   if (r > 0) g_last_cuda = r; else cu_fail(e);
   return COSMOS_ERR_CUDA;

@@ -21,6 +21,12 @@ struct FwdParams {
   float* row_lse2;
   float* diag_raw;
   float2* col_part;  // [gx*gy][n_slabs][n_cols] (max2, sum)
+  // optional (stored-exponential route): every 2^(S2 - m) the statistics loop forms anyway, as bf16, and the offsets m
+  uint16_t* e_out;   // [gx*gy][n_row_tiles][n_steps] tiles of [16 column pieces][128 rows][8] bf16 (32 KB each):
+                     // 2^(s2[r][c] - off[c / 32][r]), s2 = logit in log2 units
+  float* off_out;    // [gx*gy][n_chunks][n_rows]: the row's running maximum (of its 64-column group) when the chunk was processed
+  int n_steps;       // ceil(n_cols / 128)
+  int n_chunks;      // ceil(n_cols / 32)
 };
 
 struct BwdParams {
@@ -49,6 +55,29 @@ cudaError_t launch_infonce_bwd_pair(const CUtensorMap& tmX, const CUtensorMap& t
                                     cudaStream_t stream);
 
 cudaError_t launch_infonce_bwd_quad(const CUtensorMap& tmX, const CUtensorMap& tmY64, const BwdParams& p, cudaStream_t stream);
+
+// Backward from the exponentials the forward stored (infonce_bwd_e.cu): no logit is recomputed.
+struct BwdEParams {
+  int gx, gy, n_rows, n_cols, label_offset;
+  int n_row_tiles, n_col_tiles;   // 128-row tiles, 128-column steps
+  int n_chunks;                   // ceil(n_cols / 32)
+  int dtype;                      // dtype of y, dx and g_out (the A operand is converted to it in shared memory)
+  int dbg;
+  uint32_t idesc_g;
+  float a_row, a_col, s_row, s_col, weight;
+  const float* scale;
+  const float* upstream;
+  const void* e;          // the forward's e_out
+  const float* off;       // [gx*gy][n_chunks][n_rows]
+  const float* row_lse2;  // [gx*gy][n_rows]
+  const float* col_lse2;  // [gx*gy][n_cols]
+  const void* x;          // [gx][n_rows][512]: only read at the end, for d(scale) = sum_r <x_r, (G y)_r>
+  void* dx;               // [gx][n_rows][512]
+  float* dscale_part;     // [gx * n_row_tiles] partial sums of <dscale-mix, raw logits>, may be null
+  void* g_out;            // optional copy of every G tile, [gx * n_rows][g_ld], column j * n_cols + c
+  long long g_ld;
+};
+cudaError_t launch_infonce_bwd_e(const CUtensorMap& tmE, const CUtensorMap& tmY64, const BwdEParams& p, cudaStream_t stream);
 
 // infonce_aux.cu
 cudaError_t launch_col_combine(const float2* col_part, float* col_lse2, int pairs, int n_slabs, int n_cols, cudaStream_t stream);

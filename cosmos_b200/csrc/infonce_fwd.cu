@@ -202,6 +202,15 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 
     float m_run = NEG_INF, l_run = 0.f, diag = 0.f;
     float2* col_part = p.col_part + (static_cast<size_t>(pair) * p.n_slabs + tr * 4 + q) * p.n_cols;
+    // stored-exponential route (infonce_bwd_e.cu): this row's 2^(s2 - m_run) of every chunk as bf16, and m_run itself
+    // Layout of e_out: one contiguous 32 KB image per (pair, 128-row tile, 128-column step): [16 pieces of 8 columns][128 rows]
+    // [8 elements] - a warp's store of one piece is 512 contiguous bytes, and the backward's TMA box of a 64-column slab
+    // (8 pieces) is 16 contiguous KB that land as the no-swizzle K-major core-matrix layout of tcgen05.
+    const bool keep_e = p.e_out != nullptr && row_valid && tr < p.n_row_tiles;
+    uint4* e_tile = keep_e ? reinterpret_cast<uint4*>(p.e_out) +
+                                 (static_cast<size_t>(pair) * p.n_row_tiles + tr) * p.n_steps * 2048 + (q * 32 + lane)
+                           : nullptr;       // + (step * 16 + piece) * 128 (16-byte units)
+    float* off_row = keep_e ? p.off_out + static_cast<size_t>(pair) * p.n_chunks * p.n_rows + row : nullptr;
 
     const bool eprof = (p.dbg & 1024) != 0 && (blockIdx.x % 194) == 10 && lane == 0 && (ew == 0 || ew == 7);
     long long e_wait = 0;
@@ -251,11 +260,32 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             const float f = row_valid ? ex2(m_run - mw) : 0.f;
             const float neg_m = -m_run;
             float ssum = 0.f;
+            if (keep_e) {
+              // 16-byte pieces leave as soon as their 8 exponentials exist: no extra live registers across the reduce below
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const float e = ex2(fmaf(__uint_as_float(v[k]), k2, neg_m));
-              ssum += e;
-              t[k] = e * f;
+              for (int k8 = 0; k8 < 4; ++k8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int k2i = 0; k2i < 4; ++k2i) {
+                  const int k = k8 * 8 + k2i * 2;
+                  const float e0 = ex2(fmaf(__uint_as_float(v[k]), k2, neg_m));
+                  const float e1 = ex2(fmaf(__uint_as_float(v[k + 1]), k2, neg_m));
+                  ssum += e0;
+                  ssum += e1;
+                  t[k] = e0 * f;
+                  t[k + 1] = e1 * f;
+                  pk[k2i] = pack2(e0, e1, 1);
+                }
+                e_tile[static_cast<size_t>((col0 >> 3) + k8) * 128] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+              off_row[static_cast<size_t>(col0 >> 5) * p.n_rows] = m_run;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                const float e = ex2(fmaf(__uint_as_float(v[k]), k2, neg_m));
+                ssum += e;
+                t[k] = e * f;
+              }
             }
             l_run += ssum;
             const float csum = warp_transpose_reduce(t, lane, OpAdd());
@@ -290,9 +320,31 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
         if (m_run != NEG_INF) {
           float s = 0.f;
+          if (keep_e) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) s += ex2(t[k] - m_run);
+            for (int k8 = 0; k8 < 4; ++k8) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int k2i = 0; k2i < 4; ++k2i) {
+                const int k = k8 * 8 + k2i * 2;
+                const float e0 = ex2(t[k] - m_run), e1 = ex2(t[k + 1] - m_run);    // columns past n_cols: 2^-inf = 0
+                s += e0;
+                s += e1;
+                pk[k2i] = pack2(e0, e1, 1);
+              }
+              e_tile[static_cast<size_t>((col0 >> 3) + k8) * 128] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            off_row[static_cast<size_t>(col0 >> 5) * p.n_rows] = m_run;
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) s += ex2(t[k] - m_run);
+          }
           l_run += s;
+        } else if (keep_e) {
+          // every logit of this row so far is -inf (scale * x.y = -inf cannot happen with finite inputs; kept for safety)
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8) e_tile[static_cast<size_t>((col0 >> 3) + k8) * 128] = make_uint4(0u, 0u, 0u, 0u);
+          off_row[static_cast<size_t>(col0 >> 5) * p.n_rows] = 0.f;
         }
         // columns: reduce over the warp's 32 rows
         if (!row_valid) {

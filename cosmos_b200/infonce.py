@@ -78,8 +78,10 @@ def _workspace(prob: _lib.InfoNceProblem, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-def _k_fwd(x, y, label_offset, scale):
-    """-> row_lse2 [P, b], diag_raw [P, b], col_lse2 (this rank's rows only) [P, N]; fp32."""
+def _k_fwd(x, y, label_offset, scale, keep_e=False):
+    """-> row_lse2 [P, b], diag_raw [P, b], col_lse2 (this rank's rows only) [P, N]; fp32.
+    keep_e: also -> (e, off [P, ceil(N / 32), b] fp32): the exponentials 2^(s2 - off) of every logit as bf16, in the tiled
+    layout include/cosmos_b200.h describes (stored-exponential route, csrc/infonce_bwd_e.cu)."""
     dev = x.device
     prob = _problem(x, y, label_offset, scale)
     P = prob.gx * prob.gy
@@ -87,10 +89,37 @@ def _k_fwd(x, y, label_offset, scale):
     diag_raw = torch.empty(P, prob.n_rows, dtype=torch.float32, device=dev)
     col_lse2 = torch.empty(P, prob.n_cols, dtype=torch.float32, device=dev)
     ws = _workspace(prob, dev)
-    st = _lib.lib().cosmos_infonce_fwd(C.byref(prob), row_lse2.data_ptr(), diag_raw.data_ptr(), col_lse2.data_ptr(),
-                                       ws.data_ptr(), ws.numel(), dev.index, torch.cuda.current_stream(dev).cuda_stream)
-    _lib.check(st, "infonce_fwd")
-    return row_lse2, diag_raw, col_lse2
+    if not keep_e:
+        st = _lib.lib().cosmos_infonce_fwd(C.byref(prob), row_lse2.data_ptr(), diag_raw.data_ptr(), col_lse2.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), dev.index, torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(st, "infonce_fwd")
+        return row_lse2, diag_raw, col_lse2
+    e = torch.empty(_lib.lib().cosmos_infonce_e_bytes(C.byref(prob)) // 2, dtype=torch.bfloat16, device=dev)
+    off = torch.empty(P, (prob.n_cols + 31) // 32, prob.n_rows, dtype=torch.float32, device=dev)
+    st = _lib.lib().cosmos_infonce_fwd_e(C.byref(prob), row_lse2.data_ptr(), diag_raw.data_ptr(), col_lse2.data_ptr(),
+                                         e.data_ptr(), off.data_ptr(), ws.data_ptr(), ws.numel(), dev.index,
+                                         torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(st, "infonce_fwd_e")
+    return row_lse2, diag_raw, col_lse2, e, off
+
+
+def _k_bwd_e(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream,
+             want_dscale, g_out=None):
+    """Backward from the stored exponentials: -> dx [gx, b, 512] in x.dtype, dscale fp32 [1] (or None).  No logit is
+    recomputed; x is only read for d(scale) = sum_r <x_r, (G y)_r>."""
+    dev = x.device
+    prob = _problem(x, y, label_offset, scale)
+    dx = torch.empty_like(x)
+    dscale = torch.empty(1, dtype=torch.float32, device=dev) if want_dscale else None
+    ws = torch.empty(max(4 * prob.gx * ((prob.n_rows + 127) // 128) * 8, 256) + 256, dtype=torch.uint8, device=dev)
+    st = _lib.lib().cosmos_infonce_bwd_e(C.byref(prob), e.data_ptr(), off.data_ptr(), row_lse2.data_ptr(),
+                                         col_lse2.data_ptr(), a_row, a_col, s_row, s_col, weight,
+                                         upstream.data_ptr(), dx.data_ptr(), dscale.data_ptr() if want_dscale else None,
+                                         g_out.data_ptr() if g_out is not None else None,
+                                         g_out.stride(0) if g_out is not None else 0, ws.data_ptr(), ws.numel(), dev.index,
+                                         torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(st, "infonce_bwd_e")
+    return dx, dscale
 
 
 def _k_loss_sums(x, y, label_offset, scale, row_lse2, diag_raw, col_lse2):
@@ -284,6 +313,36 @@ def _reduce_scatter_rows(d_all: torch.Tensor, comm: Comm, b: int) -> torch.Tenso
     return d_all[:, rank * b:(rank + 1) * b].contiguous()
 
 
+_E_STORE_MAX_BYTES = int(float(os.environ.get("COSMOS_B200_ESTORE_MAX_GB", "40")) * (1 << 30))
+# small problems: the recompute kernels finish in microseconds and one launch per group beats the chunk loop
+_E_STORE_MIN_BYTES = int(float(os.environ.get("COSMOS_B200_ESTORE_MIN_GB", "0.25")) * (1 << 30))
+
+
+def _e_store_chunk(x_r: torch.Tensor, y_c: torch.Tensor, comm: Comm) -> int:
+    """Row tensors per pass of the stored-exponential route (csrc/infonce_bwd_e.cu), 0 = use the recompute kernels.
+
+    The route needs dim 512 (a [128 x 512] fp32 dX accumulator is exactly the tensor memory of an SM) and gradient mixes
+    that weigh d(scale) like dX (every mode but local_loss).  The forward keeps 2 bytes per logit; the gradients are formed
+    right away, chunk of row tensors by chunk, so only one chunk of exponentials is alive at a time."""
+    n_r, b, dim = x_r.shape
+    n_c, n_all, _ = y_c.shape
+    if dim != 512 or _E_STORE_MAX_BYTES <= 0 or (comm.distributed and comm.local_loss):
+        return 0
+    per_tensor = n_c * (-(-b // 128) * 128) * (-(-n_all // 128) * 128) * 2
+    if per_tensor * n_r < _E_STORE_MIN_BYTES:
+        return 0
+    budget = _E_STORE_MAX_BYTES
+    if x_r.is_cuda:
+        free, _total = torch.cuda.mem_get_info(x_r.device)
+        free += torch.cuda.memory_reserved(x_r.device) - torch.cuda.memory_allocated(x_r.device)   # cached blocks are reusable
+        budget = min(budget, free // 3)          # exponentials + (CLIP group) the G tiles of the same chunk + headroom
+    most = min(n_r, budget // per_tensor)
+    if most <= 0:
+        return 0
+    passes = -(-n_r // most)
+    return -(-n_r // passes)                     # equal passes: 16 tensors at most 5 at a time -> 4 + 4 + 4 + 4, not 5 + 5 + 5 + 1
+
+
 class _PairsInfoNCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, scale: torch.Tensor, comm: Comm, n_r: int, prefetch, *feats: torch.Tensor):
@@ -308,10 +367,43 @@ class _PairsInfoNCE(torch.autograd.Function):
         scale_f = scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
 
         y_c = pre_c[1].get() if pre_c is not None else gather_stack(x_c, comm)     # [n_c, N, D]
-        row_lse2, diag_raw, col_lse2_part = _k_fwd(x_r, y_c, off, scale_f)
-        col_lse2 = _allreduce_lse2(col_lse2_part, comm)   # global over all rows
-        sums = _k_loss_sums(x_r, y_c, off, scale_f, row_lse2, diag_raw, col_lse2)   # [P, 2]
         P = n_r * n_c
+        need_scale = ctx.needs_input_grad[0]
+        need_rows = any(ctx.needs_input_grad[4:4 + n_r])
+        need_cols = any(ctx.needs_input_grad[4 + n_r:])
+        chunk = _e_store_chunk(x_r, y_c, comm) if need_rows else 0
+        ctx.eager = chunk > 0
+        if ctx.eager:
+            # Stored-exponential route: per chunk of row tensors, forward (statistics + 2^(s2 - max) of every logit, bf16) and,
+            # as soon as the chunk's column statistics are complete, the gradients for a unit upstream gradient - dX = G Y is
+            # the only contraction left, no logit is recomputed.  backward() only scales by the upstream gradient.
+            boost = float(W) if (comm.distributed and comm.gather_with_grad) else 1.0
+            weight = boost / (2.0 * N * P)
+            one = torch.ones(1, dtype=torch.float32, device=dev)
+            row_parts, diag_parts, col_parts, dx_parts = [], [], [], []
+            ds_unit = None
+            d_all = None
+            for i0 in range(0, n_r, chunk):
+                xs = x_r[i0:i0 + chunk]
+                r_, d_, c_part, e_, o_ = _k_fwd(xs, y_c, off, scale_f, True)
+                c_ = _allreduce_lse2(c_part, comm)
+                g_tiles = torch.empty(xs.shape[0] * b, n_c * N, dtype=x_r.dtype, device=dev) if need_cols else None
+                dx_, ds_ = _k_bwd_e(xs, y_c, off, scale_f, e_, o_, r_, c_, 1.0, 1.0, 1.0 / boost, 1.0 / boost, weight, one,
+                                    need_scale, g_tiles)
+                del e_, o_
+                if g_tiles is not None:
+                    part = _k_colgrad(g_tiles, xs.reshape(xs.shape[0] * b, xs.shape[2]), n_c, N)    # [n_c, N, D] fp32
+                    d_all = part if d_all is None else d_all.add_(part)
+                    del g_tiles
+                if ds_ is not None:
+                    ds_unit = ds_ if ds_unit is None else ds_unit + ds_
+                row_parts.append(r_); diag_parts.append(d_); col_parts.append(c_); dx_parts.append(dx_)
+            row_lse2, diag_raw, col_lse2 = (torch.cat(t) if len(t) > 1 else t[0] for t in (row_parts, diag_parts, col_parts))
+            ctx.unit = (torch.cat(dx_parts) if len(dx_parts) > 1 else dx_parts[0], ds_unit, d_all, weight)
+        else:
+            row_lse2, diag_raw, col_lse2_part = _k_fwd(x_r, y_c, off, scale_f)
+            col_lse2 = _allreduce_lse2(col_lse2_part, comm)   # global over all rows
+        sums = _k_loss_sums(x_r, y_c, off, scale_f, row_lse2, diag_raw, col_lse2)   # [P, 2]
         total = sums.sum()
         if comm.distributed and not comm.local_loss:
             dist.all_reduce(total, op=dist.ReduceOp.SUM, group=comm.group)
@@ -323,11 +415,16 @@ class _PairsInfoNCE(torch.autograd.Function):
         ctx.pre_r = pre_r[1] if pre_r is not None else None
         ctx.in_dtypes = [t.dtype for t in feats]
         ctx.scale_dtype = scale.dtype
-        ctx.save_for_backward(x_r, x_c, y_c, scale_f, row_lse2, col_lse2)
+        if ctx.eager:
+            ctx.save_for_backward(scale_f)
+        else:
+            ctx.save_for_backward(x_r, x_c, y_c, scale_f, row_lse2, col_lse2)
         return loss
 
     @staticmethod
     def backward(ctx, g: torch.Tensor):
+        if ctx.eager:
+            return _PairsInfoNCE._backward_eager(ctx, g)
         x_r, x_c, y_c, scale_f, row_lse2, col_lse2 = ctx.saved_tensors
         comm, n_r, n_c, b, off = ctx.comm, ctx.n_r, ctx.n_c, ctx.b, ctx.off
         W = comm.world_size
@@ -383,6 +480,34 @@ class _PairsInfoNCE(torch.autograd.Function):
             grads.append(d_cols[k].to(ctx.in_dtypes[n_r + k])
                          if (d_cols is not None and ctx.needs_input_grad[4 + n_r + k]) else None)
         g_scale = d_scale.reshape(()).to(ctx.scale_dtype) if need_scale else None
+        return (g_scale, None, None, None, *grads)
+
+
+    @staticmethod
+    def _backward_eager(ctx, g: torch.Tensor):
+        """The gradients for a unit upstream gradient were formed in forward(): scale them (and finish the collectives)."""
+        (scale_f,) = ctx.saved_tensors
+        comm, n_r, n_c, b = ctx.comm, ctx.n_r, ctx.n_c, ctx.b
+        dx_unit, ds_unit, d_all, weight = ctx.unit
+        ctx.unit = None
+        up = g.detach().to(torch.float32).reshape(1)
+        grads: List[Optional[torch.Tensor]] = []
+        d_rows = (dx_unit.float() * up).to(dx_unit.dtype) if any(ctx.needs_input_grad[4:4 + n_r]) else None
+        for k in range(n_r):
+            grads.append(d_rows[k].to(ctx.in_dtypes[k]) if (d_rows is not None and ctx.needs_input_grad[4 + k]) else None)
+        d_cols = None
+        if d_all is not None:
+            d_loc = _reduce_scatter_rows(d_all, comm, b)                                  # [n_c, b, D], all ranks' rows
+            d_cols = (d_loc * (up * scale_f.reshape(1) * weight)).to(dx_unit.dtype)
+        for k in range(n_c):
+            grads.append(d_cols[k].to(ctx.in_dtypes[n_r + k])
+                         if (d_cols is not None and ctx.needs_input_grad[4 + n_r + k]) else None)
+        g_scale = None
+        if ctx.needs_input_grad[0]:
+            d_scale = ds_unit * up
+            if comm.distributed:
+                dist.all_reduce(d_scale, op=dist.ReduceOp.SUM, group=comm.group)
+            g_scale = d_scale.reshape(()).to(ctx.scale_dtype)
         return (g_scale, None, None, None, *grads)
 
 

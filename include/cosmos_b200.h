@@ -192,6 +192,21 @@ int cosmos_addnorm_bwd(const void* g_out, const void* out, int32_t f_dtype, cons
 int cosmos_colsum(const void* src, int32_t dtype, float* dst, int64_t rows, int32_t n, int64_t ld, int device,
                   void* stream);
 
+/* Stored-exponential route (dim 512): the forward keeps, next to its statistics, every 2^(s2 - m) it forms
+ * (s2 = logit in log2 units) as bf16 in e_out - cosmos_infonce_e_bytes(p) bytes: one contiguous 32 KB image
+ * [16 column pieces][128 rows][8] per (pair, 128-row tile, 128-column step) - and the offsets m in off_out
+ * (fp32 [gx*gy][ceil(n_cols/32)][n_rows]: the row's running maximum when that 32-column chunk was processed).
+ * cosmos_infonce_bwd_e then recomputes no logit: dx = G y is its only contraction.  Same outputs and mode scalars
+ * as cosmos_infonce_bwd / _bwd_g (the two d(scale) weights must be proportional to the two gradient weights);
+ * col_lse2 must be the complete (all ranks) column log-sum-exps. */
+int64_t cosmos_infonce_e_bytes(const cosmos_infonce_problem* p);
+int cosmos_infonce_fwd_e(const cosmos_infonce_problem* p, float* row_lse2, float* diag_raw, float* col_lse2, void* e_out,
+                         float* off_out, void* workspace, int64_t workspace_bytes, int device, void* stream);
+int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const float* off, const float* row_lse2,
+                         const float* col_lse2, float a_row, float a_col, float s_row, float s_col,
+                         float weight, const float* upstream, void* dx, float* dscale, void* g_out, int64_t g_ld, void* workspace,
+                         int64_t workspace_bytes, int device, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Retrieval ranks for the evaluation metrics  (src/training/train.py:766-785 get_clip_metrics and
  * 712-763 compute_retrieval: similarity matrix on the CPU + argsort of every row + position search)

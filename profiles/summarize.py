@@ -17,7 +17,9 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__shared_mem_per_block_dynamic", "launch__block_size",
         "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "l1tex__m_l1tex2xbar_write_bytes_mem_dshared.sum", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
-        "l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed"]
+        "l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed", "launch__waves_per_multiprocessor",
+        "sm__cycles_active.avg", "sm__cycles_elapsed.max", "launch__occupancy_cluster_max_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"]
 
 
 def launches(path, out):
@@ -41,16 +43,20 @@ def launches(path, out):
 def raw(rep, out):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(txt.splitlines()))
-    hdr, units, vals = r[0], r[1], r[2]
+    hdr, units = r[0], r[1]
     with open(out, "w") as fh:
-        fh.write("# %s : kernel %s\n" % (rep, dict(zip(hdr, vals)).get("Kernel Name", "?")))
-        for h, u, v in zip(hdr, units, vals):
-            if h in KEYS:
-                fh.write("%-95s %18s %s\n" % (h, v, u))
+        for vals in r[2:]:          # one block per captured launch
+            d = dict(zip(hdr, vals))
+            fh.write("# %s : kernel %s  grid %s  cluster %s\n" % (rep, d.get("Kernel Name", "?"), d.get("launch__grid_size", "?"),
+                                                                 d.get("launch__cluster_size", "?")))
+            for h, u, v in zip(hdr, units, vals):
+                if h in KEYS:
+                    fh.write("%-95s %18s %s\n" % (h, v, u))
+            fh.write("\n")
 
 
 launches("gpurun_out/launches_%s.csv" % tag, "profiles/launches_%s.txt" % tag)
-for k in ("bwd", "fwd", "ema"):
+for k in ("bwd", "fwd", "ema", "retrieval"):
     try:
         raw("gpurun_out/prof_%s_%s.ncu-rep" % (k, tag), "profiles/ncu_%s_%s.txt" % (k, tag))
     except Exception as e:  # noqa

@@ -1,4 +1,4 @@
-"""Test-only CPU emulation of the three kernel entry points of cosmos_b200.infonce.
+"""Test-only CPU emulation of the kernel entry points of cosmos_b200.infonce.
 
 It restates exactly what include/cosmos_b200.h documents for cosmos_infonce_fwd / _loss_sums / _bwd in
 fp64 torch, so that the HOST logic (stacking, gathers, mode coefficients, LSE all-reduce, transposed
@@ -16,7 +16,10 @@ def _raw(x, y):
     return torch.einsum("ibd,jnd->ijbn", x.double(), y.double())       # [gx, gy, b, N]
 
 
-def emu_fwd(x, y, label_offset, scale):
+def emu_fwd(x, y, label_offset, scale, keep_e=False):
+    if keep_e:
+        # stored-exponential route: the emulation keeps the logits themselves (the layout of e / off is private to the kernels)
+        return emu_fwd(x, y, label_offset, scale) + (_raw(x, y) * (float(scale) * LOG2E), None)
     gx, b, _ = x.shape
     gy, N, _ = y.shape
     raw = _raw(x, y)
@@ -61,6 +64,29 @@ def emu_bwd(x, y, label_offset, scale, row_lse2, col_lse2, a_row, a_col, s_row, 
     return dx, dscale
 
 
+def emu_bwd_e(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream, want_dscale,
+              g_out=None):
+    """cosmos_infonce_bwd_e: the same gradient, formed from what the forward kept (here: the logits) - no x y^T."""
+    assert abs(a_row * s_col - a_col * s_row) < 1e-12, "bwd_e needs proportional d(scale) / gradient mixes"
+    gx, b, D = x.shape
+    gy, N, _ = y.shape
+    S2 = e
+    R = torch.exp2(S2 - row_lse2.double().view(gx, gy, b, 1))
+    Cm = torch.exp2(S2 - col_lse2.double().view(gx, gy, 1, N))
+    eye = torch.zeros(b, N, dtype=torch.float64)
+    eye[torch.arange(b), label_offset + torch.arange(b)] = 1
+    G = a_row * R + a_col * Cm - (a_row + a_col) * eye
+    if g_out is not None:
+        g_out[:, :gy * N] = G.permute(0, 2, 1, 3).reshape(gx * b, gy * N).to(g_out.dtype)
+    up = float(upstream)
+    acc = torch.einsum("ijbn,jnd->ibd", G, y.double())                      # the dX accumulators
+    dx = ((up * weight * float(scale)) * acc).to(x.dtype)
+    dscale = None
+    if want_dscale:       # sum_r <x_r, (G y)_r>, re-weighted to the d(scale) mix
+        dscale = ((up * weight * (s_row + s_col) / (a_row + a_col)) * (acc * x.double()).sum()).float().reshape(1)
+    return dx, dscale
+
+
 def emu_colgrad(g, x2d, n_c, n_cols):
     """infonce._k_colgrad: fp32 [n_c, n_cols, D] = sum over rows of G^T x."""
     D = x2d.shape[1]
@@ -74,11 +100,13 @@ def install(monkeypatch=None):
         monkeypatch.setattr(infonce, "_k_fwd", emu_fwd)
         monkeypatch.setattr(infonce, "_k_loss_sums", emu_loss_sums)
         monkeypatch.setattr(infonce, "_k_bwd", emu_bwd)
+        monkeypatch.setattr(infonce, "_k_bwd_e", emu_bwd_e)
         monkeypatch.setattr(infonce, "_k_colgrad", emu_colgrad)
         monkeypatch.setattr(_lib, "require_cuda", lambda t, what: None)
         monkeypatch.setattr(infonce, "compute_dtype", lambda dt: dt)
     else:
         infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd = emu_fwd, emu_loss_sums, emu_bwd
         infonce._k_colgrad = emu_colgrad
+        infonce._k_bwd_e = emu_bwd_e
         _lib.require_cuda = lambda t, what: None
         infonce.compute_dtype = lambda dt: dt

@@ -149,11 +149,20 @@ def test_cosmos_loss_golden_small(golden_dir, dtype):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("batch,dim,scale,keep_g", [(256, 512, 14.2857, False), (384, 512, 100.0, False), (1000, 256, 30.0, False),
-                                                    (256, 512, 14.2857, True), (392, 512, 100.0, True)])
+                                                    (256, 512, 14.2857, True), (392, 512, 100.0, True),
+                                                    (256, 512, 14.2857, "e"), (392, 512, 100.0, "e"), (77, 512, 50.0, "e")])
 def test_cosmos_loss_vs_oracle(batch, dim, scale, keep_g, monkeypatch):
     """BASELINE config 1 shape (batch 256, dim 512, 2 global + 6 local crops) and two more.  keep_g: the image-side CLIP
-    gradient through the stored G tiles + GEMM (cosmos_infonce_bwd_g), the route large batches take, forced at this size."""
-    if keep_g:
+    gradient through the stored G tiles + GEMM (cosmos_infonce_bwd_g), the route large batches take, forced at this size.
+    "e": the stored-exponential route (cosmos_infonce_fwd_e / _bwd_e, gradients formed in forward in chunks of three row
+    tensors), the route the headline batch takes, forced at this size (ragged batches included)."""
+    if keep_g == "e":
+        from cosmos_b200 import infonce
+        calls = []
+        real = infonce._k_bwd_e
+        monkeypatch.setattr(infonce, "_e_store_chunk", lambda x_r, y_c, comm: min(3, x_r.shape[0]))
+        monkeypatch.setattr(infonce, "_k_bwd_e", lambda *a: calls.append(1) or real(*a))
+    elif keep_g:
         from cosmos_b200 import infonce
         monkeypatch.setattr(infonce, "_G_STORE_MIN_BYTES", 0)
         calls = []
@@ -165,16 +174,18 @@ def test_cosmos_loss_vs_oracle(batch, dim, scale, keep_g, monkeypatch):
     ref = _run_oracle(inp, scale, scale, up, torch.bfloat16)
     _compare(ours, ref, up)
     if keep_g:
-        assert calls, "the stored-G route was not taken"
+        assert calls, "the forced route was not taken"
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("batch,scale", [(200, 14.2857), (130, 60.0)])
-def test_cosmos_loss_fp16_dim512(batch, scale, monkeypatch):
+@pytest.mark.parametrize("batch,scale,route", [(200, 14.2857, "g"), (130, 60.0, "g"), (200, 14.2857, "e"), (130, 60.0, "e")])
+def test_cosmos_loss_fp16_dim512(batch, scale, route, monkeypatch):
     """fp16 features (the reference's `--precision amp`) through the dim-512 cluster kernels, ragged batch; batch 200 also
     takes the stored-G route for the image-side CLIP gradient (130 is not a multiple of 8 and falls back to the second sweep)."""
     from cosmos_b200 import infonce
     monkeypatch.setattr(infonce, "_G_STORE_MIN_BYTES", 0)
+    if route == "e":     # stored exponentials are bf16 whatever the feature dtype is; G is converted to fp16 in shared memory
+        monkeypatch.setattr(infonce, "_e_store_chunk", lambda x_r, y_c, comm: x_r.shape[0])
     inp = O.make_features(batch, 512, seed=77)
     up = (65536.0, 65536.0)          # GradScaler's initial scale
     ours = _run_ours(inp, scale, scale * 0.7, up, torch.float16)

@@ -23,7 +23,10 @@ def _worker(rank, world, port, tmpdir, keep_g=False):
         from oracle import cosmos_oracle as O
         # (b, D, n_img, n_txt): dim 128 runs the CTA-pair backward, dim 512 the 4-CTA-cluster backward
         configs = ((160, 128, 3, 4), (192, 512, 4, 4))
-        if keep_g:      # non-local modes at dim 512: image-side CLIP gradient = NCCL reduce-scatter of G^T x over the stored tiles
+        if keep_g == "e":   # stored-exponential route in the non-local modes (the local-loss modes keep the recompute kernels)
+            infonce._e_store_chunk = lambda x_r, y_c, comm: 0 if comm.local_loss else min(3, x_r.shape[0])
+            configs = ((192, 512, 4, 4),)
+        elif keep_g:      # non-local modes at dim 512: image-side CLIP gradient = NCCL reduce-scatter of G^T x over the stored tiles
             infonce._G_STORE_MIN_BYTES = 0
             configs = ((192, 512, 4, 4),)
         cases = [(cfg, ll, gwg) for cfg in configs for ll, gwg in ((False, False), (False, True), (True, True), (True, False))]
@@ -70,7 +73,7 @@ def _worker(rank, world, port, tmpdir, keep_g=False):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("keep_g,port", [(False, 29731), (True, 29732)])
+@pytest.mark.parametrize("keep_g,port", [(False, 29731), (True, 29732), ("e", 29733)])
 def test_two_rank_nccl_all_modes(keep_g, port):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

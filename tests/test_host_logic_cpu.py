@@ -19,13 +19,22 @@ def _close(a, b, rtol=2e-4, atol=2e-6):
     torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
 
 
-@pytest.mark.parametrize("keep_g", [False, True])
+def _force_e_route(comm_free=True):
+    """Stored-exponential route (forward keeps what the backward needs, gradients formed chunk by chunk in forward) in chunks
+    of three row tensors, wherever the product would allow it (not in the local-loss modes)."""
+    return lambda x_r, y_c, comm: 0 if (comm.distributed and comm.local_loss) else min(3, x_r.shape[0])
+
+
+@pytest.mark.parametrize("keep_g", [False, True, "e"])
 def test_cosmos_api_single_process(monkeypatch, keep_g):
     from tests import emulation
     emulation.install(monkeypatch)
     from cosmos_b200 import COSMOSLoss, infonce
     used = []
-    if keep_g:      # column-side gradient through the stored G tiles + GEMM (the dim-512 route of the GPU path)
+    if keep_g == "e":
+        chunker = _force_e_route()
+        monkeypatch.setattr(infonce, "_e_store_chunk", lambda *a: used.append(1) or chunker(*a))
+    elif keep_g:      # column-side gradient through the stored G tiles + GEMM (the dim-512 route of the GPU path)
         monkeypatch.setattr(infonce, "_g_store_ok", lambda x_r, y_c: used.append(1) or True)
     for case in torch.load(os.path.join(GOLDEN, "cosmos_w1_small.pt"), weights_only=False):
         leaf = {k: [t.clone().requires_grad_(True) for t in v] for k, v in case["inputs"].items()}
@@ -51,7 +60,7 @@ def test_cosmos_api_single_process(monkeypatch, keep_g):
         total = COSMOSLoss()(leaf["s_image"], leaf["s_text"], ls, leaf["t_image"], leaf["t_text"], False, ds,
                              leaf["s_img_x"], leaf["s_txt_x"])
         _close(total.detach(), case["out"]["distill_loss"] + case["out"]["clip_loss"], rtol=2e-5)
-    assert bool(used) == keep_g
+    assert bool(used) == bool(keep_g)
 
 
 def test_stack_views_zero_copy():
@@ -95,7 +104,9 @@ def _rank_worker(rank, world, port, fname, tmpdir, keep_g=False):
         from tests import emulation
         emulation.install()
         from cosmos_b200 import ClipLoss, COSMOSLoss, infonce
-        if keep_g:      # non-local modes: column-side gradient = reduce-scatter of G^T x (stored G tiles) instead of a second sweep
+        if keep_g == "e":
+            infonce._e_store_chunk = _force_e_route()
+        elif keep_g:      # non-local modes: column-side gradient = reduce-scatter of G^T x (stored G tiles) instead of a second sweep
             infonce._g_store_ok = lambda x_r, y_c: True
         rec = torch.load(os.path.join(GOLDEN, fname), weights_only=False)
         for name, spec in rec["payload"].items():
@@ -140,7 +151,8 @@ def _rank_worker(rank, world, port, fname, tmpdir, keep_g=False):
 
 
 @pytest.mark.parametrize("world,fname,port,keep_g", [(2, "multirank_w2.pt", 29721, False), (4, "multirank_w4.pt", 29722, False),
-                                                     (2, "multirank_w2.pt", 29723, True), (4, "multirank_w4.pt", 29724, True)])
+                                                     (2, "multirank_w2.pt", 29723, True), (4, "multirank_w4.pt", 29724, True),
+                                                     (2, "multirank_w2.pt", 29725, "e"), (4, "multirank_w4.pt", 29726, "e")])
 def test_multirank_modes_gloo(world, fname, port, keep_g):
     ctx = mp.get_context("spawn")
     with tempfile.TemporaryDirectory() as tmpdir:
