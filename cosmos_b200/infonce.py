@@ -371,7 +371,8 @@ class _PairsInfoNCE(torch.autograd.Function):
         need_scale = ctx.needs_input_grad[0]
         need_rows = any(ctx.needs_input_grad[4:4 + n_r])
         need_cols = any(ctx.needs_input_grad[4 + n_r:])
-        chunk = _e_store_chunk(x_r, y_c, comm) if need_rows else 0
+        # (the column-side gradient of this route is a GEMM over stored G tiles, whose 16-byte pieces need N % 8 == 0)
+        chunk = _e_store_chunk(x_r, y_c, comm) if (need_rows and not (need_cols and N % 8 != 0)) else 0
         ctx.eager = chunk > 0
         if ctx.eager:
             # Stored-exponential route: per chunk of row tensors, forward (statistics + 2^(s2 - max) of every logit, bf16) and,

@@ -13,18 +13,8 @@ timeout 300 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TA
 timeout 90 python bench.py --global-batch 4096 --no-extras --no-cpu-baseline > gpurun_out/bench_4096_$TAG.json 2> gpurun_out/bench_4096_$TAG.err
 PROF="python bench.py --steps 1 --warmup 3 --no-extras --no-e2e --no-cpu-baseline"
 timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $PROF > gpurun_out/ncu_launches_$TAG.log 2>&1
-timeout 240 ncu --set full --clock-control none --import-source on -k regex:infonce_bwd_quad -s 6 -c 2 -f -o gpurun_out/prof_bwd_$TAG $PROF > gpurun_out/ncu_bwd_$TAG.log 2>&1
-timeout 120 ncu --set full --clock-control none --import-source on -k regex:retrieval_count -s 1 -c 1 -f -o gpurun_out/prof_retrieval_$TAG \
-  python -c "
-import torch, sys
-sys.path.insert(0, '.')
-from cosmos_b200 import retrieval_ranks
-g = torch.Generator(device='cuda').manual_seed(1)
-a = torch.nn.functional.normalize(torch.randn(16384, 512, generator=g, device='cuda'), dim=-1)
-b = torch.nn.functional.normalize(torch.randn(16384, 512, generator=g, device='cuda'), dim=-1)
-for _ in range(3): r = retrieval_ranks(a, b)
-torch.cuda.synchronize(); print(r[:8])
-" > gpurun_out/ncu_retrieval_$TAG.log 2>&1
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:infonce_bwd_e -s 15 -c 1 -f -o gpurun_out/prof_bwd_$TAG $PROF > gpurun_out/ncu_bwd_$TAG.log 2>&1
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:infonce_fwd -s 15 -c 1 -f -o gpurun_out/prof_fwd_$TAG $PROF > gpurun_out/ncu_fwd_$TAG.log 2>&1
 ls -la gpurun_out
 tail -5 gpurun_out/pytest_gpu_$TAG.log
 cat gpurun_out/bench_$TAG.json | cut -c1-600
