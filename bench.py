@@ -39,9 +39,9 @@ def algorithmic_flops(n_global: int, dim: int = DIM) -> float:
     return 352.0 * n_global * n_global * dim
 
 
-def ncu_traffic(kind):
-    """DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full summary (global batch 4096)."""
-    path = os.path.join(ROOT, "profiles", "ncu_%s_r01.txt" % kind)
+def ncu_traffic(kind, tag="r01"):
+    """DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full summary."""
+    path = os.path.join(ROOT, "profiles", "ncu_%s_%s.txt" % (kind, tag))
     try:
         tot = 0.0
         for line in open(path):
@@ -309,8 +309,11 @@ def run_ours(args):
             "roofline": {"bound": "tensor",
                          "kernel": Instrument.NAMES[dom],
                          "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-                         "traffic": ncu_traffic(dom) if (n_global == 4096 and dom in ("fwd", "bwd")) else None,
-                         "traffic_note": "dram__bytes_read+write of one launch from profiles/ncu_*_r01.txt (captured at global batch 4096)",
+                         "traffic": (ncu_traffic("bwd", "r01c") if (dom == "bwd_e" and n_global == 32768 and world == 1) else
+                                     ncu_traffic(dom) if (n_global == 4096 and dom in ("fwd", "bwd")) else None),
+                         "traffic_note": "dram__bytes_read+write of one launch of this kernel from the committed ncu --set full "
+                                         "summary (profiles/ncu_bwd_r01c.txt: global batch 32768, one GPU, 16 pairs per launch; "
+                                         "profiles/ncu_*_r01.txt: global batch 4096); null for other configurations",
                          "executed_tflops": achieved * (2.0 if dom == "bwd" else 1.0),   # the recompute backward runs S and dX
                          "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step); burst %.1f" % (src, burst),
                          "launch_ms_avg": k["ms_avg"], "launches_timed": k["launches"],

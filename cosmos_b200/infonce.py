@@ -318,6 +318,9 @@ _E_STORE_MAX_BYTES = int(float(os.environ.get("COSMOS_B200_ESTORE_MAX_GB", "40")
 _E_STORE_MIN_BYTES = int(float(os.environ.get("COSMOS_B200_ESTORE_MIN_GB", "0.25")) * (1 << 30))
 
 
+_e_chunk_cache: dict = {}
+
+
 def _e_store_chunk(x_r: torch.Tensor, y_c: torch.Tensor, comm: Comm) -> int:
     """Row tensors per pass of the stored-exponential route (csrc/infonce_bwd_e.cu), 0 = use the recompute kernels.
 
@@ -331,16 +334,25 @@ def _e_store_chunk(x_r: torch.Tensor, y_c: torch.Tensor, comm: Comm) -> int:
     per_tensor = n_c * (-(-b // 128) * 128) * (-(-n_all // 128) * 128) * 2
     if per_tensor * n_r < _E_STORE_MIN_BYTES:
         return 0
-    budget = _E_STORE_MAX_BYTES
-    if x_r.is_cuda:
-        free, _total = torch.cuda.mem_get_info(x_r.device)
-        free += torch.cuda.memory_reserved(x_r.device) - torch.cuda.memory_allocated(x_r.device)   # cached blocks are reusable
-        budget = min(budget, free // 3)          # exponentials + (CLIP group) the G tiles of the same chunk + headroom
-    most = min(n_r, budget // per_tensor)
-    if most <= 0:
-        return 0
-    passes = -(-n_r // most)
-    return -(-n_r // passes)                     # equal passes: 16 tensors at most 5 at a time -> 4 + 4 + 4 + 4, not 5 + 5 + 5 + 1
+    key = (n_r, b, n_c, n_all, x_r.device)
+    chunk = _e_chunk_cache.get(key)
+    if chunk is None:
+        # decided once per problem shape: cudaMemGetInfo stalls the launch queue, which a per-step call would pay every step
+        budget = _E_STORE_MAX_BYTES
+        if x_r.is_cuda:
+            free, _total = torch.cuda.mem_get_info(x_r.device)
+            free += torch.cuda.memory_reserved(x_r.device) - torch.cuda.memory_allocated(x_r.device)   # cached blocks are reusable
+            budget = min(budget, free // 3)      # exponentials + (CLIP group) the G tiles of the same chunk + headroom
+        most = min(n_r, budget // per_tensor)
+        if most <= 0:
+            chunk = 0
+        else:
+            passes = -(-n_r // most)
+            chunk = -(-n_r // passes)            # equal passes: 16 tensors at most 5 at a time -> 4 + 4 + 4 + 4, not 5 + 5 + 5 + 1
+        if len(_e_chunk_cache) > 64:
+            _e_chunk_cache.clear()
+        _e_chunk_cache[key] = chunk
+    return chunk
 
 
 class _PairsInfoNCE(torch.autograd.Function):
@@ -490,7 +502,6 @@ class _PairsInfoNCE(torch.autograd.Function):
         (scale_f,) = ctx.saved_tensors
         comm, n_r, n_c, b = ctx.comm, ctx.n_r, ctx.n_c, ctx.b
         dx_unit, ds_unit, d_all, weight = ctx.unit
-        ctx.unit = None
         up = g.detach().to(torch.float32).reshape(1)
         grads: List[Optional[torch.Tensor]] = []
         d_rows = (dx_unit.float() * up).to(dx_unit.dtype) if any(ctx.needs_input_grad[4:4 + n_r]) else None

@@ -44,6 +44,8 @@ def raw(rep, out):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(txt.splitlines()))
     hdr, units = r[0], r[1]
+    if len(r) < 3:
+        raise RuntimeError("no launches in " + rep)
     with open(out, "w") as fh:
         for vals in r[2:]:          # one block per captured launch
             d = dict(zip(hdr, vals))
@@ -56,7 +58,10 @@ def raw(rep, out):
 
 
 launches("gpurun_out/launches_%s.csv" % tag, "profiles/launches_%s.txt" % tag)
+import os
 for k in ("bwd", "fwd", "ema", "retrieval"):
+    if not os.path.exists("gpurun_out/prof_%s_%s.ncu-rep" % (k, tag)):
+        continue
     try:
         raw("gpurun_out/prof_%s_%s.ncu-rep" % (k, tag), "profiles/ncu_%s_%s.txt" % (k, tag))
     except Exception as e:  # noqa

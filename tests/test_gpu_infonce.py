@@ -236,3 +236,38 @@ def test_clip_loss_api_and_errors():
     with pytest.raises(RuntimeError):
         x = torch.randn(8, 100, device="cuda").bfloat16()            # dim not a multiple of 64
         ClipLoss()(x, x, 1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,n_all,off,gx,gy,scale,dtype", [(200, 600, 400, 2, 3, 30.0, torch.bfloat16),
+                                                           (128, 256, 128, 1, 1, 100.0, torch.bfloat16),
+                                                           (77, 231, 77, 3, 2, 14.2857, torch.float16),
+                                                           (300, 1200, 0, 2, 2, 60.0, torch.bfloat16)])
+def test_stored_exponential_kernels_match_recompute_kernels(b, n_all, off, gx, gy, scale, dtype):
+    """cosmos_infonce_fwd_e + _bwd_e against cosmos_infonce_fwd + _bwd on a row block that is NOT the first of its batch
+    (label_offset = rank * b as on rank > 0 of a multi-GPU job), ragged sizes, both 16-bit dtypes, a_row != a_col."""
+    from cosmos_b200 import infonce as K
+    g = torch.Generator().manual_seed(b + n_all + off)
+    z = torch.randn(n_all, 512, generator=g)
+    y = torch.nn.functional.normalize(z[None] + 1.5 * torch.randn(gy, n_all, 512, generator=g), dim=-1).to(dtype).cuda()
+    x = torch.nn.functional.normalize(z[None, off:off + b] + 1.5 * torch.randn(gx, b, 512, generator=g), dim=-1).to(dtype).cuda()
+    sc = torch.tensor([scale], device="cuda")
+    up = torch.tensor([3.0], device="cuda")
+    row, diag, col = K._k_fwd(x, y, off, sc)
+    row_e, diag_e, col_e, e, offs = K._k_fwd(x, y, off, sc, True)
+    assert torch.equal(row, row_e) and torch.equal(diag, diag_e) and torch.equal(col, col_e)
+    for a_row, a_col, ratio in ((1.0, 1.0, 1.0), (1.0, 0.0, 0.5), (0.25, 1.0, 2.0)):
+        mix = (a_row, a_col, ratio * a_row, ratio * a_col, 0.125)
+        dx_ref, ds_ref = K._k_bwd(x, y, off, sc, row, col, *mix, up, True, True)
+        dx, ds = K._k_bwd_e(x, y, off, sc, e, offs, row, col, *mix, up, True)
+        assert cosine(dx.float().cpu(), dx_ref.float().cpu()) >= 0.99999
+        assert abs(float(dx.float().norm()) / float(dx_ref.float().norm()) - 1.0) <= 2e-3
+        assert abs(float(ds) - float(ds_ref)) <= 2e-3 * abs(float(ds_ref)) + 1e-6
+    if n_all % 8 == 0:
+        g1 = torch.zeros(gx * b, gy * n_all, dtype=dtype, device="cuda")
+        g2 = torch.zeros_like(g1)
+        K._k_bwd(x, y, off, sc, row, col, 1.0, 1.0, 1.0, 1.0, 0.125, up, True, False, g1)
+        K._k_bwd_e(x, y, off, sc, e, offs, row, col, 1.0, 1.0, 1.0, 1.0, 0.125, up, False, g2)
+        assert cosine(g1.float().cpu(), g2.float().cpu()) >= 0.99999
+    with pytest.raises(RuntimeError, match="unsupported"):      # d(scale) weights not proportional to the gradient weights
+        K._k_bwd_e(x, y, off, sc, e, offs, row, col, 1.0, 1.0, 1.0, 0.0, 0.125, up, True)
