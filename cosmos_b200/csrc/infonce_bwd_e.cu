@@ -11,15 +11,19 @@
 // S / G buffers compete for it, so there are no "parts", no 4-CTA clusters and no DSMEM exchange.
 //
 // One CTA pair (cluster of 2, tcgen05 cta_group::2, M = 256) = 256 rows of one row tensor; per 128-column step and CTA:
-//   TMA: E tile [128 rows x 128 columns] bf16, stored by the forward as 16 contiguous [128 rows][8 columns] pieces ->
-//        two slabs of 8 pieces = the unswizzled K-major core-matrix layout (A operand: LBO 2048, SBO 128)
-//   8 scaling warps: e -> G in place (stack dtype), diagonal, d(scale) partial sums, optional copy of G to HBM
+//   8 scaling warps: E tile [128 rows x 128 columns] bf16 - stored by the forward as 16 contiguous [128 rows][8 columns]
+//        pieces - straight from global memory into registers (loaded one step ahead; a warp load is 512 contiguous bytes;
+//        one warp prefetches the tiles into L2 six steps ahead), e -> G (stack dtype, positives subtracted), one store
+//        into a 3-stage shared-memory ring in the unswizzled K-major core-matrix layout [piece][row][16 bytes]
+//        (A operand: LBO 2048, SBO 128), optional copy of G to HBM for the column-side GEMM of the CLIP term
 //   fence.proxy.async, then  dX[:, 0:256] += G Y[:, 0:256],  dX[:, 256:512] += G Y[:, 256:512]  (A and B from shared memory,
 //   B = MN-major view of the Y slabs the other kernels read K-major; each CTA supplies 128 of the 256 N columns)
-// HBM traffic: 2 bytes per logit read here + 2 written by the forward (~2.5 TB/s each at the tensor rate, K = D = 512).
+// At the end d(scale) = sum_r <x_r, (G Y)_r> is read off the fp32 accumulators while they are drained.
+// HBM traffic: 2 bytes per logit read here + 2 written by the forward (~2.4 TB/s each while the tensor pipe is busy).
 // Elements more than 2^-126 below their row's running maximum are zero in E: their row-softmax weight is below fp32
 // resolution (the reference's own softmax flushes them too); a column-softmax weight such an element may still carry
-// (a column whose every entry is that far below its row's maximum) is dropped - DESIGN.md "stored exponentials".
+// (a column whose every entry is that far below its row's maximum) is dropped - DESIGN.md section 3.
+// COSMOS_B200_DBG (diagnostics): 1024 print stall counters (results unchanged), 2048 no scaling math (wrong results).
 #include <cstdio>
 #include "common.cuh"
 #include "infonce.h"
@@ -29,20 +33,20 @@ namespace cb {
 
 namespace {
 
-constexpr int kSlabE = 128 * 64 * 2;   // 16 KB: 8 pieces of [128 rows][8 columns]
-constexpr int kStageE = 2 * kSlabE;    // one 128-column step
-constexpr int kStagesE = 3;              // G tiles (A operand): being written / waiting / being read
-constexpr int kAheadE = 6;             // steps by which the L2 prefetch of E runs ahead of the shared-memory ring
+constexpr int kSlabG = 128 * 64 * 2;   // 16 KB: 8 pieces of [128 rows][8 columns] = one 64-column (K) slab of a G tile
+constexpr int kStageG = 2 * kSlabG;    // one 128-column step
+constexpr int kStagesG = 3;            // G tiles (A operand): being written / waiting / being read
+constexpr int kAheadE = 6;             // steps by which the L2 prefetch of E runs ahead of its use
 constexpr int kSlabB = 64 * 64 * 2;    // 8 KB: 64 columns (K) x 64 embedding elements
 constexpr int kUnitB = 2 * kSlabB;     // this CTA's 128 embedding columns of one N half, for one 64-column half step
-constexpr int kUnitsB = 8;               // two steps of B slabs
+constexpr int kUnitsB = 8;             // two steps of B slabs
 constexpr int kSmemMisc = 3072;
 constexpr int kThreads = 384;          // warps 0-3: roles; warps 4-11: scaling + dX drain
 constexpr int kScale = 256;
 
 struct Misc {
-  uint64_t e_empty[kStagesE];   // per CTA: tcgen05.commit (multicast) once the step's MMAs have read the G tile of this stage
-  uint64_t g_full[kStagesE];    // pair leader: one arrive per scaling warp of both CTAs
+  uint64_t g_empty[kStagesG];   // per CTA: tcgen05.commit (multicast) once the step's MMAs have read the G tile of this stage
+  uint64_t g_full[kStagesG];    // pair leader: one arrive per scaling warp of both CTAs
   uint64_t b_full[kUnitsB];     // pair leader: TMA bytes of both CTAs
   uint64_t b_empty[kUnitsB];
   uint64_t dx_full;
@@ -53,7 +57,7 @@ struct Misc {
   alignas(16) float lc[2][128];   // lse_col itself (slow path)
 };
 static_assert(sizeof(Misc) <= kSmemMisc, "misc smem");
-static_assert(kStagesE * kStageE + kUnitsB * kUnitB + kSmemMisc <= 232448, "shared memory budget");
+static_assert(kStagesG * kStageG + kUnitsB * kUnitB + kSmemMisc <= 232448, "shared memory budget");
 
 __device__ __forceinline__ uint32_t bar_red_or(uint32_t id, uint32_t nthreads, bool pred) {
   uint32_t out;
@@ -66,11 +70,6 @@ __device__ __forceinline__ uint32_t bar_red_or(uint32_t id, uint32_t nthreads, b
       : "r"(id), "r"(nthreads), "r"(static_cast<uint32_t>(pred))
       : "memory");
   return out;
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -95,14 +94,14 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
   const int n_ct = p.n_col_tiles;
   const int T = p.gy * n_ct;
 
-  uint8_t* sE = smem;
-  uint8_t* sB = sE + kStagesE * kStageE;
+  uint8_t* sG = smem;
+  uint8_t* sB = sG + kStagesG * kStageG;
   Misc* misc = reinterpret_cast<Misc*>(sB + kUnitsB * kUnitB);
 
   cluster_sync_all();
   if (tid == 0) {
-    for (int s = 0; s < kStagesE; ++s) {
-      mbar_init(&misc->e_empty[s], 1);
+    for (int s = 0; s < kStagesG; ++s) {
+      mbar_init(&misc->g_empty[s], 1);
       mbar_init(&misc->g_full[s], 2 * 8);
     }
     for (int u = 0; u < kUnitsB; ++u) {
@@ -139,13 +138,13 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
       }
     __syncwarp();
     for (int t = 0; t + kAheadE < T; ++t) {
-      mbar_wait(&misc->e_empty[s], ph ^ 1);        // paced by the consumption of the G stages
+      mbar_wait(&misc->g_empty[s], ph ^ 1);        // paced by the consumption of the G stages
       if (elect_one()) {
         tma_prefetch_3d(&tmE, 0, 0, piece_of(t + kAheadE));
         tma_prefetch_3d(&tmE, 0, 0, piece_of(t + kAheadE) + 8);
       }
       __syncwarp();
-      if (++s == kStagesE) { s = 0; ph ^= 1; }
+      if (++s == kStagesG) { s = 0; ph ^= 1; }
     }
   } else if (warp == 3) {
     // ---------------- TMA producer: Y slabs (B operand), in the order the MMA warp consumes them ----------------
@@ -191,7 +190,7 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
           for (int nh = 0; nh < 2; ++nh) {
             wait_t(&misc->b_full[u], ph, w_b);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(sE + s * kStageE + half * kSlabE);
+            const uint32_t a_base = smem_u32(sG + s * kStageG + half * kSlabG);
             const uint32_t b_base = smem_u32(sB + u * kUnitB);
             if (elect_one()) {
 #pragma unroll
@@ -199,13 +198,13 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
                 umma_ss_pair(tmem + nh * 256, make_smem_desc_noswizzle(a_base + kk * 4096, 2048, 128),
                              make_smem_desc(b_base + kk * 2048, kSlabB, 1024), p.idesc_g, (t | half | kk) != 0);
               tc_commit_pair(&misc->b_empty[u], 3);
-              if (half == 1 && nh == 1) tc_commit_pair(&misc->e_empty[s], 3);
+              if (half == 1 && nh == 1) tc_commit_pair(&misc->g_empty[s], 3);
             }
             __syncwarp();
             if (++u == kUnitsB) { u = 0; ph ^= 1; }
           }
         }
-        if (++s == kStagesE) { s = 0; phs ^= 1; }
+        if (++s == kStagesG) { s = 0; phs ^= 1; }
       }
       if (elect_one()) tc_commit_pair(&misc->dx_full, 3);
       __syncwarp();
@@ -294,9 +293,9 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
 
       long long c0 = 0, c1 = 0;
       if (eprof) c0 = clock64();
-      mbar_wait(&misc->e_empty[s], phs ^ 1);        // the MMAs that read this stage three steps ago are done
+      mbar_wait(&misc->g_empty[s], phs ^ 1);        // the MMAs that read this stage three steps ago are done
       if (eprof) c1 = clock64();
-      const uint32_t stage = smem_u32(sE + s * kStageE);
+      const uint32_t stage = smem_u32(sG + s * kStageG);
 #pragma unroll
       for (int sl = 0; sl < 2; ++sl) {
         float A1 = 0.f, A2 = 0.f;
@@ -309,7 +308,7 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
 #pragma unroll
         for (int p4 = 0; p4 < 4; ++p4) {
           const uint32_t lp = hr * 4 + p4;                                    // 8-column piece of the slab
-          const uint32_t addr = stage + sl * kSlabE + lp * 2048 + row_t * 16;   // 8 lanes = 128 contiguous bytes: no bank conflicts
+          const uint32_t addr = stage + sl * kSlabG + lp * 2048 + row_t * 16;   // 8 lanes = 128 contiguous bytes: no bank conflicts
           const int c0 = col_base + sl * 64 + static_cast<int>(lp) * 8;
           const uint4 w = e_cur[sl * 4 + p4];
           if (!row_valid || c0 >= p.n_cols || (p.dbg & 2048)) {   // 2048: diagnostics, no scaling math (wrong results)
@@ -363,7 +362,7 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
         e_work += clock64() - c1;
         e_pre += c0 - c_top;
       }
-      if (++s == kStagesE) { s = 0; phs ^= 1; }
+      if (++s == kStagesG) { s = 0; phs ^= 1; }
     }
     if (eprof)
       printf("bwd_e prof cluster %d cta %u warp %u: scaling warps: stats+barrier %lld, stage wait %lld, scale+publish %lld (steps %d)\n",
@@ -434,7 +433,7 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
 }
 
 cudaError_t launch_infonce_bwd_e(const CUtensorMap& tmE, const CUtensorMap& tmY64, const BwdEParams& p, cudaStream_t stream) {
-  const int smem_bytes = kStagesE * kStageE + kUnitsB * kUnitB + kSmemMisc;
+  const int smem_bytes = kStagesG * kStageG + kUnitsB * kUnitB + kSmemMisc;
   cudaError_t e = cudaFuncSetAttribute(infonce_bwd_e_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
