@@ -393,6 +393,8 @@ int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const f
   bp.n_chunks = (p->n_cols + 31) / 32;
   bp.dtype = p->dtype;
   bp.dbg = dbg_flags();
+  bp.e_ahead = 6;
+  if (const char* ea = getenv("COSMOS_B200_EAHEAD")) bp.e_ahead = atoi(ea) < 0 ? 0 : atoi(ea);   // diagnostics
   bp.idesc_g = cb::make_idesc(bf, 0, 1, 2 * cb::kFwdBM, 256);
   bp.a_row = a_row; bp.a_col = a_col; bp.s_row = s_row; bp.s_col = s_col; bp.weight = weight;
   bp.scale = reinterpret_cast<const float*>(p->scale);

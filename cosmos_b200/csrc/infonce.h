@@ -63,6 +63,7 @@ struct BwdEParams {
   int n_chunks;                   // ceil(n_cols / 32)
   int dtype;                      // dtype of y, dx and g_out (the A operand is converted to it in shared memory)
   int dbg;
+  int e_ahead;                    // steps by which the L2 prefetch of E runs ahead of its use (0: no prefetch)
   uint32_t idesc_g;
   float a_row, a_col, s_row, s_col, weight;
   const float* scale;

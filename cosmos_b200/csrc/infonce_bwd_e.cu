@@ -36,7 +36,6 @@ namespace {
 constexpr int kSlabG = 128 * 64 * 2;   // 16 KB: 8 pieces of [128 rows][8 columns] = one 64-column (K) slab of a G tile
 constexpr int kStageG = 2 * kSlabG;    // one 128-column step
 constexpr int kStagesG = 3;            // G tiles (A operand): being written / waiting / being read
-constexpr int kAheadE = 6;             // steps by which the L2 prefetch of E runs ahead of its use
 constexpr int kSlabB = 64 * 64 * 2;    // 8 KB: 64 columns (K) x 64 embedding elements
 constexpr int kUnitB = 2 * kSlabB;     // this CTA's 128 embedding columns of one N half, for one 64-column half step
 constexpr int kUnitsB = 8;             // two steps of B slabs
@@ -125,23 +124,24 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
     // ---------------- L2 prefetch of this CTA's E tiles ----------------
     // E comes from HBM and is read exactly once, by plain loads of the scaling warps (a TMA landing buffer would cost
     // shared-memory bandwidth the tensor core needs: the A and B operands of every MMA are read from shared memory).
-    // Those loads run only one step ahead, so the tiles are pulled into L2 kAheadE steps early.
+    // Those loads run only one step ahead, so the tiles are pulled into L2 p.e_ahead steps early.
     uint32_t s = 0, ph = 0;
     auto piece_of = [&](int t) {
       const int j = t / n_ct, tc = t - j * n_ct;
       return (((i * p.gy + j) * p.n_row_tiles + (tile_valid ? tr : 0)) * n_ct + tc) * 16;
     };
+    const int ahead = p.e_ahead;
     if (elect_one())
-      for (int t = 0; t < kAheadE && t < T; ++t) {
+      for (int t = 0; t < ahead && t < T; ++t) {
         tma_prefetch_3d(&tmE, 0, 0, piece_of(t));
         tma_prefetch_3d(&tmE, 0, 0, piece_of(t) + 8);
       }
     __syncwarp();
-    for (int t = 0; t + kAheadE < T; ++t) {
+    for (int t = 0; ahead > 0 && t + ahead < T; ++t) {
       mbar_wait(&misc->g_empty[s], ph ^ 1);        // paced by the consumption of the G stages
       if (elect_one()) {
-        tma_prefetch_3d(&tmE, 0, 0, piece_of(t + kAheadE));
-        tma_prefetch_3d(&tmE, 0, 0, piece_of(t + kAheadE) + 8);
+        tma_prefetch_3d(&tmE, 0, 0, piece_of(t + ahead));
+        tma_prefetch_3d(&tmE, 0, 0, piece_of(t + ahead) + 8);
       }
       __syncwarp();
       if (++s == kStagesG) { s = 0; ph ^= 1; }

@@ -250,3 +250,28 @@ def test_retrieval_rejects_cpu_tensors():
     from cosmos_b200 import retrieval_ranks
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         retrieval_ranks(torch.randn(4, 8), torch.randn(5, 8))
+
+
+def test_stored_exponential_chunking(monkeypatch):
+    """_e_store_chunk: route selection and equal passes (shapes only; meta tensors)."""
+    from cosmos_b200 import infonce
+    from cosmos_b200.infonce import Comm, _e_store_chunk
+
+    def stacks(n_r, b, n_c, n_all, dim=512):
+        return (torch.empty(n_r, b, dim, dtype=torch.bfloat16, device="meta"),
+                torch.empty(n_c, n_all, dim, dtype=torch.bfloat16, device="meta"))
+
+    monkeypatch.setattr(infonce, "_e_chunk_cache", {})
+    monkeypatch.setattr(infonce, "_E_STORE_MAX_BYTES", 40 << 30)
+    monkeypatch.setattr(infonce, "_E_STORE_MIN_BYTES", 1 << 28)
+    assert _e_store_chunk(*stacks(16, 32768, 4, 32768), Comm()) == 4        # 8.6 GB per row tensor: 4 + 4 + 4 + 4
+    assert _e_store_chunk(*stacks(8, 32768, 2, 32768), Comm()) == 8         # CLIP group, one GPU: one pass
+    assert _e_store_chunk(*stacks(16, 4096, 4, 32768), Comm(rank=1, world_size=8)) == 16     # 8 GPUs: one pass
+    assert _e_store_chunk(*stacks(16, 4096, 4, 32768), Comm(rank=1, world_size=8, local_loss=True)) == 0
+    assert _e_store_chunk(*stacks(16, 4096, 4, 32768, dim=256), Comm()) == 0                 # other widths: recompute kernels
+    assert _e_store_chunk(*stacks(8, 256, 2, 256), Comm()) == 0                              # tiny: one launch per group wins
+    monkeypatch.setattr(infonce, "_E_STORE_MAX_BYTES", 30 << 30)
+    monkeypatch.setattr(infonce, "_e_chunk_cache", {})
+    assert _e_store_chunk(*stacks(16, 32768, 4, 32768), Comm()) == 3        # at most 3 fit: 6 passes of 3, 3, 3, 3, 3, 1
+    monkeypatch.setattr(infonce, "_E_STORE_MAX_BYTES", 0)
+    assert _e_store_chunk(*stacks(16, 32768, 4, 32768), Comm()) == 0        # COSMOS_B200_ESTORE_MAX_GB=0 switches the route off
