@@ -3,17 +3,23 @@
 `pairs_infonce(rows, cols, scale, ...)` is the mean, over the cartesian product of two feature
 lists, of the symmetric InfoNCE loss the reference computes pair by pair in
 `ClipLoss.forward` (src/open_clip/loss.py:121-142), including the multi-rank gather semantics of
-`gather_features` / `get_logits` (loss.py:21-65, 103-119).  All pairs of one call go through ONE
-forward kernel launch and one (row side) or two (both sides need gradients) backward launches.
+`gather_features` / `get_logits` (loss.py:21-65, 103-119).  All pairs of one call go through a
+few grouped launches (one forward + one backward per chunk of row tensors, see below).
 
 Partitioning: this rank owns `b` rows of every tensor.  The forward computes the
 row block  S[local rows of R_i, all N rows of C_j]  for every pair; that yields
   * the complete row log-sum-exp of the local rows,
   * this rank's partial column log-sum-exp for all N columns  -> combined with two all-reduces,
   * the positives (diagonal).
-The backward recomputes the same block and needs nothing else from other ranks for the row side;
-the column side (only when it needs gradients, i.e. the CLIP term) is the same kernel run on the
-transposed block  S^T[local rows of C_j, all N rows of R_i].
+Gradients, two routes:
+  * stored exponentials (dim 512, every mode but local_loss): the forward keeps 2^(s2 - max) of every
+    logit (bf16) and cosmos_infonce_bwd_e forms dX = G Y from them - no logit is recomputed.  The
+    gradients for a unit upstream gradient are formed inside forward(), chunk of row tensors by chunk,
+    so only one chunk of exponentials is alive; backward() scales them.  The column side (CLIP term) is
+    one GEMM G^T X over the G tiles the same kernel writes out (+ reduce-scatter across ranks).
+  * recompute: the backward recomputes the same block and needs nothing else from other ranks for
+    the row side; the column side is either the G^T X GEMM over tiles stored by the row pass or the
+    same kernel run on the transposed block  S^T[local rows of C_j, all N rows of R_i].
 
 Mode table (probed against the reference on gloo ranks, tests/golden/multirank_w*.pt), N = W*b,
 P = number of pairs, R/C = row/column softmax, I = positives:
