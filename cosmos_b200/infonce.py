@@ -340,7 +340,7 @@ def _e_store_chunk(x_r: torch.Tensor, y_c: torch.Tensor, comm: Comm) -> int:
     per_tensor = n_c * (-(-b // 128) * 128) * (-(-n_all // 128) * 128) * 2
     if per_tensor * n_r < _E_STORE_MIN_BYTES:
         return 0
-    key = (n_r, b, n_c, n_all, x_r.device)
+    key = (n_r, b, n_c, n_all, x_r.device, comm.world_size, id(comm.group))
     chunk = _e_chunk_cache.get(key)
     if chunk is None:
         # decided once per problem shape: cudaMemGetInfo stalls the launch queue, which a per-step call would pay every step
@@ -355,6 +355,12 @@ def _e_store_chunk(x_r: torch.Tensor, y_c: torch.Tensor, comm: Comm) -> int:
         else:
             passes = -(-n_r // most)
             chunk = -(-n_r // passes)            # equal passes: 16 tensors at most 5 at a time -> 4 + 4 + 4 + 4, not 5 + 5 + 5 + 1
+        if comm.distributed:
+            # every rank must make the same number of passes (each pass all-reduces its column statistics): agree on the
+            # smallest chunk once per shape; ranks see the same shapes in the same order, so they all arrive here together
+            agreed = torch.tensor([chunk], dtype=torch.int32, device=x_r.device if x_r.is_cuda else "cpu")
+            dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=comm.group)
+            chunk = int(agreed.item())
         if len(_e_chunk_cache) > 64:
             _e_chunk_cache.clear()
         _e_chunk_cache[key] = chunk

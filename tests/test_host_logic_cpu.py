@@ -261,12 +261,17 @@ def test_stored_exponential_chunking(monkeypatch):
         return (torch.empty(n_r, b, dim, dtype=torch.bfloat16, device="meta"),
                 torch.empty(n_c, n_all, dim, dtype=torch.bfloat16, device="meta"))
 
+    agreed = []
+    # ranks agree on the smallest chunk with one MIN all-reduce per shape; here: a rank whose peers can only take 5 at a time
+    monkeypatch.setattr(infonce.dist, "all_reduce", lambda t, op=None, group=None: (agreed.append(int(t)), t.clamp_(max=5))[1])
     monkeypatch.setattr(infonce, "_e_chunk_cache", {})
     monkeypatch.setattr(infonce, "_E_STORE_MAX_BYTES", 40 << 30)
     monkeypatch.setattr(infonce, "_E_STORE_MIN_BYTES", 1 << 28)
     assert _e_store_chunk(*stacks(16, 32768, 4, 32768), Comm()) == 4        # 8.6 GB per row tensor: 4 + 4 + 4 + 4
     assert _e_store_chunk(*stacks(8, 32768, 2, 32768), Comm()) == 8         # CLIP group, one GPU: one pass
-    assert _e_store_chunk(*stacks(16, 4096, 4, 32768), Comm(rank=1, world_size=8)) == 16     # 8 GPUs: one pass
+    assert _e_store_chunk(*stacks(16, 4096, 4, 32768), Comm()) == 16        # the per-rank problem of an 8-GPU job: one pass
+    assert _e_store_chunk(*stacks(16, 4096, 4, 32768), Comm(rank=1, world_size=8)) == 5 and agreed == [16]
+    assert _e_store_chunk(*stacks(16, 4096, 4, 32768), Comm(rank=1, world_size=8)) == 5 and agreed == [16]   # cached: no second collective
     assert _e_store_chunk(*stacks(16, 4096, 4, 32768), Comm(rank=1, world_size=8, local_loss=True)) == 0
     assert _e_store_chunk(*stacks(16, 4096, 4, 32768, dim=256), Comm()) == 0                 # other widths: recompute kernels
     assert _e_store_chunk(*stacks(8, 256, 2, 256), Comm()) == 0                              # tiny: one launch per group wins
@@ -275,3 +280,37 @@ def test_stored_exponential_chunking(monkeypatch):
     assert _e_store_chunk(*stacks(16, 32768, 4, 32768), Comm()) == 3        # at most 3 fit: 6 passes of 3, 3, 3, 3, 3, 1
     monkeypatch.setattr(infonce, "_E_STORE_MAX_BYTES", 0)
     assert _e_store_chunk(*stacks(16, 32768, 4, 32768), Comm()) == 0        # COSMOS_B200_ESTORE_MAX_GB=0 switches the route off
+
+
+def _chunk_agreement_worker(rank, world, port, tmpdir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cosmos_b200 import infonce
+        infonce._E_STORE_MIN_BYTES = 0
+        per_tensor = 2 * 128 * 256 * 2                      # n_c = 2, b = 100 -> 128, N = 200 -> 256
+        infonce._E_STORE_MAX_BYTES = per_tensor * (7 if rank == 0 else 3)     # the ranks could take 7 and 3 row tensors at a time
+        x = torch.empty(7, 100, 512, dtype=torch.bfloat16)
+        y = torch.empty(2, 200, 512, dtype=torch.bfloat16)
+        comm = infonce.Comm(rank=rank, world_size=world, group=dist.group.WORLD)
+        got = infonce._e_store_chunk(x, y, comm)
+        assert got == 3, got                                # 3 + 3 + 1 on BOTH ranks: same number of column-statistics all-reduces
+        assert infonce._e_store_chunk(x, y, comm) == 3      # cached, no collective (a hang here would mean it was not)
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_stored_exponential_chunk_agreement_gloo():
+    ctx = mp.get_context("spawn")
+    with tempfile.TemporaryDirectory() as tmpdir:
+        procs = [ctx.Process(target=_chunk_agreement_worker, args=(r, 2, 29741, tmpdir)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+        for r, p in enumerate(procs):
+            assert p.exitcode == 0, f"rank {r} failed"
+            assert os.path.exists(os.path.join(tmpdir, f"ok{r}"))
