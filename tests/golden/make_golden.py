@@ -184,6 +184,20 @@ def case_ema():
     torch.save(dict(teacher=t0, student=student, outs=outs), os.path.join(HERE, "ema.pt"))
 
 
+def case_clamp():
+    """Logit-scale clamps at the end of the training step, literal train.py:237-243 on seeded scalars."""
+    import math
+    vals = [4.7, -0.3, 2.6593, 4.60517, 100.0, 0.0, 4.6051702, 4.605171, float("nan")]
+    out = {}
+    for name, dt in (("float32", torch.float32), ("bfloat16", torch.bfloat16), ("float16", torch.float16)):
+        ts = [torch.tensor(v, dtype=dt) for v in vals]
+        with torch.no_grad():
+            for t in ts:
+                t.clamp_(0, math.log(100))
+        out[name] = torch.stack(ts)
+    torch.save(dict(values=vals, outs=out), os.path.join(HERE, "clamp.pt"))
+
+
 def ref_train_functions(*names):
     """The named top-level functions of the reference's src/training/train.py, compiled from the file where it lies
     (the module itself cannot be imported here: it needs open_clip's package __init__, PIL, tqdm, ...)."""
@@ -226,6 +240,7 @@ if __name__ == "__main__":
     case_pooler(T)
     case_ema()
     case_retrieval()
+    case_clamp()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -114,3 +114,15 @@ def test_clamp_logit_scales_bit_exact(dtype):
     assert [float(t) for t in ts] == [min(max(float(i) - 3.0, 0.0), 4.0) for i in range(11)]
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         clamp_logit_scales_([torch.tensor(1.0)])
+
+
+@pytest.mark.gpu
+def test_clamp_golden(golden_dir):
+    from cosmos_b200 import clamp_logit_scales_
+    rec = torch.load(os.path.join(golden_dir, "clamp.pt"), weights_only=False)
+    for name, want in rec["outs"].items():
+        ts = [torch.tensor(v, dtype=want.dtype, device="cuda") for v in rec["values"]]
+        clamp_logit_scales_(ts)
+        got = torch.stack(ts).cpu()
+        assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0)), name
+        assert torch.isnan(got).tolist() == torch.isnan(want).tolist()

@@ -314,3 +314,24 @@ def test_stored_exponential_chunk_agreement_gloo():
         for r, p in enumerate(procs):
             assert p.exitcode == 0, f"rank {r} failed"
             assert os.path.exists(os.path.join(tmpdir, f"ok{r}"))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path through the oracle restatement): one JSON line with the keys the
+    driver reads; non-zero ranks of a multi-rank launch print nothing."""
+    import json
+    import subprocess
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-batch", "32"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "0"})
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    assert rec["impl"] == "reference" and rec["unit"] == "samples/s" and rec["higher_is_better"] is True
+    assert rec["metric"].startswith("loss-head fwd+bwd samples/s at global batch")
+    assert rec["value"] > 0 and rec["steps"] == 1
+    assert rec["cpu_baseline"]["kind"] == "port" and rec["cpu_baseline"]["cores"] >= 1 and rec["cpu_baseline"]["value"] == rec["value"]
+    assert rec["e2e"] == {"value": rec["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in rec["config"]
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "1"})
+    assert other.returncode == 0 and other.stdout.strip() == ""

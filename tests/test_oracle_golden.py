@@ -170,3 +170,13 @@ def test_retrieval_metrics_match_reference(golden_dir):
             assert got.keys() == rec["get_clip_metrics"].keys()
             for k, v in rec["get_clip_metrics"].items():
                 assert got[k] == pytest.approx(v, rel=1e-12, abs=0), k
+
+
+def test_clamp_matches_reference(golden_dir):
+    rec = _load(golden_dir, "clamp.pt")
+    for name, want in rec["outs"].items():
+        ts = [torch.tensor(v, dtype=want.dtype) for v in rec["values"]]
+        O.clamp_logit_scales_(ts)
+        got = torch.stack(ts)
+        assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(want, nan=-7.0)), name
+        assert torch.isnan(got).tolist() == torch.isnan(want).tolist()
