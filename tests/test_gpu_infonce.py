@@ -262,7 +262,9 @@ def test_stored_exponential_kernels_match_recompute_kernels(b, n_all, off, gx, g
         dx, ds = K._k_bwd_e(x, y, off, sc, e, offs, row, col, *mix, up, True)
         assert cosine(dx.float().cpu(), dx_ref.float().cpu()) >= 0.99999
         assert abs(float(dx.float().norm()) / float(dx_ref.float().norm()) - 1.0) <= 2e-3
-        assert abs(float(ds) - float(ds_ref)) <= 5e-3 * abs(float(ds_ref)) + 1e-5      # bf16 G in one, fp32 G in the other
+        # bf16 G in one kernel, fp32 G in the other; the floor covers mixes whose d(scale) nearly cancels (confident rows at
+        # scale 100: sum (R - I) raw ~ 1e-3 of its terms' magnitude)
+        assert abs(float(ds) - float(ds_ref)) <= 5e-3 * abs(float(ds_ref)) + 1e-4
     if n_all % 8 == 0:
         g1 = torch.zeros(gx * b, gy * n_all, dtype=dtype, device="cuda")
         g2 = torch.zeros_like(g1)
