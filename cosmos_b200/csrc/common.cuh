@@ -115,6 +115,12 @@ __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, in
                : "memory");
 }
 
+// The same for a contiguous range of global memory (16-byte aligned, a multiple of 16 bytes): one request per range instead of
+// one per box row - a tensor prefetch whose box rows are 16 bytes makes the L2 tag stage look up every 128-byte line 8 times.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, fences, commit
 // ----------------------------------------------------------------------------------------------

@@ -64,6 +64,7 @@ struct BwdEParams {
   int dtype;                      // dtype of y, dx and g_out (the A operand is converted to it in shared memory)
   int dbg;
   int e_ahead;                    // steps by which the L2 prefetch of E runs ahead of its use (0: no prefetch)
+  int e_bulk;                     // 1: prefetch each 32 KB tile image with one cp.async.bulk.prefetch (diagnostics, see api.cu)
   uint32_t idesc_g;
   float a_row, a_col, s_row, s_col, weight;
   const float* scale;

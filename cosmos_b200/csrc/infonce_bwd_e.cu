@@ -131,18 +131,20 @@ infonce_bwd_e_kernel(const __grid_constant__ CUtensorMap tmE, const __grid_const
       return (((i * p.gy + j) * p.n_row_tiles + (tile_valid ? tr : 0)) * n_ct + tc) * 16;
     };
     const int ahead = p.e_ahead;
-    if (elect_one())
-      for (int t = 0; t < ahead && t < T; ++t) {
+    auto prefetch_tile = [&](int t) {
+      if (p.e_bulk) {          // the 32 KB image of a tile is contiguous: 16 pieces of 2 KB
+        bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.e) + static_cast<size_t>(piece_of(t)) * 2048, 32768);
+      } else {
         tma_prefetch_3d(&tmE, 0, 0, piece_of(t));
         tma_prefetch_3d(&tmE, 0, 0, piece_of(t) + 8);
       }
+    };
+    if (elect_one())
+      for (int t = 0; t < ahead && t < T; ++t) prefetch_tile(t);
     __syncwarp();
     for (int t = 0; ahead > 0 && t + ahead < T; ++t) {
       mbar_wait(&misc->g_empty[s], ph ^ 1);        // paced by the consumption of the G stages
-      if (elect_one()) {
-        tma_prefetch_3d(&tmE, 0, 0, piece_of(t + ahead));
-        tma_prefetch_3d(&tmE, 0, 0, piece_of(t + ahead) + 8);
-      }
+      if (elect_one()) prefetch_tile(t + ahead);
       __syncwarp();
       if (++s == kStagesG) { s = 0; ph ^= 1; }
     }
