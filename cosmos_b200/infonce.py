@@ -404,7 +404,11 @@ class _PairsInfoNCE(torch.autograd.Function):
             # the only contraction left, no logit is recomputed.  backward() only scales by the upstream gradient.
             boost = float(W) if (comm.distributed and comm.gather_with_grad) else 1.0
             weight = boost / (2.0 * N * P)
-            one = torch.ones(1, dtype=torch.float32, device=dev)
+            # The unit gradients are held in the feature dtype.  Under GradScaler (fp16 features) the upstream factor exists
+            # precisely because |dX| ~ weight * scale would underflow fp16, so they are formed with a power-of-two stand-in
+            # for it (exact in every dtype; |dX * pre| <= 2 * scale / 64) and backward() multiplies by upstream / pre.
+            pre = 2.0 ** (math.floor(math.log2(1.0 / weight)) - 6)
+            one = torch.full((1,), pre, dtype=torch.float32, device=dev)
             row_parts, diag_parts, col_parts, dx_parts = [], [], [], []
             ds_unit = None
             d_all = None
@@ -424,7 +428,7 @@ class _PairsInfoNCE(torch.autograd.Function):
                     ds_unit = ds_ if ds_unit is None else ds_unit + ds_
                 row_parts.append(r_); diag_parts.append(d_); col_parts.append(c_); dx_parts.append(dx_)
             row_lse2, diag_raw, col_lse2 = (torch.cat(t) if len(t) > 1 else t[0] for t in (row_parts, diag_parts, col_parts))
-            ctx.unit = (torch.cat(dx_parts) if len(dx_parts) > 1 else dx_parts[0], ds_unit, d_all, weight)
+            ctx.unit = (torch.cat(dx_parts) if len(dx_parts) > 1 else dx_parts[0], ds_unit, d_all, weight, pre)
         else:
             row_lse2, diag_raw, col_lse2_part = _k_fwd(x_r, y_c, off, scale_f)
             col_lse2 = _allreduce_lse2(col_lse2_part, comm)   # global over all rows
@@ -513,10 +517,10 @@ class _PairsInfoNCE(torch.autograd.Function):
         """The gradients for a unit upstream gradient were formed in forward(): scale them (and finish the collectives)."""
         (scale_f,) = ctx.saved_tensors
         comm, n_r, n_c, b = ctx.comm, ctx.n_r, ctx.n_c, ctx.b
-        dx_unit, ds_unit, d_all, weight = ctx.unit
+        dx_unit, ds_unit, d_all, weight, pre = ctx.unit
         up = g.detach().to(torch.float32).reshape(1)
         grads: List[Optional[torch.Tensor]] = []
-        d_rows = (dx_unit.float() * up).to(dx_unit.dtype) if any(ctx.needs_input_grad[4:4 + n_r]) else None
+        d_rows = (dx_unit.float() * (up / pre)).to(dx_unit.dtype) if any(ctx.needs_input_grad[4:4 + n_r]) else None
         for k in range(n_r):
             grads.append(d_rows[k].to(ctx.in_dtypes[k]) if (d_rows is not None and ctx.needs_input_grad[4 + k]) else None)
         d_cols = None
@@ -528,7 +532,7 @@ class _PairsInfoNCE(torch.autograd.Function):
                          if (d_cols is not None and ctx.needs_input_grad[4 + n_r + k]) else None)
         g_scale = None
         if ctx.needs_input_grad[0]:
-            d_scale = ds_unit * up
+            d_scale = ds_unit * (up / pre)
             if comm.distributed:
                 dist.all_reduce(d_scale, op=dist.ReduceOp.SUM, group=comm.group)
             g_scale = d_scale.reshape(()).to(ctx.scale_dtype)
