@@ -406,7 +406,7 @@ class _PairsInfoNCE(torch.autograd.Function):
             weight = boost / (2.0 * N * P)
             # The unit gradients are held in the feature dtype.  Under GradScaler (fp16 features) the upstream factor exists
             # precisely because |dX| ~ weight * scale would underflow fp16, so they are formed with a power-of-two stand-in
-            # for it (exact in every dtype; |dX * pre| <= 2 * scale / 64) and backward() multiplies by upstream / pre.
+            # for it (exact in every dtype; |dX * pre| <= 2 * n_c * scale / 64) and backward() multiplies by upstream / pre.
             pre = 2.0 ** (math.floor(math.log2(1.0 / weight)) - 6)
             one = torch.full((1,), pre, dtype=torch.float32, device=dev)
             row_parts, diag_parts, col_parts, dx_parts = [], [], [], []
