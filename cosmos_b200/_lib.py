@@ -93,7 +93,7 @@ _POOL_SIGS = {
     "cosmos_addnorm_fwd": [vp_, i32_, vp_, vp_, vp_, i64_, i32_, i32_, vp_],
     "cosmos_addnorm_bwd": [vp_, vp_, i32_, vp_, vp_, vp_, i32_, i64_, i32_, i32_, vp_],
     "cosmos_colsum": [vp_, i32_, vp_, i64_, i32_, i64_, i32_, vp_],
-    "cosmos_retrieval_ranks": [vp_, vp_, i32_, i32_, i32_, i32_, i64_, i64_, vp_, vp_, vp_, vp_, i32_, vp_],
+    "cosmos_retrieval_ranks": [vp_, vp_, i32_, i32_, i32_, i32_, i64_, i64_, vp_, vp_, vp_, vp_, vp_, i32_, vp_],
 }
 
 

@@ -33,9 +33,35 @@ struct DeviceGuard {
   }
 };
 
+// Diagnostic switches are read from the environment ONCE per process (function-local statics: thread-safe since C++11), not on
+// every call: the library keeps no other host state.
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 int dbg_flags() {
-  const char* e = getenv("COSMOS_B200_DBG");
-  return e ? atoi(e) : 0;
+  static const int v = env_int("COSMOS_B200_DBG", 0);
+  return v;
+}
+int bwd_e_generation() {                 // COSMOS_B200_BWDE=1: first-generation stored-exponential backward (diagnostics)
+  static const int v = env_int("COSMOS_B200_BWDE", 2);
+  return v;
+}
+int bwd_e_ahead() {                      // first generation only: steps by which E is prefetched into L2 (0: none, the fastest)
+  static const int v = env_int("COSMOS_B200_EAHEAD", 0);
+  return v < 0 ? 0 : v;
+}
+int bwd_e_bulk() {                       // first generation only: COSMOS_B200_EPREFETCH=bulk
+  static const int v = [] { const char* e = getenv("COSMOS_B200_EPREFETCH"); return (e && e[0] == 'b') ? 1 : 0; }();
+  return v;
+}
+int bwd_t_splits() {
+  static const int v = env_int("COSMOS_B200_TSPLIT", 1);
+  return v;
+}
+int gemm_cta_cap() {                     // diagnostics (tools/overlap_probe.py): persistent CTAs of cosmos_gemm
+  static const int v = env_int("COSMOS_B200_GEMM_CTAS", 0);
+  return v;
 }
 
 int sm_count_of(int device) {
@@ -332,8 +358,7 @@ int cosmos_infonce_bwd_g(const cosmos_infonce_problem* p, const float* row_lse2,
   if (pair && dx != nullptr && !(dbg_flags() & 64)) {
     const int clusters = p->gx * ((d.n_row_tiles + 1) / 2) * bp.n_parts;
     (void)clusters;   // measured: splitting the sweep does not pay (per-item prologue + atomics eat the wave-tail gain)
-    bp.t_splits = 1;
-    if (const char* e = getenv("COSMOS_B200_TSPLIT")) bp.t_splits = atoi(e);   // diagnostics
+    bp.t_splits = bwd_t_splits();   // diagnostics (COSMOS_B200_TSPLIT)
     if (bp.t_splits > 1) {
       bp.dx32 = reinterpret_cast<float*>(static_cast<char*>(workspace) + bwd_partials_bytes(p, d));
       if (cu_fail(cudaMemsetAsync(bp.dx32, 0, static_cast<size_t>(p->gx) * p->n_rows * p->dim * sizeof(float), s))) return COSMOS_ERR_CUDA;
@@ -393,14 +418,9 @@ int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const f
   bp.n_chunks = (p->n_cols + 31) / 32;
   bp.dtype = p->dtype;
   bp.dbg = dbg_flags();
-  bp.e_ahead = 6;
-  if (const char* ea = getenv("COSMOS_B200_EAHEAD")) bp.e_ahead = atoi(ea) < 0 ? 0 : atoi(ea);   // diagnostics
-  // The round-1 ncu capture shows 8.6 G of the kernel's 17.3 G L2 tag lookups coming from the tensor-map prefetch (its box
-  // rows are 16 bytes, so every 128-byte line is looked up 8 times) and the tag stage at 84 % of its peak.  The tile images
-  // are contiguous, so one bulk prefetch per tile does the same job with 1/8 of the lookups: COSMOS_B200_EPREFETCH=bulk.
-  // Written after the round's GPU budget was spent, hence not the default until it has been measured.
-  bp.e_bulk = 0;
-  if (const char* ep = getenv("COSMOS_B200_EPREFETCH")) bp.e_bulk = (ep[0] == 'b') ? 1 : 0;
+  // first generation only (measured in round 2, profiles/README_r02.md: no prefetch at all is its fastest setting)
+  bp.e_ahead = bwd_e_ahead();
+  bp.e_bulk = bwd_e_bulk();
   bp.idesc_g = cb::make_idesc(bf, 0, 1, 2 * cb::kFwdBM, 256);
   bp.a_row = a_row; bp.a_col = a_col; bp.s_row = s_row; bp.s_col = s_col; bp.weight = weight;
   bp.scale = reinterpret_cast<const float*>(p->scale);
@@ -412,7 +432,8 @@ int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const f
   bp.g_out = g_out;
   bp.g_ld = g_ld;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cu_fail(cb::launch_infonce_bwd_e(tmE, tmY64, bp, s))) return COSMOS_ERR_CUDA;
+  if (cu_fail(bwd_e_generation() == 1 ? cb::launch_infonce_bwd_e(tmE, tmY64, bp, s) : cb::launch_infonce_bwd_e2(tmY64, bp, s)))
+    return COSMOS_ERR_CUDA;
   // partial sums hold <G, raw> with G's mix; (s_row + s_col) / (a_row + a_col) turns it into the requested one
   if (dscale != nullptr && cu_fail(cb::launch_dscale_reduce(bp.dscale_part, p->gx * d.n_row_tiles,
                                                             weight * (s_row + s_col) / (a_row + a_col), upstream, dscale, s)))
@@ -448,10 +469,7 @@ int cosmos_gemm(const void* a, const void* b, void* d, const float* bias, int32_
   ga.splits = splits; ga.alpha = alpha;
   cudaError_t e = cudaSuccess;
   int ctas = sm_count_of(device);
-  if (const char* cap = getenv("COSMOS_B200_GEMM_CTAS")) {   // diagnostics (tools/overlap_probe.py): persistent CTAs of this launch
-    const int c = atoi(cap);
-    if (c > 0 && c < ctas) ctas = c;
-  }
+  if (const int c = gemm_cta_cap(); c > 0 && c < ctas) ctas = c;
   const int r = cb::launch_gemm(ga, ctas, static_cast<cudaStream_t>(stream), &e);
   if (r == 0) return COSMOS_OK;
   if (r > 0) g_last_cuda = r; else cu_fail(e);
@@ -544,15 +562,15 @@ int cosmos_colsum(const void* src, int32_t dtype, float* dst, int64_t rows, int3
 }
 
 int cosmos_retrieval_ranks(const void* q, const void* gal, int dtype, int32_t M, int32_t N, int32_t D, int64_t ldq, int64_t ldg,
-                           const int32_t* gt_offsets, const int32_t* gt_index, float* best, int32_t* ranks, int device,
-                           void* stream) {
-  if (!q || !gal || !best || !ranks || M <= 0 || N <= 0 || D <= 0 || ldq < D || ldg < D) return COSMOS_ERR_INVALID_ARGUMENT;
+                           const int32_t* gt_offsets, const int32_t* gt_index, float* best, int32_t* best_col, int32_t* ranks,
+                           int device, void* stream) {
+  if (!q || !gal || !best || !best_col || !ranks || M <= 0 || N <= 0 || D <= 0 || ldq < D || ldg < D) return COSMOS_ERR_INVALID_ARGUMENT;
   if (gt_index != nullptr && gt_offsets == nullptr) return COSMOS_ERR_INVALID_ARGUMENT;
   if (!dtype_any(dtype)) return COSMOS_ERR_UNSUPPORTED;
   if (M > 65535 * 128) return COSMOS_ERR_UNSUPPORTED;
   DeviceGuard g(device);
   if (!g.ok) return COSMOS_ERR_CUDA;
-  return cu_fail(cb::launch_retrieval_ranks(q, gal, dtype, M, N, D, ldq, ldg, gt_offsets, gt_index, best, ranks,
+  return cu_fail(cb::launch_retrieval_ranks(q, gal, dtype, M, N, D, ldq, ldg, gt_offsets, gt_index, best, best_col, ranks,
                                             static_cast<cudaStream_t>(stream)))
              ? COSMOS_ERR_CUDA : COSMOS_OK;
 }

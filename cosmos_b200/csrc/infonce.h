@@ -80,6 +80,8 @@ struct BwdEParams {
   long long g_ld;
 };
 cudaError_t launch_infonce_bwd_e(const CUtensorMap& tmE, const CUtensorMap& tmY64, const BwdEParams& p, cudaStream_t stream);
+// second generation (infonce_bwd_e2.cu): 16 independent scaling warps, E two steps ahead in registers, no L2 prefetch role
+cudaError_t launch_infonce_bwd_e2(const CUtensorMap& tmY64, const BwdEParams& p, cudaStream_t stream);
 
 // infonce_aux.cu
 cudaError_t launch_col_combine(const float2* col_part, float* col_lse2, int pairs, int n_slabs, int n_cols, cudaStream_t stream);

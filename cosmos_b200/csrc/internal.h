@@ -21,7 +21,8 @@ cudaError_t launch_clamp_scalars(const ClampTable& t, double lo, double hi, int 
 
 // ---- retrieval ranks for the eval metrics (retrieval.cu) ----
 cudaError_t launch_retrieval_ranks(const void* q, const void* g, int dtype, int M, int N, int D, long long ldq, long long ldg,
-                                   const int* gt_offsets, const int* gt_index, float* best, int* ranks, cudaStream_t stream);
+                                   const int* gt_offsets, const int* gt_index, float* best, int* best_col, int* ranks,
+                                   cudaStream_t stream);
 
 // ---- generic tcgen05 GEMM (gemm.cu) ----
 struct GemmParams {

@@ -59,7 +59,9 @@ class EmaPlan:
             if entries < 0:
                 raise RuntimeError("cosmos_b200.ema: bad parameter sizes")
             host = torch.empty(entries * C.sizeof(_lib.EmaChunk), dtype=torch.uint8, pin_memory=True)
-            _lib.check(lib.cosmos_ema_table_fill(n, kp, qp, numel, k.element_size(), host.data_ptr()), "ema_table_fill")
+            # the element size of THIS bucket (mixed-precision models keep fp32 norms / embeddings next to 16-bit weights)
+            elem_size = torch.empty((), dtype=dtype).element_size()
+            _lib.check(lib.cosmos_ema_table_fill(n, kp, qp, numel, elem_size, host.data_ptr()), "ema_table_fill")
             table = host.to(torch.device("cuda", dev), non_blocking=False)
             self.groups.append((_lib.torch_dtype_code(dtype), dev, table, entries))
 
@@ -82,26 +84,20 @@ def ema_update_(student: Union[torch.nn.Module, Iterable[torch.Tensor]],
                 teacher: Union[torch.nn.Module, Iterable[torch.Tensor]], momentum: float) -> None:
     """teacher <- teacher * momentum + (1 - momentum) * student, in place, on the current stream.
 
-    The chunk table is cached per parameter set (keyed by the identity of the parameter objects); a few
-    storage pointers are re-checked on every call and all of them every 64th call, so a re-allocated
-    parameter rebuilds the table instead of updating stale memory.  Hold an `EmaPlan` yourself to skip
-    even that bookkeeping."""
+    The chunk table is cached per parameter set (keyed by the identity of the parameter objects) and holds raw
+    device pointers, so every (pointer, pointer, numel) triple is re-checked on every call - a few hundred Python
+    ints, against the 969 launches this replaces: a parameter whose storage moved (`p.data = ...`, `.to()`,
+    `load_state_dict(assign=True)`, offload) rebuilds the table instead of updating freed memory.  Hold an
+    `EmaPlan` yourself (and call `plan.apply(m)`) to skip even that bookkeeping; then pointer stability is yours."""
     sp, tp = _params(student), _params(teacher)
     ident = (tuple(map(id, tp)), tuple(map(id, sp)))
-    entry = _plans.get(ident)
-    if entry is not None:
-        plan, calls = entry
-        probe = (0, len(tp) // 2, len(tp) - 1) if tp else ()
-        ok = all(plan.key[i] == (tp[i].data_ptr(), sp[i].data_ptr(), tp[i].numel()) for i in probe)
-        if ok and calls % 64 == 63:
-            ok = plan.key == _full_key(sp, tp)
-        if not ok:
-            entry = None
-    if entry is None:
+    plan = _plans.get(ident)
+    if plan is not None and plan.key != _full_key(sp, tp):
+        plan = None
+    if plan is None:
         if len(_plans) > 16:
             _plans.clear()
-        plan, calls = EmaPlan(sp, tp), 0
-    _plans[ident] = (plan, calls + 1)
+        plan = _plans[ident] = EmaPlan(sp, tp)
     plan.apply(momentum)
 
 

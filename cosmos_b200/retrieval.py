@@ -10,8 +10,10 @@ The position of the ground-truth item in a descending sort of a row is the numbe
 so `retrieval_ranks` counts instead of sorting (csrc/retrieval.cu: fp32 dot products on the CUDA cores, nothing of
 size queries x gallery is ever stored).  Only the integer ranks come back to the host; the metric dictionaries are then
 formed with the reference's own expressions and key names.  A positive `logit_scale` does not change any rank and is
-not applied; ranks can differ from the reference's only where two scores tie to within fp32 summation-order noise
-(the reference's own unstable argsort is arbitrary there too).
+not applied.  Ties and NaN are ordered as torch.sort orders them when it is stable (NaN above every number, equal
+scores by index): a collapsed or diverged model gets chance-level ranks like in the reference, never "rank 0 for every
+query".  Ranks can differ from the reference's only where two scores tie to within fp32 summation-order noise (the
+reference's own unstable argsort is arbitrary there too).
 """
 from __future__ import annotations
 
@@ -25,7 +27,8 @@ from . import _lib
 
 def retrieval_ranks(queries: torch.Tensor, gallery: torch.Tensor, gt_offsets: Optional[torch.Tensor] = None,
                     gt_index: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """int32 [M]: for every query row, how many gallery rows score higher than its best ground-truth row.
+    """int32 [M]: for every query row, the 0-based position of its best ground-truth row in a stable descending sort
+    of its scores (rows scoring higher + tied rows with a lower index; NaN sorts above every number).
 
     Ground truth in CSR form (int32 CUDA tensors): rows gt_index[gt_offsets[r]:gt_offsets[r+1]] of the gallery; both
     None = row r; gt_index None = the contiguous range gt_offsets[r]:gt_offsets[r+1]."""
@@ -61,11 +64,12 @@ def retrieval_ranks(queries: torch.Tensor, gallery: torch.Tensor, gt_offsets: Op
             raise RuntimeError("cosmos_b200.retrieval: gt_offsets needs M + 1 entries")
     dev = queries.device
     best = torch.empty(M, dtype=torch.float32, device=dev)
+    best_col = torch.empty(M, dtype=torch.int32, device=dev)
     ranks = torch.empty(M, dtype=torch.int32, device=dev)
     st = _lib.lib().cosmos_retrieval_ranks(
         queries.data_ptr(), gallery.data_ptr(), _lib.torch_dtype_code(queries.dtype), M, N, D, queries.stride(0), gallery.stride(0),
         gt_offsets.data_ptr() if gt_offsets is not None else None, gt_index.data_ptr() if gt_index is not None else None,
-        best.data_ptr(), ranks.data_ptr(), dev.index, torch.cuda.current_stream(dev).cuda_stream)
+        best.data_ptr(), best_col.data_ptr(), ranks.data_ptr(), dev.index, torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(st, "retrieval_ranks")
     return ranks
 

@@ -211,16 +211,17 @@ int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const f
  * Retrieval ranks for the evaluation metrics  (src/training/train.py:766-785 get_clip_metrics and
  * 712-763 compute_retrieval: similarity matrix on the CPU + argsort of every row + position search)
  * ------------------------------------------------------------------------------------------------
- * ranks[r] = number of gallery items whose fp32 dot product with query r is larger than the best dot
- * product of r's ground-truth items = the 0-based position of the best ground-truth item in a descending
- * sort of row r.  q is [M][D] with row stride ldq, g is [N][D] with row stride ldg (elements; dtype f32,
+ * ranks[r] = the 0-based position of r's best ground-truth item in a STABLE descending sort of row r's fp32
+ * dot products with the gallery, in torch.sort's order (NaN above every number, equal scores in index
+ * order): the number of items scoring higher plus the tied items with a lower index.  A collapsed model
+ * (all scores equal) or NaN features give chance-level ranks, as the reference's argsort does, not 0.  q is [M][D] with row stride ldq, g is [N][D] with row stride ldg (elements; dtype f32,
  * bf16 or f16, products and sums in fp32).  Ground truth in CSR form: items gt_index[gt_offsets[r] ..
  * gt_offsets[r+1]) (device int32 arrays); both null = item r for query r (get_clip_metrics); gt_index
- * null = the contiguous range [gt_offsets[r], gt_offsets[r+1]).  best [M] fp32 receives the threshold
- * scores (raw dot products), ranks [M] int32 the result.  No similarity matrix is written to memory. */
+ * null = the contiguous range [gt_offsets[r], gt_offsets[r+1]).  best [M] fp32 / best_col [M] int32 receive
+ * score (raw dot product) and gallery index of that ground-truth item, ranks [M] int32 the result.  No similarity matrix is written to memory. */
 int cosmos_retrieval_ranks(const void* q, const void* g, int dtype, int32_t M, int32_t N, int32_t D, int64_t ldq, int64_t ldg,
-                           const int32_t* gt_offsets, const int32_t* gt_index, float* best, int32_t* ranks, int device,
-                           void* stream);
+                           const int32_t* gt_offsets, const int32_t* gt_index, float* best, int32_t* best_col, int32_t* ranks,
+                           int device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,45 @@ def test_ema_bit_exact(dtype):
 
 
 @pytest.mark.gpu
+def test_ema_mixed_dtypes_and_moved_storage():
+    """Mixed-precision parameter sets (the reference's --precision bf16/fp16 keeps norms, embeddings and the logit
+    scales fp32 next to 16-bit weights, src/open_clip/model.py:156-157): every (dtype, device) bucket must chunk with its
+    own element size, incl. tensors over one 8192-element chunk.  Then a parameter whose storage is re-allocated between
+    calls must be picked up on the very next call (the cached table holds raw pointers)."""
+    from cosmos_b200 import ema_update_
+    g = torch.Generator().manual_seed(5)
+    spec = [((20000,), torch.float32), ((300, 77), torch.bfloat16), ((9001,), torch.float32), ((8193, 3), torch.float16),
+            ((), torch.float32), ((40000,), torch.bfloat16), ((5,), torch.float16), ((3, 8192), torch.float32)]
+    for order in (spec, spec[::-1]):          # either dtype may be the "last teacher parameter"
+        student = [(torch.randn(s, generator=g) * 0.02).to(dt).cuda() for s, dt in order]
+        teacher = [(torch.randn(s, generator=g) * 0.02).to(dt).cuda() for s, dt in order]
+        guard = [torch.full((64,), 7.0, device="cuda") for _ in range(4)]        # neighbours an overrun would hit
+        for m in (0.99, 0.5):
+            want = [t.clone() for t in teacher]
+            O.ema_update_(want, student, m)
+            ema_update_(student, teacher, m)
+            torch.cuda.synchronize()
+            for a, b in zip(teacher, want):
+                assert torch.equal(a, b)
+        assert all(bool((t == 7.0).all()) for t in guard)
+    # moved storage: same Parameter objects, new memory (p.data = ...)
+    ps = [torch.nn.Parameter(torch.randn(20000, generator=g).cuda()) for _ in range(5)]
+    pt = [torch.nn.Parameter(torch.randn(20000, generator=g).cuda(), requires_grad=False) for _ in range(5)]
+    ema_update_(ps, pt, 0.9)
+    old = pt[1].data
+    old_copy = old.clone()
+    pt[1].data = old.clone()                    # parameter 1 (neither first, middle nor last) now lives elsewhere
+    ps[3].data = ps[3].data.clone() * 2
+    want = [t.detach().clone() for t in pt]
+    O.ema_update_(want, [p.detach() for p in ps], 0.9)
+    ema_update_(ps, pt, 0.9)
+    torch.cuda.synchronize()
+    for a, b in zip(pt, want):
+        assert torch.equal(a.detach(), b)
+    assert torch.equal(old, old_copy)            # the abandoned storage was not written through a stale pointer
+
+
+@pytest.mark.gpu
 def test_ema_golden(golden_dir):
     from cosmos_b200 import ema_update_
     rec = torch.load(os.path.join(golden_dir, "ema.pt"), weights_only=False)

@@ -113,3 +113,55 @@ def test_full_size_properties():
     r64 = ranks.long()
     assert bool(((r64 >= lo) & (r64 <= hi)).all())
     assert 0.0 < float((ranks == 0).float().mean()) < 1.0
+
+
+def _stable_ranks(scores: torch.Tensor, gt) -> torch.Tensor:
+    """Position of the best ground-truth item of every row in torch's STABLE descending sort (NaN first, ties by index)."""
+    out = torch.zeros(scores.shape[0], dtype=torch.long)
+    for r, row in enumerate(scores):
+        order = torch.argsort(row, descending=True, stable=True)
+        pos = torch.empty_like(order)
+        pos[order] = torch.arange(order.numel())
+        out[r] = min(int(pos[t]) for t in gt[r])
+    return out
+
+
+@pytest.mark.gpu
+def test_ties_and_nan_rank_like_a_stable_sort():
+    """A collapsed model (every score ties) or a diverged one (NaN features) must not report R@1 = 1: tied items with a
+    lower index come first and NaN sorts above every number, as in torch.sort (which the reference's argsort,
+    src/training/train.py:722-748, 776-777, goes through)."""
+    from cosmos_b200.retrieval import get_clip_metrics, retrieval_ranks
+    g = torch.Generator().manual_seed(3)
+    M, D = 300, 64
+    # (1) collapsed: all rows identical -> all scores tie -> item r sits at position r
+    one = torch.randn(1, D, generator=g)
+    q = one.expand(M, D).contiguous().cuda()
+    ranks = retrieval_ranks(q, q.clone()).cpu().long()
+    assert torch.equal(ranks, torch.arange(M))
+    m = get_clip_metrics(q, q.clone(), 1.0)
+    assert m["image_to_text_R@1"] == pytest.approx(1.0 / M) and m["image_to_text_mean_rank"] == pytest.approx((M - 1) / 2 + 1)
+    # (2) duplicated gallery rows: integer-valued features make the duplicates' scores exactly equal
+    qi = torch.randint(-3, 4, (M, D), generator=g).float()
+    gi = torch.randint(-3, 4, (M, D), generator=g).float()
+    gi[1::2] = gi[0::2]                                  # every odd row duplicates the even row before it
+    gt = [[r] for r in range(M)]
+    want = _stable_ranks(qi @ gi.t(), gt)
+    got = retrieval_ranks(qi.cuda(), gi.cuda()).cpu().long()
+    assert torch.equal(got, want)
+    assert bool((want[1::2] >= 1).all())                 # the duplicate with the higher index never ranks first
+    # several ground-truth items per row, some tied with each other and with distractors
+    gts = [[(3 * r) % M, (3 * r + 1) % M, (7 * r + 2) % M] for r in range(M)]
+    off = torch.arange(0, 3 * M + 1, 3, dtype=torch.int32).cuda()
+    idx = torch.tensor([t for row in gts for t in row], dtype=torch.int32).cuda()
+    got = retrieval_ranks(qi.cuda(), gi.cuda(), off, idx).cpu().long()
+    assert torch.equal(got, _stable_ranks(qi @ gi.t(), gts))
+    # (3) NaN: a NaN query row ties everything (position = own index); a NaN gallery row outranks every number
+    qn, gn = qi.clone(), gi.clone()
+    qn[5, 0] = float("nan")
+    gn[17, 3] = float("nan")
+    gn[200] = float("nan")
+    want = _stable_ranks(qn @ gn.t(), gt)
+    got = retrieval_ranks(qn.cuda(), gn.cuda()).cpu().long()
+    assert torch.equal(got, want)
+    assert int(got[5]) == 5 and int(got[17]) == 0 and int(got[200]) == 1 and int(got[0]) >= 2
