@@ -32,6 +32,7 @@ DIM = 512
 N_IMG, N_TXT = 8, 8
 KEYS = (("s_image", N_IMG), ("s_text", N_TXT), ("s_img_x", N_IMG), ("s_txt_x", N_TXT), ("t_image", 2), ("t_text", 2))
 LOGIT_SCALE = 14.2857
+PROFILE_TAG = "r02"     # profiles/ncu_<kernel>_<tag>.txt: the committed ncu summaries this round's roofline.traffic comes from
 
 
 def algorithmic_flops(n_global: int, dim: int = DIM) -> float:
@@ -39,7 +40,7 @@ def algorithmic_flops(n_global: int, dim: int = DIM) -> float:
     return 352.0 * n_global * n_global * dim
 
 
-def ncu_traffic(kind, tag="r01"):
+def ncu_traffic(kind, tag="r02"):
     """DRAM bytes of one launch of the dominant kernel, from the committed ncu --set full summary."""
     path = os.path.join(ROOT, "profiles", "ncu_%s_%s.txt" % (kind, tag))
     try:
@@ -132,7 +133,7 @@ class Instrument:
     """Counts our kernel launches and times the InfoNCE launches with CUDA events on the launching stream."""
     KINDS = ("fwd", "bwd", "bwd_e", "colgrad")
     NAMES = {"fwd": "infonce_fwd_kernel<pair> (+ column merge)", "bwd": "infonce_bwd_quad_kernel (+ dscale reduce)",
-             "bwd_e": "infonce_bwd_e_kernel (+ dscale reduce)", "colgrad": "gemm_kernel<256> (column-side gradient)"}
+             "bwd_e": "infonce_bwd_e2_kernel (+ dscale reduce)", "colgrad": "gemm_kernel<256> (column-side gradient)"}
 
     def __init__(self):
         from cosmos_b200 import infonce
@@ -146,21 +147,21 @@ class Instrument:
         infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd, infonce._k_colgrad = self.fwd, self.loss, self.bwd, self.colgrad
         infonce._k_bwd_e = self.bwd_e
 
-    def _timed(self, kind, flops, fn, *a):
+    def _timed(self, kind, flops, fn, *a, **kw):
         if not self.enabled:
-            return fn(*a)
+            return fn(*a, **kw)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        r = fn(*a)
+        r = fn(*a, **kw)
         e1.record()
         self.events[kind].append((e0, e1))
         self.flops[kind].append(flops)
         return r
 
-    def fwd(self, x, y, *a):
+    def fwd(self, x, y, *a, **kw):
         self.launches += 2   # tile kernel + column-statistics merge
         fl = 2.0 * x.shape[0] * y.shape[0] * x.shape[1] * y.shape[1] * x.shape[2]
-        return self._timed("fwd", fl, self._fwd, x, y, *a)
+        return self._timed("fwd", fl, self._fwd, x, y, *a, **kw)
 
     def loss(self, *a):
         self.launches += 1
@@ -172,15 +173,20 @@ class Instrument:
         fl = 2.0 * x.shape[0] * y.shape[0] * x.shape[1] * y.shape[1] * x.shape[2] if want_dx else 0.0
         return self._timed("bwd", fl, self._bwd, x, y, *a)
 
-    def bwd_e(self, x, y, *a):
+    def bwd_e(self, x, y, *a, **kw):
         want_ds = a[12]          # (label_offset, scale, e, off, row, col, a_row, a_col, s_row, s_col, weight, upstream, want_dscale[, g_out])
         self.launches += 1 + (1 if want_ds else 0)
         fl = 2.0 * x.shape[0] * y.shape[0] * x.shape[1] * y.shape[1] * x.shape[2]
-        return self._timed("bwd_e", fl, self._bwd_e, x, y, *a)
+        return self._timed("bwd_e", fl, self._bwd_e, x, y, *a, **kw)
 
     def colgrad(self, g, x2d, n_c, n_cols):
         self.launches += 1                       # the column-side gradient GEMM (G^T x) on the stored tiles
         return self._timed("colgrad", 2.0 * x2d.shape[0] * n_c * n_cols * x2d.shape[1], self._colgrad, g, x2d, n_c, n_cols)
+
+    def reset(self):
+        self.launches = 0
+        self.events = {k: [] for k in self.KINDS}
+        self.flops = {k: [] for k in self.KINDS}
 
     def summary(self):
         out = {}
@@ -192,9 +198,160 @@ class Instrument:
         return out
 
 
+class LossHead:
+    """The timed workload at one global batch: synthetic inputs (pinned host + device copies), the drop-in COSMOSLoss and the
+    step / timing helpers shared by the headline line, the config-2 entry and the same-size CPU/GPU pair."""
+
+    def __init__(self, n_global, dev, rank, world, inst, flush):
+        from cosmos_b200 import COSMOSLoss
+        assert n_global % world == 0
+        self.n_global, self.dev, self.rank, self.world, self.inst, self.flush = n_global, dev, rank, world, inst, flush
+        self.b = n_global // world
+        self.host = host_inputs(self.b, rank, pinned=True)
+        self.dev_buf = {k: torch.empty_like(v, device=dev).requires_grad_(k not in ("t_image", "t_text")) for k, v in self.host.items()}
+        with torch.no_grad():
+            for k in self.host:
+                self.dev_buf[k].copy_(self.host[k])
+        self.logit_scale = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
+        self.distill_scale = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
+        self.loss_mod = COSMOSLoss(local_loss=False, gather_with_grad=False, cache_labels=True, rank=rank, world_size=world)
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+
+    def step(self, from_host: bool):
+        host, dev_buf = self.host, self.dev_buf
+        if from_host:
+            with torch.no_grad():
+                for k in host:
+                    dev_buf[k].copy_(host[k], non_blocking=True)
+        for t in list(dev_buf.values()) + [self.logit_scale, self.distill_scale]:
+            t.grad = None
+        n = dict(KEYS)
+        out = self.loss_mod(dev_buf["s_image"].chunk(n["s_image"]), dev_buf["s_text"].chunk(n["s_text"]), self.logit_scale,
+                            t_image_features=dev_buf["t_image"].chunk(2), t_text_features=dev_buf["t_text"].chunk(2),
+                            output_dict=True, distill_logit_scale=self.distill_scale,
+                            s_img_crossmodal_features=dev_buf["s_img_x"].chunk(n["s_img_x"]),
+                            s_txt_crossmodal_features=dev_buf["s_txt_x"].chunk(n["s_txt_x"]))
+        total = out["distill_loss"] + out["clip_loss"]
+        total.backward()
+        if from_host:
+            return torch.stack([out["distill_loss"].detach(), out["clip_loss"].detach()]).cpu()   # 8-byte D2H
+        return out
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, from_host: bool, steps: int):
+        """Total ms of `steps` steps, each bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks."""
+        total_ms = 0.0
+        for _ in range(steps):
+            self.flush.fill_(1)                  # evict L2 between timed iterations (256 MB > 126 MB L2)
+            self.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.step(from_host)
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        t = torch.tensor([total_ms], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def measure(self, steps, warmup, e2e=True):
+        """-> dict(ms_per_step, e2e_ms_per_step, launches, kernels, loss): warm-up, device-resident leg, host-buffer leg."""
+        inst = self.inst
+        for _ in range(max(warmup, 3)):
+            self.step(False)
+        self.barrier()
+        inst.reset()
+        inst.enabled = True
+        dev_ms = self.timed(False, steps)
+        launches = inst.launches
+        inst.enabled = False
+        kernels = inst.summary()
+        if e2e:
+            for _ in range(2):
+                self.step(True)
+            e2e_ms = self.timed(True, steps)
+            last = self.step(True)
+            last = [float(x) for x in last]
+        else:
+            out = self.step(False)
+            e2e_ms, last = float("nan"), [float(out["distill_loss"].detach()), float(out["clip_loss"].detach())]
+        return {"ms_per_step": dev_ms / steps, "e2e_ms_per_step": e2e_ms / steps, "launches": launches, "kernels": kernels, "loss": last}
+
+
+def parity_check(dev, rank, world):
+    """Before the timed loop, at THIS world size and through the same route as the headline step (stored exponentials, forced
+    at this small size): a global batch of 512 (rows sharded over the ranks) in the default mode and with gather_with_grad,
+    rank 0 against the oracle's per-rank restatement of the reference (oracle.cosmos_loss_rank: src/open_clip/loss.py:21-65,
+    103-142, 176-207).  The driver's scaling run so carries gradient parity under NCCL at every N, not only throughput."""
+    from cosmos_b200 import COSMOSLoss, infonce
+    from oracle import cosmos_oracle as O
+    b = max(64, 512 // world)
+    saved = infonce._E_STORE_MIN_BYTES
+    infonce._E_STORE_MIN_BYTES = 0
+    modes = {}
+    try:
+        for name, gwg in (("default", False), ("gather_with_grad", True)):
+            mine = O.make_features(b, DIM, seed=900 + rank)
+            x = {k: [t.bfloat16().to(dev).requires_grad_(k not in ("t_image", "t_text")) for t in v] for k, v in mine.items()}
+            ls = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
+            ds = torch.tensor(30.0, device=dev, requires_grad=True)
+            out = COSMOSLoss(local_loss=False, gather_with_grad=gwg, cache_labels=True, rank=rank, world_size=world)(
+                x["s_image"], x["s_text"], ls, t_image_features=x["t_image"], t_text_features=x["t_text"], output_dict=True,
+                distill_logit_scale=ds, s_img_crossmodal_features=x["s_img_x"], s_txt_crossmodal_features=x["s_txt_x"])
+            (out["distill_loss"] + out["clip_loss"]).backward()
+            torch.cuda.synchronize()
+            if rank != 0:
+                continue
+            torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
+            leafs = []
+            for r in range(world):
+                d = {k: [t.bfloat16().float().requires_grad_(True) for t in v] for k, v in O.make_features(b, DIM, seed=900 + r).items()}
+                d["logit_scale"] = torch.tensor(LOGIT_SCALE, requires_grad=True)
+                d["distill_logit_scale"] = torch.tensor(30.0, requires_grad=True)
+                leafs.append(d)
+            # what rank 0 sees: its own scalar; with gather_with_grad the all_gather's backward sums every rank's scalar
+            outs = [O.cosmos_loss_rank(leafs, r, False, gwg) for r in (range(world) if gwg else (0,))]
+            sum(o["distill_loss"] + o["clip_loss"] for o in outs).backward()
+            ref, rl = outs[0], leafs[0]
+            rec = {"loss_rel": 0.0, "grad_cos_min": 1.0, "grad_norm_rel": 0.0, "dscale_rel": 0.0}
+            for k in ("distill_loss", "clip_loss"):
+                rec["loss_rel"] = max(rec["loss_rel"], abs(float(out[k]) - float(ref[k])) / abs(float(ref[k])))
+            for k in ("s_image", "s_text", "s_img_x", "s_txt_x"):
+                for t, r_ in zip(x[k], rl[k]):
+                    if r_.grad is None or float(r_.grad.abs().max()) == 0.0:
+                        if t.grad is not None and float(t.grad.abs().max()) != 0.0:
+                            rec["grad_cos_min"] = 0.0            # a gradient where the reference has none
+                        continue
+                    ga, gb = t.grad.float().cpu().flatten().double(), r_.grad.flatten().double()
+                    rec["grad_cos_min"] = min(rec["grad_cos_min"], float(ga @ gb / (ga.norm() * gb.norm())))
+                    rec["grad_norm_rel"] = max(rec["grad_norm_rel"], abs(float(ga.norm() / gb.norm()) - 1.0))
+            for name_s, t in (("logit_scale", ls), ("distill_logit_scale", ds)):
+                c = float(rl[name_s].grad)
+                rec["dscale_rel"] = max(rec["dscale_rel"], abs(float(t.grad) - c) / abs(c))
+            rec["ok"] = bool(rec["loss_rel"] <= 1e-4 and rec["grad_cos_min"] >= 0.9999 and rec["grad_norm_rel"] <= 5e-3
+                             and rec["dscale_rel"] <= 3e-3)
+            modes[name] = rec
+    finally:
+        infonce._E_STORE_MIN_BYTES = saved
+    if rank != 0:
+        return None
+    return {"ok": all(m["ok"] for m in modes.values()), "world_size": world, "batch_per_rank": b, "global_batch": b * world,
+            "route": "stored exponentials (the headline route), bf16 features, dim 512, 80 pairs",
+            "checker": "oracle.cosmos_loss_rank on host cores (fp32 on the same bf16-valued inputs)",
+            "tolerance": {"loss_rel": 1e-4, "grad_cos": 0.9999, "grad_norm_rel": 5e-3, "dscale_rel": 3e-3},
+            "max_loss_rel": max(m["loss_rel"] for m in modes.values()),
+            "min_grad_cos": min(m["grad_cos_min"] for m in modes.values()), "modes": modes}
+
+
 def run_ours(args):
     import torch.distributed as dist
-    from cosmos_b200 import COSMOSLoss
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -209,89 +366,42 @@ def run_ours(args):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     n_global = args.global_batch
-    assert n_global % world == 0
-    b = n_global // world
-    host = host_inputs(b, rank, pinned=True)
-    dev_buf = {k: torch.empty_like(v, device=dev).requires_grad_(k not in ("t_image", "t_text")) for k, v in host.items()}
-    with torch.no_grad():
-        for k in host:
-            dev_buf[k].copy_(host[k])
-    logit_scale = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
-    distill_scale = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
-    loss_mod = COSMOSLoss(local_loss=False, gather_with_grad=False, cache_labels=True, rank=rank, world_size=world)
+    parity = None if args.no_parity_check else parity_check(dev, rank, world)
     inst = Instrument()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
-
-    def step(from_host: bool):
-        if from_host:
-            with torch.no_grad():
-                for k in host:
-                    dev_buf[k].copy_(host[k], non_blocking=True)
-        for t in list(dev_buf.values()) + [logit_scale, distill_scale]:
-            t.grad = None
-        n = dict(KEYS)
-        out = loss_mod(dev_buf["s_image"].chunk(n["s_image"]), dev_buf["s_text"].chunk(n["s_text"]), logit_scale,
-                       t_image_features=dev_buf["t_image"].chunk(2), t_text_features=dev_buf["t_text"].chunk(2),
-                       output_dict=True, distill_logit_scale=distill_scale,
-                       s_img_crossmodal_features=dev_buf["s_img_x"].chunk(n["s_img_x"]),
-                       s_txt_crossmodal_features=dev_buf["s_txt_x"].chunk(n["s_txt_x"]))
-        total = out["distill_loss"] + out["clip_loss"]
-        total.backward()
-        if from_host:
-            return torch.stack([out["distill_loss"].detach(), out["clip_loss"].detach()]).cpu()   # 8-byte D2H
-        return out
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(from_host: bool, steps: int):
-        total_ms = 0.0
-        for _ in range(steps):
-            flush.fill_(1)                       # evict L2 between timed iterations (256 MB > 126 MB L2)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            step(from_host)
-            e1.record()
-            torch.cuda.synchronize()
-            total_ms += e0.elapsed_time(e1)
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    head = LossHead(n_global, dev, rank, world, inst, flush)
+    b, h2d_bytes = head.b, head.h2d_bytes
 
     clocks = Clocks(local_rank) if rank == 0 else None     # sampled from the warm-up on: short timed regions still get samples
     for _ in range(max(args.warmup, 3)):
-        step(False)
-    barrier()
+        head.step(False)
+    head.barrier()
+    inst.reset()
     inst.enabled = True
-    inst.launches = 0
-    dev_ms = timed(False, args.steps)
+    dev_ms = head.timed(False, args.steps)
     launches = inst.launches
     inst.enabled = False
+    ksum = inst.summary()
     clk = clocks.stop() if clocks else None
     if args.no_e2e:
-        out = step(False)
+        out = head.step(False)
         e2e_ms, last = float("nan"), [float(out["distill_loss"].detach()), float(out["clip_loss"].detach())]
     else:
         for _ in range(2):
-            step(True)
-        e2e_ms = timed(True, args.steps)
-        last = step(True)
+            head.step(True)
+        e2e_ms = head.timed(True, args.steps)
+        last = head.step(True)
 
     if rank == 0:
         burst, sustained, hbm, src = peaks()
         ms_per_step = dev_ms / args.steps
         value = n_global / (ms_per_step * 1e-3)
         e2e_value = n_global / (e2e_ms / args.steps * 1e-3)
-        ksum = inst.summary()
         dom = max(ksum, key=lambda kind: ksum[kind]["ms_total"])
         k = ksum[dom]
         achieved = k["flops_avg"] / (k["ms_avg"] * 1e-3) / 1e12
         step_tflops = algorithmic_flops(n_global) / world / (ms_per_step * 1e-3) / 1e12
+        kernel_ms = sum(v["ms_total"] for v in ksum.values()) / args.steps
         line = {
             "metric": "loss-head fwd+bwd samples/s at global batch %d" % n_global,
             "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -306,23 +416,27 @@ def run_ours(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "clocks": clk,
+            "parity_check": parity,
             "roofline": {"bound": "tensor",
                          "kernel": Instrument.NAMES[dom],
                          "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-                         "traffic": (ncu_traffic("bwd", "r01c") if (dom == "bwd_e" and n_global == 32768 and world == 1) else
-                                     ncu_traffic(dom) if (n_global == 4096 and dom in ("fwd", "bwd")) else None),
+                         "traffic": ncu_traffic(dom, PROFILE_TAG) if (n_global == 32768 and world == 1) else None,
                          "traffic_note": "dram__bytes_read+write of one launch of this kernel from the committed ncu --set full "
-                                         "summary (profiles/ncu_bwd_r01c.txt: global batch 32768, one GPU, 16 pairs per launch; "
-                                         "profiles/ncu_*_r01.txt: global batch 4096); null for other configurations",
+                                         "summary (profiles/ncu_<kernel>_%s.txt: global batch 32768, one GPU, 16 pairs per "
+                                         "launch); null for other configurations" % PROFILE_TAG,
                          "executed_tflops": achieved * (2.0 if dom == "bwd" else 1.0),   # the recompute backward runs S and dX
                          "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step); burst %.1f" % (src, burst),
                          "launch_ms_avg": k["ms_avg"], "launches_timed": k["launches"],
                          "step_algorithmic_tflops_per_gpu": step_tflops, "step_frac": step_tflops / sustained,
+                         "step_minus_kernels_ms": ms_per_step - kernel_ms,
                          "kernels": ksum},
         }
+    del head
+    torch.cuda.empty_cache()
+    if rank == 0:
         if world == 1 and not args.no_extras:
-            del dev_buf, host
-            torch.cuda.empty_cache()
+            line["config2_global_batch_4096"] = bench_other_batch(4096, dev, inst, flush, steps=10)
+            line["same_size_cpu_vs_gpu"] = bench_same_size(dev, inst, flush, args.cpu_seconds)
             line["ema"] = bench_ema(dev, flush)
             line["xattn"] = bench_xattn(dev, flush)
             line["retrieval"] = bench_retrieval(dev, flush)
@@ -334,6 +448,43 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
 
+
+def bench_other_batch(n_global, dev, inst, flush, steps=10):
+    """BASELINE config 2 (global batch 4096, dim 512, bf16, one B200) through the same LossHead as the headline line."""
+    head = LossHead(n_global, dev, 0, 1, inst, flush)
+    m = head.measure(steps, 3)
+    burst, sustained, _, src = peaks()
+    tf = algorithmic_flops(n_global) / (m["ms_per_step"] * 1e-3) / 1e12
+    return {"workload": "COSMOS ViT-B/16 loss head fwd+bwd, global batch %d, dim 512, bf16, 1 B200" % n_global,
+            "ms_per_step": m["ms_per_step"], "value": n_global / (m["ms_per_step"] * 1e-3), "unit": "samples/s",
+            "e2e": {"value": n_global / (m["e2e_ms_per_step"] * 1e-3), "unit": "samples/s", "ms_per_step": m["e2e_ms_per_step"],
+                    "h2d_bytes_per_step": head.h2d_bytes, "d2h_bytes_per_step": 8},
+            "algorithmic_tflops": tf, "frac_of_sustained_peak": tf / sustained, "frac_of_burst_peak": tf / burst, "peak_source": src,
+            "gpu_launches": m["launches"], "kernels": m["kernels"], "loss": m["loss"], "steps": steps}
+
+
+def bench_same_size(dev, inst, flush, seconds, n_global=1024):
+    """One ratio on the SAME configuration for both arms: global batch 1024 (what the reference arm's bounded sample is) on the
+    B200 through the public API (device-resident and from pinned host buffers) and on the host cores through the oracle port."""
+    head = LossHead(n_global, dev, 0, 1, inst, flush)
+    m = head.measure(20, 3)
+    del head
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(n_global)
+    step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < 2 or (time.perf_counter() - t0 < min(seconds, 8.0) and n < 50):
+        step()
+        n += 1
+    cpu_ms = (time.perf_counter() - t0) / n * 1e3
+    gpu, e2e, cpu = n_global / (m["ms_per_step"] * 1e-3), n_global / (m["e2e_ms_per_step"] * 1e-3), n_global / (cpu_ms * 1e-3)
+    return {"workload": "COSMOS loss head fwd+bwd, global batch %d, dim 512, 80 pairs: the same configuration on both arms "
+                        "(GPU: bf16 kernels; CPU: fp32 oracle port, %d torch threads)" % (n_global, cores),
+            "gpu_ms_per_step": m["ms_per_step"], "gpu_samples_per_s": gpu, "gpu_e2e_ms_per_step": m["e2e_ms_per_step"],
+            "gpu_e2e_samples_per_s": e2e, "cpu_port_ms_per_step": cpu_ms, "cpu_port_samples_per_s": cpu, "cpu_cores": cores,
+            "cpu_steps": n, "same_config": True, "ratio": gpu / cpu, "e2e_ratio": e2e / cpu}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -438,7 +589,7 @@ def bench_xattn(dev, flush):
     # BASELINE config 4 as literally written (token sequences as queries: 77 x 197 and 197 x 77, width 768, 12 heads),
     # through the module's forward(x, q); SURVEY §0 D2 explains why the reference never runs this shape.
     for name, (Lq, Lk) in (("literal_77q_x_197kv_w768", (77, 197)), ("literal_197q_x_77kv_w768", (197, 77))):
-        d2, h2, B2 = 768, 12, 256
+        d2, h2, B2 = 768, 12, 1024      # BASELINE config 4: batch 1024
         params, _, _, _ = O.make_pooler_case(d2, 4, 1, 1, seed=4)
         mod = AttentionalCrossPooler(d2, d2, h2).to(dev)
         mod.load_state_dict(params)
@@ -594,6 +745,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the EMA / cross-attention / eager-GPU entries")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the small oracle check before the timed loop")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -274,6 +274,15 @@ int cosmos_infonce_fwd_e(const cosmos_infonce_problem* p, float* row_lse2, float
   return COSMOS_OK;
 }
 
+int cosmos_lse2_merge(const float* parts, float* out, int32_t n_parts, int64_t n, int device, void* stream) {
+  if (!parts || !out || n_parts <= 0 || n < 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (n == 0) return COSMOS_OK;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  return cu_fail(cb::launch_lse2_merge(parts, out, n_parts, static_cast<size_t>(n), static_cast<cudaStream_t>(stream)))
+             ? COSMOS_ERR_CUDA : COSMOS_OK;
+}
+
 int cosmos_infonce_loss_sums(const cosmos_infonce_problem* p, const float* row_lse2, const float* diag_raw,
                              const float* col_lse2, int32_t use_rows, int32_t use_cols, float* out, void* workspace,
                              int device, void* stream) {

@@ -88,6 +88,7 @@ cudaError_t launch_col_combine(const float2* col_part, float* col_lse2, int pair
 cudaError_t launch_loss_sums(const float* row_lse2, const float* diag_raw, const float* col_lse2, const float* scale, int pairs,
                              int n_rows, int n_cols, int label_offset, int use_rows, int use_cols, float* out,
                              cudaStream_t stream);
+cudaError_t launch_lse2_merge(const float* parts, float* out, int n_parts, size_t n, cudaStream_t stream);
 cudaError_t launch_convert_dx(const float* src, void* dst, int dtype, size_t n, cudaStream_t stream);
 cudaError_t launch_dscale_reduce(const float* part, int n, float weight, const float* upstream, float* dscale,
                                  cudaStream_t stream);

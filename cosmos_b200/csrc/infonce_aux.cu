@@ -30,6 +30,28 @@ cudaError_t launch_col_combine(const float2* col_part, float* col_lse2, int pair
   return cudaGetLastError();
 }
 
+// parts [n_parts][n] -> out [n]: log2-sum-exp2 over the parts (the per-rank partial column statistics of a sharded forward,
+// all-gathered: ONE collective and one pass instead of a MAX all-reduce, an exp, a SUM all-reduce and a log).
+__global__ void __launch_bounds__(256)
+lse2_merge_kernel(const float* __restrict__ parts, float* __restrict__ out, int n_parts, size_t n) {
+  const size_t k = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (k >= n) return;
+  float m = -INFINITY;
+  for (int q = 0; q < n_parts; ++q) m = fmaxf(m, __ldcs(parts + static_cast<size_t>(q) * n + k));
+  if (m == -INFINITY || m == INFINITY) {
+    out[k] = m;
+    return;
+  }
+  float l = 0.f;
+  for (int q = 0; q < n_parts; ++q) l += ex2(__ldcs(parts + static_cast<size_t>(q) * n + k) - m);
+  out[k] = m + log2f(l);
+}
+
+cudaError_t launch_lse2_merge(const float* parts, float* out, int n_parts, size_t n, cudaStream_t stream) {
+  lse2_merge_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(parts, out, n_parts, n);
+  return cudaGetLastError();
+}
+
 // out[pair][0] = sum_r (ln2 * row_lse2[r] - scale * diag[r])
 // out[pair][1] = sum_r (ln2 * col_lse2[label_offset + r] - scale * diag[r])      (this rank's diagonal columns)
 __global__ void __launch_bounds__(256)

@@ -84,16 +84,20 @@ def _workspace(prob: _lib.InfoNceProblem, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-def _k_fwd(x, y, label_offset, scale, keep_e=False):
+def _k_fwd(x, y, label_offset, scale, keep_e=False, out=None):
     """-> row_lse2 [P, b], diag_raw [P, b], col_lse2 (this rank's rows only) [P, N]; fp32.
     keep_e: also -> (e, off [P, ceil(N / 32), b] fp32): the exponentials 2^(s2 - off) of every logit as bf16, in the tiled
-    layout include/cosmos_b200.h describes (stored-exponential route, csrc/infonce_bwd_e.cu)."""
+    layout include/cosmos_b200.h describes (stored-exponential route, csrc/infonce_bwd_e2.cu).
+    out: (row_lse2, diag_raw, col_lse2) to write into (contiguous slices of per-group buffers) instead of new tensors."""
     dev = x.device
     prob = _problem(x, y, label_offset, scale)
     P = prob.gx * prob.gy
-    row_lse2 = torch.empty(P, prob.n_rows, dtype=torch.float32, device=dev)
-    diag_raw = torch.empty(P, prob.n_rows, dtype=torch.float32, device=dev)
-    col_lse2 = torch.empty(P, prob.n_cols, dtype=torch.float32, device=dev)
+    if out is not None:
+        row_lse2, diag_raw, col_lse2 = out
+    else:
+        row_lse2 = torch.empty(P, prob.n_rows, dtype=torch.float32, device=dev)
+        diag_raw = torch.empty(P, prob.n_rows, dtype=torch.float32, device=dev)
+        col_lse2 = torch.empty(P, prob.n_cols, dtype=torch.float32, device=dev)
     ws = _workspace(prob, dev)
     if not keep_e:
         st = _lib.lib().cosmos_infonce_fwd(C.byref(prob), row_lse2.data_ptr(), diag_raw.data_ptr(), col_lse2.data_ptr(),
@@ -110,12 +114,12 @@ def _k_fwd(x, y, label_offset, scale, keep_e=False):
 
 
 def _k_bwd_e(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream,
-             want_dscale, g_out=None):
+             want_dscale, g_out=None, dx_out=None):
     """Backward from the stored exponentials: -> dx [gx, b, 512] in x.dtype, dscale fp32 [1] (or None).  No logit is
-    recomputed; x is only read for d(scale) = sum_r <x_r, (G y)_r>."""
+    recomputed; x is only read for d(scale) = sum_r <x_r, (G y)_r>.  dx_out: where to write dx (a slice of the group's buffer)."""
     dev = x.device
     prob = _problem(x, y, label_offset, scale)
-    dx = torch.empty_like(x)
+    dx = dx_out if dx_out is not None else torch.empty_like(x)
     dscale = torch.empty(1, dtype=torch.float32, device=dev) if want_dscale else None
     ws = torch.empty(max(4 * prob.gx * ((prob.n_rows + 127) // 128) * 8, 256) + 256, dtype=torch.uint8, device=dev)
     st = _lib.lib().cosmos_infonce_bwd_e(C.byref(prob), e.data_ptr(), off.data_ptr(), row_lse2.data_ptr(),
@@ -126,6 +130,15 @@ def _k_bwd_e(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_col
                                          torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(st, "infonce_bwd_e")
     return dx, dscale
+
+
+def _k_lse2_merge(parts: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """parts [W, ...] fp32 (every rank's partial column log2-sum-exp, all-gathered) -> out [...]: their log2-sum-exp2."""
+    dev = parts.device
+    st = _lib.lib().cosmos_lse2_merge(parts.data_ptr(), out.data_ptr(), parts.shape[0], out.numel(), dev.index,
+                                      torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(st, "lse2_merge")
+    return out
 
 
 def _k_loss_sums(x, y, label_offset, scale, row_lse2, diag_raw, col_lse2):
@@ -250,15 +263,27 @@ class Prefetch:
         self.handles[tuple(id(t) for t in tensors)] = (st, GatherHandle(st, comm), tensors)   # keeps the ids alive
 
 
+class _LseGather:
+    """Per-rank partial column statistics [P, N] -> the global ones: ONE all-gather (started with async_op=True, so the
+    caller keeps launching kernels behind it) and one merge kernel, instead of a MAX all-reduce, an eager exp, a SUM
+    all-reduce and an eager log."""
+
+    def __init__(self, part: torch.Tensor, comm: Comm):
+        self.part, self.comm = part, comm
+        # (flat leading dimension: the gloo backend of the CPU tests accepts no other output shape)
+        self.gathered = torch.empty(comm.world_size * part.shape[0], *part.shape[1:], dtype=part.dtype, device=part.device)
+        self.work = dist.all_gather_into_tensor(self.gathered, part, group=comm.group, async_op=True)
+
+    def finish(self, out: torch.Tensor) -> torch.Tensor:
+        self.work.wait()                       # the current stream waits; the host does not (NCCL)
+        return _k_lse2_merge(self.gathered.view(self.comm.world_size, *self.part.shape), out)
+
+
 def _allreduce_lse2(lse2: torch.Tensor, comm: Comm) -> torch.Tensor:
-    """log2-sum-exp2 over ranks of per-rank partial column statistics (max all-reduce + sum all-reduce)."""
+    """log2-sum-exp2 over ranks of per-rank partial column statistics."""
     if not comm.distributed:
         return lse2
-    m = lse2.clone()
-    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=comm.group)
-    s = torch.exp((lse2 - m) * LN2)          # exp / log instead of exp2 / log2: the latter are NVRTC-jitted by torch
-    dist.all_reduce(s, op=dist.ReduceOp.SUM, group=comm.group)
-    return m + torch.log(s) / LN2
+    return _LseGather(lse2.contiguous(), comm).finish(torch.empty_like(lse2))
 
 
 def _gather_rows(t: torch.Tensor, comm: Comm) -> torch.Tensor:
@@ -304,19 +329,21 @@ def _g_store_ok(x_r: torch.Tensor, y_c: torch.Tensor) -> bool:
     return True
 
 
-def _reduce_scatter_rows(d_all: torch.Tensor, comm: Comm, b: int) -> torch.Tensor:
-    """[n_c, W * b, D] per-rank partial sums -> [n_c, b, D]: the sum over ranks of this rank's rows."""
+def _reduce_scatter_rows(d_all: torch.Tensor, comm: Comm, b: int, async_op: bool = False):
+    """[n_c, W * b, D] per-rank partial sums -> [n_c, b, D]: the sum over ranks of this rank's rows.
+    async_op: -> (result, work) with the collective still running (work is None when nothing was started)."""
     if not comm.distributed:
-        return d_all
+        return (d_all, None) if async_op else d_all
     W, rank = comm.world_size, comm.rank
     n_c, _, D = d_all.shape
     if dist.get_backend(comm.group) == "nccl":
         send = d_all.view(n_c, W, b, D).transpose(0, 1).contiguous()          # rank-major chunks
         out = torch.empty(n_c, b, D, dtype=d_all.dtype, device=d_all.device)
-        dist.reduce_scatter_tensor(out, send, op=dist.ReduceOp.SUM, group=comm.group)
-        return out
+        work = dist.reduce_scatter_tensor(out, send, op=dist.ReduceOp.SUM, group=comm.group, async_op=async_op)
+        return (out, work) if async_op else out
     dist.all_reduce(d_all, op=dist.ReduceOp.SUM, group=comm.group)           # backends without reduce-scatter (gloo, CPU tests)
-    return d_all[:, rank * b:(rank + 1) * b].contiguous()
+    out = d_all[:, rank * b:(rank + 1) * b].contiguous()
+    return (out, None) if async_op else out
 
 
 _E_STORE_MAX_BYTES = int(float(os.environ.get("COSMOS_B200_ESTORE_MAX_GB", "40")) * (1 << 30))
@@ -327,12 +354,19 @@ _E_STORE_MIN_BYTES = int(float(os.environ.get("COSMOS_B200_ESTORE_MIN_GB", "0.25
 _e_chunk_cache: dict = {}
 
 
+def _reusable_bytes(device) -> int:
+    """Free device memory as this process can use it: cudaMemGetInfo plus the allocator's cached blocks."""
+    free, _total = torch.cuda.mem_get_info(device)
+    return free + torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+
+
 def _e_store_chunk(x_r: torch.Tensor, y_c: torch.Tensor, comm: Comm) -> int:
-    """Row tensors per pass of the stored-exponential route (csrc/infonce_bwd_e.cu), 0 = use the recompute kernels.
+    """Row tensors per pass of the stored-exponential route (csrc/infonce_bwd_e2.cu), 0 = use the recompute kernels.
 
     The route needs dim 512 (a [128 x 512] fp32 dX accumulator is exactly the tensor memory of an SM) and gradient mixes
     that weigh d(scale) like dX (every mode but local_loss).  The forward keeps 2 bytes per logit; the gradients are formed
-    right away, chunk of row tensors by chunk, so only one chunk of exponentials is alive at a time."""
+    right away, chunk of row tensors by chunk, so only one chunk of exponentials is alive at a time - two in a distributed
+    run, where the forward of the next chunk is launched behind the all-gather of this chunk's column statistics."""
     n_r, b, dim = x_r.shape
     n_c, n_all, _ = y_c.shape
     if dim != 512 or _E_STORE_MAX_BYTES <= 0 or (comm.distributed and comm.local_loss):
@@ -340,38 +374,48 @@ def _e_store_chunk(x_r: torch.Tensor, y_c: torch.Tensor, comm: Comm) -> int:
     per_tensor = n_c * (-(-b // 128) * 128) * (-(-n_all // 128) * 128) * 2
     if per_tensor * n_r < _E_STORE_MIN_BYTES:
         return 0
+    in_flight = 2 if comm.distributed else 1
     key = (n_r, b, n_c, n_all, x_r.device, comm.world_size, id(comm.group))
-    chunk = _e_chunk_cache.get(key)
-    if chunk is None:
-        # decided once per problem shape: cudaMemGetInfo stalls the launch queue, which a per-step call would pay every step
-        budget = _E_STORE_MAX_BYTES
-        if x_r.is_cuda:
-            free, _total = torch.cuda.mem_get_info(x_r.device)
-            free += torch.cuda.memory_reserved(x_r.device) - torch.cuda.memory_allocated(x_r.device)   # cached blocks are reusable
-            budget = min(budget, free // 3)      # exponentials + (CLIP group) the G tiles of the same chunk + headroom
-        most = min(n_r, budget // per_tensor)
-        if most <= 0:
-            chunk = 0
-        else:
-            passes = -(-n_r // most)
-            chunk = -(-n_r // passes)            # equal passes: 16 tensors at most 5 at a time -> 4 + 4 + 4 + 4, not 5 + 5 + 5 + 1
-        if comm.distributed:
-            # every rank must make the same number of passes (each pass all-reduces its column statistics): agree on the
-            # smallest chunk once per shape; ranks see the same shapes in the same order, so they all arrive here together
-            agreed = torch.tensor([chunk], dtype=torch.int32, device=x_r.device if x_r.is_cuda else "cpu")
-            dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=comm.group)
-            chunk = int(agreed.item())
-        if len(_e_chunk_cache) > 64:
-            _e_chunk_cache.clear()
-        _e_chunk_cache[key] = chunk
+    hit = _e_chunk_cache.get(key)
+    if hit is not None:
+        chunk, allocated_then = hit
+        # Decided once per problem shape (cudaMemGetInfo stalls the launch queue, which a per-step call would pay every step)
+        # and re-checked with the allocator's own host-side counter: if this process holds much more memory than when the
+        # decision was taken (optimizer state, activations of a later phase), decide again instead of running out of memory.
+        if not x_r.is_cuda or torch.cuda.memory_allocated(x_r.device) <= allocated_then + in_flight * chunk * per_tensor:
+            return chunk
+    budget = _E_STORE_MAX_BYTES // in_flight
+    if x_r.is_cuda:
+        budget = min(budget, _reusable_bytes(x_r.device) // (3 * in_flight))   # exponentials + (CLIP group) G tiles + headroom
+    most = min(n_r, budget // per_tensor)
+    if most <= 0:
+        chunk = 0
+    else:
+        passes = -(-n_r // most)
+        chunk = -(-n_r // passes)            # equal passes: 16 tensors at most 5 at a time -> 4 + 4 + 4 + 4, not 5 + 5 + 5 + 1
+    if comm.distributed:
+        # every rank must make the same number of passes (each pass gathers its column statistics): agree on the smallest
+        # chunk; ranks see the same shapes in the same order, so they all arrive here together.  (A re-decision on one rank
+        # only would desynchronise the collectives: the re-check above uses the same counter on every rank of a symmetric
+        # job; asymmetric jobs should pin COSMOS_B200_ESTORE_MAX_GB.)
+        agreed = torch.tensor([chunk], dtype=torch.int32, device=x_r.device if x_r.is_cuda else "cpu")
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=comm.group)
+        chunk = int(agreed.item())
+    if len(_e_chunk_cache) > 64:
+        _e_chunk_cache.clear()
+    _e_chunk_cache[key] = (chunk, torch.cuda.memory_allocated(x_r.device) if x_r.is_cuda else 0)
     return chunk
 
 
-class _PairsInfoNCE(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, scale: torch.Tensor, comm: Comm, n_r: int, prefetch, *feats: torch.Tensor):
-        rows, cols = feats[:n_r], feats[n_r:]
-        n_c = len(cols)
+# ------------------------------------------------------------------------------------------------
+# stored-exponential route: the schedule shared by one group (ClipLoss) and two (COSMOSLoss)
+# ------------------------------------------------------------------------------------------------
+
+class _Group:
+    """One cartesian product rows x cols with its logit scale: stacked inputs, outputs, and the unit gradients."""
+
+    def __init__(self, rows, cols, scale, comm: Comm, prefetch, need_scale: bool, need_rows: bool, need_cols: bool):
+        self.n_r, self.n_c = len(rows), len(cols)
         dev = rows[0].device
         dt = compute_dtype(rows[0].dtype)
         x_r = stack_views(rows, dt)                       # [n_r, b, D]
@@ -379,88 +423,205 @@ class _PairsInfoNCE(torch.autograd.Function):
         if prefetch is not None and comm.distributed:
             pre_c = prefetch.handles.get(tuple(id(t) for t in cols))
             pre_r = prefetch.handles.get(tuple(id(t) for t in rows))
-        x_c = pre_c[0] if pre_c is not None else stack_views(cols, dt)   # [n_c, b, D]
+        self.x_c = pre_c[0] if pre_c is not None else stack_views(cols, dt)   # [n_c, b, D]
         if pre_r is not None:
             x_r = pre_r[0]
-        b = x_r.shape[1]
-        if x_c.shape[1] != b:
+        self.x_r = x_r
+        self.pre_c, self.pre_r = pre_c, pre_r
+        self.b = x_r.shape[1]
+        if self.x_c.shape[1] != self.b:
             raise RuntimeError("cosmos_b200: both feature lists must have the same batch size")
-        W = comm.world_size
-        N = W * b
-        off = comm.rank * b if comm.distributed else 0
-        scale_f = scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        self.comm = comm
+        self.N = comm.world_size * self.b
+        self.P = self.n_r * self.n_c
+        self.off = comm.rank * self.b if comm.distributed else 0
+        self.scale_f = scale.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        self.need_scale, self.need_rows, self.need_cols = need_scale, need_rows, need_cols
+        self._y_c = None
 
-        y_c = pre_c[1].get() if pre_c is not None else gather_stack(x_c, comm)     # [n_c, N, D]
-        P = n_r * n_c
-        need_scale = ctx.needs_input_grad[0]
-        need_rows = any(ctx.needs_input_grad[4:4 + n_r])
-        need_cols = any(ctx.needs_input_grad[4 + n_r:])
+    @property
+    def y_c(self) -> torch.Tensor:                        # [n_c, N, D]; waits for the prefetched all-gather on first use
+        if self._y_c is None:
+            self._y_c = self.pre_c[1].get() if self.pre_c is not None else gather_stack(self.x_c, self.comm)
+        return self._y_c
+
+    def eager_chunk(self) -> int:
         # (the column-side gradient of this route is a GEMM over stored G tiles, whose 16-byte pieces need N % 8 == 0)
-        chunk = _e_store_chunk(x_r, y_c, comm) if (need_rows and not (need_cols and N % 8 != 0)) else 0
-        ctx.eager = chunk > 0
+        if not self.need_rows or (self.need_cols and self.N % 8 != 0):
+            return 0
+        # shapes only: the gathered column stack need not have arrived for this decision
+        y_shape = torch.empty(self.n_c, self.N, self.x_r.shape[2], dtype=self.x_r.dtype, device="meta")
+        return _e_store_chunk(self.x_r, y_shape, self.comm)
+
+
+def _eager_schedule(groups: Sequence[_Group], comm: Comm):
+    """Stored-exponential route for one or more groups: per chunk of row tensors, forward (statistics + 2^(s2 - max) of every
+    logit, bf16) and, once the chunk's column statistics are complete, the gradients for a unit upstream gradient - dX = G Y
+    is the only contraction left, no logit is recomputed.  backward() only scales by the upstream gradient.
+
+    Distributed runs are software-pipelined so that no collective is waited for right after it was started: the forward of
+    chunk k + 1 is launched behind the all-gather of chunk k's column statistics, the reduce-scatter of a group's column-side
+    gradient runs behind the next group's kernels, and the loss sums and d(scale) of ALL groups share one small all-reduce
+    at the end.  Returns the local loss totals; fills g.dx_unit, g.ds_unit, g.d_cols_unit, g.weight, g.pre per group."""
+    W = comm.world_size
+    items = []
+    for g in groups:
+        dev = g.x_r.device
+        boost = float(W) if (comm.distributed and comm.gather_with_grad) else 1.0
+        g.boost = boost
+        g.weight = boost / (2.0 * g.N * g.P)
+        # The unit gradients are held in the feature dtype.  Under GradScaler (fp16 features) the upstream factor exists
+        # precisely because |dX| ~ weight * scale would underflow fp16, so they are formed with a power-of-two stand-in
+        # for it (exact in every dtype; |dX * pre| <= 2 * n_c * scale / 64) and backward() multiplies by upstream / pre.
+        g.pre = 2.0 ** (math.floor(math.log2(1.0 / g.weight)) - 6)
+        g.one = torch.full((1,), g.pre, dtype=torch.float32, device=dev)
+        g.row_lse2 = torch.empty(g.P, g.b, dtype=torch.float32, device=dev)
+        g.diag_raw = torch.empty(g.P, g.b, dtype=torch.float32, device=dev)
+        g.col_lse2 = torch.empty(g.P, g.N, dtype=torch.float32, device=dev)
+        g.dx_unit = torch.empty_like(g.x_r)
+        g.ds_unit = None
+        g.d_all = None
+        g.d_cols_unit = None
+        g.rs_work = None
+        starts = list(range(0, g.n_r, g.chunk))
+        for i0 in starts:
+            items.append((g, i0, i0 == starts[-1]))
+
+    def forward_of(item):
+        g, i0, last = item
+        xs = g.x_r[i0:i0 + g.chunk]
+        sl = slice(i0 * g.n_c, (i0 + xs.shape[0]) * g.n_c)
+        col_out = g.col_lse2[sl]
+        part = torch.empty_like(col_out) if comm.distributed else col_out
+        _r, _d, _c, e_, o_ = _k_fwd(xs, g.y_c, g.off, g.scale_f, True, out=(g.row_lse2[sl], g.diag_raw[sl], part))
+        gather = _LseGather(part, comm) if comm.distributed else None
+        return (g, i0, last, xs, sl, e_, o_, gather)
+
+    def backward_of(state):
+        g, i0, last, xs, sl, e_, o_, gather = state
+        if gather is not None:
+            gather.finish(g.col_lse2[sl])
+        g_tiles = torch.empty(xs.shape[0] * g.b, g.n_c * g.N, dtype=g.x_r.dtype, device=xs.device) if g.need_cols else None
+        _dx, ds_ = _k_bwd_e(xs, g.y_c, g.off, g.scale_f, e_, o_, g.row_lse2[sl], g.col_lse2[sl], 1.0, 1.0, 1.0 / g.boost,
+                            1.0 / g.boost, g.weight, g.one, g.need_scale, g_tiles, dx_out=g.dx_unit[i0:i0 + xs.shape[0]])
+        if g_tiles is not None:
+            part = _k_colgrad(g_tiles, xs.reshape(xs.shape[0] * g.b, xs.shape[2]), g.n_c, g.N)    # [n_c, N, D] fp32
+            g.d_all = part if g.d_all is None else g.d_all.add_(part)
+        if ds_ is not None:
+            g.ds_unit = ds_ if g.ds_unit is None else g.ds_unit + ds_
+        if last and g.d_all is not None:
+            # column-side gradient of this rank's rows -> sum over ranks of every rank's own rows; started now, needed by
+            # backward(): it runs behind whatever is launched next
+            g.d_cols_unit, g.rs_work = _reduce_scatter_rows(g.d_all, comm, g.b, async_op=True)
+            g.d_all = None
+
+    if comm.distributed:
+        pending = None
+        for item in items:
+            state = forward_of(item)
+            if pending is not None:
+                backward_of(pending)
+            pending = state
+        backward_of(pending)
+    else:
+        for item in items:
+            backward_of(forward_of(item))
+
+    totals = []
+    for g in groups:
+        sums = _k_loss_sums(g.x_r, g.y_c, g.off, g.scale_f, g.row_lse2, g.diag_raw, g.col_lse2)   # [P, 2]
+        totals.append(sums.sum().reshape(1))
+    if comm.distributed:
+        # one small all-reduce for everything that is a global scalar: the loss sums and the unit d(scale) of every group
+        zero = torch.zeros(1, dtype=torch.float32, device=totals[0].device)
+        vec = torch.cat(totals + [g.ds_unit.reshape(1) if g.ds_unit is not None else zero for g in groups])
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=comm.group)
+        n = len(groups)
+        totals = [vec[k:k + 1] for k in range(n)]
+        for k, g in enumerate(groups):
+            if g.ds_unit is not None:
+                g.ds_unit = vec[n + k:n + k + 1]
+        for g in groups:
+            if g.rs_work is not None:
+                g.rs_work.wait()
+                g.rs_work = None
+    return totals
+
+
+def _eager_grads(g: _Group, up: torch.Tensor, in_dtypes, needs_rows, needs_cols, scale_dtype):
+    """The gradients of one group for the upstream gradient `up` (fp32 [1]) from its unit gradients."""
+    factor = up / g.pre
+    grads: List[Optional[torch.Tensor]] = []
+    # one pass; a 0-dim factor does not promote the result: it keeps the stack dtype (products formed in fp32, rounded once)
+    d_rows = torch.mul(g.dx_unit, factor.reshape(())) if any(needs_rows) else None
+    for k in range(g.n_r):
+        grads.append(d_rows[k].to(in_dtypes[k]) if (d_rows is not None and needs_rows[k]) else None)
+    d_cols = None
+    if g.d_cols_unit is not None and any(needs_cols):
+        d_cols = (g.d_cols_unit * (up * g.scale_f.reshape(1) * g.weight)).to(g.dx_unit.dtype)
+    for k in range(g.n_c):
+        grads.append(d_cols[k].to(in_dtypes[g.n_r + k]) if (d_cols is not None and needs_cols[k]) else None)
+    g_scale = (g.ds_unit.reshape(()) * factor.reshape(())).to(scale_dtype) if (g.need_scale and g.ds_unit is not None) else None
+    return g_scale, grads
+
+
+class _PairsInfoNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scale: torch.Tensor, comm: Comm, n_r: int, prefetch, want_grad: bool, *feats: torch.Tensor):
+        rows, cols = feats[:n_r], feats[n_r:]
+        n_c = len(cols)
+        # needs_input_grad stays True under torch.no_grad(): a validation loss must not pay for gradients nobody will ask for
+        need_scale = want_grad and ctx.needs_input_grad[0]
+        need_rows = want_grad and any(ctx.needs_input_grad[5:5 + n_r])
+        need_cols = want_grad and any(ctx.needs_input_grad[5 + n_r:])
+        g = _Group(rows, cols, scale, comm, prefetch, need_scale, need_rows, need_cols)
+        b, N, P, off = g.b, g.N, g.P, g.off
+        g.chunk = g.eager_chunk()
+        ctx.eager = g.chunk > 0
         if ctx.eager:
-            # Stored-exponential route: per chunk of row tensors, forward (statistics + 2^(s2 - max) of every logit, bf16) and,
-            # as soon as the chunk's column statistics are complete, the gradients for a unit upstream gradient - dX = G Y is
-            # the only contraction left, no logit is recomputed.  backward() only scales by the upstream gradient.
-            boost = float(W) if (comm.distributed and comm.gather_with_grad) else 1.0
-            weight = boost / (2.0 * N * P)
-            # The unit gradients are held in the feature dtype.  Under GradScaler (fp16 features) the upstream factor exists
-            # precisely because |dX| ~ weight * scale would underflow fp16, so they are formed with a power-of-two stand-in
-            # for it (exact in every dtype; |dX * pre| <= 2 * n_c * scale / 64) and backward() multiplies by upstream / pre.
-            pre = 2.0 ** (math.floor(math.log2(1.0 / weight)) - 6)
-            one = torch.full((1,), pre, dtype=torch.float32, device=dev)
-            row_parts, diag_parts, col_parts, dx_parts = [], [], [], []
-            ds_unit = None
-            d_all = None
-            for i0 in range(0, n_r, chunk):
-                xs = x_r[i0:i0 + chunk]
-                r_, d_, c_part, e_, o_ = _k_fwd(xs, y_c, off, scale_f, True)
-                c_ = _allreduce_lse2(c_part, comm)
-                g_tiles = torch.empty(xs.shape[0] * b, n_c * N, dtype=x_r.dtype, device=dev) if need_cols else None
-                dx_, ds_ = _k_bwd_e(xs, y_c, off, scale_f, e_, o_, r_, c_, 1.0, 1.0, 1.0 / boost, 1.0 / boost, weight, one,
-                                    need_scale, g_tiles)
-                del e_, o_
-                if g_tiles is not None:
-                    part = _k_colgrad(g_tiles, xs.reshape(xs.shape[0] * b, xs.shape[2]), n_c, N)    # [n_c, N, D] fp32
-                    d_all = part if d_all is None else d_all.add_(part)
-                    del g_tiles
-                if ds_ is not None:
-                    ds_unit = ds_ if ds_unit is None else ds_unit + ds_
-                row_parts.append(r_); diag_parts.append(d_); col_parts.append(c_); dx_parts.append(dx_)
-            row_lse2, diag_raw, col_lse2 = (torch.cat(t) if len(t) > 1 else t[0] for t in (row_parts, diag_parts, col_parts))
-            ctx.unit = (torch.cat(dx_parts) if len(dx_parts) > 1 else dx_parts[0], ds_unit, d_all, weight, pre)
-        else:
-            row_lse2, diag_raw, col_lse2_part = _k_fwd(x_r, y_c, off, scale_f)
-            col_lse2 = _allreduce_lse2(col_lse2_part, comm)   # global over all rows
-        sums = _k_loss_sums(x_r, y_c, off, scale_f, row_lse2, diag_raw, col_lse2)   # [P, 2]
-        total = sums.sum()
-        if comm.distributed and not comm.local_loss:
-            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=comm.group)
+            (total,) = _eager_schedule([g], comm)         # local_loss never takes this route: the total is global already
+            total = total.reshape(())
             loss = total / (2.0 * N * P)
+            ctx.group = g
         else:
-            loss = total / (2.0 * b * P)
+            row_lse2, diag_raw, col_lse2_part = _k_fwd(g.x_r, g.y_c, off, g.scale_f)
+            col_lse2 = _allreduce_lse2(col_lse2_part, comm)   # global over all rows
+            sums = _k_loss_sums(g.x_r, g.y_c, off, g.scale_f, row_lse2, diag_raw, col_lse2)   # [P, 2]
+            total = sums.sum()
+            if comm.distributed and not comm.local_loss:
+                dist.all_reduce(total, op=dist.ReduceOp.SUM, group=comm.group)
+                loss = total / (2.0 * N * P)
+            else:
+                loss = total / (2.0 * b * P)
 
         ctx.comm, ctx.n_r, ctx.n_c, ctx.b, ctx.off = comm, n_r, n_c, b, off
-        ctx.pre_r = pre_r[1] if pre_r is not None else None
+        ctx.pre_r = g.pre_r[1] if g.pre_r is not None else None
         ctx.in_dtypes = [t.dtype for t in feats]
         ctx.scale_dtype = scale.dtype
-        if ctx.eager:
-            ctx.save_for_backward(scale_f)
-        else:
-            ctx.save_for_backward(x_r, x_c, y_c, scale_f, row_lse2, col_lse2)
+        ctx.want_grad = want_grad
+        if not ctx.eager and want_grad:
+            ctx.save_for_backward(g.x_r, g.x_c, g.y_c, g.scale_f, row_lse2, col_lse2)
         return loss
 
     @staticmethod
     def backward(ctx, g: torch.Tensor):
+        if not ctx.want_grad:
+            raise RuntimeError("cosmos_b200: this loss was computed under torch.no_grad(); it has no gradients")
         if ctx.eager:
-            return _PairsInfoNCE._backward_eager(ctx, g)
+            up = g.detach().to(torch.float32).reshape(1)
+            n_r = ctx.n_r
+            g_scale, grads = _eager_grads(ctx.group, up, ctx.in_dtypes, ctx.needs_input_grad[5:5 + n_r],
+                                          ctx.needs_input_grad[5 + n_r:], ctx.scale_dtype)
+            if not ctx.needs_input_grad[0]:
+                g_scale = None
+            return (g_scale, None, None, None, None, *grads)
         x_r, x_c, y_c, scale_f, row_lse2, col_lse2 = ctx.saved_tensors
         comm, n_r, n_c, b, off = ctx.comm, ctx.n_r, ctx.n_c, ctx.b, ctx.off
         W = comm.world_size
         N, P = W * b, n_r * n_c
         need_scale = ctx.needs_input_grad[0]
-        need_rows = any(ctx.needs_input_grad[4:4 + n_r])
-        need_cols = any(ctx.needs_input_grad[4 + n_r:])
+        need_rows = any(ctx.needs_input_grad[5:5 + n_r])
+        need_cols = any(ctx.needs_input_grad[5 + n_r:])
         up = g.detach().to(torch.float32).reshape(1).contiguous()
 
         local = comm.distributed and comm.local_loss
@@ -504,39 +665,67 @@ class _PairsInfoNCE(torch.autograd.Function):
 
         grads: List[Optional[torch.Tensor]] = []
         for k in range(n_r):
-            grads.append(d_rows[k].to(ctx.in_dtypes[k]) if (d_rows is not None and ctx.needs_input_grad[4 + k]) else None)
+            grads.append(d_rows[k].to(ctx.in_dtypes[k]) if (d_rows is not None and ctx.needs_input_grad[5 + k]) else None)
         for k in range(n_c):
             grads.append(d_cols[k].to(ctx.in_dtypes[n_r + k])
-                         if (d_cols is not None and ctx.needs_input_grad[4 + n_r + k]) else None)
+                         if (d_cols is not None and ctx.needs_input_grad[5 + n_r + k]) else None)
         g_scale = d_scale.reshape(()).to(ctx.scale_dtype) if need_scale else None
-        return (g_scale, None, None, None, *grads)
+        return (g_scale, None, None, None, None, *grads)
 
+
+class _CosmosHead(torch.autograd.Function):
+    """Both InfoNCE groups of the COSMOS loss (src/open_clip/loss.py:193-206) on the stored-exponential route in ONE
+    schedule: the CLIP group (student captions x the two global student crops) first, then the distillation group (all
+    cross-modal student features x the four teacher features), so that in a distributed run the reduce-scatter of the CLIP
+    group's image-side gradient and every all-gather of column statistics run behind kernels of the other group.
+    Returns (distill_loss, clip_loss)."""
 
     @staticmethod
-    def _backward_eager(ctx, g: torch.Tensor):
-        """The gradients for a unit upstream gradient were formed in forward(): scale them (and finish the collectives)."""
-        (scale_f,) = ctx.saved_tensors
-        comm, n_r, n_c, b = ctx.comm, ctx.n_r, ctx.n_c, ctx.b
-        dx_unit, ds_unit, d_all, weight, pre = ctx.unit
-        up = g.detach().to(torch.float32).reshape(1)
-        grads: List[Optional[torch.Tensor]] = []
-        d_rows = (dx_unit.float() * (up / pre)).to(dx_unit.dtype) if any(ctx.needs_input_grad[4:4 + n_r]) else None
-        for k in range(n_r):
-            grads.append(d_rows[k].to(ctx.in_dtypes[k]) if (d_rows is not None and ctx.needs_input_grad[4 + k]) else None)
-        d_cols = None
-        if d_all is not None:
-            d_loc = _reduce_scatter_rows(d_all, comm, b)                                  # [n_c, b, D], all ranks' rows
-            d_cols = (d_loc * (up * scale_f.reshape(1) * weight)).to(dx_unit.dtype)
-        for k in range(n_c):
-            grads.append(d_cols[k].to(ctx.in_dtypes[n_r + k])
-                         if (d_cols is not None and ctx.needs_input_grad[4 + n_r + k]) else None)
-        g_scale = None
-        if ctx.needs_input_grad[0]:
-            d_scale = ds_unit * (up / pre)
-            if comm.distributed:
-                dist.all_reduce(d_scale, op=dist.ReduceOp.SUM, group=comm.group)
-            g_scale = d_scale.reshape(()).to(ctx.scale_dtype)
-        return (g_scale, None, None, None, *grads)
+    def forward(ctx, logit_scale, distill_scale, comm: Comm, counts, groups, *feats):
+        clip, dist_g = groups
+        t_clip, t_dist = _eager_schedule([clip, dist_g], comm)
+        ctx.groups = (clip, dist_g)
+        ctx.counts = counts
+        ctx.in_dtypes = [t.dtype for t in feats]
+        ctx.scale_dtypes = (logit_scale.dtype, distill_scale.dtype)
+        return (t_dist.reshape(()) / (2.0 * dist_g.N * dist_g.P), t_clip.reshape(()) / (2.0 * clip.N * clip.P))
+
+    @staticmethod
+    def backward(ctx, g_distill, g_clip):
+        clip, dist_g = ctx.groups
+        n_txt, n_img, n_x, n_t = ctx.counts
+        need = ctx.needs_input_grad
+        o = 5
+        dt = ctx.in_dtypes
+        up_c = g_clip.detach().to(torch.float32).reshape(1)
+        up_d = g_distill.detach().to(torch.float32).reshape(1)
+        gs_c, grads_c = _eager_grads(clip, up_c, dt[:n_txt + n_img], need[o:o + n_txt], need[o + n_txt:o + n_txt + n_img],
+                                     ctx.scale_dtypes[0])
+        k0 = n_txt + n_img
+        gs_d, grads_d = _eager_grads(dist_g, up_d, dt[k0:], need[o + k0:o + k0 + n_x], need[o + k0 + n_x:], ctx.scale_dtypes[1])
+        return (gs_c if need[0] else None, gs_d if need[1] else None, None, None, None, *grads_c, *grads_d)
+
+
+def cosmos_head(texts, images2, xrows, teacher, logit_scale, distill_scale, comm: Comm, prefetch=None):
+    """(distill_loss, clip_loss) of the COSMOS loss when BOTH groups can take the stored-exponential route (dim 512, not a
+    local-loss mode, large enough, gradients wanted); None otherwise - the caller then evaluates the groups one by one."""
+    if not torch.is_grad_enabled() or (comm.distributed and comm.local_loss):
+        return None
+    texts, images2, xrows, teacher = list(texts), list(images2), list(xrows), list(teacher)
+    for t in texts + images2 + xrows + teacher:
+        _lib.require_cuda(t, "feature tensor")
+    dev = texts[0].device
+    scales = []
+    for sc in (logit_scale, distill_scale):
+        scales.append(sc if isinstance(sc, torch.Tensor) else torch.tensor(float(sc), dtype=torch.float32, device=dev))
+    rg = lambda ts: any(t.requires_grad for t in ts)
+    clip = _Group(texts, images2, scales[0], comm, prefetch, scales[0].requires_grad, rg(texts), rg(images2))
+    dist_g = _Group(xrows, teacher, scales[1], comm, prefetch, scales[1].requires_grad, rg(xrows), False)
+    clip.chunk, dist_g.chunk = clip.eager_chunk(), dist_g.eager_chunk()
+    if clip.chunk <= 0 or dist_g.chunk <= 0:
+        return None
+    counts = (len(texts), len(images2), len(xrows), len(teacher))
+    return _CosmosHead.apply(scales[0], scales[1], comm, counts, (clip, dist_g), *texts, *images2, *xrows, *teacher)
 
 
 def pairs_infonce(rows: Sequence[torch.Tensor], cols: Sequence[torch.Tensor], scale, comm: Comm = Comm(),
@@ -552,4 +741,4 @@ def pairs_infonce(rows: Sequence[torch.Tensor], cols: Sequence[torch.Tensor], sc
         _lib.require_cuda(t, "feature tensor")
     if not isinstance(scale, torch.Tensor):
         scale = torch.tensor(float(scale), dtype=torch.float32, device=rows[0].device)
-    return _PairsInfoNCE.apply(scale, comm, len(rows), prefetch, *rows, *cols)
+    return _PairsInfoNCE.apply(scale, comm, len(rows), prefetch, torch.is_grad_enabled(), *rows, *cols)

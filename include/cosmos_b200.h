@@ -117,6 +117,11 @@ int64_t cosmos_infonce_workspace_bytes(const cosmos_infonce_problem* p);
 int cosmos_infonce_fwd(const cosmos_infonce_problem* p, float* row_lse2, float* diag_raw, float* col_lse2,
                        void* workspace, int64_t workspace_bytes, int device, void* stream);
 
+/* Merge of per-rank partial column statistics (row-sharded forward, src/open_clip/loss.py:21-65 gathers the features
+ * instead): parts [n_parts][n] fp32 log2-sum-exp values (every rank's col_lse2, all-gathered), out [n] their
+ * log2-sum-exp2.  -inf (a rank without rows) is the neutral element.                                              */
+int cosmos_lse2_merge(const float* parts, float* out, int32_t n_parts, int64_t n, int device, void* stream);
+
 /* Per-pair loss sums (natural-log units), out[p][0] = sum_r (LSE_row[r] - S[r, label(r)]) over local rows,
  * out[p][1] = sum_c (LSE_col[c] - S[c - label_offset, c]) over this rank's n_rows diagonal columns, with
  * col_lse2 the GLOBAL column log-sum-exp (already combined across ranks).  out: fp32 [gx*gy][2].          */

@@ -16,7 +16,12 @@ def _raw(x, y):
     return torch.einsum("ibd,jnd->ijbn", x.double(), y.double())       # [gx, gy, b, N]
 
 
-def emu_fwd(x, y, label_offset, scale, keep_e=False):
+def emu_fwd(x, y, label_offset, scale, keep_e=False, out=None):
+    if out is not None:            # write into the caller's buffers (slices of per-group tensors)
+        res = emu_fwd(x, y, label_offset, scale, keep_e)
+        for dst, src in zip(out, res[:3]):
+            dst.copy_(src)
+        return tuple(out) + tuple(res[3:])
     if keep_e:
         # stored-exponential route: the emulation keeps the logits themselves (the layout of e / off is private to the kernels)
         return emu_fwd(x, y, label_offset, scale) + (_raw(x, y) * (float(scale) * LOG2E), None)
@@ -64,8 +69,14 @@ def emu_bwd(x, y, label_offset, scale, row_lse2, col_lse2, a_row, a_col, s_row, 
     return dx, dscale
 
 
+def emu_lse2_merge(parts, out):
+    """cosmos_lse2_merge: log2-sum-exp2 over the leading (rank) dimension."""
+    out.copy_((torch.logsumexp(parts.double() * LN2, dim=0) / LN2).float())
+    return out
+
+
 def emu_bwd_e(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream, want_dscale,
-              g_out=None):
+              g_out=None, dx_out=None):
     """cosmos_infonce_bwd_e: the same gradient, formed from what the forward kept (here: the logits) - no x y^T."""
     assert abs(a_row * s_col - a_col * s_row) < 1e-12, "bwd_e needs proportional d(scale) / gradient mixes"
     gx, b, D = x.shape
@@ -81,6 +92,9 @@ def emu_bwd_e(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_co
     up = float(upstream)
     acc = torch.einsum("ijbn,jnd->ibd", G, y.double())                      # the dX accumulators
     dx = ((up * weight * float(scale)) * acc).to(x.dtype)
+    if dx_out is not None:
+        dx_out.copy_(dx)
+        dx = dx_out
     dscale = None
     if want_dscale:       # sum_r <x_r, (G y)_r>, re-weighted to the d(scale) mix
         dscale = ((up * weight * (s_row + s_col) / (a_row + a_col)) * (acc * x.double()).sum()).float().reshape(1)
@@ -102,11 +116,13 @@ def install(monkeypatch=None):
         monkeypatch.setattr(infonce, "_k_bwd", emu_bwd)
         monkeypatch.setattr(infonce, "_k_bwd_e", emu_bwd_e)
         monkeypatch.setattr(infonce, "_k_colgrad", emu_colgrad)
+        monkeypatch.setattr(infonce, "_k_lse2_merge", emu_lse2_merge)
         monkeypatch.setattr(_lib, "require_cuda", lambda t, what: None)
         monkeypatch.setattr(infonce, "compute_dtype", lambda dt: dt)
     else:
         infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd = emu_fwd, emu_loss_sums, emu_bwd
         infonce._k_colgrad = emu_colgrad
         infonce._k_bwd_e = emu_bwd_e
+        infonce._k_lse2_merge = emu_lse2_merge
         _lib.require_cuda = lambda t, what: None
         infonce.compute_dtype = lambda dt: dt

@@ -198,6 +198,149 @@ def case_clamp():
     torch.save(dict(values=vals, outs=out), os.path.join(HERE, "clamp.pt"))
 
 
+def _gather_worker(rank, world, port, payload, tmpdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L, _ = ref_modules()
+    res = {}
+    img0, txt0 = payload["image"][rank], payload["text"][rank]
+    wi, wt = payload["probe_image"], payload["probe_text"]
+    for ll in (False, True):
+        for gwg in (False, True):
+            # gather_features (src/open_clip/loss.py:21-65) + a probe loss that weighs every gathered row differently
+            img, txt = img0.clone().requires_grad_(True), txt0.clone().requires_grad_(True)
+            all_i, all_t = L.gather_features(img, txt, local_loss=ll, gather_with_grad=gwg, rank=rank, world_size=world)
+            probe = (all_i * wi).sum() + (all_t * wt).sum()
+            if probe.requires_grad:
+                probe.backward()
+            rec = dict(all_image=all_i.detach().clone(), all_text=all_t.detach().clone(),
+                       g_image=None if img.grad is None else img.grad.clone(), g_text=None if txt.grad is None else txt.grad.clone())
+            # ClipLoss.get_logits (loss.py:103-119) in the same mode
+            img, txt = img0.clone().requires_grad_(True), txt0.clone().requires_grad_(True)
+            lpi, lpt = L.ClipLoss(local_loss=ll, gather_with_grad=gwg, rank=rank, world_size=world).get_logits(img, txt, 7.5)
+            rec["logits_per_image"], rec["logits_per_text"] = lpi.detach().clone(), lpt.detach().clone()
+            (lpi * payload["probe_logits"][:lpi.shape[0], :lpi.shape[1]]).sum().backward()
+            rec["g_logits_image"] = None if img.grad is None else img.grad.clone()
+            rec["g_logits_text"] = None if txt.grad is None else txt.grad.clone()
+            res[f"ll{int(ll)}_gwg{int(gwg)}"] = rec
+    torch.save(res, os.path.join(tmpdir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def case_gather(world, port, fname):
+    """gather_features and ClipLoss.get_logits of the reference on gloo ranks, all four (local_loss, gather_with_grad) modes:
+    outputs and the gradients a probe loss sends back to the local shards."""
+    import tempfile
+    g = torch.Generator().manual_seed(500 + world)
+    b, d = 5, 16
+    payload = dict(image=[torch.randn(b, d, generator=g) for _ in range(world)], text=[torch.randn(b, d, generator=g) for _ in range(world)],
+                   probe_image=torch.randn(world * b, d, generator=g), probe_text=torch.randn(world * b, d, generator=g),
+                   probe_logits=torch.randn(world * b, world * b, generator=g))
+    ctx = mp.get_context("spawn")
+    with tempfile.TemporaryDirectory() as tmpdir:
+        procs = [ctx.Process(target=_gather_worker, args=(r, world, port, payload, tmpdir)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join()
+            assert p.exitcode == 0
+        got = [torch.load(os.path.join(tmpdir, f"rank{r}.pt")) for r in range(world)]
+    torch.save(dict(world=world, payload=payload, results=got), os.path.join(HERE, fname))
+
+
+def ref_function_source(relpath, name):
+    """One top-level function of a reference file as an ast module (compiled where the file lies, nothing is copied)."""
+    import ast
+    path = os.path.join(REF, relpath)
+    tree = ast.parse(open(path).read(), filename=path)
+    tree.body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name]
+    assert tree.body, (relpath, name)
+    return compile(tree, path, "exec")
+
+
+def ref_train_step_lines():
+    """The literal statements of the reference's training step that touch the loss head, as source text read from the file
+    where it lies: src/training/train.py:162-188 (model_out dict, loss call, sum), 190 (backward) and 195-203 (EMA loop)."""
+    import textwrap
+    lines = open(os.path.join(REF, "src", "training", "train.py")).read().split("\n")
+    block = lambda a, b: textwrap.dedent("\n".join(lines[a - 1:b]))
+    return block(162, 188) + "\n" + block(190, 190) + "\n" + block(195, 203) + "\n"
+
+
+class ToyTowers(torch.nn.Module):
+    """Stand-in for the COSMOS student / teacher (src/open_clip/model.py:348-408): per-channel gains that turn fixed inputs
+    into the feature dict train_one_epoch reads.  Outputs are rounded to bf16 values (what autocast hands the loss)."""
+
+    def __init__(self, d, seed):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+        mk = lambda: torch.nn.Parameter(1.0 + 0.3 * torch.randn(d, generator=g))
+        self.w_img, self.w_txt, self.w_imgx, self.w_txtx = mk(), mk(), mk(), mk()
+        self.bias = torch.nn.Parameter(0.05 * torch.randn(d, generator=g))
+        self.logit_scale = torch.nn.Parameter(torch.tensor(2.6593))            # ln(1 / 0.07), model.py:249
+        self.distill_logit_scale = torch.nn.Parameter(torch.tensor(3.0))
+
+    def forward(self, images, texts, batch_size=None):
+        f = lambda x, w: torch.nn.functional.normalize(x * w + self.bias, dim=-1).to(torch.bfloat16).to(torch.float32)
+        out = {"image_features": f(images, self.w_img), "text_features": f(texts, self.w_txt),
+               "logit_scale": self.logit_scale.exp(), "distill_logit_scale": self.distill_logit_scale.exp()}
+        if batch_size is not None:
+            out["img_crossmodal_features"] = f(images, self.w_imgx)
+            out["txt_crossmodal_features"] = f(texts, self.w_txtx)
+        return out
+
+
+def dropin_inputs(d, b, n_img, n_txt, seed):
+    """Seeded inputs of the drop-in case (regenerated by the test; the fixture keeps a checksum): correlated views of one
+    latent per sample, so that the losses sit where a partly trained model's do."""
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(b, d, generator=g)
+    images = torch.cat([z + 1.5 * torch.randn(b, d, generator=g) for _ in range(n_img)])
+    texts = torch.cat([z + 1.5 * torch.randn(b, d, generator=g) for _ in range(n_txt)])
+    return images, texts, 0.01 * torch.randn(7, d, generator=g)
+
+
+class FakeScaler:
+    """torch.cuda.amp.GradScaler as the step uses it (train.py:62-66): scale(loss) = loss * 65536."""
+
+    def scale(self, x):
+        return x * 65536.0
+
+
+def case_dropin():
+    """The loss-head lines of train_one_epoch executed LITERALLY (read from the reference file) with the reference's
+    create_loss(args) (factory.py:372-415): feature dict -> loss dict -> sum -> GradScaler.scale().backward() -> EMA loop."""
+    import copy
+    L, _ = ref_modules()
+    ns = {name: getattr(L, name) for name in ("ClipLoss", "COSMOSLoss", "CoCaLoss", "DistillClipLoss", "SigLipLoss")}
+    exec(ref_function_source(os.path.join("src", "open_clip", "factory.py"), "create_loss"), ns)
+    tns = {"torch": torch}
+    exec(ref_function_source(os.path.join("src", "training", "train.py"), "backward"), tns)
+    args = types.SimpleNamespace(distill=False, model="ViT-B-16", siglip=False, cosmos=True, local_loss=False, gather_with_grad=False,
+                                 rank=0, world_size=1, horovod=False, fix_momentum=True, momentum_teacher=0.99, accum_freq=1)
+    d, b, n_img, n_txt, seed = 512, 40, 8, 8, 4242
+    images, texts, noise = dropin_inputs(d, b, n_img, n_txt, seed)
+    student = ToyTowers(d, 11)
+    teacher = copy.deepcopy(student)
+    with torch.no_grad():
+        for p_, n_ in zip(teacher.parameters(), noise):
+            p_.add_(n_[:p_.numel()].reshape(p_.shape))
+            p_.requires_grad = False
+    s_model_out = student(images, texts, b)
+    t_model_out = teacher(torch.cat(images.chunk(n_img)[:2]), texts[:2 * b])
+    env = dict(torch=torch, args=args, loss=ns["create_loss"](args), scaler=FakeScaler(), backward=tns["backward"],
+               student=student, teacher=teacher, s_model_out=s_model_out, t_model_out=t_model_out,
+               logit_scale=s_model_out["logit_scale"], distill_logit_scale=s_model_out["distill_logit_scale"],
+               num_images=n_img, num_texts=n_txt, step=0, momentum_scheduler=None)
+    exec(compile(ref_train_step_lines(), "train.py:162-203", "exec"), env)
+    torch.save(dict(d=d, b=b, n_img=n_img, n_txt=n_txt, seed=seed, checksum=float(images.double().sum() + texts.double().sum()),
+                    momentum=0.99, losses={k: v.detach().clone() for k, v in env["losses"].items()},
+                    grads={k: p_.grad.clone() for k, p_ in student.named_parameters()},
+                    teacher_after={k: v.clone() for k, v in teacher.state_dict().items()}), os.path.join(HERE, "dropin.pt"))
+
+
 def ref_train_functions(*names):
     """The named top-level functions of the reference's src/training/train.py, compiled from the file where it lies
     (the module itself cannot be imported here: it needs open_clip's package __init__, PIL, tqdm, ...)."""
@@ -237,6 +380,9 @@ if __name__ == "__main__":
     case_cfg1(L)
     case_multirank(4, 29611, "multirank_w4.pt")
     case_multirank(2, 29612, "multirank_w2.pt")
+    case_gather(2, 29613, "gather_w2.pt")
+    case_gather(3, 29614, "gather_w3.pt")
+    case_dropin()
     case_pooler(T)
     case_ema()
     case_retrieval()

@@ -161,7 +161,7 @@ def test_cosmos_loss_vs_oracle(batch, dim, scale, keep_g, monkeypatch):
         calls = []
         real = infonce._k_bwd_e
         monkeypatch.setattr(infonce, "_e_store_chunk", lambda x_r, y_c, comm: min(3, x_r.shape[0]))
-        monkeypatch.setattr(infonce, "_k_bwd_e", lambda *a: calls.append(1) or real(*a))
+        monkeypatch.setattr(infonce, "_k_bwd_e", lambda *a, **k: calls.append(1) or real(*a, **k))
     elif keep_g:
         from cosmos_b200 import infonce
         monkeypatch.setattr(infonce, "_G_STORE_MIN_BYTES", 0)

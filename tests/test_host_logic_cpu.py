@@ -291,7 +291,7 @@ def _chunk_agreement_worker(rank, world, port, tmpdir):
         from cosmos_b200 import infonce
         infonce._E_STORE_MIN_BYTES = 0
         per_tensor = 2 * 128 * 256 * 2                      # n_c = 2, b = 100 -> 128, N = 200 -> 256
-        infonce._E_STORE_MAX_BYTES = per_tensor * (7 if rank == 0 else 3)     # the ranks could take 7 and 3 row tensors at a time
+        infonce._E_STORE_MAX_BYTES = per_tensor * (14 if rank == 0 else 6)    # two chunks in flight: the ranks could take 7 and 3 row tensors at a time
         x = torch.empty(7, 100, 512, dtype=torch.bfloat16)
         y = torch.empty(2, 200, 512, dtype=torch.bfloat16)
         comm = infonce.Comm(rank=rank, world_size=world, group=dist.group.WORLD)
@@ -335,3 +335,138 @@ def test_bench_reference_arm_contract():
     assert "workload" in rec["config"]
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "1"})
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def _gather_worker(rank, world, port, fname, tmpdir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cosmos_b200.loss import ClipLoss, gather_features
+        rec = torch.load(os.path.join(GOLDEN, fname), weights_only=False)
+        pay, ref = rec["payload"], rec["results"][rank]
+        for ll in (False, True):
+            for gwg in (False, True):
+                want = ref[f"ll{int(ll)}_gwg{int(gwg)}"]
+                img, txt = pay["image"][rank].clone().requires_grad_(True), pay["text"][rank].clone().requires_grad_(True)
+                all_i, all_t = gather_features(img, txt, local_loss=ll, gather_with_grad=gwg, rank=rank, world_size=world)
+                assert torch.equal(all_i.detach(), want["all_image"]) and torch.equal(all_t.detach(), want["all_text"]), (ll, gwg)
+                probe = (all_i * pay["probe_image"]).sum() + (all_t * pay["probe_text"]).sum()
+                assert probe.requires_grad == (want["g_image"] is not None), (ll, gwg)
+                if probe.requires_grad:
+                    probe.backward()
+                    _close(img.grad, want["g_image"], rtol=1e-6, atol=1e-6)
+                    _close(txt.grad, want["g_text"], rtol=1e-6, atol=1e-6)
+                img, txt = pay["image"][rank].clone().requires_grad_(True), pay["text"][rank].clone().requires_grad_(True)
+                lpi, lpt = ClipLoss(local_loss=ll, gather_with_grad=gwg, rank=rank, world_size=world).get_logits(img, txt, 7.5)
+                _close(lpi.detach(), want["logits_per_image"], rtol=1e-6, atol=1e-6)
+                _close(lpt.detach(), want["logits_per_text"], rtol=1e-6, atol=1e-6)
+                (lpi * pay["probe_logits"][:lpi.shape[0], :lpi.shape[1]]).sum().backward()
+                for got, key in ((img.grad, "g_logits_image"), (txt.grad, "g_logits_text")):
+                    if want[key] is None:
+                        assert got is None or float(got.abs().max()) == 0.0, (ll, gwg, key)
+                    else:
+                        _close(got, want[key], rtol=1e-5, atol=1e-5)
+        # different shapes on the two sides: two collectives instead of one, same semantics
+        a, b2 = torch.full((3, 4), float(rank)), torch.full((3, 6), float(rank) + 10.0)
+        ga, gb = gather_features(a, b2, rank=rank, world_size=world)
+        assert ga.shape == (3 * world, 4) and gb.shape == (3 * world, 6)
+        assert [float(v) for v in ga[::3, 0]] == [float(r) for r in range(world)]
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,fname,port", [(2, "gather_w2.pt", 29751), (3, "gather_w3.pt", 29752)])
+def test_gather_features_and_get_logits_gloo(world, fname, port):
+    """gather_features (three behaviours) and ClipLoss.get_logits (four modes) against what the unmodified reference
+    returned on the same gloo ranks (src/open_clip/loss.py:21-65, 103-119): values and the gradients of a probe loss."""
+    ctx = mp.get_context("spawn")
+    with tempfile.TemporaryDirectory() as tmpdir:
+        procs = [ctx.Process(target=_gather_worker, args=(r, world, port, fname, tmpdir)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+        for r, p in enumerate(procs):
+            assert p.exitcode == 0, f"rank {r} failed"
+            assert os.path.exists(os.path.join(tmpdir, f"ok{r}"))
+
+
+def test_get_logits_and_labels_single_process():
+    from cosmos_b200.loss import ClipLoss
+    g = torch.Generator().manual_seed(9)
+    a, b = torch.randn(7, 12, generator=g), torch.randn(7, 12, generator=g)
+    mod = ClipLoss(cache_labels=True)
+    lpi, lpt = mod.get_logits(a, b, 3.0)
+    assert torch.equal(lpi, 3.0 * a @ b.T) and torch.equal(lpt, 3.0 * b @ a.T)
+    lab = mod.get_ground_truth(torch.device("cpu"), 7)
+    assert lab.tolist() == list(range(7)) and mod.get_ground_truth(torch.device("cpu"), 7) is lab      # cached
+    assert mod.get_ground_truth(torch.device("cpu"), 5).tolist() == list(range(5))
+    sharded = ClipLoss(local_loss=True, rank=2, world_size=4)
+    assert sharded.get_ground_truth(torch.device("cpu"), 3).tolist() == [6, 7, 8]
+    assert ClipLoss(local_loss=False, rank=2, world_size=4).get_ground_truth(torch.device("cpu"), 3).tolist() == [0, 1, 2]
+
+
+def test_no_grad_forward_forms_no_gradients(monkeypatch):
+    """Under torch.no_grad() (a validation loss) the stored-exponential route must not run its backward inside forward():
+    needs_input_grad stays True there, so the decision is taken from torch.is_grad_enabled()."""
+    from tests import emulation
+    emulation.install(monkeypatch)
+    from cosmos_b200 import COSMOSLoss, infonce
+    calls = {"bwd_e": 0, "keep_e": 0}
+    monkeypatch.setattr(infonce, "_e_store_chunk", _force_e_route())
+    real_bwd_e, real_fwd = infonce._k_bwd_e, infonce._k_fwd
+    monkeypatch.setattr(infonce, "_k_bwd_e", lambda *a, **k: (calls.__setitem__("bwd_e", calls["bwd_e"] + 1), real_bwd_e(*a, **k))[1])
+    monkeypatch.setattr(infonce, "_k_fwd", lambda *a, **k: (calls.__setitem__("keep_e", calls["keep_e"] + int(bool(k.get("keep_e") or (len(a) > 4 and a[4])))),
+                                                            real_fwd(*a, **k))[1])
+    case = torch.load(os.path.join(GOLDEN, "cosmos_w1_small.pt"), weights_only=False)[0]
+    leaf = {k: [t.clone().requires_grad_(True) for t in v] for k, v in case["inputs"].items()}
+    ls = torch.tensor(case["logit_scale"], requires_grad=True)
+    args = (tuple(leaf["s_image"]), tuple(leaf["s_text"]), ls)
+    kw = dict(t_image_features=leaf["t_image"], t_text_features=leaf["t_text"], output_dict=True,
+              s_img_crossmodal_features=leaf["s_img_x"], s_txt_crossmodal_features=leaf["s_txt_x"])
+    with torch.no_grad():
+        out = COSMOSLoss()(*args, **kw)
+    assert calls == {"bwd_e": 0, "keep_e": 0}
+    assert not out["distill_loss"].requires_grad
+    ref = case["out"]
+    if case["distill_logit_scale"] is None:
+        _close(out["distill_loss"], ref["distill_loss"], rtol=2e-5)
+    _close(out["clip_loss"], ref["clip_loss"], rtol=2e-5)
+    out = COSMOSLoss()(*args, **kw)                      # with gradients: the route runs
+    assert calls["bwd_e"] > 0 and calls["keep_e"] > 0 and out["clip_loss"].requires_grad
+
+
+REFERENCE = os.environ.get("COSMOS_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFERENCE, "src", "open_clip", "factory.py")),
+                    reason="the reference checkout is only present in the build container")
+def test_reference_create_loss_builds_the_drop_in():
+    """The reference's own constructor site, create_loss(args) (src/open_clip/factory.py:372-415), compiled from the file
+    where it lies with `open_clip.loss` swapped for `cosmos_b200.loss`: every branch the COSMOS recipes can take constructs
+    the drop-in with the reference's keyword arguments; the out-of-scope losses raise loudly."""
+    import ast
+    import types
+    import cosmos_b200.loss as ours
+    path = os.path.join(REFERENCE, "src", "open_clip", "factory.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    tree.body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "create_loss"]
+    ns = {name: getattr(ours, name) for name in ("ClipLoss", "COSMOSLoss", "CoCaLoss", "DistillClipLoss", "SigLipLoss")}
+    exec(compile(tree, path, "exec"), ns)
+    base = dict(distill=False, model="ViT-B-16", siglip=False, cosmos=True, local_loss=False, gather_with_grad=False, rank=3,
+                world_size=8, horovod=False, coca_caption_loss_weight=2.0, coca_contrastive_loss_weight=1.0)
+    mod = ns["create_loss"](types.SimpleNamespace(**base))
+    assert type(mod) is ours.COSMOSLoss and (mod.rank, mod.world_size, mod.cache_labels, mod.local_loss) == (3, 8, True, False)
+    assert type(mod.clip_loss) is ours.ClipLoss and mod.clip_loss.world_size == 8
+    mod = ns["create_loss"](types.SimpleNamespace(**{**base, "local_loss": True, "gather_with_grad": True}))
+    assert mod.local_loss and mod.gather_with_grad
+    assert type(ns["create_loss"](types.SimpleNamespace(**{**base, "cosmos": False}))) is ours.ClipLoss
+    with pytest.raises(RuntimeError, match="Horovod"):
+        ns["create_loss"](types.SimpleNamespace(**{**base, "cosmos": False, "horovod": True}))
+    for other in ({"distill": True}, {"model": "coca_ViT-B-32"}, {"siglip": True}):
+        with pytest.raises(NotImplementedError):
+            ns["create_loss"](types.SimpleNamespace(**{**base, **other}))
