@@ -133,7 +133,7 @@ class Instrument:
     """Counts our kernel launches and times the InfoNCE launches with CUDA events on the launching stream."""
     KINDS = ("fwd", "bwd", "bwd_e", "colgrad")
     NAMES = {"fwd": "infonce_fwd_kernel<pair> (+ column merge)", "bwd": "infonce_bwd_quad_kernel (+ dscale reduce)",
-             "bwd_e": "infonce_bwd_e2_kernel (+ dscale reduce)", "colgrad": "gemm_kernel<256> (column-side gradient)"}
+             "bwd_e": "infonce_bwd_e2_kernel (+ dscale reduce)", "colgrad": "infonce_bwd_e2t_kernel (column-side gradient)"}
 
     def __init__(self):
         from cosmos_b200 import infonce
@@ -144,6 +144,8 @@ class Instrument:
         self.enabled = False
         self._fwd, self._loss, self._bwd, self._colgrad = infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd, infonce._k_colgrad
         self._bwd_e = infonce._k_bwd_e
+        self._bwd_e_cols = infonce._k_bwd_e_cols
+        infonce._k_bwd_e_cols = self.bwd_e_cols
         infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd, infonce._k_colgrad = self.fwd, self.loss, self.bwd, self.colgrad
         infonce._k_bwd_e = self.bwd_e
 
@@ -178,6 +180,11 @@ class Instrument:
         self.launches += 1 + (1 if want_ds else 0)
         fl = 2.0 * x.shape[0] * y.shape[0] * x.shape[1] * y.shape[1] * x.shape[2]
         return self._timed("bwd_e", fl, self._bwd_e, x, y, *a, **kw)
+
+    def bwd_e_cols(self, x, y, *a, **kw):
+        self.launches += 1                       # column-side gradient G^T x from the stored exponentials
+        fl = 2.0 * x.shape[0] * y.shape[0] * x.shape[1] * y.shape[1] * x.shape[2]
+        return self._timed("colgrad", fl, self._bwd_e_cols, x, y, *a, **kw)
 
     def colgrad(self, g, x2d, n_c, n_cols):
         self.launches += 1                       # the column-side gradient GEMM (G^T x) on the stored tiles

@@ -80,6 +80,8 @@ _INFONCE_SIGS = {
     "cosmos_infonce_fwd_e": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, vp_, vp_, vp_, i64_, i32_, vp_],
     "cosmos_infonce_bwd_e": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, vp_, f32_, f32_, f32_, f32_, f32_, vp_, vp_, vp_, vp_,
                              i64_, vp_, i64_, i32_, vp_],
+    "cosmos_infonce_bwd_e_cols_splits": [C.POINTER(InfoNceProblem), i32_],
+    "cosmos_infonce_bwd_e_cols": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, vp_, f32_, f32_, vp_, i32_, i32_, vp_],
     "cosmos_infonce_bwd_g": [C.POINTER(InfoNceProblem), vp_, vp_, f32_, f32_, f32_, f32_, f32_, vp_, vp_, vp_, vp_, i64_, vp_, i64_,
                              i32_, vp_],
 }

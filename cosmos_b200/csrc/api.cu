@@ -440,6 +440,7 @@ int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const f
   bp.dscale_part = dscale != nullptr ? reinterpret_cast<float*>(workspace) : nullptr;
   bp.g_out = g_out;
   bp.g_ld = g_ld;
+  bp.t_splits = 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (cu_fail(bwd_e_generation() == 1 ? cb::launch_infonce_bwd_e(tmE, tmY64, bp, s) : cb::launch_infonce_bwd_e2(tmY64, bp, s)))
     return COSMOS_ERR_CUDA;
@@ -448,6 +449,52 @@ int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const f
                                                             weight * (s_row + s_col) / (a_row + a_col), upstream, dscale, s)))
     return COSMOS_ERR_CUDA;
   return COSMOS_OK;
+}
+
+int32_t cosmos_infonce_bwd_e_cols_splits(const cosmos_infonce_problem* p, int device) {
+  Dims d;
+  if (check_problem(p, &d) != COSMOS_OK) return -1;
+  // the fewest slices of the row sweep for which the CTA pairs (one per 256 columns of one column tensor) fill whole waves
+  const int pairs = p->gy * ((d.n_col_tiles_bwd + 1) / 2);
+  const int steps = p->gx * d.n_row_tiles;
+  return choose_t_splits(pairs, sm_count_of(device) / 2, steps);
+}
+
+int cosmos_infonce_bwd_e_cols(const cosmos_infonce_problem* p, const void* e, const float* off, const float* row_lse2,
+                              const float* col_lse2, float a_row, float a_col, float* dy, int32_t splits, int device,
+                              void* stream) {
+  Dims d;
+  int st = check_problem(p, &d);
+  if (st != COSMOS_OK) return st;
+  if (!e || !off || !row_lse2 || !col_lse2 || !dy) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (p->dim != 512) return COSMOS_ERR_UNSUPPORTED;
+  if (splits < 1 || splits > kMaxTSplits || splits > p->gx * d.n_row_tiles) return COSMOS_ERR_INVALID_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(e) & 15) != 0 || (reinterpret_cast<uintptr_t>(dy) & 15) != 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  CUtensorMap tmX64;
+  const int bf = p->dtype == COSMOS_DTYPE_BF16;
+  {
+    const int m = cb::make_stack_map(&tmX64, reinterpret_cast<const void*>(p->x), bf, p->dim, p->n_rows, p->gx, 64);
+    if (m != 0) {
+      g_last_cuda = 100000 + m;
+      return COSMOS_ERR_CUDA;
+    }
+  }
+  cb::BwdEParams bp = {};
+  bp.gx = p->gx; bp.gy = p->gy; bp.n_rows = p->n_rows; bp.n_cols = p->n_cols; bp.label_offset = p->label_offset;
+  bp.n_row_tiles = d.n_row_tiles; bp.n_col_tiles = d.n_col_tiles_bwd;
+  bp.n_chunks = (p->n_cols + 31) / 32;
+  bp.dtype = p->dtype;
+  bp.dbg = dbg_flags();
+  bp.idesc_g = cb::make_idesc(bf, 1, 1, 2 * cb::kFwdBM, 256);     // A = G^T and B = X both read with M / N contiguous
+  bp.a_row = a_row; bp.a_col = a_col;
+  bp.scale = reinterpret_cast<const float*>(p->scale);
+  bp.e = e; bp.off = off; bp.row_lse2 = row_lse2; bp.col_lse2 = col_lse2;
+  bp.x = reinterpret_cast<const void*>(p->x);
+  bp.dx = dy;
+  bp.t_splits = splits;
+  return cu_fail(cb::launch_infonce_bwd_e2t(tmX64, bp, static_cast<cudaStream_t>(stream))) ? COSMOS_ERR_CUDA : COSMOS_OK;
 }
 
 }  // extern "C"

@@ -78,10 +78,13 @@ struct BwdEParams {
   float* dscale_part;     // [gx * n_row_tiles] partial sums of <dscale-mix, raw logits>, may be null
   void* g_out;            // optional copy of every G tile, [gx * n_rows][g_ld], column j * n_cols + c
   long long g_ld;
+  int t_splits;           // column-side kernel (infonce_bwd_e2t.cu) only: slices of the row sweep; dx = fp32 [t_splits][gy][n_cols][512]
 };
 cudaError_t launch_infonce_bwd_e(const CUtensorMap& tmE, const CUtensorMap& tmY64, const BwdEParams& p, cudaStream_t stream);
 // second generation (infonce_bwd_e2.cu): 16 independent scaling warps, E two steps ahead in registers, no L2 prefetch role
 cudaError_t launch_infonce_bwd_e2(const CUtensorMap& tmY64, const BwdEParams& p, cudaStream_t stream);
+// column side of the same route (infonce_bwd_e2t.cu): dY = G^T X from the same exponentials, no G tiles in HBM
+cudaError_t launch_infonce_bwd_e2t(const CUtensorMap& tmX64, const BwdEParams& p, cudaStream_t stream);
 
 // infonce_aux.cu
 cudaError_t launch_col_combine(const float2* col_part, float* col_lse2, int pairs, int n_slabs, int n_cols, cudaStream_t stream);

@@ -132,6 +132,22 @@ def _k_bwd_e(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_col
     return dx, dscale
 
 
+def _k_bwd_e_cols(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_col):
+    """Column side of the stored-exponential route: -> fp32 [gy, N, 512], sum over the row tensors and THIS rank's rows of
+    G^T x at unit scale (csrc/infonce_bwd_e2t.cu) - no G tile is written to memory."""
+    dev = x.device
+    prob = _problem(x, y, label_offset, scale)
+    splits = _lib.lib().cosmos_infonce_bwd_e_cols_splits(C.byref(prob), dev.index)
+    if splits < 1:
+        raise RuntimeError("cosmos_b200: unsupported problem for the column-side stored-exponential backward")
+    dy = torch.empty(splits, prob.gy, prob.n_cols, prob.dim, dtype=torch.float32, device=dev)
+    st = _lib.lib().cosmos_infonce_bwd_e_cols(C.byref(prob), e.data_ptr(), off.data_ptr(), row_lse2.data_ptr(), col_lse2.data_ptr(),
+                                              a_row, a_col, dy.data_ptr(), splits, dev.index,
+                                              torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(st, "infonce_bwd_e_cols")
+    return dy[0] if splits == 1 else dy.sum(0)
+
+
 def _k_lse2_merge(parts: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     """parts [W, ...] fp32 (every rank's partial column log2-sum-exp, all-gathered) -> out [...]: their log2-sum-exp2."""
     dev = parts.device
@@ -346,10 +362,13 @@ def _reduce_scatter_rows(d_all: torch.Tensor, comm: Comm, b: int, async_op: bool
     return (out, None) if async_op else out
 
 
-_E_STORE_MAX_BYTES = int(float(os.environ.get("COSMOS_B200_ESTORE_MAX_GB", "40")) * (1 << 30))
+_E_STORE_MAX_BYTES = int(float(os.environ.get("COSMOS_B200_ESTORE_MAX_GB", "96")) * (1 << 30))
 # small problems: the recompute kernels finish in microseconds and one launch per group beats the chunk loop
 _E_STORE_MIN_BYTES = int(float(os.environ.get("COSMOS_B200_ESTORE_MIN_GB", "0.25")) * (1 << 30))
 
+
+# COSMOS_B200_COLS=gemm: column-side gradient of the stored-exponential route through stored G tiles + a GEMM (diagnostics)
+_COLS_VIA_GEMM = os.environ.get("COSMOS_B200_COLS", "") == "gemm"
 
 _e_chunk_cache: dict = {}
 
@@ -358,6 +377,27 @@ def _reusable_bytes(device) -> int:
     """Free device memory as this process can use it: cudaMemGetInfo plus the allocator's cached blocks."""
     free, _total = torch.cuda.mem_get_info(device)
     return free + torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+
+
+_SM_PAIRS = 74      # CTA pairs resident at a time (148 SMs): the backward kernel runs one pair per 256 rows of one row tensor
+
+
+def _wave_aware_chunk(n_r: int, most: int, row_tiles: int) -> int:
+    """Row tensors per pass: at most `most`, equal passes (16 tensors at most 5 at a time -> 4 + 4 + 4 + 4, not 5 + 5 + 5 + 1),
+    and among those the split whose launches fill whole waves of CTA pairs best - 4 tensors of 128 row tiles are 256 pairs =
+    3.46 waves (the fourth 46 % full), 8 of them 6.92; ties go to the smaller chunk (less memory alive)."""
+    if most <= 0:
+        return 0
+    pairs_per_tensor = (row_tiles + 1) // 2
+    best, best_eff = 0, -1.0
+    for passes in range(-(-n_r // most), n_r + 1):
+        chunk = -(-n_r // passes)
+        sizes = [min(chunk, n_r - k) for k in range(0, n_r, chunk)]
+        waves = sum(-(-(c * pairs_per_tensor) // _SM_PAIRS) for c in sizes)
+        eff = n_r * pairs_per_tensor / (waves * _SM_PAIRS) - 0.002 * len(sizes)      # a pass costs a few launches and allocations
+        if eff > best_eff + 1e-9:
+            best, best_eff = chunk, eff
+    return best
 
 
 def _e_store_chunk(x_r: torch.Tensor, y_c: torch.Tensor, comm: Comm) -> int:
@@ -386,13 +426,11 @@ def _e_store_chunk(x_r: torch.Tensor, y_c: torch.Tensor, comm: Comm) -> int:
             return chunk
     budget = _E_STORE_MAX_BYTES // in_flight
     if x_r.is_cuda:
-        budget = min(budget, _reusable_bytes(x_r.device) // (3 * in_flight))   # exponentials + (CLIP group) G tiles + headroom
+        # ~70 % of what is free for everything alive at once: the chunks in flight plus one more chunk's worth for the G tiles
+        # of a group with column-side gradients (as large as its exponentials); the rest is headroom for the caller
+        budget = min(budget, (_reusable_bytes(x_r.device) * 7 // 10) // (in_flight + 1))
     most = min(n_r, budget // per_tensor)
-    if most <= 0:
-        chunk = 0
-    else:
-        passes = -(-n_r // most)
-        chunk = -(-n_r // passes)            # equal passes: 16 tensors at most 5 at a time -> 4 + 4 + 4 + 4, not 5 + 5 + 5 + 1
+    chunk = _wave_aware_chunk(n_r, most, -(-b // 128))
     if comm.distributed:
         # every rank must make the same number of passes (each pass gathers its column statistics): agree on the smallest
         # chunk; ranks see the same shapes in the same order, so they all arrive here together.  (A re-decision on one rank
@@ -501,11 +539,15 @@ def _eager_schedule(groups: Sequence[_Group], comm: Comm):
         g, i0, last, xs, sl, e_, o_, gather = state
         if gather is not None:
             gather.finish(g.col_lse2[sl])
-        g_tiles = torch.empty(xs.shape[0] * g.b, g.n_c * g.N, dtype=g.x_r.dtype, device=xs.device) if g.need_cols else None
+        via_gemm = g.need_cols and _COLS_VIA_GEMM
+        g_tiles = torch.empty(xs.shape[0] * g.b, g.n_c * g.N, dtype=g.x_r.dtype, device=xs.device) if via_gemm else None
         _dx, ds_ = _k_bwd_e(xs, g.y_c, g.off, g.scale_f, e_, o_, g.row_lse2[sl], g.col_lse2[sl], 1.0, 1.0, 1.0 / g.boost,
                             1.0 / g.boost, g.weight, g.one, g.need_scale, g_tiles, dx_out=g.dx_unit[i0:i0 + xs.shape[0]])
-        if g_tiles is not None:
-            part = _k_colgrad(g_tiles, xs.reshape(xs.shape[0] * g.b, xs.shape[2]), g.n_c, g.N)    # [n_c, N, D] fp32
+        if g.need_cols:
+            if via_gemm:      # diagnostics: G tiles through HBM + one GEMM (the first version of this route)
+                part = _k_colgrad(g_tiles, xs.reshape(xs.shape[0] * g.b, xs.shape[2]), g.n_c, g.N)    # [n_c, N, D] fp32
+            else:             # the same exponentials once more, read as G^T: nothing but dY goes to memory
+                part = _k_bwd_e_cols(xs, g.y_c, g.off, g.scale_f, e_, o_, g.row_lse2[sl], g.col_lse2[sl], 1.0, 1.0)
             g.d_all = part if g.d_all is None else g.d_all.add_(part)
         if ds_ is not None:
             g.ds_unit = ds_ if g.ds_unit is None else g.ds_unit + ds_

@@ -212,6 +212,18 @@ int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const f
                          float weight, const float* upstream, void* dx, float* dscale, void* g_out, int64_t g_ld, void* workspace,
                          int64_t workspace_bytes, int device, void* stream);
 
+/* Column side of the same route (the CLIP term needs gradients on both sides of its logits, src/open_clip/loss.py:206):
+ *   dy[s][j][c][:] = sum over row tensors i and the rows r of slice s of  G_ij[r][c] * x_i[r][:]      (fp32, UNIT scale)
+ * from the same exponentials - no G tile is written to memory, nothing is transposed (the stored tile image read with
+ * its contiguous dimension as M is the MN-major operand G^T).  a_row / a_col as in cosmos_infonce_bwd_e.  dy is
+ * [splits][gy][n_cols][512]; the caller sums the slices, all-reduces / reduce-scatters over ranks and multiplies by
+ * upstream * scale * weight.  cosmos_infonce_bwd_e_cols_splits proposes the number of slices of the row sweep for which
+ * the launch fills whole waves of SM pairs (1 .. 4; -1: unsupported problem).                                            */
+int32_t cosmos_infonce_bwd_e_cols_splits(const cosmos_infonce_problem* p, int device);
+int cosmos_infonce_bwd_e_cols(const cosmos_infonce_problem* p, const void* e, const float* off, const float* row_lse2,
+                              const float* col_lse2, float a_row, float a_col, float* dy, int32_t splits, int device,
+                              void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Retrieval ranks for the evaluation metrics  (src/training/train.py:766-785 get_clip_metrics and
  * 712-763 compute_retrieval: similarity matrix on the CPU + argsort of every row + position search)

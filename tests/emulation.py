@@ -101,6 +101,19 @@ def emu_bwd_e(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_co
     return dx, dscale
 
 
+def emu_bwd_e_cols(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_col):
+    """cosmos_infonce_bwd_e_cols: fp32 [gy, N, D] = sum over row tensors and local rows of G^T x, unit scale."""
+    gx, b, D = x.shape
+    gy, N, _ = y.shape
+    S2 = e
+    R = torch.exp2(S2 - row_lse2.double().view(gx, gy, b, 1))
+    Cm = torch.exp2(S2 - col_lse2.double().view(gx, gy, 1, N))
+    eye = torch.zeros(b, N, dtype=torch.float64)
+    eye[torch.arange(b), label_offset + torch.arange(b)] = 1
+    G = a_row * R + a_col * Cm - (a_row + a_col) * eye
+    return torch.einsum("ijbn,ibd->jnd", G, x.double()).float()
+
+
 def emu_colgrad(g, x2d, n_c, n_cols):
     """infonce._k_colgrad: fp32 [n_c, n_cols, D] = sum over rows of G^T x."""
     D = x2d.shape[1]
@@ -117,6 +130,7 @@ def install(monkeypatch=None):
         monkeypatch.setattr(infonce, "_k_bwd_e", emu_bwd_e)
         monkeypatch.setattr(infonce, "_k_colgrad", emu_colgrad)
         monkeypatch.setattr(infonce, "_k_lse2_merge", emu_lse2_merge)
+        monkeypatch.setattr(infonce, "_k_bwd_e_cols", emu_bwd_e_cols)
         monkeypatch.setattr(_lib, "require_cuda", lambda t, what: None)
         monkeypatch.setattr(infonce, "compute_dtype", lambda dt: dt)
     else:
@@ -124,5 +138,6 @@ def install(monkeypatch=None):
         infonce._k_colgrad = emu_colgrad
         infonce._k_bwd_e = emu_bwd_e
         infonce._k_lse2_merge = emu_lse2_merge
+        infonce._k_bwd_e_cols = emu_bwd_e_cols
         _lib.require_cuda = lambda t, what: None
         infonce.compute_dtype = lambda dt: dt

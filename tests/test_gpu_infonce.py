@@ -273,3 +273,25 @@ def test_stored_exponential_kernels_match_recompute_kernels(b, n_all, off, gx, g
         assert cosine(g1.float().cpu(), g2.float().cpu()) >= 0.99999
     with pytest.raises(RuntimeError, match="unsupported"):      # d(scale) weights not proportional to the gradient weights
         K._k_bwd_e(x, y, off, sc, e, offs, row, col, 1.0, 1.0, 1.0, 0.0, 0.125, up, True)
+    # column side from the same exponentials (cosmos_infonce_bwd_e_cols: dY = G^T X, nothing transposed, no G in memory)
+    # against fp64 from first principles: G = a_row softmax_rows + a_col softmax_cols - (a_row + a_col) positives
+    S2 = torch.einsum("ibd,jnd->ijbn", x.double(), y.double()) * (scale * math.log2(math.e))
+    pos = torch.zeros(b, n_all, dtype=torch.float64, device="cuda")
+    pos[torch.arange(b), off + torch.arange(b)] = 1
+    for a_row, a_col in ((1.0, 1.0), (1.0, 0.0), (0.25, 1.0)):
+        G = (a_row * torch.exp2(S2 - row.double().view(gx, gy, b, 1)) + a_col * torch.exp2(S2 - col.double().view(gx, gy, 1, n_all))
+             - (a_row + a_col) * pos)
+        want = torch.einsum("ijbn,ibd->jnd", G, x.double())
+        got = K._k_bwd_e_cols(x, y, off, sc, e, offs, row, col, a_row, a_col)
+        assert got.shape == (gy, n_all, 512) and got.dtype == torch.float32
+        # G is a bf16 operand in the kernel: at scale 100 (confident rows, G = R + C - 2 I nearly cancels) its rounding shows
+        floor = 0.9999 if scale >= 100.0 else 0.99999
+        assert cosine(got.cpu(), want.cpu()) >= floor, (a_row, a_col, cosine(got.cpu(), want.cpu()))
+        assert abs(float(got.double().norm() / want.norm()) - 1.0) <= 2e-3
+        # every column tensor on its own (a column tensor with a wrong neighbour's tiles would still pass the global cosine)
+        for jj in range(gy):
+            assert cosine(got[jj].cpu(), want[jj].cpu()) >= floor, (a_row, a_col, jj)
+        if n_all % 8 == 0 and (a_row, a_col) == (1.0, 1.0):
+            # and against the first version of this route: the row pass's own G tiles (same bf16 values) through a GEMM
+            via_gemm = K._k_colgrad(g2, x.reshape(gx * b, 512), gy, n_all)
+            assert cosine(got.cpu(), via_gemm.cpu()) >= 0.999999
