@@ -176,7 +176,7 @@ class Instrument:
         return self._timed("bwd", fl, self._bwd, x, y, *a)
 
     def bwd_e(self, x, y, *a, **kw):
-        want_ds = a[12]          # (label_offset, scale, e, off, row, col, a_row, a_col, s_row, s_col, weight, upstream, want_dscale[, g_out])
+        want_ds = a[13]          # (label_offset, scale, e, off, diag, row, col, a_row, a_col, s_row, s_col, weight, upstream, want_dscale[, g_out])
         self.launches += 1 + (1 if want_ds else 0)
         fl = 2.0 * x.shape[0] * y.shape[0] * x.shape[1] * y.shape[1] * x.shape[2]
         return self._timed("bwd_e", fl, self._bwd_e, x, y, *a, **kw)

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcosmos_b200.so")
 
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 CLAMP_MAX = 8   # COSMOS_CLAMP_MAX
 
 _DEBUG_SYNC = os.environ.get("COSMOS_B200_DEBUG_SYNC", "0") == "1"
@@ -78,10 +78,10 @@ _INFONCE_SIGS = {
     "cosmos_infonce_bwd": [C.POINTER(InfoNceProblem), vp_, vp_, f32_, f32_, f32_, f32_, f32_, vp_, vp_, vp_, vp_, i64_, i32_, vp_],
     "cosmos_infonce_e_bytes": [C.POINTER(InfoNceProblem)],
     "cosmos_infonce_fwd_e": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, vp_, vp_, vp_, i64_, i32_, vp_],
-    "cosmos_infonce_bwd_e": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, vp_, f32_, f32_, f32_, f32_, f32_, vp_, vp_, vp_, vp_,
+    "cosmos_infonce_bwd_e": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, vp_, vp_, f32_, f32_, f32_, f32_, f32_, vp_, vp_, vp_, vp_,
                              i64_, vp_, i64_, i32_, vp_],
     "cosmos_infonce_bwd_e_cols_splits": [C.POINTER(InfoNceProblem), i32_],
-    "cosmos_infonce_bwd_e_cols": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, vp_, f32_, f32_, vp_, i32_, i32_, vp_],
+    "cosmos_infonce_bwd_e_cols": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, vp_, vp_, f32_, f32_, vp_, i32_, i32_, vp_],
     "cosmos_infonce_bwd_g": [C.POINTER(InfoNceProblem), vp_, vp_, f32_, f32_, f32_, f32_, f32_, vp_, vp_, vp_, vp_, i64_, vp_, i64_,
                              i32_, vp_],
 }

@@ -43,16 +43,8 @@ int dbg_flags() {
   static const int v = env_int("COSMOS_B200_DBG", 0);
   return v;
 }
-int bwd_e_generation() {                 // COSMOS_B200_BWDE=1: first-generation stored-exponential backward (diagnostics)
-  static const int v = env_int("COSMOS_B200_BWDE", 2);
-  return v;
-}
-int bwd_e_ahead() {                      // first generation only: steps by which E is prefetched into L2 (0: none, the fastest)
-  static const int v = env_int("COSMOS_B200_EAHEAD", 0);
-  return v < 0 ? 0 : v;
-}
-int bwd_e_bulk() {                       // first generation only: COSMOS_B200_EPREFETCH=bulk
-  static const int v = [] { const char* e = getenv("COSMOS_B200_EPREFETCH"); return (e && e[0] == 'b') ? 1 : 0; }();
+int fwd_generation() {                   // COSMOS_B200_FWD=1: first-generation forward epilogue (diagnostics)
+  static const int v = env_int("COSMOS_B200_FWD", 2);
   return v;
 }
 int bwd_t_splits() {
@@ -269,7 +261,9 @@ int cosmos_infonce_fwd_e(const cosmos_infonce_problem* p, float* row_lse2, float
   fp.n_steps = d.n_col_tiles_bwd;
   fp.n_chunks = (p->n_cols + 31) / 32;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cu_fail(cb::launch_infonce_fwd(tmX, tmY, fp, pair, s))) return COSMOS_ERR_CUDA;
+  // COSMOS_B200_FWD=1: first-generation epilogue (diagnostics); the single-CTA kernel (COSMOS_B200_DBG=4) only has that one
+  if (cu_fail((pair && fwd_generation() != 1) ? cb::launch_infonce_fwd2(tmX, tmY, fp, s) : cb::launch_infonce_fwd(tmX, tmY, fp, pair, s)))
+    return COSMOS_ERR_CUDA;
   if (cu_fail(cb::launch_col_combine(fp.col_part, col_lse2, d.pairs, d.n_slabs, p->n_cols, s))) return COSMOS_ERR_CUDA;
   return COSMOS_OK;
 }
@@ -392,14 +386,14 @@ int cosmos_infonce_bwd_g(const cosmos_infonce_problem* p, const float* row_lse2,
   return COSMOS_OK;
 }
 
-int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const float* off, const float* row_lse2,
-                         const float* col_lse2, float a_row, float a_col, float s_row, float s_col,
+int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const float* off, const float* diag_raw,
+                         const float* row_lse2, const float* col_lse2, float a_row, float a_col, float s_row, float s_col,
                          float weight, const float* upstream, void* dx, float* dscale, void* g_out, int64_t g_ld, void* workspace,
                          int64_t workspace_bytes, int device, void* stream) {
   Dims d;
   int st = check_problem(p, &d);
   if (st != COSMOS_OK) return st;
-  if (!e || !off || !row_lse2 || !col_lse2 || !upstream || !dx) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (!e || !off || !diag_raw || !row_lse2 || !col_lse2 || !upstream || !dx) return COSMOS_ERR_INVALID_ARGUMENT;
   if (p->dim != 512) return COSMOS_ERR_UNSUPPORTED;     // the dX accumulator of 128 rows x 512 columns is the whole tensor memory
   // d(scale) is read off the dX accumulators, which weigh the two softmax terms like G: the mixes must be proportional
   if (dscale != nullptr && (fabsf(a_row * s_col - a_col * s_row) > 1e-12f || a_row + a_col == 0.f)) return COSMOS_ERR_UNSUPPORTED;
@@ -410,14 +404,13 @@ int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const f
   if (workspace == nullptr || workspace_bytes < bwd_partials_bytes(p, d)) return COSMOS_ERR_WORKSPACE;
   DeviceGuard g(device);
   if (!g.ok) return COSMOS_ERR_CUDA;
-  CUtensorMap tmE, tmY64;
+  CUtensorMap tmY64;
   const int bf = p->dtype == COSMOS_DTYPE_BF16;
   {
-    // E is bf16 whatever the stack dtype is (fp16 has no range for 2^(s2 - max)); the kernel converts in shared memory
-    const int m1 = cb::make_piece_map(&tmE, e, static_cast<uint64_t>(d.pairs) * d.n_row_tiles * d.n_col_tiles_bwd * 16);
+    // (E is bf16 whatever the stack dtype is - fp16 has no range for 2^(s2 - offset); the kernel converts G in registers)
     const int m2 = cb::make_stack_map(&tmY64, reinterpret_cast<const void*>(p->y), bf, p->dim, p->n_cols, p->gy, 64);
-    if (m1 != 0 || m2 != 0) {
-      g_last_cuda = 100000 + (m1 != 0 ? m1 : m2);
+    if (m2 != 0) {
+      g_last_cuda = 100000 + m2;
       return COSMOS_ERR_CUDA;
     }
   }
@@ -427,14 +420,11 @@ int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const f
   bp.n_chunks = (p->n_cols + 31) / 32;
   bp.dtype = p->dtype;
   bp.dbg = dbg_flags();
-  // first generation only (measured in round 2, profiles/README_r02.md: no prefetch at all is its fastest setting)
-  bp.e_ahead = bwd_e_ahead();
-  bp.e_bulk = bwd_e_bulk();
   bp.idesc_g = cb::make_idesc(bf, 0, 1, 2 * cb::kFwdBM, 256);
   bp.a_row = a_row; bp.a_col = a_col; bp.s_row = s_row; bp.s_col = s_col; bp.weight = weight;
   bp.scale = reinterpret_cast<const float*>(p->scale);
   bp.upstream = upstream;
-  bp.e = e; bp.off = off; bp.row_lse2 = row_lse2; bp.col_lse2 = col_lse2;
+  bp.e = e; bp.off = off; bp.row_lse2 = row_lse2; bp.col_lse2 = col_lse2; bp.diag_raw = diag_raw;
   bp.x = reinterpret_cast<const void*>(p->x);
   bp.dx = dx;
   bp.dscale_part = dscale != nullptr ? reinterpret_cast<float*>(workspace) : nullptr;
@@ -442,8 +432,7 @@ int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const f
   bp.g_ld = g_ld;
   bp.t_splits = 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (cu_fail(bwd_e_generation() == 1 ? cb::launch_infonce_bwd_e(tmE, tmY64, bp, s) : cb::launch_infonce_bwd_e2(tmY64, bp, s)))
-    return COSMOS_ERR_CUDA;
+  if (cu_fail(cb::launch_infonce_bwd_e2(tmY64, bp, s))) return COSMOS_ERR_CUDA;
   // partial sums hold <G, raw> with G's mix; (s_row + s_col) / (a_row + a_col) turns it into the requested one
   if (dscale != nullptr && cu_fail(cb::launch_dscale_reduce(bp.dscale_part, p->gx * d.n_row_tiles,
                                                             weight * (s_row + s_col) / (a_row + a_col), upstream, dscale, s)))
@@ -460,13 +449,13 @@ int32_t cosmos_infonce_bwd_e_cols_splits(const cosmos_infonce_problem* p, int de
   return choose_t_splits(pairs, sm_count_of(device) / 2, steps);
 }
 
-int cosmos_infonce_bwd_e_cols(const cosmos_infonce_problem* p, const void* e, const float* off, const float* row_lse2,
-                              const float* col_lse2, float a_row, float a_col, float* dy, int32_t splits, int device,
-                              void* stream) {
+int cosmos_infonce_bwd_e_cols(const cosmos_infonce_problem* p, const void* e, const float* off, const float* diag_raw,
+                              const float* row_lse2, const float* col_lse2, float a_row, float a_col, float* dy, int32_t splits,
+                              int device, void* stream) {
   Dims d;
   int st = check_problem(p, &d);
   if (st != COSMOS_OK) return st;
-  if (!e || !off || !row_lse2 || !col_lse2 || !dy) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (!e || !off || !diag_raw || !row_lse2 || !col_lse2 || !dy) return COSMOS_ERR_INVALID_ARGUMENT;
   if (p->dim != 512) return COSMOS_ERR_UNSUPPORTED;
   if (splits < 1 || splits > kMaxTSplits || splits > p->gx * d.n_row_tiles) return COSMOS_ERR_INVALID_ARGUMENT;
   if ((reinterpret_cast<uintptr_t>(e) & 15) != 0 || (reinterpret_cast<uintptr_t>(dy) & 15) != 0) return COSMOS_ERR_INVALID_ARGUMENT;
@@ -490,7 +479,7 @@ int cosmos_infonce_bwd_e_cols(const cosmos_infonce_problem* p, const void* e, co
   bp.idesc_g = cb::make_idesc(bf, 1, 1, 2 * cb::kFwdBM, 256);     // A = G^T and B = X both read with M / N contiguous
   bp.a_row = a_row; bp.a_col = a_col;
   bp.scale = reinterpret_cast<const float*>(p->scale);
-  bp.e = e; bp.off = off; bp.row_lse2 = row_lse2; bp.col_lse2 = col_lse2;
+  bp.e = e; bp.off = off; bp.row_lse2 = row_lse2; bp.col_lse2 = col_lse2; bp.diag_raw = diag_raw;
   bp.x = reinterpret_cast<const void*>(p->x);
   bp.dx = dy;
   bp.t_splits = splits;

@@ -121,6 +121,17 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t byte
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
 }
 
+// Bulk asynchronous copy shared memory -> global memory (contiguous, 16-byte aligned, a multiple of 16 bytes), tracked by
+// the issuing thread's bulk async-groups: commit, then wait until the group's reads of shared memory are done (the buffer
+// may be rewritten) or until it has completed.
+__device__ __forceinline__ void bulk_store_s2g(void* gptr, uint32_t smem_addr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(smem_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, fences, commit
 // ----------------------------------------------------------------------------------------------

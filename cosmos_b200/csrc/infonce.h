@@ -22,7 +22,7 @@ struct FwdParams {
   float* diag_raw;
   float2* col_part;  // [gx*gy][n_slabs][n_cols] (max2, sum)
   // optional (stored-exponential route): every 2^(S2 - m) the statistics loop forms anyway, as bf16, and the offsets m
-  uint16_t* e_out;   // [gx*gy][n_row_tiles][n_steps] tiles of [16 column pieces][128 rows][8] bf16 (32 KB each):
+  uint16_t* e_out;   // [gx*gy][n_row_tiles][n_steps] tiles of [4 slabs of 32 rows][16 column pieces][32 rows][8] bf16 (32 KB each):
                      // 2^(s2[r][c] - off[c / 32][r]), s2 = logit in log2 units
   float* off_out;    // [gx*gy][n_chunks][n_rows]: the row's running maximum (of its 64-column group) when the chunk was processed
   int n_steps;       // ceil(n_cols / 128)
@@ -49,6 +49,8 @@ struct BwdParams {
 };
 
 cudaError_t launch_infonce_fwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, bool pair, cudaStream_t stream);
+// second-generation epilogue (infonce_fwd2.cu; CTA pairs): 4 x 8 values per thread, one lazily updated offset per warp
+cudaError_t launch_infonce_fwd2(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, cudaStream_t stream);
 cudaError_t launch_infonce_bwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const BwdParams& p, cudaStream_t stream);
 
 cudaError_t launch_infonce_bwd_pair(const CUtensorMap& tmX, const CUtensorMap& tmY64, const CUtensorMap& tmY128, const BwdParams& p,
@@ -56,15 +58,13 @@ cudaError_t launch_infonce_bwd_pair(const CUtensorMap& tmX, const CUtensorMap& t
 
 cudaError_t launch_infonce_bwd_quad(const CUtensorMap& tmX, const CUtensorMap& tmY64, const BwdParams& p, cudaStream_t stream);
 
-// Backward from the exponentials the forward stored (infonce_bwd_e.cu): no logit is recomputed.
+// Backward from the exponentials the forward stored (infonce_bwd_e2.cu / infonce_bwd_e2t.cu): no logit is recomputed.
 struct BwdEParams {
   int gx, gy, n_rows, n_cols, label_offset;
   int n_row_tiles, n_col_tiles;   // 128-row tiles, 128-column steps
   int n_chunks;                   // ceil(n_cols / 32)
   int dtype;                      // dtype of y, dx and g_out (the A operand is converted to it in shared memory)
   int dbg;
-  int e_ahead;                    // steps by which the L2 prefetch of E runs ahead of its use (0: no prefetch)
-  int e_bulk;                     // 1: prefetch each 32 KB tile image with one cp.async.bulk.prefetch (diagnostics, see api.cu)
   uint32_t idesc_g;
   float a_row, a_col, s_row, s_col, weight;
   const float* scale;
@@ -73,6 +73,7 @@ struct BwdEParams {
   const float* off;       // [gx*gy][n_chunks][n_rows]
   const float* row_lse2;  // [gx*gy][n_rows]
   const float* col_lse2;  // [gx*gy][n_cols]
+  const float* diag_raw;  // [gx*gy][n_rows]: raw dot product of every row with its positive (the forward's output)
   const void* x;          // [gx][n_rows][512]: only read at the end, for d(scale) = sum_r <x_r, (G y)_r>
   void* dx;               // [gx][n_rows][512]
   float* dscale_part;     // [gx * n_row_tiles] partial sums of <dscale-mix, raw logits>, may be null
@@ -80,8 +81,7 @@ struct BwdEParams {
   long long g_ld;
   int t_splits;           // column-side kernel (infonce_bwd_e2t.cu) only: slices of the row sweep; dx = fp32 [t_splits][gy][n_cols][512]
 };
-cudaError_t launch_infonce_bwd_e(const CUtensorMap& tmE, const CUtensorMap& tmY64, const BwdEParams& p, cudaStream_t stream);
-// second generation (infonce_bwd_e2.cu): 16 independent scaling warps, E two steps ahead in registers, no L2 prefetch role
+// infonce_bwd_e2.cu: 16 independent scaling warps, E two steps ahead in registers
 cudaError_t launch_infonce_bwd_e2(const CUtensorMap& tmY64, const BwdEParams& p, cudaStream_t stream);
 // column side of the same route (infonce_bwd_e2t.cu): dY = G^T X from the same exponentials, no G tiles in HBM
 cudaError_t launch_infonce_bwd_e2t(const CUtensorMap& tmX64, const BwdEParams& p, cudaStream_t stream);

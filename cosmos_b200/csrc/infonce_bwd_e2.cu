@@ -180,7 +180,7 @@ infonce_bwd_e2_kernel(const __grid_constant__ CUtensorMap tmY64, BwdEParams p) {
       return st;
     };
     // this thread's 4 pieces (16 bytes = 8 columns of its row) of a step's E tile: pieces ch * 4 .. + 3 of the tile's 16
-    const uint4* e_base = reinterpret_cast<const uint4*>(p.e) + row_t + ch * 4 * 128;
+    const uint4* e_base = reinterpret_cast<const uint4*>(p.e) + (row_t >> 5) * 512 + (row_t & 31) + ch * 4 * 32;
     auto load_e = [&](uint4 (&dst)[4]) {
       const uint4* src = e_base + (static_cast<size_t>((i * p.gy + j_pf) * p.n_row_tiles + tr) * n_ct + tc_pf) * 2048;
       const int c_first = tc_pf * 128 + static_cast<int>(ch) * 32;
@@ -188,7 +188,7 @@ infonce_bwd_e2_kernel(const __grid_constant__ CUtensorMap tmY64, BwdEParams p) {
       for (int p4 = 0; p4 < 4; ++p4) {
         // pieces the forward never wrote (rows past the batch, columns past the last chunk) must not reach the tensor core
         const bool ok = row_valid && c_first + p4 * 8 < p.n_cols;
-        dst[p4] = ok ? __ldcs(src + p4 * 128) : make_uint4(0u, 0u, 0u, 0u);
+        dst[p4] = ok ? __ldcs(src + p4 * 32) : make_uint4(0u, 0u, 0u, 0u);
       }
     };
     auto advance_pf = [&]() {
@@ -271,35 +271,36 @@ infonce_bwd_e2_kernel(const __grid_constant__ CUtensorMap tmY64, BwdEParams p) {
           sts128(stage + p4 * 2048, outv);          // a warp's store of one piece: 512 contiguous bytes, no bank conflicts
           if (g_row != nullptr && row_valid && col0 + p4 * 8 < p.n_cols) *reinterpret_cast<uint4*>(g_row + p4 * 8) = outv;
         }
-        // the row's positive (once per row and column tensor): G - (a_row + a_col), from the fp32 product - the packed
-        // product's rounding (2^-9 of ~2) would not survive the cancellation of a confident positive
+        // the row's positive (once per row and column tensor): R + C - (a_row + a_col) nearly cancels for a confident row, so
+        // it is formed in fp32 from the forward's own dot product of the pair, not from the bf16 exponential
         const int lrel = label - col0;
         if (row_valid && static_cast<uint32_t>(lrel) < 32u) {
           const int pi = lrel >> 3, k = lrel & 7;
-          const uint4 w = pi == 0 ? e_cur[0] : pi == 1 ? e_cur[1] : pi == 2 ? e_cur[2] : e_cur[3];
-          const uint32_t word = (k >> 1) == 0 ? w.x : (k >> 1) == 1 ? w.y : (k >> 1) == 2 ? w.z : w.w;
-          const float e = __uint_as_float((k & 1) ? (word & 0xffff0000u) : (word << 16));
-          const float g = e * fmaf(A2, kc_w[lrel], A1) - a_sum;
+          const float g = positive_grad(p, i * p.gy + j, grow, label, scale * kLog2e, lr);
           const uint16_t gb = static_cast<uint16_t>(pack2(g, 0.f, 1) & 0xffffu);
           asm volatile("st.shared.b16 [%0], %1;" ::"r"(stage + pi * 2048 + k * 2), "h"(gb) : "memory");
           if (g_row != nullptr) g_row[lrel] = gb;
         }
       } else if (kBf16) {
         // rare in a bf16 launch (a factor out of range): not unrolled, so that its registers do not weigh on the loop above
+        const float g_pos = (row_valid && static_cast<uint32_t>(label - col0) < 32u)
+                                ? positive_grad(p, i * p.gy + j, grow, label, scale * kLog2e, lr) : 0.f;
 #pragma unroll 1
         for (int p4 = 0; p4 < 4; ++p4) {
           const uint4 w = p4 == 0 ? e_cur[0] : p4 == 1 ? e_cur[1] : p4 == 2 ? e_cur[2] : e_cur[3];
           const int c0p = col0 + p4 * 8;
-          const uint4 outv = scale_piece_generic(w, p4, st.off, st.lcv, A1, A2, slow, fmt, label, c0p, row_valid, kc_w, p.n_cols, a_sum, p.dbg);
+          const uint4 outv = scale_piece_generic(w, p4, st.off, st.lcv, A1, A2, slow, fmt, label, c0p, row_valid, kc_w, p.n_cols, g_pos, p.dbg);
           sts128(stage + p4 * 2048, outv);
           if (g_row != nullptr && row_valid && c0p < p.n_cols) *reinterpret_cast<uint4*>(g_row + p4 * 8) = outv;
         }
       } else {
+        const float g_pos = (row_valid && static_cast<uint32_t>(label - col0) < 32u)
+                                ? positive_grad(p, i * p.gy + j, grow, label, scale * kLog2e, lr) : 0.f;
 #pragma unroll
         for (int p4 = 0; p4 < 4; ++p4) {
           const int c0p = col0 + p4 * 8;
           const uint4 outv = scale_piece_generic(e_cur[p4], p4, st.off, st.lcv, A1, A2, slow, fmt, label, c0p, row_valid, kc_w, p.n_cols,
-                                                 a_sum, p.dbg);
+                                                 g_pos, p.dbg);
           sts128(stage + p4 * 2048, outv);
           if (g_row != nullptr && row_valid && c0p < p.n_cols) *reinterpret_cast<uint4*>(g_row + p4 * 8) = outv;
         }

@@ -135,7 +135,7 @@ infonce_bwd_e2t_kernel(const __grid_constant__ CUtensorMap tmX64, BwdEParams p) 
     const int row_t = static_cast<int>(ts & 127);  // row of the step's tile this thread scales (lanes = consecutive rows)
     const uint32_t ch = ts >> 7;                   // 32-column chunk of this CTA's column tile (warp-uniform)
     const uint32_t khalf = (sw >> 1) & 1;          // which 64-row half of the step (K half) this warp's rows belong to
-    const float a_sum = p.a_row + p.a_col;
+    const float k2 = __ldg(p.scale) * kLog2e;
     constexpr int fmt = kBf16 ? 1 : 0;
     float* kc_w = misc->kc[sw];
     const int col0 = tc * 128 + static_cast<int>(ch) * 32;            // first column of this warp's chunk: fixed for the CTA
@@ -146,10 +146,11 @@ infonce_bwd_e2t_kernel(const __grid_constant__ CUtensorMap tmX64, BwdEParams p) 
     // Prefetch position (two steps ahead of the step being scaled): row tensor i_pf, row tile tr_pf (no division in the loop)
     int i_pf = i_first, tr_pf = tr_first;
     // statistics of one step: this row's chunk offset and log-sum-exp, and (lane = column) one column's log-sum-exp
-    struct Stats { float off, lr, lcv; int grow; };
+    struct Stats { float off, lr, lcv; int grow, pair; };
     auto load_stats = [&]() {
       Stats st;
       const int pair = i_pf * p.gy + j;
+      st.pair = pair;
       st.grow = tr_pf * 128 + row_t;
       const bool rv = chunk_valid && st.grow < p.n_rows;
       st.off = rv ? __ldg(p.off + (static_cast<size_t>(pair) * p.n_chunks + chunk) * p.n_rows + st.grow) : 0.f;
@@ -159,7 +160,7 @@ infonce_bwd_e2t_kernel(const __grid_constant__ CUtensorMap tmX64, BwdEParams p) 
       return st;
     };
     // this thread's 4 pieces (16 bytes = 8 columns of its row) of a step's E tile: pieces ch * 4 .. + 3 of the tile's 16
-    const uint4* e_base = reinterpret_cast<const uint4*>(p.e) + row_t + ch * 4 * 128;
+    const uint4* e_base = reinterpret_cast<const uint4*>(p.e) + (row_t >> 5) * 512 + (row_t & 31) + ch * 4 * 32;
     auto load_e = [&](uint4 (&dst)[4]) {
       const uint4* src = e_base + (static_cast<size_t>((i_pf * p.gy + j) * n_rt + tr_pf) * n_ct + (tile_valid ? tc : 0)) * 2048;
       const bool rv = chunk_valid && tr_pf * 128 + row_t < p.n_rows;
@@ -167,7 +168,7 @@ infonce_bwd_e2t_kernel(const __grid_constant__ CUtensorMap tmX64, BwdEParams p) 
       for (int p4 = 0; p4 < 4; ++p4) {
         // pieces the forward never wrote (rows past the batch, columns past the last chunk) must not reach the tensor core
         const bool ok = rv && col0 + p4 * 8 < p.n_cols;
-        dst[p4] = ok ? __ldcs(src + p4 * 128) : make_uint4(0u, 0u, 0u, 0u);
+        dst[p4] = ok ? __ldcs(src + p4 * 32) : make_uint4(0u, 0u, 0u, 0u);
       }
     };
     auto advance_pf = [&]() {
@@ -199,6 +200,7 @@ infonce_bwd_e2t_kernel(const __grid_constant__ CUtensorMap tmX64, BwdEParams p) 
       }
       const bool row_valid = st.grow >= 0;
       const int label = p.label_offset + st.grow;
+      const int pair_cur = st.pair;
       // column factors of this chunk, relative to o = lse_col of its first column (valid whenever the chunk is)
       const float o = __shfl_sync(0xffffffffu, st.lcv, 0);
       bool risky = false;
@@ -233,22 +235,20 @@ infonce_bwd_e2t_kernel(const __grid_constant__ CUtensorMap tmX64, BwdEParams p) 
           sts128(stage + p4 * 2048,
                  make_uint4(mul_bf16x2(w.x, f01), mul_bf16x2(w.y, f23), mul_bf16x2(w.z, f45), mul_bf16x2(w.w, f67)));
         }
-        const int lrel = label - col0;              // the row's positive, from the fp32 product (cancellation)
+        const int lrel = label - col0;              // the row's positive, in fp32 from the forward's dot product (cancellation)
         if (row_valid && static_cast<uint32_t>(lrel) < 32u) {
-          const int pi = lrel >> 3, k = lrel & 7;
-          const uint4 w = pi == 0 ? e_cur[0] : pi == 1 ? e_cur[1] : pi == 2 ? e_cur[2] : e_cur[3];
-          const uint32_t word = (k >> 1) == 0 ? w.x : (k >> 1) == 1 ? w.y : (k >> 1) == 2 ? w.z : w.w;
-          const float e = __uint_as_float((k & 1) ? (word & 0xffff0000u) : (word << 16));
-          const float g = e * fmaf(A2, kc_w[lrel], A1) - a_sum;
+          const float g = positive_grad(p, pair_cur, st.grow, label, k2, st.lr);
           const uint16_t gb = static_cast<uint16_t>(pack2(g, 0.f, 1) & 0xffffu);
-          asm volatile("st.shared.b16 [%0], %1;" ::"r"(stage + pi * 2048 + k * 2), "h"(gb) : "memory");
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(stage + (lrel >> 3) * 2048 + (lrel & 7) * 2), "h"(gb) : "memory");
         }
       } else {
+        const float g_pos = (row_valid && static_cast<uint32_t>(label - col0) < 32u) ? positive_grad(p, pair_cur, st.grow, label, k2, st.lr)
+                                                                                     : 0.f;
 #pragma unroll 1
         for (int p4 = 0; p4 < 4; ++p4) {
           const uint4 w = p4 == 0 ? e_cur[0] : p4 == 1 ? e_cur[1] : p4 == 2 ? e_cur[2] : e_cur[3];
           sts128(stage + p4 * 2048, scale_piece_generic(w, p4, st.off, st.lcv, A1, A2, slow, fmt, label, col0 + p4 * 8, row_valid,
-                                                        kc_w, p.n_cols, a_sum, 0));
+                                                        kc_w, p.n_cols, g_pos, 0));
         }
       }
       fence_proxy_async_smem();      // ordinary shared-memory stores -> visible to the tensor core's (async proxy) reads

@@ -45,10 +45,20 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
 }
 
 
+// The gradient of a row's positive: a_row softmax_row + a_col softmax_col - (a_row + a_col).  For a confident row the three
+// terms nearly cancel, so it is formed in fp32 from the forward's own dot product of the pair (diag_raw) and the final
+// log-sum-exps - not from the stored bf16 exponential, whose 2^-9 rounding would be most of the result.
+__device__ __forceinline__ float positive_grad(const BwdEParams& p, int pair, int grow, int label, float k2, float lr) {
+  const float s2 = __ldg(p.diag_raw + static_cast<size_t>(pair) * p.n_rows + grow) * k2;
+  const float lc = __ldg(p.col_lse2 + static_cast<size_t>(pair) * p.n_cols + label);
+  return p.a_row * ex2(s2 - lr) + p.a_col * ex2(s2 - lc) - (p.a_row + p.a_col);
+}
+
 // One 16-byte piece (8 columns of one row) outside the common case (fp16 stacks, a factor that may leave fp32's range,
 // diagnostics): unpack to fp32, scale, pack.  Every lane of the warp calls it (shuffles inside).
+// g_pos: the gradient of the row's positive, formed by the caller in fp32 from the forward's dot product (positive_grad).
 __device__ __forceinline__ uint4 scale_piece_generic(uint4 w, int p4, float off, float lcv, float A1, float A2, bool slow, int fmt,
-                                                      int label, int c0p, bool row_valid, const float* kc_w, int n_cols, float a_sum,
+                                                      int label, int c0p, bool row_valid, const float* kc_w, int n_cols, float g_pos,
                                                       int dbg) {
   float kcv[8];
   if (!slow) {
@@ -70,7 +80,7 @@ __device__ __forceinline__ uint4 scale_piece_generic(uint4 w, int p4, float off,
   const int idx = label - c0p;                          // 0..7 when this piece holds the row's positive
   if (idx >= 0 && idx < 8) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g[k] -= (k == idx) ? a_sum : 0.f;   // selects, not an indexed store: g stays in registers
+    for (int k = 0; k < 8; ++k) g[k] = (k == idx) ? g_pos : g[k];   // selects, not an indexed store: g stays in registers
   }
   return make_uint4(pack2(g[0], g[1], fmt), pack2(g[2], g[3], fmt), pack2(g[4], g[5], fmt), pack2(g[6], g[7], fmt));
 }

@@ -38,6 +38,10 @@ constexpr int kEpiWarps = 16;            // 4 TMEM lane quarters x 4 column grou
 constexpr int kThreads = 128 + 32 * kEpiWarps;   // 4 warps per scheduler hide what 2 could not
 constexpr int kEpiThreads = 32 * kEpiWarps;
 
+// E tile images (include/cosmos_b200.h): per 128-column step [4 slabs of 32 rows][16 pieces of 8 columns][32 rows][8] bf16;
+// offset (16-byte units) of global piece gp = step * 16 + piece inside a row tile's images, without the slab / row part
+__device__ __forceinline__ size_t e_piece_offset(int gp) { return static_cast<size_t>(gp >> 4) * 2048 + (gp & 15) * 32; }
+
 struct Misc {
   uint64_t x_full;
   uint64_t y_full[kMaxStages];
@@ -203,12 +207,11 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     float m_run = NEG_INF, l_run = 0.f, diag = 0.f;
     float2* col_part = p.col_part + (static_cast<size_t>(pair) * p.n_slabs + tr * 4 + q) * p.n_cols;
     // stored-exponential route (infonce_bwd_e.cu): this row's 2^(s2 - m_run) of every chunk as bf16, and m_run itself
-    // Layout of e_out: one contiguous 32 KB image per (pair, 128-row tile, 128-column step): [16 pieces of 8 columns][128 rows]
-    // [8 elements] - a warp's store of one piece is 512 contiguous bytes, and the backward's TMA box of a 64-column slab
-    // (8 pieces) is 16 contiguous KB that land as the no-swizzle K-major core-matrix layout of tcgen05.
+    // Layout of e_out: one contiguous 32 KB image per (pair, 128-row tile, 128-column step): [4 slabs of 32 rows][16 pieces of 8
+    // columns][32 rows][8 elements] - a warp's store of one piece is 512 contiguous bytes, its four pieces of a chunk 2 KB.
     const bool keep_e = p.e_out != nullptr && row_valid && tr < p.n_row_tiles;
     uint4* e_tile = keep_e ? reinterpret_cast<uint4*>(p.e_out) +
-                                 (static_cast<size_t>(pair) * p.n_row_tiles + tr) * p.n_steps * 2048 + (q * 32 + lane)
+                                 (static_cast<size_t>(pair) * p.n_row_tiles + tr) * p.n_steps * 2048 + (q * 512 + lane)
                            : nullptr;       // + (step * 16 + piece) * 128 (16-byte units)
     float* off_row = keep_e ? p.off_out + static_cast<size_t>(pair) * p.n_chunks * p.n_rows + row : nullptr;
 
@@ -276,7 +279,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                   t[k + 1] = e1 * f;
                   pk[k2i] = pack2(e0, e1, 1);
                 }
-                e_tile[static_cast<size_t>((col0 >> 3) + k8) * 128] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                e_tile[e_piece_offset((col0 >> 3) + k8)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
               off_row[static_cast<size_t>(col0 >> 5) * p.n_rows] = m_run;
             } else {
@@ -332,7 +335,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 s += e1;
                 pk[k2i] = pack2(e0, e1, 1);
               }
-              e_tile[static_cast<size_t>((col0 >> 3) + k8) * 128] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              e_tile[e_piece_offset((col0 >> 3) + k8)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
             off_row[static_cast<size_t>(col0 >> 5) * p.n_rows] = m_run;
           } else {
@@ -343,7 +346,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         } else if (keep_e) {
           // every logit of this row so far is -inf (scale * x.y = -inf cannot happen with finite inputs; kept for safety)
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8) e_tile[static_cast<size_t>((col0 >> 3) + k8) * 128] = make_uint4(0u, 0u, 0u, 0u);
+          for (int k8 = 0; k8 < 4; ++k8) e_tile[e_piece_offset((col0 >> 3) + k8)] = make_uint4(0u, 0u, 0u, 0u);
           off_row[static_cast<size_t>(col0 >> 5) * p.n_rows] = 0.f;
         }
         // columns: reduce over the warp's 32 rows

@@ -113,7 +113,7 @@ def _k_fwd(x, y, label_offset, scale, keep_e=False, out=None):
     return row_lse2, diag_raw, col_lse2, e, off
 
 
-def _k_bwd_e(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream,
+def _k_bwd_e(x, y, label_offset, scale, e, off, diag_raw, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream,
              want_dscale, g_out=None, dx_out=None):
     """Backward from the stored exponentials: -> dx [gx, b, 512] in x.dtype, dscale fp32 [1] (or None).  No logit is
     recomputed; x is only read for d(scale) = sum_r <x_r, (G y)_r>.  dx_out: where to write dx (a slice of the group's buffer)."""
@@ -122,7 +122,7 @@ def _k_bwd_e(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_col
     dx = dx_out if dx_out is not None else torch.empty_like(x)
     dscale = torch.empty(1, dtype=torch.float32, device=dev) if want_dscale else None
     ws = torch.empty(max(4 * prob.gx * ((prob.n_rows + 127) // 128) * 8, 256) + 256, dtype=torch.uint8, device=dev)
-    st = _lib.lib().cosmos_infonce_bwd_e(C.byref(prob), e.data_ptr(), off.data_ptr(), row_lse2.data_ptr(),
+    st = _lib.lib().cosmos_infonce_bwd_e(C.byref(prob), e.data_ptr(), off.data_ptr(), diag_raw.data_ptr(), row_lse2.data_ptr(),
                                          col_lse2.data_ptr(), a_row, a_col, s_row, s_col, weight,
                                          upstream.data_ptr(), dx.data_ptr(), dscale.data_ptr() if want_dscale else None,
                                          g_out.data_ptr() if g_out is not None else None,
@@ -132,7 +132,7 @@ def _k_bwd_e(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_col
     return dx, dscale
 
 
-def _k_bwd_e_cols(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_col):
+def _k_bwd_e_cols(x, y, label_offset, scale, e, off, diag_raw, row_lse2, col_lse2, a_row, a_col):
     """Column side of the stored-exponential route: -> fp32 [gy, N, 512], sum over the row tensors and THIS rank's rows of
     G^T x at unit scale (csrc/infonce_bwd_e2t.cu) - no G tile is written to memory."""
     dev = x.device
@@ -141,7 +141,8 @@ def _k_bwd_e_cols(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, 
     if splits < 1:
         raise RuntimeError("cosmos_b200: unsupported problem for the column-side stored-exponential backward")
     dy = torch.empty(splits, prob.gy, prob.n_cols, prob.dim, dtype=torch.float32, device=dev)
-    st = _lib.lib().cosmos_infonce_bwd_e_cols(C.byref(prob), e.data_ptr(), off.data_ptr(), row_lse2.data_ptr(), col_lse2.data_ptr(),
+    st = _lib.lib().cosmos_infonce_bwd_e_cols(C.byref(prob), e.data_ptr(), off.data_ptr(), diag_raw.data_ptr(), row_lse2.data_ptr(),
+                                              col_lse2.data_ptr(),
                                               a_row, a_col, dy.data_ptr(), splits, dev.index,
                                               torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(st, "infonce_bwd_e_cols")
@@ -541,13 +542,13 @@ def _eager_schedule(groups: Sequence[_Group], comm: Comm):
             gather.finish(g.col_lse2[sl])
         via_gemm = g.need_cols and _COLS_VIA_GEMM
         g_tiles = torch.empty(xs.shape[0] * g.b, g.n_c * g.N, dtype=g.x_r.dtype, device=xs.device) if via_gemm else None
-        _dx, ds_ = _k_bwd_e(xs, g.y_c, g.off, g.scale_f, e_, o_, g.row_lse2[sl], g.col_lse2[sl], 1.0, 1.0, 1.0 / g.boost,
+        _dx, ds_ = _k_bwd_e(xs, g.y_c, g.off, g.scale_f, e_, o_, g.diag_raw[sl], g.row_lse2[sl], g.col_lse2[sl], 1.0, 1.0, 1.0 / g.boost,
                             1.0 / g.boost, g.weight, g.one, g.need_scale, g_tiles, dx_out=g.dx_unit[i0:i0 + xs.shape[0]])
         if g.need_cols:
             if via_gemm:      # diagnostics: G tiles through HBM + one GEMM (the first version of this route)
                 part = _k_colgrad(g_tiles, xs.reshape(xs.shape[0] * g.b, xs.shape[2]), g.n_c, g.N)    # [n_c, N, D] fp32
             else:             # the same exponentials once more, read as G^T: nothing but dY goes to memory
-                part = _k_bwd_e_cols(xs, g.y_c, g.off, g.scale_f, e_, o_, g.row_lse2[sl], g.col_lse2[sl], 1.0, 1.0)
+                part = _k_bwd_e_cols(xs, g.y_c, g.off, g.scale_f, e_, o_, g.diag_raw[sl], g.row_lse2[sl], g.col_lse2[sl], 1.0, 1.0)
             g.d_all = part if g.d_all is None else g.d_all.add_(part)
         if ds_ is not None:
             g.ds_unit = ds_ if g.ds_unit is None else g.ds_unit + ds_

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define COSMOS_B200_ABI_VERSION 1
+#define COSMOS_B200_ABI_VERSION 2
 
 /* status codes */
 #define COSMOS_OK 0
@@ -199,16 +199,19 @@ int cosmos_colsum(const void* src, int32_t dtype, float* dst, int64_t rows, int3
 
 /* Stored-exponential route (dim 512): the forward keeps, next to its statistics, every 2^(s2 - m) it forms
  * (s2 = logit in log2 units) as bf16 in e_out - cosmos_infonce_e_bytes(p) bytes: one contiguous 32 KB image
- * [16 column pieces][128 rows][8] per (pair, 128-row tile, 128-column step) - and the offsets m in off_out
- * (fp32 [gx*gy][ceil(n_cols/32)][n_rows]: the row's running maximum when that 32-column chunk was processed).
+ * [4 slabs of 32 rows][16 pieces of 8 columns][32 rows][8] per (pair, 128-row tile, 128-column step) - and the offsets m
+ * in off_out (fp32 [gx*gy][ceil(n_cols/32)][n_rows]: the offset row r used in that 32-column chunk; any value works
+ * for which the row's significant terms stay inside 2^+-126 - the kernels use a lazily updated per-warp reference).
  * cosmos_infonce_bwd_e then recomputes no logit: dx = G y is its only contraction.  Same outputs and mode scalars
  * as cosmos_infonce_bwd / _bwd_g (the two d(scale) weights must be proportional to the two gradient weights);
- * col_lse2 must be the complete (all ranks) column log-sum-exps. */
+ * col_lse2 must be the complete (all ranks) column log-sum-exps; diag_raw is the forward's output of that name: the
+ * gradient of a row's positive (softmax terms minus their weights, nearly cancelling for a confident row) is formed
+ * from it in fp32, not from the bf16 exponential. */
 int64_t cosmos_infonce_e_bytes(const cosmos_infonce_problem* p);
 int cosmos_infonce_fwd_e(const cosmos_infonce_problem* p, float* row_lse2, float* diag_raw, float* col_lse2, void* e_out,
                          float* off_out, void* workspace, int64_t workspace_bytes, int device, void* stream);
-int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const float* off, const float* row_lse2,
-                         const float* col_lse2, float a_row, float a_col, float s_row, float s_col,
+int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const float* off, const float* diag_raw,
+                         const float* row_lse2, const float* col_lse2, float a_row, float a_col, float s_row, float s_col,
                          float weight, const float* upstream, void* dx, float* dscale, void* g_out, int64_t g_ld, void* workspace,
                          int64_t workspace_bytes, int device, void* stream);
 
@@ -220,9 +223,9 @@ int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const f
  * upstream * scale * weight.  cosmos_infonce_bwd_e_cols_splits proposes the number of slices of the row sweep for which
  * the launch fills whole waves of SM pairs (1 .. 4; -1: unsupported problem).                                            */
 int32_t cosmos_infonce_bwd_e_cols_splits(const cosmos_infonce_problem* p, int device);
-int cosmos_infonce_bwd_e_cols(const cosmos_infonce_problem* p, const void* e, const float* off, const float* row_lse2,
-                              const float* col_lse2, float a_row, float a_col, float* dy, int32_t splits, int device,
-                              void* stream);
+int cosmos_infonce_bwd_e_cols(const cosmos_infonce_problem* p, const void* e, const float* off, const float* diag_raw,
+                              const float* row_lse2, const float* col_lse2, float a_row, float a_col, float* dy, int32_t splits,
+                              int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Retrieval ranks for the evaluation metrics  (src/training/train.py:766-785 get_clip_metrics and

@@ -75,8 +75,8 @@ def emu_lse2_merge(parts, out):
     return out
 
 
-def emu_bwd_e(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream, want_dscale,
-              g_out=None, dx_out=None):
+def emu_bwd_e(x, y, label_offset, scale, e, off, diag_raw, row_lse2, col_lse2, a_row, a_col, s_row, s_col, weight, upstream,
+              want_dscale, g_out=None, dx_out=None):
     """cosmos_infonce_bwd_e: the same gradient, formed from what the forward kept (here: the logits) - no x y^T."""
     assert abs(a_row * s_col - a_col * s_row) < 1e-12, "bwd_e needs proportional d(scale) / gradient mixes"
     gx, b, D = x.shape
@@ -101,7 +101,7 @@ def emu_bwd_e(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_co
     return dx, dscale
 
 
-def emu_bwd_e_cols(x, y, label_offset, scale, e, off, row_lse2, col_lse2, a_row, a_col):
+def emu_bwd_e_cols(x, y, label_offset, scale, e, off, diag_raw, row_lse2, col_lse2, a_row, a_col):
     """cosmos_infonce_bwd_e_cols: fp32 [gy, N, D] = sum over row tensors and local rows of G^T x, unit scale."""
     gx, b, D = x.shape
     gy, N, _ = y.shape

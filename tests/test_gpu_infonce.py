@@ -259,9 +259,9 @@ def test_stored_exponential_kernels_match_recompute_kernels(b, n_all, off, gx, g
     for a_row, a_col, ratio in ((1.0, 1.0, 1.0), (1.0, 0.0, 0.5), (0.25, 1.0, 2.0)):
         mix = (a_row, a_col, ratio * a_row, ratio * a_col, 0.125)
         dx_ref, ds_ref = K._k_bwd(x, y, off, sc, row, col, *mix, up, True, True)
-        dx, ds = K._k_bwd_e(x, y, off, sc, e, offs, row, col, *mix, up, True)
+        dx, ds = K._k_bwd_e(x, y, off, sc, e, offs, diag, row, col, *mix, up, True)
         assert cosine(dx.float().cpu(), dx_ref.float().cpu()) >= 0.99999
-        assert abs(float(dx.float().norm()) / float(dx_ref.float().norm()) - 1.0) <= 2e-3
+        assert abs(float(dx.float().norm()) / float(dx_ref.float().norm()) - 1.0) <= (5e-3 if scale >= 100.0 else 2e-3)
         # bf16 G in one kernel, fp32 G in the other; the floor covers mixes whose d(scale) nearly cancels (confident rows at
         # scale 100: sum (R - I) raw ~ 1e-3 of its terms' magnitude)
         assert abs(float(ds) - float(ds_ref)) <= 5e-3 * abs(float(ds_ref)) + 1e-4
@@ -269,10 +269,10 @@ def test_stored_exponential_kernels_match_recompute_kernels(b, n_all, off, gx, g
         g1 = torch.zeros(gx * b, gy * n_all, dtype=dtype, device="cuda")
         g2 = torch.zeros_like(g1)
         K._k_bwd(x, y, off, sc, row, col, 1.0, 1.0, 1.0, 1.0, 0.125, up, True, False, g1)
-        K._k_bwd_e(x, y, off, sc, e, offs, row, col, 1.0, 1.0, 1.0, 1.0, 0.125, up, False, g2)
+        K._k_bwd_e(x, y, off, sc, e, offs, diag, row, col, 1.0, 1.0, 1.0, 1.0, 0.125, up, False, g2)
         assert cosine(g1.float().cpu(), g2.float().cpu()) >= 0.99999
     with pytest.raises(RuntimeError, match="unsupported"):      # d(scale) weights not proportional to the gradient weights
-        K._k_bwd_e(x, y, off, sc, e, offs, row, col, 1.0, 1.0, 1.0, 0.0, 0.125, up, True)
+        K._k_bwd_e(x, y, off, sc, e, offs, diag, row, col, 1.0, 1.0, 1.0, 0.0, 0.125, up, True)
     # column side from the same exponentials (cosmos_infonce_bwd_e_cols: dY = G^T X, nothing transposed, no G in memory)
     # against fp64 from first principles: G = a_row softmax_rows + a_col softmax_cols - (a_row + a_col) positives
     S2 = torch.einsum("ibd,jnd->ijbn", x.double(), y.double()) * (scale * math.log2(math.e))
@@ -282,7 +282,7 @@ def test_stored_exponential_kernels_match_recompute_kernels(b, n_all, off, gx, g
         G = (a_row * torch.exp2(S2 - row.double().view(gx, gy, b, 1)) + a_col * torch.exp2(S2 - col.double().view(gx, gy, 1, n_all))
              - (a_row + a_col) * pos)
         want = torch.einsum("ijbn,ibd->jnd", G, x.double())
-        got = K._k_bwd_e_cols(x, y, off, sc, e, offs, row, col, a_row, a_col)
+        got = K._k_bwd_e_cols(x, y, off, sc, e, offs, diag, row, col, a_row, a_col)
         assert got.shape == (gy, n_all, 512) and got.dtype == torch.float32
         # G is a bf16 operand in the kernel: at scale 100 (confident rows, G = R + C - 2 I nearly cancels) its rounding shows
         floor = 0.9999 if scale >= 100.0 else 0.99999

@@ -33,7 +33,7 @@ dx_ref, ds_ref = K._k_bwd(x, y, 0, sc, row, col, *mix, up, True, True)
 row2, diag2, col2, e, off = K._k_fwd(x, y, 0, sc, keep_e=True)
 torch.cuda.synchronize()
 print("fwd statistics identical:", torch.equal(row, row2), torch.equal(col, col2), torch.equal(diag, diag2), flush=True)
-dx, ds = K._k_bwd_e(x, y, 0, sc, e, off, row2, col2, *mix, up, True)
+dx, ds = K._k_bwd_e(x, y, 0, sc, e, off, diag2, row2, col2, *mix, up, True)
 torch.cuda.synchronize()
 a, r = dx.float().flatten(), dx_ref.float().flatten()
 print("dX cosine %.7f  max|diff| %.3e  max|ref| %.3e  |dX|/|ref| %.5f" % (
@@ -53,7 +53,7 @@ if SMALL:
     want = (Gm @ yj) * scale * 0.25 * 1.7
     # the kernels sum over the gy column tensors: isolate tensor gy-1 by a second launch with gy = 1
     r1, d1, c1, e1, o1 = K._k_fwd(x[1:2], y[gy - 1:gy], 0, sc, keep_e=True)
-    dx1, _ = K._k_bwd_e(x[1:2], y[gy - 1:gy], 0, sc, e1, o1, r1, c1, *mix, up, False)
+    dx1, _ = K._k_bwd_e(x[1:2], y[gy - 1:gy], 0, sc, e1, o1, d1, r1, c1, *mix, up, False)
     dxq, _ = K._k_bwd(x[1:2], y[gy - 1:gy], 0, sc, r1, c1, *mix, up, True, False)
     w = want.flatten()
     for name, t in (("stored-e", dx1), ("recompute", dxq)):
@@ -64,7 +64,7 @@ if N % 8 == 0 and SMALL:
     g1 = torch.zeros(gx * b, gy * N, dtype=x.dtype, device="cuda")
     g2 = torch.zeros_like(g1)
     K._k_bwd(x, y, 0, sc, row, col, *mix, up, True, False, g1)
-    K._k_bwd_e(x, y, 0, sc, e, off, row2, col2, *mix, up, False, g2)
+    K._k_bwd_e(x, y, 0, sc, e, off, diag2, row2, col2, *mix, up, False, g2)
     torch.cuda.synchronize()
     print("G tiles: cosine %.7f  max|diff| %.3e" % (float((g1.float() * g2.float()).sum() / (g1.float().norm() * g2.float().norm())),
                                                    float((g1.float() - g2.float()).abs().max())), flush=True)
@@ -85,13 +85,13 @@ def timed(fn, reps=5):
 
 fl = 2.0 * gx * gy * b * N * D
 if len(sys.argv) > 6:      # timing of the stored-exponential backward only (diagnostic flags in the environment)
-    t_be = timed(lambda: K._k_bwd_e(x, y, 0, sc, e, off, row2, col2, *mix, up, True))
+    t_be = timed(lambda: K._k_bwd_e(x, y, 0, sc, e, off, diag2, row2, col2, *mix, up, True))
     print("bwd stored-e %.3f ms (%.0f TF/s)" % (t_be, fl / t_be * 1e-9), flush=True)
     sys.exit(0)
 t_f = timed(lambda: K._k_fwd(x, y, 0, sc))
 t_fe = timed(lambda: K._k_fwd(x, y, 0, sc, keep_e=True))
 t_b = timed(lambda: K._k_bwd(x, y, 0, sc, row, col, *mix, up, True, True))
-t_be = timed(lambda: K._k_bwd_e(x, y, 0, sc, e, off, row2, col2, *mix, up, True))
+t_be = timed(lambda: K._k_bwd_e(x, y, 0, sc, e, off, diag2, row2, col2, *mix, up, True))
 print("fwd %.3f ms (%.0f TF/s)   fwd+E %.3f ms (%.0f TF/s)   bwd recompute %.3f ms   bwd stored-e %.3f ms (%.0f TF/s)" % (
     t_f, fl / t_f * 1e-9, t_fe, fl / t_fe * 1e-9, t_b, t_be, fl / t_be * 1e-9), flush=True)
 print("route total: recompute %.3f ms, stored-e %.3f ms" % (t_f + t_b, t_fe + t_be), flush=True)
