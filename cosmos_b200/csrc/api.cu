@@ -43,8 +43,11 @@ int dbg_flags() {
   static const int v = env_int("COSMOS_B200_DBG", 0);
   return v;
 }
-int fwd_generation() {                   // COSMOS_B200_FWD=1: first-generation forward epilogue (diagnostics)
-  static const int v = env_int("COSMOS_B200_FWD", 2);
+// COSMOS_B200_FWD=2: second-generation forward epilogue (infonce_fwd2.cu).  Measured in round 2 (profiles/README_r02.md): 37 %
+// fewer instructions, equal in isolation, 23 % SLOWER inside the step - the forward is bound by L2 -> SM traffic, not by
+// its epilogue's issue slots - so the first generation stays the default.
+int fwd_generation() {
+  static const int v = env_int("COSMOS_B200_FWD", 1);
   return v;
 }
 int bwd_t_splits() {
@@ -261,8 +264,8 @@ int cosmos_infonce_fwd_e(const cosmos_infonce_problem* p, float* row_lse2, float
   fp.n_steps = d.n_col_tiles_bwd;
   fp.n_chunks = (p->n_cols + 31) / 32;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // COSMOS_B200_FWD=1: first-generation epilogue (diagnostics); the single-CTA kernel (COSMOS_B200_DBG=4) only has that one
-  if (cu_fail((pair && fwd_generation() != 1) ? cb::launch_infonce_fwd2(tmX, tmY, fp, s) : cb::launch_infonce_fwd(tmX, tmY, fp, pair, s)))
+  // (the single-CTA kernel, COSMOS_B200_DBG=4, only has the first-generation epilogue)
+  if (cu_fail((pair && fwd_generation() == 2) ? cb::launch_infonce_fwd2(tmX, tmY, fp, s) : cb::launch_infonce_fwd(tmX, tmY, fp, pair, s)))
     return COSMOS_ERR_CUDA;
   if (cu_fail(cb::launch_col_combine(fp.col_part, col_lse2, d.pairs, d.n_slabs, p->n_cols, s))) return COSMOS_ERR_CUDA;
   return COSMOS_OK;
@@ -446,6 +449,8 @@ int32_t cosmos_infonce_bwd_e_cols_splits(const cosmos_infonce_problem* p, int de
   // the fewest slices of the row sweep for which the CTA pairs (one per 256 columns of one column tensor) fill whole waves
   const int pairs = p->gy * ((d.n_col_tiles_bwd + 1) / 2);
   const int steps = p->gx * d.n_row_tiles;
+  static const int forced = env_int("COSMOS_B200_COLS_SPLITS", 0);      // diagnostics
+  if (forced > 0) return forced <= kMaxTSplits && forced <= steps ? forced : 1;
   return choose_t_splits(pairs, sm_count_of(device) / 2, steps);
 }
 
