@@ -51,7 +51,8 @@ def _declare(lib):
         fn.argtypes = args
     for name, args in _INFONCE_SIGS.items():
         fn = getattr(lib, name)
-        fn.restype = i64 if name in ("cosmos_infonce_workspace_bytes", "cosmos_infonce_e_bytes") else i32
+        fn.restype = i64 if name in ("cosmos_infonce_workspace_bytes", "cosmos_infonce_e_bytes",
+                                     "cosmos_infonce_bwd_e_workspace_bytes") else i32
         fn.argtypes = args
 
 
@@ -77,6 +78,7 @@ _INFONCE_SIGS = {
     "cosmos_infonce_loss_sums": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, i32_, i32_, vp_, vp_, i32_, vp_],
     "cosmos_infonce_bwd": [C.POINTER(InfoNceProblem), vp_, vp_, f32_, f32_, f32_, f32_, f32_, vp_, vp_, vp_, vp_, i64_, i32_, vp_],
     "cosmos_infonce_e_bytes": [C.POINTER(InfoNceProblem)],
+    "cosmos_infonce_bwd_e_workspace_bytes": [C.POINTER(InfoNceProblem), i32_],
     "cosmos_infonce_fwd_e": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, vp_, vp_, vp_, i64_, i32_, vp_],
     "cosmos_infonce_bwd_e": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, vp_, vp_, f32_, f32_, f32_, f32_, f32_, vp_, vp_, vp_, vp_,
                              i64_, vp_, i64_, i32_, vp_],

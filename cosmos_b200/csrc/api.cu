@@ -202,9 +202,29 @@ int choose_t_splits(int clusters, int slots, int T_all) {
   return best;
 }
 
+// Slices of the column sweep of the stored-exponential row-side backward: the fewest for which its CTA pairs (one per 256
+// rows of one row tensor) fill whole waves.  COSMOS_B200_ROWS_SPLITS forces a value (diagnostics).
+int bwd_e_splits(const cosmos_infonce_problem* p, const Dims& d, int device) {
+  static const int forced = env_int("COSMOS_B200_ROWS_SPLITS", 0);
+  const int steps = p->gy * d.n_col_tiles_bwd;
+  if (forced > 0) return (forced <= kMaxTSplits && 2 * forced <= steps) ? forced : 1;
+  // at most two slices: measured at the per-rank shapes of an 8-GPU job (b = 4096, N = 32768), two slices take the
+  // distillation group from 3.46 to 6.92 waves (8.85 -> 8.24 ms); four slices of the CLIP group's 128 pairs cost more in
+  // fp32 partials and per-item prologues than their fuller last wave returns (2.18 -> 2.30 ms)
+  const int ts = choose_t_splits(p->gx * ((d.n_row_tiles + 1) / 2), sm_count_of(device) / 2, steps);
+  return ts > 2 ? 1 : ts;
+}
+
 }  // namespace
 
 extern "C" {
+
+int64_t cosmos_infonce_bwd_e_workspace_bytes(const cosmos_infonce_problem* p, int device) {
+  Dims d;
+  if (check_problem(p, &d) != COSMOS_OK) return -1;
+  const int splits = bwd_e_splits(p, d, device);
+  return bwd_partials_bytes(p, d) + (splits > 1 ? static_cast<int64_t>(splits) * p->gx * p->n_rows * 512 * static_cast<int64_t>(sizeof(float)) : 0);
+}
 
 int64_t cosmos_infonce_workspace_bytes(const cosmos_infonce_problem* p) {
   Dims d;
@@ -404,7 +424,9 @@ int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const f
   if (g_out != nullptr && ((p->n_cols & 7) != 0 || (g_ld & 7) != 0 || g_ld < static_cast<int64_t>(p->gy) * p->n_cols ||
                            (reinterpret_cast<uintptr_t>(g_out) & 15) != 0))
     return COSMOS_ERR_INVALID_ARGUMENT;
-  if (workspace == nullptr || workspace_bytes < bwd_partials_bytes(p, d)) return COSMOS_ERR_WORKSPACE;
+  const int splits = bwd_e_splits(p, d, device);
+  const int64_t part_bytes = splits > 1 ? static_cast<int64_t>(splits) * p->gx * p->n_rows * 512 * static_cast<int64_t>(sizeof(float)) : 0;
+  if (workspace == nullptr || workspace_bytes < bwd_partials_bytes(p, d) + part_bytes) return COSMOS_ERR_WORKSPACE;
   DeviceGuard g(device);
   if (!g.ok) return COSMOS_ERR_CUDA;
   CUtensorMap tmY64;
@@ -433,11 +455,14 @@ int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const f
   bp.dscale_part = dscale != nullptr ? reinterpret_cast<float*>(workspace) : nullptr;
   bp.g_out = g_out;
   bp.g_ld = g_ld;
-  bp.t_splits = 1;
+  bp.t_splits = splits;
+  bp.dx32 = splits > 1 ? reinterpret_cast<float*>(static_cast<char*>(workspace) + bwd_partials_bytes(p, d)) : nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (cu_fail(cb::launch_infonce_bwd_e2(tmY64, bp, s))) return COSMOS_ERR_CUDA;
+  if (splits > 1 && cu_fail(cb::launch_reduce_dx(bp.dx32, splits, dx, p->dtype, static_cast<size_t>(p->gx) * p->n_rows * 512, s)))
+    return COSMOS_ERR_CUDA;
   // partial sums hold <G, raw> with G's mix; (s_row + s_col) / (a_row + a_col) turns it into the requested one
-  if (dscale != nullptr && cu_fail(cb::launch_dscale_reduce(bp.dscale_part, p->gx * d.n_row_tiles,
+  if (dscale != nullptr && cu_fail(cb::launch_dscale_reduce(bp.dscale_part, splits * p->gx * d.n_row_tiles,
                                                             weight * (s_row + s_col) / (a_row + a_col), upstream, dscale, s)))
     return COSMOS_ERR_CUDA;
   return COSMOS_OK;

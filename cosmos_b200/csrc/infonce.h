@@ -79,7 +79,9 @@ struct BwdEParams {
   float* dscale_part;     // [gx * n_row_tiles] partial sums of <dscale-mix, raw logits>, may be null
   void* g_out;            // optional copy of every G tile, [gx * n_rows][g_ld], column j * n_cols + c
   long long g_ld;
-  int t_splits;           // column-side kernel (infonce_bwd_e2t.cu) only: slices of the row sweep; dx = fp32 [t_splits][gy][n_cols][512]
+  int t_splits;           // slices of the sweep.  Column-side kernel: of the row sweep, dx = fp32 [t_splits][gy][n_cols][512];
+                          // row-side kernel: of the column sweep, partial dX go to dx32 when > 1
+  float* dx32;            // row-side kernel, t_splits > 1: fp32 [t_splits][gx][n_rows][512] partial dX (else null)
 };
 // infonce_bwd_e2.cu: 16 independent scaling warps, E two steps ahead in registers
 cudaError_t launch_infonce_bwd_e2(const CUtensorMap& tmY64, const BwdEParams& p, cudaStream_t stream);
@@ -92,6 +94,7 @@ cudaError_t launch_loss_sums(const float* row_lse2, const float* diag_raw, const
                              int n_rows, int n_cols, int label_offset, int use_rows, int use_cols, float* out,
                              cudaStream_t stream);
 cudaError_t launch_lse2_merge(const float* parts, float* out, int n_parts, size_t n, cudaStream_t stream);
+cudaError_t launch_reduce_dx(const float* parts, int n_parts, void* dst, int dtype, size_t n, cudaStream_t stream);
 cudaError_t launch_convert_dx(const float* src, void* dst, int dtype, size_t n, cudaStream_t stream);
 cudaError_t launch_dscale_reduce(const float* part, int n, float weight, const float* upstream, float* dscale,
                                  cudaStream_t stream);

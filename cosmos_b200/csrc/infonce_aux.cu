@@ -126,6 +126,25 @@ convert_dx_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int f
   }
 }
 
+// dst[k] = sum over the n_parts slices of parts[q][k], rounded once to the stack dtype (partial dX of a sliced column sweep)
+__global__ void __launch_bounds__(256)
+reduce_dx_kernel(const float4* __restrict__ parts, int n_parts, uint2* __restrict__ dst, int fmt, size_t n4) {
+  for (size_t k = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; k < n4; k += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 a = __ldcs(parts + k);
+    for (int q = 1; q < n_parts; ++q) {
+      const float4 b = __ldcs(parts + static_cast<size_t>(q) * n4 + k);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    dst[k] = make_uint2(pack2(a.x, a.y, fmt), pack2(a.z, a.w, fmt));
+  }
+}
+
+cudaError_t launch_reduce_dx(const float* parts, int n_parts, void* dst, int dtype, size_t n, cudaStream_t stream) {
+  reduce_dx_kernel<<<148 * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(parts), n_parts, reinterpret_cast<uint2*>(dst),
+                                                dtype == 1 ? 1 : 0, n / 4);      // n is a multiple of 512
+  return cudaGetLastError();
+}
+
 cudaError_t launch_convert_dx(const float* src, void* dst, int dtype, size_t n, cudaStream_t stream) {
   const size_t n4 = n / 4;   // n is a multiple of 64
   convert_dx_kernel<<<148 * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst),

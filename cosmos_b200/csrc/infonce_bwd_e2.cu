@@ -38,13 +38,22 @@ infonce_bwd_e2_kernel(const __grid_constant__ CUtensorMap tmY64, BwdEParams p) {
   const uint32_t r = cluster_ctarank();
   const bool leader = r == 0;
 
+  // work item: (slice of the column sweep, row tensor i, row tile tr); the two CTAs of a pair take consecutive row tiles.
+  // t_splits > 1 cuts the sweep over the gy * n_col_tiles steps into slices so that small launches (a rank of an 8-GPU job
+  // has 256 pairs = 3.46 waves of 74) fill whole waves; the slices' fp32 partial dX are summed by reduce_dx_kernel.
   const int tiles_padded = 2 * ((p.n_row_tiles + 1) / 2);
-  const int rt = (blockIdx.x >> 1) * 2 + static_cast<int>(r);
+  const int per_split = p.gx * tiles_padded;
+  const int item = (blockIdx.x >> 1) * 2 + static_cast<int>(r);
+  const int split = item / per_split;
+  const int rt = item - split * per_split;
   const int i = rt / tiles_padded;
   const int tr = rt - i * tiles_padded;
   const bool tile_valid = tr < p.n_row_tiles;
   const int n_ct = p.n_col_tiles;
-  const int T = p.gy * n_ct;
+  const int T_all = p.gy * n_ct;
+  const int t_first = static_cast<int>(static_cast<long long>(T_all) * split / p.t_splits);
+  const int T = static_cast<int>(static_cast<long long>(T_all) * (split + 1) / p.t_splits) - t_first;
+  const int j_first = t_first / n_ct, tc_first = t_first - j_first * n_ct;
 
   uint8_t* sG = smem;
   uint8_t* sB = sG + kStagesG * kStageG;
@@ -74,8 +83,8 @@ infonce_bwd_e2_kernel(const __grid_constant__ CUtensorMap tmY64, BwdEParams p) {
   if (warp == 3) {
     // ---------------- TMA producer: Y slabs (B operand), in the order the MMA warp consumes them ----------------
     uint32_t u = 0, ph = 0;
+    int j = j_first, tc = tc_first;
     for (int t = 0; t < T; ++t) {
-      const int j = t / n_ct, tc = t - j * n_ct;
       for (int half = 0; half < 2; ++half) {
         for (int nh = 0; nh < 2; ++nh) {
           mbar_wait(&misc->b_empty[u], ph ^ 1);
@@ -90,6 +99,7 @@ infonce_bwd_e2_kernel(const __grid_constant__ CUtensorMap tmY64, BwdEParams p) {
           if (++u == kUnitsB) { u = 0; ph ^= 1; }
         }
       }
+      if (++tc == n_ct) { tc = 0; ++j; }
     }
   } else if (warp == 1) {
     if (leader) {
@@ -165,7 +175,7 @@ infonce_bwd_e2_kernel(const __grid_constant__ CUtensorMap tmY64, BwdEParams p) {
 
     // Prefetch position (two steps ahead of the step being scaled): column tensor j_pf, 128-column step tc_pf.  Kept as a
     // pair of counters: no integer division in the loop.
-    int j_pf = 0, tc_pf = 0;
+    int j_pf = j_first, tc_pf = tc_first;
     // statistics of one step: this row's chunk offset and (lane = column) one column's log-sum-exp; the row's own
     // log-sum-exp changes only with the column tensor
     struct Stats { float off, lcv; };
@@ -207,8 +217,8 @@ infonce_bwd_e2_kernel(const __grid_constant__ CUtensorMap tmY64, BwdEParams p) {
     const bool eprof = kProf && ((blockIdx.x >> 1) % 97) == 5 && lane == 0 && (sw == 0 || sw == 15);
     long long e_wait = 0, e_work = 0, e_pre = 0, e_fence = 0, e_arrive = 0;
     uint32_t s = 0, phs = 0;
-    int j = 0, tc = 0;
-    float lr = row_valid ? __ldg(p.row_lse2 + static_cast<size_t>(i * p.gy) * p.n_rows + grow) : INFINITY;
+    int j = j_first, tc = tc_first;
+    float lr = row_valid ? __ldg(p.row_lse2 + static_cast<size_t>(i * p.gy + j_first) * p.n_rows + grow) : INFINITY;
     for (int t = 0; t < T; ++t) {
       const long long c_top = eprof ? clock64() : 0;
       const int col0 = tc * 128 + static_cast<int>(ch) * 32;      // first column of this warp's chunk
@@ -327,7 +337,7 @@ infonce_bwd_e2_kernel(const __grid_constant__ CUtensorMap tmY64, BwdEParams p) {
       if (++tc == n_ct) {
         tc = 0;
         ++j;
-        if (j < p.gy && row_valid) lr = __ldg(p.row_lse2 + static_cast<size_t>(i * p.gy + j) * p.n_rows + grow);
+        if (j < p.gy && row_valid && t + 1 < T) lr = __ldg(p.row_lse2 + static_cast<size_t>(i * p.gy + j) * p.n_rows + grow);
       }
     }
     if (eprof)
@@ -370,13 +380,21 @@ infonce_bwd_e2_kernel(const __grid_constant__ CUtensorMap tmY64, BwdEParams p) {
             }
           }
         }
-        uint32_t ow[16];
+        if (p.dx32 != nullptr) {       // sliced sweep: this slice's fp32 partial, [slice][gx][n_rows][512]
+          float4* dst = reinterpret_cast<float4*>(p.dx32 + ((static_cast<size_t>(split) * p.gx + i) * p.n_rows + drow) * 512 + c);
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk)
-          ow[kk] = pack2(__uint_as_float(v[2 * kk]) * coef, __uint_as_float(v[2 * kk + 1]) * coef, fmt);
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dx) + (static_cast<size_t>(i) * p.n_rows + drow) * 512 + c);
+          for (int kk = 0; kk < 8; ++kk)
+            dst[kk] = make_float4(__uint_as_float(v[4 * kk]) * coef, __uint_as_float(v[4 * kk + 1]) * coef,
+                                  __uint_as_float(v[4 * kk + 2]) * coef, __uint_as_float(v[4 * kk + 3]) * coef);
+        } else {
+          uint32_t ow[16];
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) dst[kk] = make_uint4(ow[4 * kk], ow[4 * kk + 1], ow[4 * kk + 2], ow[4 * kk + 3]);
+          for (int kk = 0; kk < 16; ++kk)
+            ow[kk] = pack2(__uint_as_float(v[2 * kk]) * coef, __uint_as_float(v[2 * kk + 1]) * coef, fmt);
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dx) + (static_cast<size_t>(i) * p.n_rows + drow) * 512 + c);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) dst[kk] = make_uint4(ow[4 * kk], ow[4 * kk + 1], ow[4 * kk + 2], ow[4 * kk + 3]);
+        }
       }
     }
     if (want_ds) {
@@ -387,7 +405,7 @@ infonce_bwd_e2_kernel(const __grid_constant__ CUtensorMap tmY64, BwdEParams p) {
       if (ts == 0 && tile_valid) {
         float sum = 0.f;
         for (int w = 0; w < kScaleWarps; ++w) sum += misc->red[w];
-        p.dscale_part[i * p.n_row_tiles + tr] = sum;      // <G, raw dot products> of this tile's rows
+        p.dscale_part[(split * p.gx + i) * p.n_row_tiles + tr] = sum;      // <G, raw dot products> of this tile's rows and slice
       }
     }
   }
@@ -406,7 +424,7 @@ cudaError_t launch_infonce_bwd_e2(const CUtensorMap& tmY64, const BwdEParams& p,
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(p.gx * ((p.n_row_tiles + 1) / 2) * 2);
+  cfg.gridDim = dim3(p.t_splits * p.gx * ((p.n_row_tiles + 1) / 2) * 2);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;

@@ -121,7 +121,8 @@ def _k_bwd_e(x, y, label_offset, scale, e, off, diag_raw, row_lse2, col_lse2, a_
     prob = _problem(x, y, label_offset, scale)
     dx = dx_out if dx_out is not None else torch.empty_like(x)
     dscale = torch.empty(1, dtype=torch.float32, device=dev) if want_dscale else None
-    ws = torch.empty(max(4 * prob.gx * ((prob.n_rows + 127) // 128) * 8, 256) + 256, dtype=torch.uint8, device=dev)
+    ws = torch.empty(max(int(_lib.lib().cosmos_infonce_bwd_e_workspace_bytes(C.byref(prob), dev.index)), 256), dtype=torch.uint8,
+                     device=dev)
     st = _lib.lib().cosmos_infonce_bwd_e(C.byref(prob), e.data_ptr(), off.data_ptr(), diag_raw.data_ptr(), row_lse2.data_ptr(),
                                          col_lse2.data_ptr(), a_row, a_col, s_row, s_col, weight,
                                          upstream.data_ptr(), dx.data_ptr(), dscale.data_ptr() if want_dscale else None,

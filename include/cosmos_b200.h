@@ -208,6 +208,9 @@ int cosmos_colsum(const void* src, int32_t dtype, float* dst, int64_t rows, int3
  * gradient of a row's positive (softmax terms minus their weights, nearly cancelling for a confident row) is formed
  * from it in fp32, not from the bf16 exponential. */
 int64_t cosmos_infonce_e_bytes(const cosmos_infonce_problem* p);
+/* workspace of cosmos_infonce_bwd_e: d(scale) partials, plus fp32 partial dX when the column sweep is cut into slices so
+ * that a small launch fills whole waves of SM pairs (-1: unsupported problem) */
+int64_t cosmos_infonce_bwd_e_workspace_bytes(const cosmos_infonce_problem* p, int device);
 int cosmos_infonce_fwd_e(const cosmos_infonce_problem* p, float* row_lse2, float* diag_raw, float* col_lse2, void* e_out,
                          float* off_out, void* workspace, int64_t workspace_bytes, int device, void* stream);
 int cosmos_infonce_bwd_e(const cosmos_infonce_problem* p, const void* e, const float* off, const float* diag_raw,
