@@ -211,8 +211,10 @@ int bwd_e_splits(const cosmos_infonce_problem* p, const Dims& d, int device) {
   // at most two slices: measured at the per-rank shapes of an 8-GPU job (b = 4096, N = 32768), two slices take the
   // distillation group from 3.46 to 6.92 waves (8.85 -> 8.24 ms); four slices of the CLIP group's 128 pairs cost more in
   // fp32 partials and per-item prologues than their fuller last wave returns (2.18 -> 2.30 ms)
-  const int ts = choose_t_splits(p->gx * ((d.n_row_tiles + 1) / 2), sm_count_of(device) / 2, steps);
-  return ts > 2 ? 1 : ts;
+  const int clusters = p->gx * ((d.n_row_tiles + 1) / 2), slots = sm_count_of(device) / 2;
+  if (steps < 4) return 1;
+  auto eff = [&](int c) { return static_cast<double>(c) / (static_cast<double>((c + slots - 1) / slots) * slots); };
+  return eff(2 * clusters) - 0.01 > eff(clusters) + 1e-9 ? 2 : 1;
 }
 
 }  // namespace
