@@ -554,12 +554,12 @@ int cosmos_gemm(const void* a, const void* b, void* d, const float* bias, int32_
 }
 
 int cosmos_layernorm_fwd(const void* x, int32_t x_dtype, const float* w, const float* b, void* y, int32_t y_dtype, float* mean,
-                         float* rstd, int64_t rows, int32_t dim, int device, void* stream) {
-  if (!x || !w || !b || !y || !mean || !rstd || rows < 0 || dim <= 0) return COSMOS_ERR_INVALID_ARGUMENT;
+                         float* rstd, int64_t rows, int32_t dim, float eps, int device, void* stream) {
+  if (!x || !w || !b || !y || !mean || !rstd || rows < 0 || dim <= 0 || !(eps >= 0.f)) return COSMOS_ERR_INVALID_ARGUMENT;
   if (dim > 1024 || !dtype_any(x_dtype) || !dtype_any(y_dtype)) return COSMOS_ERR_UNSUPPORTED;
   DeviceGuard g(device);
   if (!g.ok) return COSMOS_ERR_CUDA;
-  return cu_fail(cb::launch_layernorm_fwd(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim, static_cast<cudaStream_t>(stream)))
+  return cu_fail(cb::launch_layernorm_fwd(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim, eps, static_cast<cudaStream_t>(stream)))
              ? COSMOS_ERR_CUDA : COSMOS_OK;
 }
 

@@ -47,7 +47,7 @@ int launch_gemm(const GemmArgs& a, int sm_count, cudaStream_t stream, cudaError_
 
 // ---- pooler helpers (xpool.cu) ----
 cudaError_t launch_layernorm_fwd(const void* x, int x_dtype, const float* w, const float* b, void* y, int y_dtype, float* mean,
-                                 float* rstd, int64_t rows, int dim, cudaStream_t s);
+                                 float* rstd, int64_t rows, int dim, float eps, cudaStream_t s);
 cudaError_t launch_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* w, const float* mean,
                                  const float* rstd, void* dx, int dx_dtype, int accumulate, float* dw, float* db, int64_t rows,
                                  int dim, cudaStream_t s);

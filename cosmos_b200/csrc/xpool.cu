@@ -91,7 +91,7 @@ __device__ __forceinline__ void store_row(void* base, int dtype, int64_t row, in
 template <int V>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ w, const float* __restrict__ b,
-                     void* __restrict__ y, int y_dtype, float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int dim) {
+                     void* __restrict__ y, int y_dtype, float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int dim, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -110,7 +110,7 @@ layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __res
     const float d = c < dim ? v[k] - mu : 0.f;
     q += d * d;
   }
-  const float rs = rsqrtf(warp_sum(q) / dim + 1e-5f);
+  const float rs = rsqrtf(warp_sum(q) / dim + eps);
 #pragma unroll
   for (int k = 0; k < V; ++k) v[k] = (v[k] - mu) * rs * wv[k] + bv[k];
   store_row(y, y_dtype, row, dim, lane, v);
@@ -551,12 +551,12 @@ colsum_kernel(const void* __restrict__ src, int dtype, float* __restrict__ dst, 
 // launchers
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_layernorm_fwd(const void* x, int x_dtype, const float* w, const float* b, void* y, int y_dtype, float* mean,
-                                 float* rstd, int64_t rows, int dim, cudaStream_t s) {
+                                 float* rstd, int64_t rows, int dim, float eps, cudaStream_t s) {
   if (rows == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-  if (dim <= 256) layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim);
-  else if (dim <= 512) layernorm_fwd_kernel<16><<<grid, 256, 0, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim);
-  else layernorm_fwd_kernel<32><<<grid, 256, 0, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim);
+  if (dim <= 256) layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim, eps);
+  else if (dim <= 512) layernorm_fwd_kernel<16><<<grid, 256, 0, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim, eps);
+  else layernorm_fwd_kernel<32><<<grid, 256, 0, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim, eps);
   return cudaGetLastError();
 }
 

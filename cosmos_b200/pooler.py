@@ -80,14 +80,14 @@ def _colsum(src, n):
     return dst
 
 
-def _ln_fwd(x2d, w, b, out_dtype):
+def _ln_fwd(x2d, w, b, out_dtype, eps=1e-5):
     rows, dim = x2d.shape
     dev = x2d.device
     y = torch.empty(rows, dim, dtype=out_dtype, device=dev)
     mean = torch.empty(rows, dtype=torch.float32, device=dev)
     rstd = torch.empty(rows, dtype=torch.float32, device=dev)
     st = _lib.lib().cosmos_layernorm_fwd(x2d.data_ptr(), _code(x2d), w.data_ptr(), b.data_ptr(), y.data_ptr(), _code(y),
-                                         mean.data_ptr(), rstd.data_ptr(), rows, dim, dev.index, _stream(dev))
+                                         mean.data_ptr(), rstd.data_ptr(), rows, dim, float(eps), dev.index, _stream(dev))
     _lib.check(st, "layernorm_fwd")
     return y, mean, rstd
 
@@ -149,7 +149,8 @@ class _CrossPool(torch.autograd.Function):
     fuse_norm: return normalize(queries + pooled) (model.py:379-380) instead of pooled."""
 
     @staticmethod
-    def forward(ctx, tokens, queries, lnq_w, lnq_b, lnk_w, lnk_b, in_w, in_b, out_w, out_b, heads, q_per_set, qs, qq, fuse_norm):
+    def forward(ctx, tokens, queries, lnq_w, lnq_b, lnk_w, lnk_b, in_w, in_b, out_w, out_b, heads, q_per_set, qs, qq, fuse_norm,
+                eps_q=1e-5, eps_k=1e-5):
         for t in (tokens, queries, lnq_w, lnq_b, lnk_w, lnk_b, in_w, in_b, out_w, out_b):
             _lib.require_cuda(t, "pooler tensor")
         n_sets, L, C = tokens.shape
@@ -169,9 +170,9 @@ class _CrossPool(torch.autograd.Function):
         b_in = f32(in_b)
         lnq_w32, lnq_b32, lnk_w32, lnk_b32 = f32(lnq_w), f32(lnq_b), f32(lnk_w), f32(lnk_b)
 
-        xn, mean_k, rstd_k = _ln_fwd(tokens2d, lnk_w32, lnk_b32, cd)               # once per unique token set
+        xn, mean_k, rstd_k = _ln_fwd(tokens2d, lnk_w32, lnk_b32, cd, eps_k)        # once per unique token set
         kv = _linear(xn, w_kv, b_in[d:], cd)                                       # [n_sets*L, 2d]
-        fn, mean_q, rstd_q = _ln_fwd(q_in, lnq_w32, lnq_b32, cd)
+        fn, mean_q, rstd_q = _ln_fwd(q_in, lnq_w32, lnq_b32, cd, eps_q)
         qp = _linear(fn, w_q, b_in[:d], cd)                                        # [n_q, d]
         o = torch.empty(n_q, d, dtype=cd, device=dev)
         lse = torch.empty(n_q, heads, dtype=torch.float32, device=dev)
@@ -239,7 +240,7 @@ class _CrossPool(torch.autograd.Function):
         g_in_w = torch.cat([g_wq, g_wkv], dim=0).to(dt_inw)
         g_in_b = torch.cat([g_bq, g_bkv], dim=0).to(dt_inb)
         return (g_tokens.view(n_sets, L, d), g_queries.to(dt_q), g_lnq_w.to(dt_lnq), g_lnq_b.to(dt_lnq), g_lnk_w.to(dt_lnk),
-                g_lnk_b.to(dt_lnk), g_in_w, g_in_b, g_wo.to(dt_ow), g_bo.to(dt_ob), None, None, None, None, None)
+                g_lnk_b.to(dt_lnk), g_in_w, g_in_b, g_wo.to(dt_ow), g_bo.to(dt_ob), None, None, None, None, None, None, None)
 
 
 class AttentionalCrossPooler(nn.Module):
@@ -262,10 +263,14 @@ class AttentionalCrossPooler(nn.Module):
         return (self.ln_q.weight, self.ln_q.bias, self.ln_k.weight, self.ln_k.bias, self.attn.in_proj_weight,
                 self.attn.in_proj_bias, self.attn.out_proj.weight, self.attn.out_proj.bias)
 
+    def _eps(self):
+        """The eps of the two norm layers (a custom norm_layer may carry its own; nn.LayerNorm: 1e-5)."""
+        return (float(getattr(self.ln_q, "eps", 1e-5)), float(getattr(self.ln_k, "eps", 1e-5)))
+
     def forward(self, x: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
         """x: [N, L, C] keys/values, q: [N, Lq, d] queries -> [N, Lq, d] (transformer.py:225-230)."""
         N, Lq, d = q.shape
-        out = _CrossPool.apply(x, q.reshape(N * Lq, d), *self._params(), self.n_head, Lq, Lq, 1, False)
+        out = _CrossPool.apply(x, q.reshape(N * Lq, d), *self._params(), self.n_head, Lq, Lq, 1, False, *self._eps())
         return out.view(N, Lq, d)
 
 
@@ -275,4 +280,4 @@ def crossmodal_features(pooler: AttentionalCrossPooler, tokens: torch.Tensor, fe
     n = features.shape[0] // batch_size
     if n * batch_size != features.shape[0]:
         raise RuntimeError("cosmos_b200.pooler: features rows must be a multiple of batch_size")
-    return _CrossPool.apply(tokens[:batch_size], features, *pooler._params(), pooler.n_head, n, 1, batch_size, True)
+    return _CrossPool.apply(tokens[:batch_size], features, *pooler._params(), pooler.n_head, n, 1, batch_size, True, *pooler._eps())

@@ -24,6 +24,10 @@
 #include <stddef.h>
 #include <stdint.h>
 
+/* The library is built with -fvisibility=hidden: only the functions declared below are exported. */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -165,10 +169,10 @@ int cosmos_gemm(const void* a, const void* b, void* d, const float* bias, int32_
                 int64_t lda, int64_t ldb, int64_t ldd, int32_t a_kmajor, int32_t b_kmajor, int32_t in_dtype,
                 int32_t out_dtype, int32_t splits, float alpha, int device, void* stream);
 
-/* LayerNorm over the last dim (eps = 1e-5): y = (x - mean) * rstd * w + b, one row per warp.
+/* LayerNorm over the last dim (eps: the module's own, nn.LayerNorm default 1e-5): y = (x - mean) * rstd * w + b, one row per warp.
  * x: [rows, dim] of x_dtype; y: [rows, dim] bf16/f16 (y_dtype); mean, rstd: fp32 [rows] (saved for backward). */
 int cosmos_layernorm_fwd(const void* x, int32_t x_dtype, const float* w, const float* b, void* y, int32_t y_dtype,
-                         float* mean, float* rstd, int64_t rows, int32_t dim, int device, void* stream);
+                         float* mean, float* rstd, int64_t rows, int32_t dim, float eps, int device, void* stream);
 /* dx = LayerNorm backward of dy (dy_dtype) w.r.t. x, written as dx_dtype (added to dx when accumulate != 0);
  * dw, db: fp32 [dim], accumulated with atomics (caller zeroes them).                                          */
 int cosmos_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* w,
@@ -248,5 +252,8 @@ int cosmos_retrieval_ranks(const void* q, const void* g, int dtype, int32_t M, i
 
 #ifdef __cplusplus
 }
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility pop
 #endif
 #endif /* COSMOS_B200_H_ */

@@ -190,3 +190,36 @@ def test_map_tokens_matches_linear_on_the_tokens_the_pooler_reads(K, N, L, n, B,
         assert cosine(bc.grad, b32.grad) > 0.9999
     with pytest.raises(RuntimeError):
         map_tokens(tok, w, b, B)                               # CPU tensors: no fallback
+
+
+@pytest.mark.gpu
+def test_custom_norm_layer_eps_is_honoured():
+    """A norm_layer with its own eps (the reference passes `norm_layer` through, src/open_clip/transformer.py:210-223): the
+    kernels use the module's eps, not a hard-coded 1e-5.  Inputs with a tiny variance make the difference large."""
+    import functools
+    from cosmos_b200 import pooler as P
+    from cosmos_b200.pooler import AttentionalCrossPooler
+    g = torch.Generator().manual_seed(6)
+    x = (0.3 + 1e-2 * torch.randn(64, 512, generator=g))
+    w, b = 1 + 0.1 * torch.randn(512, generator=g), 0.1 * torch.randn(512, generator=g)
+    for eps in (1e-5, 1e-3, 1e-1):
+        y, _, rstd = P._ln_fwd(x.cuda(), w.cuda(), b.cuda(), torch.float32, eps)
+        assert relerr(y, O.layer_norm(x, w, b, eps)) < 1e-5, eps
+    assert relerr(P._ln_fwd(x.cuda(), w.cuda(), b.cuda(), torch.float32, 1e-1)[0], O.layer_norm(x, w, b, 1e-5)) > 0.5
+    mod = AttentionalCrossPooler(64, 64, 4, norm_layer=functools.partial(torch.nn.LayerNorm, eps=1e-2)).cuda()
+    assert mod._eps() == (1e-2, 1e-2)
+    tokens = (0.5 + 1e-2 * torch.randn(3, 7, 64, generator=g)).bfloat16().cuda()
+    q = (0.5 + 1e-2 * torch.randn(3, 2, 64, generator=g)).bfloat16().cuda()
+    got = mod(tokens, q).float().cpu()
+    p = {k: v.detach().float().cpu() for k, v in mod.state_dict().items()}
+    # the oracle's cross_pool with the module's eps
+    import oracle.cosmos_oracle as OO
+    real = OO.layer_norm
+    try:
+        OO.layer_norm = lambda t, w_, b_, eps=1e-2: real(t, w_, b_, 1e-2)
+        want = OO.cross_pool(tokens.float().cpu(), q.float().cpu(), p, 4)
+        OO.layer_norm = lambda t, w_, b_, eps=1e-5: real(t, w_, b_, 1e-5)
+        other = OO.cross_pool(tokens.float().cpu(), q.float().cpu(), p, 4)
+    finally:
+        OO.layer_norm = real
+    assert relerr(got, want) < 2e-2 and relerr(got, other) > 5 * relerr(got, want)
