@@ -204,36 +204,33 @@ infonce_bwd_e2_kernel(const __grid_constant__ CUtensorMap tmY64, BwdEParams p) {
     auto advance_pf = [&]() {
       if (++tc_pf == n_ct) { tc_pf = 0; ++j_pf; }
     };
-    uint4 e1[4], e2[4];
-    Stats s1 = load_stats(), s2 = s1;
-    load_e(e1);
-    advance_pf();
-    if (T > 1) {
-      s2 = load_stats();
-      load_e(e2);
+    // Three register sets (statistics + the four E pieces of a step) used round-robin by a loop unrolled three times: the
+    // loads of step t + 2 go into the set that was consumed at step t - 1, and NO register is moved from one set to another.
+    // (The first version rotated two sets through a third with moves; a move waits for its source, so the loads were
+    // effectively consumed one step after their issue, and the warps spent 40 % of their time - ncu: 30 % of all samples
+    // at the first use of the step's offset - waiting for them.)
+    Stats sA, sB, sC;
+    uint4 eA[4], eB[4], eC[4];
+    auto issue = [&](Stats& st, uint4 (&e)[4]) {
+      st = load_stats();
+      load_e(e);
       advance_pf();
-    }
+    };
+    sA = sB = sC = Stats{0.f, INFINITY};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) eA[k] = eB[k] = eC[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (T > 0) issue(sA, eA);
+    if (T > 1) issue(sB, eB);
 
     const bool eprof = kProf && ((blockIdx.x >> 1) % 97) == 5 && lane == 0 && (sw == 0 || sw == 15);
     long long e_wait = 0, e_work = 0, e_pre = 0, e_fence = 0, e_arrive = 0;
     uint32_t s = 0, phs = 0;
     int j = j_first, tc = tc_first;
     float lr = row_valid ? __ldg(p.row_lse2 + static_cast<size_t>(i * p.gy + j_first) * p.n_rows + grow) : INFINITY;
-    for (int t = 0; t < T; ++t) {
+    int t = 0;
+    auto step = [&](const Stats& st, const uint4 (&e_cur)[4]) {
       const long long c_top = eprof ? clock64() : 0;
       const int col0 = tc * 128 + static_cast<int>(ch) * 32;      // first column of this warp's chunk
-      const Stats st = s1;
-      uint4 e_cur[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) e_cur[k] = e1[k];
-      s1 = s2;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) e1[k] = e2[k];
-      if (t + 2 < T) {
-        s2 = load_stats();
-        load_e(e2);
-        advance_pf();
-      }
       const bool chunk_valid = col0 < p.n_cols;                  // warp-uniform
       // column factors of this chunk, relative to o = lse_col of its first column (valid whenever the chunk is)
       const float o = __shfl_sync(0xffffffffu, st.lcv, 0);
@@ -339,6 +336,17 @@ infonce_bwd_e2_kernel(const __grid_constant__ CUtensorMap tmY64, BwdEParams p) {
         ++j;
         if (j < p.gy && row_valid && t + 1 < T) lr = __ldg(p.row_lse2 + static_cast<size_t>(i * p.gy + j) * p.n_rows + grow);
       }
+      ++t;
+    };
+    while (t < T) {
+      if (t + 2 < T) issue(sC, eC);
+      step(sA, eA);
+      if (t >= T) break;
+      if (t + 2 < T) issue(sA, eA);
+      step(sB, eB);
+      if (t >= T) break;
+      if (t + 2 < T) issue(sB, eB);
+      step(sC, eC);
     }
     if (eprof)
       printf("bwd_e2 prof cluster %d cta %u warp %u: scaling warps: loads+factors %lld, stage wait %lld, scale+store %lld, proxy fence %lld, "

@@ -59,7 +59,7 @@ def raw(rep, out):
 
 launches("gpurun_out/launches_%s.csv" % tag, "profiles/launches_%s.txt" % tag)
 import os
-for k in ("bwd", "fwd", "ema", "retrieval"):
+for k in ("bwd", "bwd_e", "fwd", "colgrad", "ema", "retrieval", "pooler"):
     if not os.path.exists("gpurun_out/prof_%s_%s.ncu-rep" % (k, tag)):
         continue
     try:
