@@ -56,7 +56,7 @@ static_assert(sizeof(Misc) <= kSmemMisc, "misc smem");
 
 }  // namespace
 
-template <bool kPair>
+template <bool kPair, bool kProf>
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, FwdParams p) {
   constexpr int kStages = kPair ? 6 : 3;
@@ -146,9 +146,9 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   } else if (warp == 1) {
     if (leader) {
       // ---------------- MMA issuer (leader CTA of the pair only; whole warp waits, one elected lane issues) ----------------
-      const bool prof = (p.dbg & 1024) != 0;          // diagnostics: where the issuing warp waits
+      constexpr bool prof = kProf;                    // diagnostics (COSMOS_B200_DBG=1024): where the issuing warp waits
       long long w_acc = 0, w_y = 0;
-      const long long t_begin = clock64();
+      const long long t_begin = kProf ? clock64() : 0;
       auto wait_t = [&](uint64_t* bar, uint32_t ph, long long& acc) {
         if (prof) {
           const long long c0 = clock64();
@@ -215,9 +215,9 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                            : nullptr;       // + (step * 16 + piece) * 128 (16-byte units)
     float* off_row = keep_e ? p.off_out + static_cast<size_t>(pair) * p.n_chunks * p.n_rows + row : nullptr;
 
-    const bool eprof = (p.dbg & 1024) != 0 && (blockIdx.x % 194) == 10 && lane == 0 && (ew == 0 || ew == 7);
+    const bool eprof = kProf && (blockIdx.x % 194) == 10 && lane == 0 && (ew == 0 || ew == 7);
     long long e_wait = 0;
-    const long long e_begin = clock64();
+    const long long e_begin = kProf ? clock64() : 0;
     for (int tc = 0; tc < n_ct; ++tc) {
       const uint32_t as = tc & 1;
       if (eprof) {
@@ -299,9 +299,14 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
               continue;
             }
             need_exact = true;
-            // undo this block's row update: the exact path below redoes it from scratch
+            // undo this block's row update: the exact path below redoes it from scratch - from the accumulator, which is still
+            // in tensor memory: reading it again (rare) instead of keeping its 32 registers alive across the column reduce
+            // above takes the spills out of the common path (ncu, round 2: ~10 local-memory accesses per chunk, and the
+            // instructions behind them held ~15 % of the kernel's stall samples)
             m_run = m_before;
             l_run = l_before;
+            tmem_ld32(tmem + ((q * 32u) << 16) + as * BN + h * 64 + chunk * 32, v);
+            tmem_ld_wait();
           } else {
             if (tr < p.n_row_tiles) col_part[col0 + lane] = make_float2(NEG_INF, 0.f);
             continue;
@@ -419,28 +424,25 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 cudaError_t launch_infonce_fwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, bool pair, cudaStream_t stream) {
   const int smem_bytes = kSmemX + kSmemY + kSmemMisc;
   static_assert(kSmemX + kSmemY + kSmemMisc <= 232448, "shared memory budget");
-  cudaError_t e;
-  if (pair) {
-    e = cudaFuncSetAttribute(infonce_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(p.gy * p.gx * 2 * ((p.n_row_tiles + 1) / 2));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, infonce_fwd_kernel<true>, tmX, tmY, p);
-  }
-  e = cudaFuncSetAttribute(infonce_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  const bool prof = (p.dbg & 1024) != 0;
+  void (*kern)(CUtensorMap, CUtensorMap, FwdParams) =
+      pair ? (prof ? infonce_fwd_kernel<true, true> : infonce_fwd_kernel<true, false>)
+           : (prof ? infonce_fwd_kernel<false, true> : infonce_fwd_kernel<false, false>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return e;
-  infonce_fwd_kernel<false><<<p.gy * p.gx * p.n_row_tiles, kThreads, smem_bytes, stream>>>(tmX, tmY, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = pair ? dim3(p.gy * p.gx * 2 * ((p.n_row_tiles + 1) / 2)) : dim3(p.gy * p.gx * p.n_row_tiles);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tmX, tmY, p);
 }
 
 }  // namespace cb
