@@ -146,6 +146,8 @@ class Instrument:
         self._bwd_e = infonce._k_bwd_e
         self._bwd_e_cols = infonce._k_bwd_e_cols
         infonce._k_bwd_e_cols = self.bwd_e_cols
+        self._scale16, self._lse2_merge = infonce._k_scale16, infonce._k_lse2_merge
+        infonce._k_scale16, infonce._k_lse2_merge = self.scale16, self.lse2_merge
         infonce._k_fwd, infonce._k_loss_sums, infonce._k_bwd, infonce._k_colgrad = self.fwd, self.loss, self.bwd, self.colgrad
         infonce._k_bwd_e = self.bwd_e
 
@@ -185,6 +187,14 @@ class Instrument:
         self.launches += 1                       # column-side gradient G^T x from the stored exponentials
         fl = 2.0 * x.shape[0] * y.shape[0] * x.shape[1] * y.shape[1] * x.shape[2]
         return self._timed("colgrad", fl, self._bwd_e_cols, x, y, *a, **kw)
+
+    def scale16(self, *a, **kw):
+        self.launches += 1                       # unit gradients x upstream / stand-in (backward)
+        return self._scale16(*a, **kw)
+
+    def lse2_merge(self, *a, **kw):
+        self.launches += 1                       # merge of the all-gathered column statistics (sharded runs)
+        return self._lse2_merge(*a, **kw)
 
     def colgrad(self, g, x2d, n_c, n_cols):
         self.launches += 1                       # the column-side gradient GEMM (G^T x) on the stored tiles

@@ -74,6 +74,7 @@ class InfoNceProblem(C.Structure):
 _INFONCE_SIGS = {
     "cosmos_infonce_workspace_bytes": [C.POINTER(InfoNceProblem)],
     "cosmos_infonce_fwd": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, vp_, i64_, i32_, vp_],
+    "cosmos_scale16": [vp_, vp_, vp_, f32_, i32_, i64_, i32_, vp_],
     "cosmos_lse2_merge": [vp_, vp_, i32_, i64_, i32_, vp_],
     "cosmos_infonce_loss_sums": [C.POINTER(InfoNceProblem), vp_, vp_, vp_, i32_, i32_, vp_, vp_, i32_, vp_],
     "cosmos_infonce_bwd": [C.POINTER(InfoNceProblem), vp_, vp_, f32_, f32_, f32_, f32_, f32_, vp_, vp_, vp_, vp_, i64_, i32_, vp_],

@@ -293,6 +293,17 @@ int cosmos_infonce_fwd_e(const cosmos_infonce_problem* p, float* row_lse2, float
   return COSMOS_OK;
 }
 
+int cosmos_scale16(const void* src, void* dst, const float* num, float den, int32_t dtype, int64_t n, int device, void* stream) {
+  if (!src || !dst || !num || n < 0 || (n & 7) != 0 || !(den != 0.f)) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (dtype != COSMOS_DTYPE_BF16 && dtype != COSMOS_DTYPE_F16) return COSMOS_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (n == 0) return COSMOS_OK;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  return cu_fail(cb::launch_scale16(src, dst, num, den, dtype, static_cast<size_t>(n), static_cast<cudaStream_t>(stream)))
+             ? COSMOS_ERR_CUDA : COSMOS_OK;
+}
+
 int cosmos_lse2_merge(const float* parts, float* out, int32_t n_parts, int64_t n, int device, void* stream) {
   if (!parts || !out || n_parts <= 0 || n < 0) return COSMOS_ERR_INVALID_ARGUMENT;
   if (n == 0) return COSMOS_OK;

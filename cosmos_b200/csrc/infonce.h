@@ -95,6 +95,7 @@ cudaError_t launch_loss_sums(const float* row_lse2, const float* diag_raw, const
                              cudaStream_t stream);
 cudaError_t launch_lse2_merge(const float* parts, float* out, int n_parts, size_t n, cudaStream_t stream);
 cudaError_t launch_reduce_dx(const float* parts, int n_parts, void* dst, int dtype, size_t n, cudaStream_t stream);
+cudaError_t launch_scale16(const void* src, void* dst, const float* num, float den, int dtype, size_t n, cudaStream_t stream);
 cudaError_t launch_convert_dx(const float* src, void* dst, int dtype, size_t n, cudaStream_t stream);
 cudaError_t launch_dscale_reduce(const float* part, int n, float weight, const float* upstream, float* dscale,
                                  cudaStream_t stream);

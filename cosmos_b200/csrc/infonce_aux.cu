@@ -145,6 +145,38 @@ cudaError_t launch_reduce_dx(const float* parts, int n_parts, void* dst, int dty
   return cudaGetLastError();
 }
 
+// dst[k] = src[k] * (*num / den), 16-bit in and out, product formed in fp32 and rounded once (the unit gradients of the
+// stored-exponential route times upstream / stand-in: one vectorised pass instead of ATen's mixed-dtype elementwise kernel)
+__global__ void __launch_bounds__(256)
+scale16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const float* __restrict__ num, float den, int fmt, size_t n8) {
+  const float f = __ldg(num) / den;
+  for (size_t k = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; k < n8; k += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const uint4 v = __ldcs(src + k);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float a, b;
+      if (fmt) {
+        a = __uint_as_float(w[q] << 16);
+        b = __uint_as_float(w[q] & 0xffff0000u);
+      } else {
+        const __half2 h = *reinterpret_cast<const __half2*>(&w[q]);
+        a = __low2float(h);
+        b = __high2float(h);
+      }
+      o[q] = pack2(a * f, b * f, fmt);
+    }
+    dst[k] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+cudaError_t launch_scale16(const void* src, void* dst, const float* num, float den, int dtype, size_t n, cudaStream_t stream) {
+  scale16_kernel<<<148 * 8, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), num, den,
+                                              dtype == 1 ? 1 : 0, n / 8);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_convert_dx(const float* src, void* dst, int dtype, size_t n, cudaStream_t stream) {
   const size_t n4 = n / 4;   // n is a multiple of 64
   convert_dx_kernel<<<148 * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst),

@@ -150,6 +150,16 @@ def _k_bwd_e_cols(x, y, label_offset, scale, e, off, diag_raw, row_lse2, col_lse
     return dy[0] if splits == 1 else dy.sum(0)
 
 
+def _k_scale16(src: torch.Tensor, num: torch.Tensor, den: float) -> torch.Tensor:
+    """src * (num / den) for a 16-bit tensor and a device scalar num (fp32 [1]); a new tensor of src's dtype."""
+    dev = src.device
+    dst = torch.empty_like(src)
+    st = _lib.lib().cosmos_scale16(src.data_ptr(), dst.data_ptr(), num.data_ptr(), float(den), _lib.torch_dtype_code(src.dtype),
+                                   src.numel(), dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(st, "scale16")
+    return dst
+
+
 def _k_lse2_merge(parts: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     """parts [W, ...] fp32 (every rank's partial column log2-sum-exp, all-gathered) -> out [...]: their log2-sum-exp2."""
     dev = parts.device
@@ -596,8 +606,8 @@ def _eager_grads(g: _Group, up: torch.Tensor, in_dtypes, needs_rows, needs_cols,
     """The gradients of one group for the upstream gradient `up` (fp32 [1]) from its unit gradients."""
     factor = up / g.pre
     grads: List[Optional[torch.Tensor]] = []
-    # one pass; a 0-dim factor does not promote the result: it keeps the stack dtype (products formed in fp32, rounded once)
-    d_rows = torch.mul(g.dx_unit, factor.reshape(())) if any(needs_rows) else None
+    # one vectorised pass, products formed in fp32 and rounded once to the stack dtype
+    d_rows = _k_scale16(g.dx_unit, up.contiguous(), g.pre) if any(needs_rows) else None
     for k in range(g.n_r):
         grads.append(d_rows[k].to(in_dtypes[k]) if (d_rows is not None and needs_rows[k]) else None)
     d_cols = None

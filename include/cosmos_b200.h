@@ -121,6 +121,11 @@ int64_t cosmos_infonce_workspace_bytes(const cosmos_infonce_problem* p);
 int cosmos_infonce_fwd(const cosmos_infonce_problem* p, float* row_lse2, float* diag_raw, float* col_lse2,
                        void* workspace, int64_t workspace_bytes, int device, void* stream);
 
+/* dst[k] = src[k] * (*num / den) for n 16-bit values (n % 8 == 0, 16-byte aligned; products in fp32, rounded once): the
+ * gradients of the stored-exponential route are formed in the forward for a power-of-two stand-in `den` of the upstream
+ * gradient `*num` (a device scalar: GradScaler's factor, src/training/train.py:62-66) and scaled when backward() learns it. */
+int cosmos_scale16(const void* src, void* dst, const float* num, float den, int32_t dtype, int64_t n, int device, void* stream);
+
 /* Merge of per-rank partial column statistics (row-sharded forward, src/open_clip/loss.py:21-65 gathers the features
  * instead): parts [n_parts][n] fp32 log2-sum-exp values (every rank's col_lse2, all-gathered), out [n] their
  * log2-sum-exp2.  -inf (a rank without rows) is the neutral element.                                              */

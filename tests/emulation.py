@@ -69,6 +69,11 @@ def emu_bwd(x, y, label_offset, scale, row_lse2, col_lse2, a_row, a_col, s_row, 
     return dx, dscale
 
 
+def emu_scale16(src, num, den):
+    """cosmos_scale16: src * (num / den), products in fp32, in src's dtype."""
+    return (src.float() * (float(num) / den)).to(src.dtype)
+
+
 def emu_lse2_merge(parts, out):
     """cosmos_lse2_merge: log2-sum-exp2 over the leading (rank) dimension."""
     out.copy_((torch.logsumexp(parts.double() * LN2, dim=0) / LN2).float())
@@ -130,6 +135,7 @@ def install(monkeypatch=None):
         monkeypatch.setattr(infonce, "_k_bwd_e", emu_bwd_e)
         monkeypatch.setattr(infonce, "_k_colgrad", emu_colgrad)
         monkeypatch.setattr(infonce, "_k_lse2_merge", emu_lse2_merge)
+        monkeypatch.setattr(infonce, "_k_scale16", emu_scale16)
         monkeypatch.setattr(infonce, "_k_bwd_e_cols", emu_bwd_e_cols)
         monkeypatch.setattr(_lib, "require_cuda", lambda t, what: None)
         monkeypatch.setattr(infonce, "compute_dtype", lambda dt: dt)
@@ -138,6 +144,7 @@ def install(monkeypatch=None):
         infonce._k_colgrad = emu_colgrad
         infonce._k_bwd_e = emu_bwd_e
         infonce._k_lse2_merge = emu_lse2_merge
+        infonce._k_scale16 = emu_scale16
         infonce._k_bwd_e_cols = emu_bwd_e_cols
         _lib.require_cuda = lambda t, what: None
         infonce.compute_dtype = lambda dt: dt
