@@ -61,19 +61,22 @@ def _dgrad(g, w, out_dtype):
     return _gemm(g, w, out, M, K, N, g.stride(0), w.stride(0), True, False)
 
 
-def _wgrad(g, x):
-    """g [R, N]^T @ x [R, K] -> [N, K] fp32   (weight gradient of x @ w^T); contraction over the rows, split for parallelism"""
+def _wgrad(g, x, out=None):
+    """g [R, N]^T @ x [R, K] -> [N, K] fp32   (weight gradient of x @ w^T); contraction over the rows, split for parallelism.
+    out: a ZEROED [N, K] fp32 view to accumulate into (one memset for all of a step's parameter gradients)."""
     R, N = g.shape
     K = x.shape[1]
-    out = torch.zeros(N, K, dtype=torch.float32, device=g.device)
+    if out is None:
+        out = torch.zeros(N, K, dtype=torch.float32, device=g.device)
     bn = 256 if K >= 256 else 128                      # output tile of the GEMM kernel (csrc/gemm.cu)
     tiles = ((N + 127) // 128) * ((K + bn - 1) // bn)
     splits = max(1, min((R + 1023) // 1024, 148 // tiles if tiles <= 148 else 1))    # one wave of persistent CTAs
     return _gemm(g, x, out, N, K, R, g.stride(0), x.stride(0), False, False, splits=splits)
 
 
-def _colsum(src, n):
-    dst = torch.zeros(n, dtype=torch.float32, device=src.device)
+def _colsum(src, n, dst=None):
+    if dst is None:
+        dst = torch.zeros(n, dtype=torch.float32, device=src.device)
     st = _lib.lib().cosmos_colsum(src.data_ptr(), _code(src), dst.data_ptr(), src.shape[0], n, src.stride(0), src.device.index,
                                   _stream(src.device))
     _lib.check(st, "colsum")
@@ -92,11 +95,12 @@ def _ln_fwd(x2d, w, b, out_dtype, eps=1e-5):
     return y, mean, rstd
 
 
-def _ln_bwd(dy, x2d, w, mean, rstd, dx, accumulate):
+def _ln_bwd(dy, x2d, w, mean, rstd, dx, accumulate, dw=None, db=None):
     rows, dim = x2d.shape
     dev = x2d.device
-    dw = torch.zeros(dim, dtype=torch.float32, device=dev)
-    db = torch.zeros(dim, dtype=torch.float32, device=dev)
+    if dw is None:
+        dw = torch.zeros(dim, dtype=torch.float32, device=dev)
+        db = torch.zeros(dim, dtype=torch.float32, device=dev)
     st = _lib.lib().cosmos_layernorm_bwd(dy.data_ptr(), _code(dy), x2d.data_ptr(), _code(x2d), w.data_ptr(), mean.data_ptr(),
                                          rstd.data_ptr(), dx.data_ptr(), _code(dx), int(accumulate), dw.data_ptr(), db.data_ptr(),
                                          rows, dim, dev.index, _stream(dev))
@@ -164,8 +168,8 @@ class _CrossPool(torch.autograd.Function):
         f32 = lambda t: t.detach().to(torch.float32).contiguous()
         tokens2d = tokens.detach().contiguous().view(n_sets * L, C)
         q_in = queries.detach().contiguous()
-        w_q = in_w.detach()[:d].to(cd).contiguous()
-        w_kv = in_w.detach()[d:].to(cd).contiguous()
+        w_in = in_w.detach().to(cd).contiguous()       # one cast of the packed projection; its query / key-value parts are row ranges
+        w_q, w_kv = w_in[:d], w_in[d:]
         w_o = out_w.detach().to(cd).contiguous()
         b_in = f32(in_b)
         lnq_w32, lnq_b32, lnk_w32, lnk_b32 = f32(lnq_w), f32(lnq_b), f32(lnk_w), f32(lnk_b)
@@ -205,6 +209,13 @@ class _CrossPool(torch.autograd.Function):
         n_q = q_in.shape[0]
         lib = _lib.lib()
         g_out = g_out.contiguous()
+        # every parameter gradient of the step accumulates (split-K GEMMs, column sums, LayerNorm partials use fp32 atomics)
+        # into ONE zeroed workspace: a single memset instead of ten, and the packed in-projection gradient needs no torch.cat
+        ws = torch.zeros(3 * d * d + d * d + 3 * d + d + 4 * d, dtype=torch.float32, device=dev)
+        g_in_w, g_wo = ws[:3 * d * d].view(3 * d, d), ws[3 * d * d:4 * d * d].view(d, d)
+        vec = ws[4 * d * d:]
+        g_in_b, g_bo = vec[:3 * d], vec[3 * d:4 * d]
+        g_lnq_w, g_lnq_b, g_lnk_w, g_lnk_b = vec[4 * d:5 * d], vec[5 * d:6 * d], vec[6 * d:7 * d], vec[7 * d:8 * d]
         if fuse_norm:
             g_z32 = torch.empty(n_q, d, dtype=torch.float32, device=dev)
             g_p = torch.empty(n_q, d, dtype=cd, device=dev)
@@ -212,13 +223,13 @@ class _CrossPool(torch.autograd.Function):
                                         g_z32.data_ptr(), g_p.data_ptr(), _code(g_p), n_q, d, dev.index, _stream(dev))
             _lib.check(st, "addnorm_bwd")
             g_queries = g_z32                                  # residual branch; the LN_q path is accumulated below
-            g_bo = _colsum(g_z32, d)
+            _colsum(g_z32, d, g_bo)
         else:
             g_p = g_out.to(cd)
             g_queries = torch.zeros(n_q, d, dtype=torch.float32, device=dev)
-            g_bo = _colsum(g_out, d)
+            _colsum(g_out, d, g_bo)
         # out-projection
-        g_wo = _wgrad(g_p, o)                                  # [d, d]
+        _wgrad(g_p, o, g_wo)                                   # [d, d]
         g_o = _dgrad(g_p, w_o, cd)                             # [n_q, d]
         # attention core
         dq = torch.empty(n_q, d, dtype=cd, device=dev)
@@ -227,20 +238,19 @@ class _CrossPool(torch.autograd.Function):
                                       _code(qp), n_sets, L, d, heads, q_per_set, qs, qq, dev.index, _stream(dev))
         _lib.check(st, "attn_core_bwd")
         # query in-projection + LayerNorm_q
-        g_wq = _wgrad(dq, fn)
-        g_bq = _colsum(dq, d)
+        _wgrad(dq, fn, g_in_w[:d])
+        _colsum(dq, d, g_in_b[:d])
         g_fn = _dgrad(dq, w_q, cd)
-        g_lnq_w, g_lnq_b = _ln_bwd(g_fn, q_in, lnq_w32, mean_q, rstd_q, g_queries, True)
+        _ln_bwd(g_fn, q_in, lnq_w32, mean_q, rstd_q, g_queries, True, g_lnq_w, g_lnq_b)
         # key/value in-projection + LayerNorm_k (once per unique token set)
-        g_wkv = _wgrad(dkv, xn)
-        g_bkv = _colsum(dkv, 2 * d)
+        _wgrad(dkv, xn, g_in_w[d:])
+        _colsum(dkv, 2 * d, g_in_b[d:])
         g_xn = _dgrad(dkv, w_kv, cd)
         g_tokens = torch.empty(n_sets * L, d, dtype=dt_tok, device=dev)
-        g_lnk_w, g_lnk_b = _ln_bwd(g_xn, tokens2d, lnk_w32, mean_k, rstd_k, g_tokens, False)
-        g_in_w = torch.cat([g_wq, g_wkv], dim=0).to(dt_inw)
-        g_in_b = torch.cat([g_bq, g_bkv], dim=0).to(dt_inb)
+        _ln_bwd(g_xn, tokens2d, lnk_w32, mean_k, rstd_k, g_tokens, False, g_lnk_w, g_lnk_b)
         return (g_tokens.view(n_sets, L, d), g_queries.to(dt_q), g_lnq_w.to(dt_lnq), g_lnq_b.to(dt_lnq), g_lnk_w.to(dt_lnk),
-                g_lnk_b.to(dt_lnk), g_in_w, g_in_b, g_wo.to(dt_ow), g_bo.to(dt_ob), None, None, None, None, None, None, None)
+                g_lnk_b.to(dt_lnk), g_in_w.to(dt_inw), g_in_b.to(dt_inb), g_wo.to(dt_ow), g_bo.to(dt_ob), None, None, None, None,
+                None, None, None)
 
 
 class AttentionalCrossPooler(nn.Module):

@@ -223,3 +223,37 @@ def test_custom_norm_layer_eps_is_honoured():
     finally:
         OO.layer_norm = real
     assert relerr(got, want) < 2e-2 and relerr(got, other) > 5 * relerr(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,L,B,n,heads,seed", [(512, 77, 16, 8, 8, 1), (512, 196, 16, 8, 8, 2), (512, 49, 5, 8, 8, 3), (768, 197, 4, 2, 12, 4)])
+def test_pooler_meets_north_star_tolerance_on_16bit_values(d, L, B, n, heads, seed):
+    """The north_star tolerance (gradient cosine >= 0.9999) for the pooler, measured the way it is defined for the loss: against
+    the fp32 oracle evaluated on the SAME bf16-valued tokens, features and matrix weights (autocast hands the reference module
+    exactly those).  What is left is the kernels' own arithmetic: bf16 intermediates of the LayerNorm -> projection ->
+    attention -> projection chain.  Measured (tools/pooler_parity.py, profiles/pooler_parity_r02.txt): output relative L2
+    error 2.4e-3, every gradient cosine >= 0.99998, norms within 3e-4.  The looser tolerances of the fixture tests above are
+    against the reference in fp32 on UN-rounded inputs and weights: there the rounding of the inputs dominates."""
+    from cosmos_b200.pooler import AttentionalCrossPooler, crossmodal_features
+    params, tokens, feats, w = O.make_pooler_case(d, L, B, n, seed)
+    r16 = lambda t: t.bfloat16().float()
+    p32 = {k: (r16(v) if v.dim() == 2 else v.clone()).requires_grad_(True) for k, v in params.items()}
+    t32, f32 = r16(tokens).requires_grad_(True), r16(feats).requires_grad_(True)
+    ref = O.cosmos_crossmodal(f32, t32, p32, heads, B)
+    (ref * w).sum().backward()
+    mod = AttentionalCrossPooler(d, d, heads).cuda()
+    mod.load_state_dict({k: (r16(v) if v.dim() == 2 else v) for k, v in params.items()})
+    tok = tokens.bfloat16().cuda().requires_grad_(True)
+    f = feats.bfloat16().cuda().requires_grad_(True)
+    xm = crossmodal_features(mod, tok, f, B)
+    (xm.float() * w.cuda()).sum().backward()
+    assert relerr(xm.float(), ref.detach()) < 5e-3
+    assert cosine(f.grad.float(), f32.grad) >= 0.9999 and cosine(tok.grad.float(), t32.grad) >= 0.9999
+    assert abs(float(tok.grad.float().norm().cpu() / t32.grad.norm()) - 1) < 2e-3
+    for k, p in mod.named_parameters():
+        g, gr = p.grad, p32[k].grad
+        if k == "attn.in_proj_bias":          # the key third is exactly zero in exact arithmetic (softmax shift invariance)
+            sel = torch.cat([torch.arange(0, d), torch.arange(2 * d, 3 * d)])
+            g, gr = g[sel], gr[sel]
+        assert cosine(g, gr) >= 0.9999, (k, cosine(g, gr))
+        assert abs(float(g.float().norm().cpu() / gr.norm()) - 1) < 2e-3, k
