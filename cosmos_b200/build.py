@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "libcosmos_b200.so")
 SELFTEST = os.path.join(HERE, "selftest_sm100")
 STAMP = os.path.join(HERE, ".build_stamp")
 
-LIB_SOURCES = ["api.cu", "ema.cu", "infonce_fwd.cu", "infonce_fwd2.cu", "infonce_bwd.cu", "infonce_bwd_pair.cu", "infonce_bwd_quad.cu", "infonce_bwd_e2.cu", "infonce_bwd_e2t.cu", "infonce_aux.cu", "xpool.cu", "gemm.cu", "retrieval.cu"]
+LIB_SOURCES = ["api.cu", "ema.cu", "infonce_fwd.cu", "infonce_bwd.cu", "infonce_bwd_pair.cu", "infonce_bwd_quad.cu", "infonce_bwd_e2.cu", "infonce_bwd_e2t.cu", "infonce_aux.cu", "xpool.cu", "gemm.cu", "retrieval.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-diag-suppress", "177"]
 

@@ -43,13 +43,6 @@ int dbg_flags() {
   static const int v = env_int("COSMOS_B200_DBG", 0);
   return v;
 }
-// COSMOS_B200_FWD=2: second-generation forward epilogue (infonce_fwd2.cu).  Measured in round 2 (profiles/README_r02.md): 37 %
-// fewer instructions, equal in isolation, 23 % SLOWER inside the step - the forward is bound by L2 -> SM traffic, not by
-// its epilogue's issue slots - so the first generation stays the default.
-int fwd_generation() {
-  static const int v = env_int("COSMOS_B200_FWD", 1);
-  return v;
-}
 int bwd_t_splits() {
   static const int v = env_int("COSMOS_B200_TSPLIT", 1);
   return v;
@@ -287,7 +280,7 @@ int cosmos_infonce_fwd_e(const cosmos_infonce_problem* p, float* row_lse2, float
   fp.n_chunks = (p->n_cols + 31) / 32;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // (the single-CTA kernel, COSMOS_B200_DBG=4, only has the first-generation epilogue)
-  if (cu_fail((pair && fwd_generation() == 2) ? cb::launch_infonce_fwd2(tmX, tmY, fp, s) : cb::launch_infonce_fwd(tmX, tmY, fp, pair, s)))
+  if (cu_fail(cb::launch_infonce_fwd(tmX, tmY, fp, pair, s)))
     return COSMOS_ERR_CUDA;
   if (cu_fail(cb::launch_col_combine(fp.col_part, col_lse2, d.pairs, d.n_slabs, p->n_cols, s))) return COSMOS_ERR_CUDA;
   return COSMOS_OK;

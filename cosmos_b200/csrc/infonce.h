@@ -49,8 +49,6 @@ struct BwdParams {
 };
 
 cudaError_t launch_infonce_fwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, bool pair, cudaStream_t stream);
-// second-generation epilogue (infonce_fwd2.cu; CTA pairs): 4 x 8 values per thread, one lazily updated offset per warp
-cudaError_t launch_infonce_fwd2(const CUtensorMap& tmX, const CUtensorMap& tmY, const FwdParams& p, cudaStream_t stream);
 cudaError_t launch_infonce_bwd(const CUtensorMap& tmX, const CUtensorMap& tmY, const BwdParams& p, cudaStream_t stream);
 
 cudaError_t launch_infonce_bwd_pair(const CUtensorMap& tmX, const CUtensorMap& tmY64, const CUtensorMap& tmY128, const BwdParams& p,
