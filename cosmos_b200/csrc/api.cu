@@ -167,7 +167,7 @@ int check_problem(const cosmos_infonce_problem* p, Dims* d) {
   d->n_row_tiles = (p->n_rows + cb::kFwdBM - 1) / cb::kFwdBM;
   d->n_col_tiles_fwd = (p->n_cols + cb::kFwdBN - 1) / cb::kFwdBN;
   d->n_col_tiles_bwd = (p->n_cols + cb::kBwdBN - 1) / cb::kBwdBN;
-  d->n_slabs = d->n_row_tiles * 4;
+  d->n_slabs = d->n_row_tiles;      // column partials: one per 128-row tile (merged over its four 32-row slabs in the CTA)
   d->ks = p->dim / 64;
   d->n_parts = (p->dim + cb::kBwdDP - 1) / cb::kBwdDP;
   return COSMOS_OK;

@@ -14,7 +14,7 @@ constexpr int kBwdDP = 256;  // embedding columns of dX one backward CTA accumul
 
 struct FwdParams {
   int gx, gy, n_rows, n_cols, ks, label_offset;
-  int n_row_tiles, n_col_tiles, n_slabs;  // n_slabs = 4 * n_row_tiles (32-row slabs)
+  int n_row_tiles, n_col_tiles, n_slabs;  // n_slabs = n_row_tiles (column partials per 128-row tile)
   uint32_t idesc;
   int dbg;  // diagnostics only (COSMOS_B200_DBG): 1 = skip epilogue math, 2 = skip MMA issue, 1024 = print stall counters
   const float* scale;

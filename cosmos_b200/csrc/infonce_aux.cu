@@ -1,4 +1,4 @@
-// Small HBM-bound helpers around the InfoNCE tile kernels: merge of per-slab column statistics,
+// Small HBM-bound helpers around the InfoNCE tile kernels: merge of per-row-tile column statistics,
 // per-pair loss sums, and the deterministic reduction of the per-CTA dscale partials.
 #include "common.cuh"
 #include "infonce.h"

@@ -1,12 +1,18 @@
-// InfoNCE backward from STORED exponentials (dim 512), second generation: 16 independent scaling warps.
+// InfoNCE backward from STORED exponentials (dim 512): 16 independent scaling warps, dX = G Y.
 //
-// Same contract and data layout as infonce_bwd_e.cu (read its header for the math): the forward kept
-//     e = 2^(s2 - m)  (bf16, tiles of [16 pieces of 8 columns][128 rows][8])  and  m  ([pair][32-column chunk][row]),
-// the gradient of a logit is  G = e * (a_row 2^(m - lse_row[r]) + a_col 2^(m - lse_col[c])) - (a_row + a_col)[c == label r],
-// and the only contraction left is dX = G Y, accumulated for 128 rows x 512 embedding columns in the whole tensor
-// memory of the SM (CTA pair, tcgen05 cta_group::2, M = 256).
+// The forward (infonce_fwd.cu, cosmos_infonce_fwd_e) kept, for every logit s2 (log2 units) of a row block,
+//     e = 2^(s2 - m)  (bf16; one contiguous 32 KB image per (pair, 128-row tile, 128-column step):
+//                      [4 slabs of 32 rows][16 pieces of 8 columns][32 rows][8])   and
+//     m              (fp32, [pair][32-column chunk][row]: the offset the chunk's exponentials are relative to).
+// With the final log-sum-exps the gradient of a logit is
+//     G = e * (a_row 2^(m - lse_row[r]) + a_col 2^(m - lse_col[c])) - (a_row + a_col)[c == label r]
+// - no exponential per element, no X Y^T - and the only contraction left is dX = G Y, accumulated for 128 rows x 512
+// embedding columns in the whole tensor memory of the SM (CTA pair, tcgen05 cta_group::2, M = 256).  The positive's own
+// gradient is formed in fp32 from the forward's diag_raw (positive_grad), not from its bf16 exponential, and
+// d(scale) = sum_r <x_r, (G Y)_r> is read off the fp32 accumulators at the end.
 //
-// What the in-kernel counters of the first generation showed (profiles/README_r02.md): its 8 scaling warps needed ~4000
+// What the in-kernel counters of the first generation of this kernel (8 scaling warps, a CTA-wide bar.red per step, L2
+// prefetch role; removed) showed (profiles/README_r02.md): its 8 scaling warps needed ~4000
 // cycles per 128-column step - the tensor core needs 2048 - because every step was one serial chain per warp: wait for
 // the E registers loaded a step earlier (L2 / HBM latency under load exceeded a step), a 256-thread bar.red that publishes
 // the step's column factors, the dependent unpack - FMA - pack - store chain of 64 elements with two warps per scheduler,

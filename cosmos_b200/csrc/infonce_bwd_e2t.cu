@@ -8,7 +8,7 @@
 // row tensor i, 128 at a step:
 //   16 scaling warps: the E tile of (i, j, row tile, column tile) from global memory into registers two steps ahead, E -> G
 //        with the same factors as the row pass (G = e * (a_row 2^(m - lse_row[r]) + a_col 2^(m - lse_col[c])) - positives),
-//        stored into the same [16 pieces of 8 columns][128 rows][8] image in shared memory.  Read with the contiguous
+//        stored into a [16 pieces of 8 columns][128 rows][8] image in shared memory (the G stage of the row pass).  Read with the contiguous
 //        dimension as M, that image IS the MN-major operand A = G^T without swizzle: core matrix = 8 rows (K) x 16 bytes
 //        (8 columns, M), next 8 rows + 128 B (LBO), next 8 columns + 2048 B (SBO).  No transpose is ever executed.
 //   B = the X rows of the step (TMA, 128-byte swizzle, MN-major like the Y slabs of the row pass), each CTA of the pair

@@ -7,7 +7,7 @@
 // (<= 8 K-slabs of 16 KB) while 256-column tiles of Y_j stream through a TMA ring.
 // kPair = true (the product path): two CTAs on neighbouring SMs form a cluster and run ONE
 // tcgen05.mma.cta_group::2 (M = 256) per K step: each CTA holds its own 128 rows of X and only HALF of
-// every Y tile (128 columns, 16 KB per stage, 6 stages), which halves the L2->SM operand traffic that
+// every Y tile (128 columns, 16 KB per stage, 5 stages), which halves the L2->SM operand traffic that
 // bounds the single-CTA version.  CTA 0 of the pair issues the MMAs; TMA loads of both CTAs complete on
 // its mbarriers; tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs.
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-19 epilogue
@@ -15,8 +15,10 @@
 //
 // Row statistics are thread-local (one thread = one row): running max / sum in log2 units.
 // Column statistics need a reduction over rows: a 31-shuffle warp transpose-reduce per 32x32 block
-// gives lane L the (max, sum) of column L over the warp's 32 rows, written as a partial to the
-// workspace [pair][32-row slab][column]; col_combine_kernel (infonce_aux.cu) merges the slabs.
+// gives lane L the (max, sum) of column L over the warp's 32 rows; the four warps that hold the same
+// columns of the tile's four 32-row slabs merge them through shared memory (four buffers, an mbarrier each:
+// only the chunk's merger waits) and ONE partial per tile goes to the workspace [pair][128-row tile][column];
+// col_combine_kernel (infonce_aux.cu) merges the tiles.
 //
 // Reference semantics: src/open_clip/loss.py:103-142 (get_logits + the two F.cross_entropy calls);
 // the positive of local row r is column label_offset + r (loss.py:90-101 with rank offset).
@@ -31,9 +33,9 @@ namespace {
 constexpr int BM = kFwdBM, BN = kFwdBN;
 constexpr int kSlabX = BM * 64 * 2;    // 16 KB : 128 rows x 64 elements
 constexpr int kSmemX = 8 * kSlabX;     // 128 KB
-constexpr int kSmemY = 96 * 1024;      // Y ring: 3 x 32 KB (single CTA) or 6 x 16 KB (pair)
-constexpr int kMaxStages = 6;
-constexpr int kSmemMisc = 3072;
+constexpr int kSmemY = 80 * 1024;      // Y ring: 2 x 32 KB (single CTA, diagnostics) or 5 x 16 KB (pair)
+constexpr int kMaxStages = 5;
+constexpr int kSmemMisc = 19456;
 constexpr int kEpiWarps = 16;            // 4 TMEM lane quarters x 4 column groups of 64: the statistics loop is latency-bound,
 constexpr int kThreads = 128 + 32 * kEpiWarps;   // 4 warps per scheduler hide what 2 could not
 constexpr int kEpiThreads = 32 * kEpiWarps;
@@ -51,6 +53,10 @@ struct Misc {
   uint32_t tmem_slot;
   uint32_t pad[5];
   float bcast[kEpiWarps][32];
+  // column partials of a chunk, (max2, sum) per warp and column, four buffers deep: the four warps that hold the four 32-row
+  // slabs of the same columns merge them here, so one partial per 128-row tile goes to memory instead of four
+  uint64_t xbar[4][4];                   // [column group][buffer]: one arrive per warp of the group
+  float2 xch[4][kEpiWarps][32];
 };
 static_assert(sizeof(Misc) <= kSmemMisc, "misc smem");
 
@@ -59,9 +65,10 @@ static_assert(sizeof(Misc) <= kSmemMisc, "misc smem");
 template <bool kPair, bool kProf>
 __global__ void __launch_bounds__(kThreads, 1)
 infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, FwdParams p) {
-  constexpr int kStages = kPair ? 6 : 3;
-  constexpr int kStageY = kSmemY / kStages;                       // bytes of Y this CTA loads per K step
+  constexpr int kStages = kPair ? 5 : 2;
   constexpr int kLoadCols = kPair ? BN / 2 : BN;                  // Y rows (= S columns) this CTA loads
+  constexpr int kStageY = kLoadCols * 64 * 2;                     // bytes of Y this CTA loads per K step
+  static_assert(kStages * kStageY <= kSmemY, "Y ring");
   constexpr uint32_t kCtas = kPair ? 2 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -96,6 +103,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       mbar_init(&misc->acc_full[s], 1);
       mbar_init(&misc->acc_empty[s], (p.dbg & 16) ? kCtas * kEpiThreads : kCtas * kEpiWarps);   // per-warp (or per-thread) arrives of both CTAs
     }
+    for (int g = 0; g < 16; ++g) mbar_init(&misc->xbar[g >> 2][g & 3], 4);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -205,8 +213,33 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const bool fast_ok = k2 > 0.f && !(p.dbg & 32);
 
     float m_run = NEG_INF, l_run = 0.f, diag = 0.f;
-    float2* col_part = p.col_part + (static_cast<size_t>(pair) * p.n_slabs + tr * 4 + q) * p.n_cols;
-    // stored-exponential route (infonce_bwd_e.cu): this row's 2^(s2 - m_run) of every chunk as bf16, and m_run itself
+    float2* col_part = p.col_part + (static_cast<size_t>(pair) * p.n_slabs + tr) * p.n_cols;       // n_slabs = row tiles
+    // Publish this warp's (max2, sum) of the chunk's 32 columns.  The four warps of a column group take turns as the chunk's
+    // merger: everybody arrives on the buffer's mbarrier (non-blocking), only the merger waits - a CTA-style barrier per chunk
+    // made the forward with E stores 2 % slower (a warp held up by its stores held up three others).  Four buffers: before a
+    // warp overwrites buffer b (chunk c + 4) it has been the merger of a chunk after c, for which every warp had already
+    // written - i.e. had finished reading chunk c.  Fixed merge order: deterministic.
+    uint32_t cc = 0;                // chunks done, the same sequence in the four warps of a group
+    auto publish = [&](int col0, float pm, float ps) {
+      const uint32_t bsel = cc & 3;
+      misc->xch[bsel][ew][lane] = make_float2(pm, ps);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&misc->xbar[h][bsel]);
+      if (q == bsel) {
+        mbar_wait(&misc->xbar[h][bsel], (cc >> 2) & 1);
+        float2 a[4];
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) a[qq] = misc->xch[bsel][h * 4 + qq][lane];
+        const float m = fmaxf(fmaxf(a[0].x, a[1].x), fmaxf(a[2].x, a[3].x));
+        float sum = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq)
+          if (a[qq].x != NEG_INF) sum = fmaf(a[qq].y, ex2(a[qq].x - m), sum);
+        if (tr < p.n_row_tiles && col0 + static_cast<int>(lane) < p.n_cols) col_part[col0 + lane] = make_float2(m, sum);
+      }
+      ++cc;
+    };
+    // stored-exponential route (infonce_bwd_e2.cu, infonce_bwd_e2t.cu): this row's 2^(s2 - m_run) of every chunk as bf16, and m_run itself
     // Layout of e_out: one contiguous 32 KB image per (pair, 128-row tile, 128-column step): [4 slabs of 32 rows][16 pieces of 8
     // columns][32 rows][8 elements] - a warp's store of one piece is 512 contiguous bytes, its four pieces of a chunk 2 KB.
     const bool keep_e = p.e_out != nullptr && row_valid && tr < p.n_row_tiles;
@@ -295,7 +328,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             // Every significant term of a column is a normal fp32 number iff the column sum is not tiny relative
             // to 2^M_w (DESIGN.md "one-exp statistics"); otherwise redo this block with true column maxima.
             if (__all_sync(0xffffffffu, csum >= 8.0779e-28f)) {   // 2^-90
-              if (tr < p.n_row_tiles) col_part[col0 + lane] = make_float2(mw, csum);
+              publish(col0, mw, csum);
               continue;
             }
             need_exact = true;
@@ -308,7 +341,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             tmem_ld32(tmem + ((q * 32u) << 16) + as * BN + h * 64 + chunk * 32, v);
             tmem_ld_wait();
           } else {
-            if (tr < p.n_row_tiles) col_part[col0 + lane] = make_float2(NEG_INF, 0.f);
+            publish(col0, NEG_INF, 0.f);
             continue;
           }
         }
@@ -372,7 +405,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
         __syncwarp();
         const float csum = warp_transpose_reduce(t, lane, OpAdd());
-        if (tr < p.n_row_tiles && col0 + static_cast<int>(lane) < p.n_cols) col_part[col0 + lane] = make_float2(cmx, csum);
+        publish(col0, cmx, csum);
       }
       tc_fence_before();
       if (p.dbg & 16) {

@@ -44,20 +44,4 @@ inline int make_stack_map(CUtensorMap* map, const void* base, int is_bf16, uint6
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
-// The stored exponentials (infonce_fwd_kernel e_out): `pieces` consecutive [128 rows][8 elements] bf16 blocks of 2 KB.  A box of
-// 8 pieces (one 64-column slab of a tile) is 16 contiguous KB and lands unswizzled as [piece][row][16 bytes]: the K-major
-// core-matrix layout tcgen05 reads with LBO = 2048 (next 8 k), SBO = 128 (next 8 rows).
-inline int make_piece_map(CUtensorMap* map, const void* base, uint64_t pieces) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  if (fn == nullptr) return -1;
-  cuuint64_t gdim[3] = {8, 128, pieces};
-  cuuint64_t gstride[2] = {16, 2048};
-  cuuint32_t box[3] = {8, 128, 8};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
-}
-
 }  // namespace cb

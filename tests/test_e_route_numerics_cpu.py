@@ -29,7 +29,7 @@ def stored_exponentials(s2: torch.Tensor):
 
 
 def gradient_matrix(e, off, lse_row, lse_col, a_row, a_col, label0):
-    """What csrc/infonce_bwd_e.cu forms (fp32 arithmetic, exponents clamped like its slow path), before the bf16 rounding of G."""
+    """What csrc/infonce_bwd_e2.cu forms (fp32 arithmetic, exponents clamped like its slow path), before the bf16 rounding of G."""
     b, n = e.shape
     o = off.repeat_interleave(32, dim=1)[:, :n]
     g = e.float() * (a_row * torch.exp2(o - lse_row[:, None]) + a_col * torch.exp2(torch.clamp(o - lse_col[None, :], max=126.0)))

@@ -22,6 +22,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--global-batch", type=int, default=32768)
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--free-run", action="store_true",
+                    help="no barrier / synchronize between the profiled steps (what the bench times): the step analysed is the "
+                         "middle one, from the end of its predecessor's last kernel, so host run-ahead and inter-step gaps count")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -36,10 +39,17 @@ def main():
     head.barrier()
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-        for _ in range(args.steps):
+        if args.free_run:
+            args.steps = max(args.steps, 3)
             head.barrier()
-            head.step(False)
+            for _ in range(args.steps):
+                head.step(False)
             torch.cuda.synchronize()
+        else:
+            for _ in range(args.steps):
+                head.barrier()
+                head.step(False)
+                torch.cuda.synchronize()
     if rank == 0:
         with tempfile.TemporaryDirectory() as d:
             path = os.path.join(d, "trace.json")
@@ -56,9 +66,20 @@ def main():
         gaps = sorted(range(1, len(ms)), key=lambda k: ms[k]["ts"] - (ms[k - 1]["ts"] + ms[k - 1]["dur"]), reverse=True)[:args.steps - 1]
         bounds = [0] + sorted(gaps) + [len(ms)]
         step_ev = ms[bounds[-2]:bounds[-1]]                    # the last profiled step
-        t0, t1 = step_ev[0]["ts"], step_ev[-1]["ts"] + step_ev[-1]["dur"]
+        t0 = step_ev[0]["ts"]
+        if args.free_run:
+            # every step launches the same kernels: split by count, take the middle step, start the clock where the step before ended
+            assert len(ms) % args.steps == 0, "steps launched different kernel counts: %d kernels over %d steps" % (len(ms), args.steps)
+            per = len(ms) // args.steps
+            mid = args.steps // 2
+            step_ev = ms[mid * per:(mid + 1) * per]
+            assert [e["name"] for e in step_ev] == [e["name"] for e in ms[:per]], "steps are not the same kernel sequence"
+            t0 = ms[mid * per - 1]["ts"] + ms[mid * per - 1]["dur"]
+        t1 = step_ev[-1]["ts"] + step_ev[-1]["dur"]
         busy = sum(e["dur"] for e in step_ev)
-        print("world size %d, global batch %d, rank 0, last of %d profiled steps" % (world, args.global_batch, args.steps))
+        print("world size %d, global batch %d, rank 0, %s of %d profiled steps%s" % (
+            world, args.global_batch, "middle" if args.free_run else "last", args.steps,
+            " (free-running: no barrier or synchronize between steps)" if args.free_run else ""))
         print("step window on the compute stream (stream %s): %.3f ms, kernels busy %.3f ms, idle %.3f ms" % (
             main_stream, (t1 - t0) / 1e3, busy / 1e3, (t1 - t0 - busy) / 1e3))
         print("\nidle gaps of the compute stream > 20 us (what ran before / after, and what the other streams did meanwhile):")
