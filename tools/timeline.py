@@ -69,12 +69,26 @@ def main():
         t0 = step_ev[0]["ts"]
         if args.free_run:
             # every step launches the same kernels: split by count, take the middle step, start the clock where the step before ended
-            assert len(ms) % args.steps == 0, "steps launched different kernel counts: %d kernels over %d steps" % (len(ms), args.steps)
-            per = len(ms) // args.steps
+            # (a few kernels before the first and after the last step belong to the barrier / the profiler: find the trim
+            #  that leaves `steps` identical name sequences)
+            names = [e["name"] for e in ms]
+            found = None
+            for lead in range(0, 12):
+                for trail in range(0, 12):
+                    n = len(ms) - lead - trail
+                    if n <= 0 or n % args.steps:
+                        continue
+                    per = n // args.steps
+                    if all(names[lead + k * per:lead + (k + 1) * per] == names[lead:lead + per] for k in range(1, args.steps)):
+                        found = (lead, per)
+                        break
+                if found:
+                    break
+            assert found, "no trim of the %d compute-stream kernels gives %d identical steps" % (len(ms), args.steps)
+            lead, per = found
             mid = args.steps // 2
-            step_ev = ms[mid * per:(mid + 1) * per]
-            assert [e["name"] for e in step_ev] == [e["name"] for e in ms[:per]], "steps are not the same kernel sequence"
-            t0 = ms[mid * per - 1]["ts"] + ms[mid * per - 1]["dur"]
+            step_ev = ms[lead + mid * per:lead + (mid + 1) * per]
+            t0 = ms[lead + mid * per - 1]["ts"] + ms[lead + mid * per - 1]["dur"]
         t1 = step_ev[-1]["ts"] + step_ev[-1]["dur"]
         busy = sum(e["dur"] for e in step_ev)
         print("world size %d, global batch %d, rank 0, %s of %d profiled steps%s" % (
