@@ -32,7 +32,7 @@ DIM = 512
 N_IMG, N_TXT = 8, 8
 KEYS = (("s_image", N_IMG), ("s_text", N_TXT), ("s_img_x", N_IMG), ("s_txt_x", N_TXT), ("t_image", 2), ("t_text", 2))
 LOGIT_SCALE = 14.2857
-PROFILE_TAG = "r02"     # profiles/ncu_<kernel>_<tag>.txt: the committed ncu summaries this round's roofline.traffic comes from
+PROFILE_TAG = "r02g"    # profiles/ncu_<kernel>_<tag>.txt: the committed ncu summaries this round's roofline.traffic comes from
 
 
 def algorithmic_flops(n_global: int, dim: int = DIM) -> float:
@@ -225,21 +225,42 @@ class LossHead:
         self.n_global, self.dev, self.rank, self.world, self.inst, self.flush = n_global, dev, rank, world, inst, flush
         self.b = n_global // world
         self.host = host_inputs(self.b, rank, pinned=True)
-        self.dev_buf = {k: torch.empty_like(v, device=dev).requires_grad_(k not in ("t_image", "t_text")) for k, v in self.host.items()}
+        # two sets of device inputs: in the host-buffer (e2e) leg the copy of step k + 1's inputs runs on a side stream while
+        # step k computes, as a data loader's prefetch would; every step's copy is inside the timed region, the first exposed
+        self.dev_bufs = [{k: torch.empty_like(v, device=dev).requires_grad_(k not in ("t_image", "t_text")) for k, v in self.host.items()}
+                         for _ in range(2)]
+        self.dev_buf = self.dev_bufs[0]
         with torch.no_grad():
             for k in self.host:
                 self.dev_buf[k].copy_(self.host[k])
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]      # copy into buffer i has landed
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]       # the step that read buffer i is done with it
+        self.in_flight = [False, False]
+        self.cur = 0
         self.logit_scale = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
         self.distill_scale = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
         self.loss_mod = COSMOSLoss(local_loss=False, gather_with_grad=False, cache_labels=True, rank=rank, world_size=world)
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
 
-    def step(self, from_host: bool):
-        host, dev_buf = self.host, self.dev_buf
+    def _issue_copy(self, i: int):
+        with torch.no_grad(), torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[i])
+            for k in self.host:
+                self.dev_bufs[i][k].copy_(self.host[k], non_blocking=True)
+            self.ready[i].record(self.copy_stream)
+        self.in_flight[i] = True
+
+    def step(self, from_host: bool, prefetch_next: bool = False):
+        host, dev_buf = self.host, self.dev_bufs[0]
         if from_host:
-            with torch.no_grad():
-                for k in host:
-                    dev_buf[k].copy_(host[k], non_blocking=True)
+            cur = self.cur
+            dev_buf = self.dev_bufs[cur]
+            if not self.in_flight[cur]:
+                self._issue_copy(cur)
+            torch.cuda.current_stream().wait_event(self.ready[cur])
+            if prefetch_next:
+                self._issue_copy(1 - cur)
         for t in list(dev_buf.values()) + [self.logit_scale, self.distill_scale]:
             t.grad = None
         n = dict(KEYS)
@@ -251,6 +272,9 @@ class LossHead:
         total = out["distill_loss"] + out["clip_loss"]
         total.backward()
         if from_host:
+            self.free[self.cur].record()
+            self.in_flight[self.cur] = False
+            self.cur ^= 1
             return torch.stack([out["distill_loss"].detach(), out["clip_loss"].detach()]).cpu()   # 8-byte D2H
         return out
 
@@ -260,18 +284,41 @@ class LossHead:
             dist.barrier()
         torch.cuda.synchronize()
 
+    L2_BYTES = 126 * 1024 * 1024
+
+    def l2_policy(self) -> str:
+        if self.h2d_bytes > self.L2_BYTES:
+            return ("inputs larger than L2 (%.0f MB per rank, plus %.1f GB of stored exponentials written and read per step): "
+                    "K steps timed back to back inside one barrier + synchronize bracket" %
+                    (self.h2d_bytes / 1e6, 80.0 * 2.0 * self.b * self.n_global / 1e9))
+        return "256 MB flush write before every timed step (inputs %.0f MB per rank fit L2), each step bracketed on its own" % (
+            self.h2d_bytes / 1e6)
+
     def timed(self, from_host: bool, steps: int):
-        """Total ms of `steps` steps, each bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks."""
+        """Total ms of `steps` steps, CUDA events on the launching stream, max over ranks.  The K steps run back to back inside
+        ONE barrier + synchronize bracket when a rank's inputs alone exceed L2 (the contract's "inputs larger than L2" option:
+        nothing of step k is still cached when step k + 1 reads it - each step also streams GBs of exponentials through L2);
+        small configurations instead flush L2 with a 256 MB write before every step and bracket each step on its own."""
         total_ms = 0.0
-        for _ in range(steps):
-            self.flush.fill_(1)                  # evict L2 between timed iterations (256 MB > 126 MB L2)
+        if self.h2d_bytes > self.L2_BYTES:
             self.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            self.step(from_host)
+            for k in range(steps):
+                self.step(from_host, prefetch_next=from_host and k + 1 < steps)
             e1.record()
-            torch.cuda.synchronize()
-            total_ms += e0.elapsed_time(e1)
+            self.barrier()
+            total_ms = e0.elapsed_time(e1)
+        else:
+            for _ in range(steps):
+                self.flush.fill_(1)                  # evict L2 between timed iterations (256 MB > 126 MB L2)
+                self.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                self.step(from_host)
+                e1.record()
+                torch.cuda.synchronize()
+                total_ms += e0.elapsed_time(e1)
         t = torch.tensor([total_ms], device=self.dev, dtype=torch.float64)
         if self.world > 1:
             import torch.distributed as dist
@@ -390,8 +437,23 @@ def run_ours(args):
     b, h2d_bytes = head.b, head.h2d_bytes
 
     clocks = Clocks(local_rank) if rank == 0 else None     # sampled from the warm-up on: short timed regions still get samples
-    for _ in range(max(args.warmup, 3)):
+    # Warm-up: the W steps asked for (at least 3), and then on until a second of steps has run - a rank of an 8-GPU job steps
+    # in 23 ms, and three of those after the seconds-long host-side parity check are over before the clocks have ramped up.
+    # Every rank runs the same count (rank 0 decides), the count is what the line reports as "warmup".
+    import time as _time
+    n_warm = 0
+    t_w = _time.perf_counter()
+    while True:
         head.step(False)
+        n_warm += 1
+        if n_warm < max(args.warmup, 3):
+            continue
+        torch.cuda.synchronize()
+        go_on = torch.tensor([1 if (_time.perf_counter() - t_w < 1.0 and n_warm < 100) else 0], device=dev)
+        if world > 1:
+            dist.broadcast(go_on, src=0)
+        if not int(go_on.item()):
+            break
     head.barrier()
     inst.reset()
     inst.enabled = True
@@ -421,16 +483,19 @@ def run_ours(args):
         kernel_ms = sum(v["ms_total"] for v in ksum.values()) / args.steps
         line = {
             "metric": "loss-head fwd+bwd samples/s at global batch %d" % n_global,
-            "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "COSMOS ViT-B/16 loss head fwd+bwd, global batch %d, dim 512, 8+8 student / 8+8 "
                                    "cross-modal / 2+2 teacher features per sample, 80 InfoNCE pairs" % n_global,
                        "global_batch": n_global, "per_gpu_batch": b, "parallelism": "dp%d (rows sharded, columns all-gathered)" % world,
-                       "l2": "256 MB flush write between timed iterations; inputs %.0f MB per rank" % (h2d_bytes / 1e6),
+                       "l2": head.l2_policy(),
                        "loss": [float(x) for x in last]},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms / args.steps,
+                    "input_pipeline": "pinned host -> one of two device input buffers on a copy stream; step k + 1's copy overlaps "
+                                      "step k's kernels (the first copy of the timed region is exposed); the loss is read back "
+                                      "to the host after every step"},
             "gpu_launches": launches,
             "clocks": clk,
             "parity_check": parity,

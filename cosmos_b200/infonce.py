@@ -133,9 +133,11 @@ def _k_bwd_e(x, y, label_offset, scale, e, off, diag_raw, row_lse2, col_lse2, a_
     return dx, dscale
 
 
-def _k_bwd_e_cols(x, y, label_offset, scale, e, off, diag_raw, row_lse2, col_lse2, a_row, a_col):
+def _k_bwd_e_cols(x, y, label_offset, scale, e, off, diag_raw, row_lse2, col_lse2, a_row, a_col, rank_major=0):
     """Column side of the stored-exponential route: -> fp32 [gy, N, 512], sum over the row tensors and THIS rank's rows of
-    G^T x at unit scale (csrc/infonce_bwd_e2t.cu) - no G tile is written to memory."""
+    G^T x at unit scale (csrc/infonce_bwd_e2t.cu) - no G tile is written to memory.
+    rank_major = W > 0: -> [W, gy, N / W, 512] instead, the layout a reduce-scatter sends (the sum over the kernel's row-sweep
+    slices and the reordering are one pass)."""
     dev = x.device
     prob = _problem(x, y, label_offset, scale)
     splits = _lib.lib().cosmos_infonce_bwd_e_cols_splits(C.byref(prob), dev.index)
@@ -147,6 +149,12 @@ def _k_bwd_e_cols(x, y, label_offset, scale, e, off, diag_raw, row_lse2, col_lse
                                               a_row, a_col, dy.data_ptr(), splits, dev.index,
                                               torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(st, "infonce_bwd_e_cols")
+    if rank_major:
+        W = rank_major
+        src = dy.view(splits, prob.gy, W, prob.n_cols // W, prob.dim).permute(0, 2, 1, 3, 4)
+        if splits == 1:
+            return src[0].contiguous()
+        return torch.sum(src, dim=0, out=torch.empty(src.shape[1:], dtype=torch.float32, device=dev))
     return dy[0] if splits == 1 else dy.sum(0)
 
 
@@ -245,9 +253,12 @@ def gather_stack(local: torch.Tensor, comm: Comm) -> torch.Tensor:
     if not comm.distributed:
         return local
     n, b, d = local.shape
-    out = torch.empty(comm.world_size * n, b, d, dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, local.contiguous(), group=comm.group)
-    return out.view(comm.world_size, n, b, d).permute(1, 0, 2, 3).reshape(n, comm.world_size * b, d)
+    local = local.contiguous()
+    # one collective per tensor, straight into its [W*b, D] slice: the rows arrive rank-major, no reordering copy afterwards
+    out = torch.empty(n, comm.world_size * b, d, dtype=local.dtype, device=local.device)
+    for k in range(n):
+        dist.all_gather_into_tensor(out[k], local[k], group=comm.group)
+    return out
 
 
 class GatherHandle:
@@ -258,22 +269,21 @@ class GatherHandle:
         self.comm, self.shape = comm, tuple(local.shape)
         if comm.distributed:
             n, b, d = local.shape
-            self.out = torch.empty(comm.world_size * n, b, d, dtype=local.dtype, device=local.device)
-            self.work = dist.all_gather_into_tensor(self.out, local.contiguous(), group=comm.group, async_op=True)
+            local = local.contiguous()
+            # one collective per tensor, straight into its [W*b, D] slice of the [n, W*b, D] result: the rows arrive rank-major
+            # (a single gather of the whole stack lands as [W, n, b, D] and needs a reordering copy on the compute stream)
+            self.out = torch.empty(n, comm.world_size * b, d, dtype=local.dtype, device=local.device)
+            self.work = [dist.all_gather_into_tensor(self.out[k], local[k], group=comm.group, async_op=True) for k in range(n)]
         else:
             self.out, self.work = local, None
-        self._result = None
+        self._waited = False
 
     def get(self) -> torch.Tensor:
-        if self._result is None:
-            if self.work is not None:
-                self.work.wait()
-                n, b, d = self.shape
-                W = self.comm.world_size
-                self._result = self.out.view(W, n, b, d).permute(1, 0, 2, 3).reshape(n, W * b, d)
-            else:
-                self._result = self.out
-        return self._result
+        if self.work is not None and not self._waited:
+            for w in self.work:
+                w.wait()
+            self._waited = True
+        return self.out
 
 
 class Prefetch:
@@ -357,15 +367,23 @@ def _g_store_ok(x_r: torch.Tensor, y_c: torch.Tensor) -> bool:
     return True
 
 
-def _reduce_scatter_rows(d_all: torch.Tensor, comm: Comm, b: int, async_op: bool = False):
-    """[n_c, W * b, D] per-rank partial sums -> [n_c, b, D]: the sum over ranks of this rank's rows.
-    async_op: -> (result, work) with the collective still running (work is None when nothing was started)."""
+def _rank_major_ok(comm: Comm) -> bool:
+    """Column-side partials can be produced in the reduce-scatter's send layout right away (NCCL groups only)."""
+    return comm.distributed and dist.get_backend(comm.group) == "nccl"
+
+
+def _reduce_scatter_rows(d_all: torch.Tensor, comm: Comm, b: int, async_op: bool = False, rank_major: bool = False):
+    """[n_c, W * b, D] per-rank partial sums (rank_major: already [W, n_c, b, D]) -> [n_c, b, D]: the sum over ranks of this
+    rank's rows.  async_op: -> (result, work) with the collective still running (work is None when nothing was started)."""
     if not comm.distributed:
         return (d_all, None) if async_op else d_all
     W, rank = comm.world_size, comm.rank
-    n_c, _, D = d_all.shape
+    if rank_major:
+        _, n_c, _, D = d_all.shape
+    else:
+        n_c, _, D = d_all.shape
     if dist.get_backend(comm.group) == "nccl":
-        send = d_all.view(n_c, W, b, D).transpose(0, 1).contiguous()          # rank-major chunks
+        send = d_all if rank_major else d_all.view(n_c, W, b, D).transpose(0, 1).contiguous()          # rank-major chunks
         out = torch.empty(n_c, b, D, dtype=d_all.dtype, device=d_all.device)
         work = dist.reduce_scatter_tensor(out, send, op=dist.ReduceOp.SUM, group=comm.group, async_op=async_op)
         return (out, work) if async_op else out
@@ -533,6 +551,7 @@ def _eager_schedule(groups: Sequence[_Group], comm: Comm):
         g.d_all = None
         g.d_cols_unit = None
         g.rs_work = None
+        g.rank_major = g.need_cols and not _COLS_VIA_GEMM and _rank_major_ok(comm)
         starts = list(range(0, g.n_r, g.chunk))
         for i0 in starts:
             items.append((g, i0, i0 == starts[-1]))
@@ -559,14 +578,15 @@ def _eager_schedule(groups: Sequence[_Group], comm: Comm):
             if via_gemm:      # diagnostics: G tiles through HBM + one GEMM (the first version of this route)
                 part = _k_colgrad(g_tiles, xs.reshape(xs.shape[0] * g.b, xs.shape[2]), g.n_c, g.N)    # [n_c, N, D] fp32
             else:             # the same exponentials once more, read as G^T: nothing but dY goes to memory
-                part = _k_bwd_e_cols(xs, g.y_c, g.off, g.scale_f, e_, o_, g.diag_raw[sl], g.row_lse2[sl], g.col_lse2[sl], 1.0, 1.0)
+                part = _k_bwd_e_cols(xs, g.y_c, g.off, g.scale_f, e_, o_, g.diag_raw[sl], g.row_lse2[sl], g.col_lse2[sl], 1.0, 1.0,
+                                     rank_major=comm.world_size if g.rank_major else 0)
             g.d_all = part if g.d_all is None else g.d_all.add_(part)
         if ds_ is not None:
             g.ds_unit = ds_ if g.ds_unit is None else g.ds_unit + ds_
         if last and g.d_all is not None:
             # column-side gradient of this rank's rows -> sum over ranks of every rank's own rows; started now, needed by
             # backward(): it runs behind whatever is launched next
-            g.d_cols_unit, g.rs_work = _reduce_scatter_rows(g.d_all, comm, g.b, async_op=True)
+            g.d_cols_unit, g.rs_work = _reduce_scatter_rows(g.d_all, comm, g.b, async_op=True, rank_major=g.rank_major)
             g.d_all = None
 
     if comm.distributed:

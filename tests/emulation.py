@@ -106,8 +106,9 @@ def emu_bwd_e(x, y, label_offset, scale, e, off, diag_raw, row_lse2, col_lse2, a
     return dx, dscale
 
 
-def emu_bwd_e_cols(x, y, label_offset, scale, e, off, diag_raw, row_lse2, col_lse2, a_row, a_col):
+def emu_bwd_e_cols(x, y, label_offset, scale, e, off, diag_raw, row_lse2, col_lse2, a_row, a_col, rank_major=0):
     """cosmos_infonce_bwd_e_cols: fp32 [gy, N, D] = sum over row tensors and local rows of G^T x, unit scale."""
+    assert not rank_major, "the reduce-scatter send layout is only produced for NCCL groups"
     gx, b, D = x.shape
     gy, N, _ = y.shape
     S2 = e
