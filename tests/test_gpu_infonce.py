@@ -291,6 +291,13 @@ def test_stored_exponential_kernels_match_recompute_kernels(b, n_all, off, gx, g
         # every column tensor on its own (a column tensor with a wrong neighbour's tiles would still pass the global cosine)
         for jj in range(gy):
             assert cosine(got[jj].cpu(), want[jj].cpu()) >= floor, (a_row, a_col, jj)
+        if (a_row, a_col) == (1.0, 1.0):
+            # the reduce-scatter's send layout (what an NCCL run asks for): [W, gy, N / W, 512], the same values
+            for W in (w for w in (1, 2, 4) if n_all % w == 0):
+                rm = K._k_bwd_e_cols(x, y, off, sc, e, offs, diag, row, col, a_row, a_col, rank_major=W)
+                assert rm.shape == (W, gy, n_all // W, 512) and rm.is_contiguous()
+                ref = got.view(gy, W, n_all // W, 512).transpose(0, 1)       # (the sum over sweep slices may associate differently)
+                assert float((rm - ref).abs().max()) <= 1e-6 * float(ref.abs().max())
         if n_all % 8 == 0 and (a_row, a_col) == (1.0, 1.0):
             # and against the first version of this route: the row pass's own G tiles (same bf16 values) through a GEMM
             via_gemm = K._k_colgrad(g2, x.reshape(gx * b, 512), gy, n_all)
