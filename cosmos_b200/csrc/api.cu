@@ -557,6 +557,55 @@ int cosmos_gemm(const void* a, const void* b, void* d, const float* bias, int32_
   return COSMOS_ERR_CUDA;
 }
 
+int cosmos_gemm_batched(const void* a, const void* b, void* d, const float* bias, int32_t M, int32_t N, int32_t K, int64_t lda,
+                        int64_t ldb, int64_t ldd, int32_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_d,
+                        int64_t stride_bias, int32_t a_kmajor, int32_t b_kmajor, int32_t in_dtype, int32_t out_dtype, int32_t splits,
+                        int32_t accumulate, float alpha, int device, void* stream) {
+  if (!a || !b || !d || M <= 0 || N <= 0 || K <= 0 || splits <= 0 || batch <= 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (!dtype16(in_dtype) || !dtype_any(out_dtype)) return COSMOS_ERR_UNSUPPORTED;
+  if ((lda & 7) || (ldb & 7) || (stride_a & 7) || (stride_b & 7) || !aligned16(a) || !aligned16(b) || !aligned16(d))
+    return COSMOS_ERR_INVALID_ARGUMENT;
+  if (accumulate && splits != 1) return COSMOS_ERR_INVALID_ARGUMENT;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  cb::GemmArgs ga;
+  ga.a = a; ga.b = b; ga.d = d; ga.bias = bias;
+  ga.M = M; ga.N = N; ga.K = K; ga.lda = lda; ga.ldb = ldb; ga.ldd = ldd;
+  ga.a_kmajor = a_kmajor; ga.b_kmajor = b_kmajor; ga.in_dtype = in_dtype; ga.out_dtype = out_dtype;
+  ga.splits = splits; ga.alpha = alpha;
+  ga.batch = batch; ga.sa = stride_a; ga.sb = stride_b; ga.sd = stride_d; ga.sbias = stride_bias; ga.accumulate = accumulate;
+  cudaError_t e = cudaSuccess;
+  int ctas = sm_count_of(device);
+  if (const int c = gemm_cta_cap(); c > 0 && c < ctas) ctas = c;
+  const int r = cb::launch_gemm(ga, ctas, static_cast<cudaStream_t>(stream), &e);
+  if (r == 0) return COSMOS_OK;
+  if (r > 0) g_last_cuda = r; else cu_fail(e);
+  return COSMOS_ERR_CUDA;
+}
+
+int cosmos_colsoftmax_fwd(const float* s, int64_t s_stride, int32_t lds, void* p, int64_t p_stride, int32_t ldp, int32_t p_dtype,
+                          int32_t n_sets, int32_t L, int32_t n_cols, int device, void* stream) {
+  if (!s || !p || n_sets < 0 || L <= 0 || n_cols <= 0 || lds < n_cols || ldp < n_cols) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (!dtype16(p_dtype)) return COSMOS_ERR_UNSUPPORTED;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  return cu_fail(cb::launch_colsoftmax_fwd(s, s_stride, lds, p, p_stride, ldp, p_dtype, n_sets, L, n_cols, static_cast<cudaStream_t>(stream)))
+             ? COSMOS_ERR_CUDA : COSMOS_OK;
+}
+
+int cosmos_colsoftmax_bwd(const void* p, int64_t p_stride, int32_t ldp, const float* dp, int64_t dp_stride, int32_t lddp, void* ds,
+                          int64_t ds_stride, int32_t ldds, int32_t dtype, int32_t n_sets, int32_t L, int32_t n_cols, int device,
+                          void* stream) {
+  if (!p || !dp || !ds || n_sets < 0 || L <= 0 || n_cols <= 0 || ldp < n_cols || lddp < n_cols || ldds < n_cols)
+    return COSMOS_ERR_INVALID_ARGUMENT;
+  if (!dtype16(dtype)) return COSMOS_ERR_UNSUPPORTED;
+  DeviceGuard g(device);
+  if (!g.ok) return COSMOS_ERR_CUDA;
+  return cu_fail(cb::launch_colsoftmax_bwd(p, p_stride, ldp, dp, dp_stride, lddp, ds, ds_stride, ldds, dtype, n_sets, L, n_cols,
+                                           static_cast<cudaStream_t>(stream)))
+             ? COSMOS_ERR_CUDA : COSMOS_OK;
+}
+
 int cosmos_layernorm_fwd(const void* x, int32_t x_dtype, const float* w, const float* b, void* y, int32_t y_dtype, float* mean,
                          float* rstd, int64_t rows, int32_t dim, float eps, int device, void* stream) {
   if (!x || !w || !b || !y || !mean || !rstd || rows < 0 || dim <= 0 || !(eps >= 0.f)) return COSMOS_ERR_INVALID_ARGUMENT;

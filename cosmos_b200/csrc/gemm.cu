@@ -1,5 +1,6 @@
 // Generic tcgen05 GEMM used by the cross-attention pooler (linear layers, their input and weight
-// gradients):   D[M,N] (+)= alpha * opA[M,K] * opB[N,K]^T (+ bias[N])
+// gradients, and - batched over samples or heads - the folded attention products):
+//   D[M,N] (+)= alpha * opA[M,K] * opB[N,K]^T (+ bias[N]),   optionally for `batch` independent problems of one shape
 //   opA stored [M,K] row-major (K-major operand) or [K,M] row-major (MN-major operand); same for opB.
 //   16-bit inputs (bf16 / fp16), fp32 accumulation in TMEM, fp32 or 16-bit output.
 // Tile 128 x 128 x 64, 6-stage TMA ring, one CTA per output tile and K split (gridDim.z); K splits
@@ -47,7 +48,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int tiles_m = (p.M + BM - 1) / BM;
   const int k_slabs = (p.K + BK - 1) / BK;
   const int per_split = (k_slabs + p.splits - 1) / p.splits;
-  const int n_items = tiles_m * tiles_n * p.splits;
+  const int per_batch = tiles_m * tiles_n * p.splits;
+  const int n_items = per_batch * p.batch;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -70,7 +72,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem = misc->tmem_slot;
 
-  auto decode = [&](int item, int& m0, int& n0, int& ks0, int& ks1) {
+  auto decode = [&](int item, int& bt, int& m0, int& n0, int& ks0, int& ks1) {
+    bt = item / per_batch;          // batch slowest: CTAs running together work on neighbouring problems
+    item -= bt * per_batch;
     const int split = item % p.splits;
     const int tile = item / p.splits;
     n0 = (tile % tiles_n) * BN;     // n fastest: CTAs running together share the A rows
@@ -84,8 +88,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0) {
     uint32_t stage = 0, phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      int m0, n0, ks0, ks1;
-      decode(item, m0, n0, ks0, ks1);
+      int bt, m0, n0, ks0, ks1;
+      decode(item, bt, m0, n0, ks0, ks1);
       for (int s = ks0; s < ks1; ++s) {
         mbar_wait(&misc->empty[stage], phase ^ 1);
         uint8_t* a = sA + stage * kABytes;
@@ -93,17 +97,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (elect_one()) {
         mbar_expect_tx(&misc->full[stage], kABytes + kBBytes);
         if (p.a_kmajor) {
-          tma_load_3d(a, &tmA, &misc->full[stage], s * BK, m0, 0);            // box 64 k x 128 rows
+          tma_load_3d(a, &tmA, &misc->full[stage], s * BK, m0, bt);           // box 64 k x 128 rows
         } else {
-          tma_load_3d(a, &tmA, &misc->full[stage], m0, s * BK, 0);            // box 64 m x 64 k-rows per 64-wide chunk
-          tma_load_3d(a + 8192, &tmA, &misc->full[stage], m0 + 64, s * BK, 0);
+          tma_load_3d(a, &tmA, &misc->full[stage], m0, s * BK, bt);           // box 64 m x 64 k-rows per 64-wide chunk
+          tma_load_3d(a + 8192, &tmA, &misc->full[stage], m0 + 64, s * BK, bt);
         }
         if (p.b_kmajor) {
 #pragma unroll
-          for (int c = 0; c < BN / 128; ++c) tma_load_3d(b + c * 16384, &tmB, &misc->full[stage], s * BK, n0 + c * 128, 0);
+          for (int c = 0; c < BN / 128; ++c) tma_load_3d(b + c * 16384, &tmB, &misc->full[stage], s * BK, n0 + c * 128, bt);
         } else {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c) tma_load_3d(b + c * 8192, &tmB, &misc->full[stage], n0 + c * 64, s * BK, 0);
+          for (int c = 0; c < BN / 64; ++c) tma_load_3d(b + c * 8192, &tmB, &misc->full[stage], n0 + c * 64, s * BK, bt);
         }
         }
         __syncwarp();
@@ -114,8 +118,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t stage = 0, phase = 0;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      int m0, n0, ks0, ks1;
-      decode(item, m0, n0, ks0, ks1);
+      int bt, m0, n0, ks0, ks1;
+      decode(item, bt, m0, n0, ks0, ks1);
       const uint32_t as = it & 1;
       mbar_wait(&misc->acc_empty[as], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -143,13 +147,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t q = warp & 3;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      int m0, n0, ks0, ks1;
-      decode(item, m0, n0, ks0, ks1);
+      int bt, m0, n0, ks0, ks1;
+      decode(item, bt, m0, n0, ks0, ks1);
       const uint32_t as = it & 1;
       const int row = m0 + q * 32 + lane;
       mbar_wait(&misc->acc_full[as], (it >> 1) & 1);
       tc_fence_after();
       const bool add_bias = p.bias != nullptr && (item % p.splits) == 0;
+      const float* bias = p.bias != nullptr ? p.bias + static_cast<size_t>(bt) * p.sbias : nullptr;
       const bool has_k = ks1 > ks0;
       for (int c = 0; c < BN; c += 32) {
         if (n0 + c >= p.N) break;
@@ -161,9 +166,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const int col = n0 + c + k;
-            o[k] = (has_k ? __uint_as_float(v[k]) * p.alpha : 0.f) + ((add_bias && col < p.N) ? __ldg(p.bias + col) : 0.f);
+            o[k] = (has_k ? __uint_as_float(v[k]) * p.alpha : 0.f) + ((add_bias && col < p.N) ? __ldg(bias + col) : 0.f);
           }
-          const size_t off = static_cast<size_t>(row) * p.ldd + n0 + c;
+          const size_t off = static_cast<size_t>(bt) * p.sd + static_cast<size_t>(row) * p.ldd + n0 + c;
+          if (p.accumulate) {             // D += ...: the caller's second product into the same output (splits == 1)
+            if (p.out_dtype == COSMOS_DTYPE_F32) {
+              const float* src = reinterpret_cast<const float*>(p.d) + off;
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (n0 + c + k < p.N) o[k] += src[k];
+            } else {
+              const uint16_t* src = reinterpret_cast<const uint16_t*>(p.d) + off;
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (n0 + c + k < p.N)
+                  o[k] += p.out_dtype == COSMOS_DTYPE_BF16 ? __uint_as_float(static_cast<uint32_t>(src[k]) << 16)
+                                                           : __half2float(__ushort_as_half(src[k]));
+            }
+          }
           if (p.splits > 1) {
             float* dst = reinterpret_cast<float*>(p.d) + off;
 #pragma unroll
@@ -212,20 +232,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 // 2-D operand map: K-major [rows, K] -> box {64 k, 128 rows}; MN-major [K, rows] -> box {64 rows, 64 k}.
-static int make_operand_map(CUtensorMap* map, const void* ptr, int is_bf16, int kmajor, int64_t rows, int64_t K, int64_t ld) {
+static int make_operand_map(CUtensorMap* map, const void* ptr, int is_bf16, int kmajor, int64_t rows, int64_t K, int64_t ld,
+                            int batch, int64_t bstride) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) return -1;
   cuuint64_t gdim[3], gstride[2];
   cuuint32_t box[3], estr[3] = {1, 1, 1};
   if (kmajor) {
-    gdim[0] = K; gdim[1] = rows; gdim[2] = 1;
+    gdim[0] = K; gdim[1] = rows; gdim[2] = batch;
     box[0] = 64; box[1] = 128; box[2] = 1;
   } else {
-    gdim[0] = rows; gdim[1] = K; gdim[2] = 1;
+    gdim[0] = rows; gdim[1] = K; gdim[2] = batch;
     box[0] = 64; box[1] = 64; box[2] = 1;
   }
+  // (the batch stride may be smaller than the row stride - per-head column blocks of one matrix: strides only have to be
+  //  multiples of 16 bytes; every dimension is bounded on its own, so tiles past M, N or K of one problem read zeros and
+  //  never its neighbour's rows)
   gstride[0] = static_cast<cuuint64_t>(ld) * 2;
-  gstride[1] = gstride[0] * gdim[1];
+  gstride[1] = batch > 1 ? static_cast<cuuint64_t>(bstride) * 2 : gstride[0] * gdim[1];
   CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), gdim,
                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -239,7 +263,7 @@ static cudaError_t launch_gemm_bn(const CUtensorMap& tmA, const CUtensorMap& tmB
   const int smem_bytes = kStages * (kABytes + BN * 64 * 2) + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return e;
-  const int items = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.splits;
+  const int items = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.splits * p.batch;
   const int grid = items < sm_count ? items : sm_count;
   gemm_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
   return cudaGetLastError();
@@ -250,14 +274,15 @@ int launch_gemm(const GemmArgs& a, int sm_count, cudaStream_t stream, cudaError_
   CUtensorMap tmA, tmB;
   const int bf = a.in_dtype == COSMOS_DTYPE_BF16;
   const bool wide = a.N >= 256;       // 128 x 256 tiles when the output is wide enough
-  int r1 = make_operand_map(&tmA, a.a, bf, a.a_kmajor, a.M, a.K, a.lda);
-  int r2 = make_operand_map(&tmB, a.b, bf, a.b_kmajor, a.N, a.K, a.ldb);
+  int r1 = make_operand_map(&tmA, a.a, bf, a.a_kmajor, a.M, a.K, a.lda, a.batch, a.sa);
+  int r2 = make_operand_map(&tmB, a.b, bf, a.b_kmajor, a.N, a.K, a.ldb, a.batch, a.sb);
   if (r1 != 0 || r2 != 0) return 100000 + (r1 != 0 ? r1 : r2);
   GemmParams p;
   p.M = a.M; p.N = a.N; p.K = a.K; p.ldd = static_cast<int>(a.ldd);
   p.a_kmajor = a.a_kmajor; p.b_kmajor = a.b_kmajor; p.splits = a.splits;
   p.out_dtype = a.splits > 1 ? COSMOS_DTYPE_F32 : a.out_dtype;
   p.alpha = a.alpha; p.bias = a.bias; p.d = a.d;
+  p.batch = a.batch; p.accumulate = a.accumulate; p.sd = a.sd; p.sbias = a.sbias;
   p.idesc = 0;
   *err = wide ? launch_gemm_bn<256>(tmA, tmB, p, bf, sm_count, stream) : launch_gemm_bn<128>(tmA, tmB, p, bf, sm_count, stream);
   return *err == cudaSuccess ? 0 : -1;

@@ -32,6 +32,8 @@ struct GemmParams {
   float alpha;
   const float* bias;
   void* d;
+  int batch, accumulate;
+  long long sd, sbias;        // batch strides (elements) of D and of the bias
 };
 struct GemmArgs {
   const void* a; const void* b; void* d; const float* bias;
@@ -40,6 +42,9 @@ struct GemmArgs {
   int a_kmajor, b_kmajor;     // 1: stored [rows, K]; 0: stored [K, rows]
   int in_dtype, out_dtype, splits;
   float alpha;
+  int batch = 1;              // independent problems of the same shape: the third dimension of the operand tensor maps
+  int64_t sa = 0, sb = 0, sd = 0, sbias = 0;    // their strides (elements); any multiple of 8 for a / b, also below the row stride
+  int accumulate = 0;         // D += ... instead of D = ... (read-modify-write in the epilogue; splits == 1)
 };
 // returns 0, -1 (CUDA error in *err) or 100000 + CUresult (tensor map)
 int launch_gemm(const GemmArgs& a, int sm_count, cudaStream_t stream, cudaError_t* err);
@@ -60,5 +65,9 @@ cudaError_t launch_addnorm_fwd(const void* f, int f_dtype, const float* pooled, 
 cudaError_t launch_addnorm_bwd(const void* g_out, const void* out, int f_dtype, const float* inv_norm, float* g_z32, void* g_z16,
                                int g_dtype, int64_t rows, int dim, cudaStream_t s);
 cudaError_t launch_colsum(const void* src, int dtype, float* dst, int64_t rows, int n, int64_t ld, cudaStream_t s);
+cudaError_t launch_colsoftmax_fwd(const float* S, int64_t s_bs, int lds, void* P, int64_t p_bs, int ldp, int dtype, int n_sets, int L,
+                                  int Nc, cudaStream_t s);
+cudaError_t launch_colsoftmax_bwd(const void* P, int64_t p_bs, int ldp, const float* dP, int64_t d_bs, int ldd, void* dS, int64_t ds_bs,
+                                  int ldds, int dtype, int n_sets, int L, int Nc, cudaStream_t s);
 
 }  // namespace cb

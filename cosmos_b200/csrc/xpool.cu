@@ -652,6 +652,96 @@ cudaError_t launch_addnorm_bwd(const void* g_out, const void* out, int f_dtype, 
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// folded attention: softmax over the KEYS (rows) of a [L, Nc] score block per token set, Nc = queries x heads columns
+// ------------------------------------------------------------------------------------------------
+// One CTA per set; thread = (column within a pass of 64, one of 4 row groups): a warp reads 32 consecutive columns of a row.
+// The block (L x Nc fp32, 50 KB at 196 x 64) is read twice; the second read hits L2.
+template <class T>
+__global__ void __launch_bounds__(256)
+colsoftmax_fwd_kernel(const float* __restrict__ S, long long s_bs, int lds, T* __restrict__ P, long long p_bs, int ldp, int L, int Nc) {
+  __shared__ float sm_m[4][64], sm_s[4][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const float* s0 = S + static_cast<size_t>(blockIdx.x) * s_bs;
+  T* p0 = P + static_cast<size_t>(blockIdx.x) * p_bs;
+  for (int c0 = 0; c0 < Nc; c0 += 64) {
+    const int c = c0 + tx;
+    float m = -INFINITY, sum = 0.f;
+    if (c < Nc) {
+      for (int l = ty; l < L; l += 4) {
+        const float v = s0[static_cast<size_t>(l) * lds + c];
+        if (v > m) {
+          sum *= __expf(m - v);
+          m = v;
+        }
+        sum += __expf(v - m);
+      }
+    }
+    __syncthreads();
+    sm_m[ty][tx] = m;
+    sm_s[ty][tx] = sum;
+    __syncthreads();
+    float M = fmaxf(fmaxf(sm_m[0][tx], sm_m[1][tx]), fmaxf(sm_m[2][tx], sm_m[3][tx]));
+    float tot = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (sm_m[g][tx] != -INFINITY) tot += sm_s[g][tx] * __expf(sm_m[g][tx] - M);
+    const float inv = 1.f / tot;
+    if (c < Nc) {
+      for (int l = ty; l < L; l += 4)
+        p0[static_cast<size_t>(l) * ldp + c] = fromf<T>(__expf(s0[static_cast<size_t>(l) * lds + c] - M) * inv);
+    }
+  }
+}
+
+// dS = P * (dP - sum_l P dP) per column
+template <class T>
+__global__ void __launch_bounds__(256)
+colsoftmax_bwd_kernel(const T* __restrict__ P, long long p_bs, int ldp, const float* __restrict__ dP, long long d_bs, int ldd,
+                      T* __restrict__ dS, long long ds_bs, int ldds, int L, int Nc) {
+  __shared__ float sm_d[4][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const T* p0 = P + static_cast<size_t>(blockIdx.x) * p_bs;
+  const float* d0 = dP + static_cast<size_t>(blockIdx.x) * d_bs;
+  T* o0 = dS + static_cast<size_t>(blockIdx.x) * ds_bs;
+  for (int c0 = 0; c0 < Nc; c0 += 64) {
+    const int c = c0 + tx;
+    float dot = 0.f;
+    if (c < Nc)
+      for (int l = ty; l < L; l += 4) dot = fmaf(tof(p0[static_cast<size_t>(l) * ldp + c]), d0[static_cast<size_t>(l) * ldd + c], dot);
+    __syncthreads();
+    sm_d[ty][tx] = dot;
+    __syncthreads();
+    const float tot = (sm_d[0][tx] + sm_d[1][tx]) + (sm_d[2][tx] + sm_d[3][tx]);
+    if (c < Nc)
+      for (int l = ty; l < L; l += 4)
+        o0[static_cast<size_t>(l) * ldds + c] =
+            fromf<T>(tof(p0[static_cast<size_t>(l) * ldp + c]) * (d0[static_cast<size_t>(l) * ldd + c] - tot));
+  }
+}
+
+cudaError_t launch_colsoftmax_fwd(const float* S, int64_t s_bs, int lds, void* P, int64_t p_bs, int ldp, int dtype, int n_sets, int L,
+                                  int Nc, cudaStream_t s) {
+  if (n_sets == 0) return cudaSuccess;
+  if (dtype == COSMOS_DTYPE_BF16)
+    colsoftmax_fwd_kernel<__nv_bfloat16><<<n_sets, 256, 0, s>>>(S, s_bs, lds, static_cast<__nv_bfloat16*>(P), p_bs, ldp, L, Nc);
+  else
+    colsoftmax_fwd_kernel<__half><<<n_sets, 256, 0, s>>>(S, s_bs, lds, static_cast<__half*>(P), p_bs, ldp, L, Nc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_colsoftmax_bwd(const void* P, int64_t p_bs, int ldp, const float* dP, int64_t d_bs, int ldd, void* dS, int64_t ds_bs,
+                                  int ldds, int dtype, int n_sets, int L, int Nc, cudaStream_t s) {
+  if (n_sets == 0) return cudaSuccess;
+  if (dtype == COSMOS_DTYPE_BF16)
+    colsoftmax_bwd_kernel<__nv_bfloat16><<<n_sets, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(P), p_bs, ldp, dP, d_bs, ldd,
+                                                            static_cast<__nv_bfloat16*>(dS), ds_bs, ldds, L, Nc);
+  else
+    colsoftmax_bwd_kernel<__half><<<n_sets, 256, 0, s>>>(static_cast<const __half*>(P), p_bs, ldp, dP, d_bs, ldd,
+                                                     static_cast<__half*>(dS), ds_bs, ldds, L, Nc);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_colsum(const void* src, int dtype, float* dst, int64_t rows, int n, int64_t ld, cudaStream_t s) {
   if (rows == 0) return cudaSuccess;
   const int rows_per_block = 256;

@@ -14,12 +14,16 @@ LayerNorm and the key/value projection run once per unique sample instead of onc
 reference executes them on 8x duplicated rows), and it fuses the residual add + L2 normalisation
 (SURVEY.md §8(f) N1).
 
-All contractions (key/value and query in-projections, out-projection, their input and weight
-gradients) run on tcgen05 tensor cores (csrc/gemm.cu); LayerNorm, the few-queries attention core and
+All contractions run on tcgen05 tensor cores (csrc/gemm.cu).  With the few queries per sample COSMOS uses (one per crop:
+8 x 8 heads = 64 score columns) the attention is FOLDED: the key projection moves into the queries and the value
+projection behind the pooling (`_folded_fwd`), so scores, pooling and all their gradients are batched GEMMs over the
+samples and no key / value tensor exists; more than 128 score columns per sample (the module's general forward(x, q) with
+many queries) keep the key / value projection GEMM and the CUDA-core attention kernel.  LayerNorm, the column softmax and
 add+normalise are HBM-bound CUDA kernels (csrc/xpool.cu).  There is no PyTorch fallback.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -43,6 +47,127 @@ def _gemm(a, b, out, M, N, K, lda, ldb, a_kmajor, b_kmajor, bias=None, splits=1,
                                 float(alpha), dev.index, _stream(dev))
     _lib.check(st, "gemm")
     return out
+
+
+def _bgemm(a, b, out, M, N, K, lda, ldb, ldd, batch, sa, sb, sd, a_kmajor, b_kmajor, bias=None, sbias=0, splits=1, accumulate=False,
+           alpha=1.0):
+    """`batch` problems D_t = alpha * opA_t opB_t^T (+ bias_t) through cosmos_gemm_batched; a, b, out, bias are tensors (views) whose
+    first element is the first problem's, every stride is in elements.  a_kmajor: A_t stored [M, K] (row stride lda), else
+    [K, M]; likewise B_t [N, K] / [K, N]."""
+    dev = a.device
+    st = _lib.lib().cosmos_gemm_batched(a.data_ptr(), b.data_ptr(), out.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                        M, N, K, lda, ldb, ldd, batch, sa, sb, sd, sbias, int(a_kmajor), int(b_kmajor), _code(a),
+                                        _code(out), splits, int(accumulate), float(alpha), dev.index, _stream(dev))
+    _lib.check(st, "gemm_batched")
+    return out
+
+
+def _colsoftmax_fwd(scores, p_out, n_sets, L, n_cols, ldp):
+    """softmax over the L keys of every column of scores [n_sets, L, n_cols] fp32 -> p_out (16-bit view, row stride ldp)."""
+    dev = scores.device
+    st = _lib.lib().cosmos_colsoftmax_fwd(scores.data_ptr(), L * n_cols, n_cols, p_out.data_ptr(), L * ldp, ldp, _code(p_out), n_sets, L,
+                                          n_cols, dev.index, _stream(dev))
+    _lib.check(st, "colsoftmax_fwd")
+
+
+def _colsoftmax_bwd(p_in, d_p, ds_out, n_sets, L, n_cols, ldp):
+    """ds = p * (dp - sum_l p dp) per column; p_in / ds_out 16-bit views with row stride ldp, d_p [n_sets, L, n_cols] fp32."""
+    dev = d_p.device
+    st = _lib.lib().cosmos_colsoftmax_bwd(p_in.data_ptr(), L * ldp, ldp, d_p.data_ptr(), L * n_cols, n_cols, ds_out.data_ptr(), L * ldp,
+                                          ldp, _code(p_in), n_sets, L, n_cols, dev.index, _stream(dev))
+    _lib.check(st, "colsoftmax_bwd")
+
+
+def _wgrad_splits(R, tiles):
+    return max(1, min((R + 1023) // 1024, 148 // tiles if tiles <= 148 else 1))    # one wave of persistent CTAs
+
+
+def _row_order(n_sets, q_per_set, qs, qq):
+    """How query c of set s (row s * qs + c * qq) relates to set-major order: 'set' (already), 'crop' (crop-major: the layout of
+    model.py:373-376, features of crop c of all samples together) or None (anything else: no folded attention)."""
+    if qq == 1 and qs == q_per_set:
+        return "set"
+    if qs == 1 and qq == n_sets:
+        return "crop"
+    return None
+
+
+def _to_set_major(t, order, n_sets, q_per_set):
+    if order == "set":
+        return t
+    return t.view(q_per_set, n_sets, t.shape[1]).transpose(0, 1).reshape(n_sets * q_per_set, t.shape[1])
+
+
+def _from_set_major(t, order, n_sets, q_per_set):
+    if order == "set":
+        return t
+    return t.view(n_sets, q_per_set, t.shape[1]).transpose(0, 1).reshape(n_sets * q_per_set, t.shape[1])
+
+
+# Folded attention (few queries per token set): COSMOS_B200_POOLER=unfolded keeps the key / value projection route (diagnostics)
+_FOLD_MAX_COLS = 0 if os.environ.get("COSMOS_B200_POOLER", "") == "unfolded" else 128
+
+
+def _fold_ok(n_sets, q_per_set, qs, qq, heads, d):
+    hd = d // heads
+    n_cols = q_per_set * heads
+    return (n_cols <= _FOLD_MAX_COLS and n_cols % 8 == 0 and hd % 8 == 0 and hd * heads == d
+            and _row_order(n_sets, q_per_set, qs, qq) is not None)
+
+
+def _folded_fwd(xn, qp, w_kv, b_in, n_sets, L, d, heads, q_per_set, order, cd):
+    """Attention of q_per_set queries per token set WITHOUT key / value tensors.  With k_l = W_k x_l + b_k the score of query q_h
+    against key l is q_h . k_l = (W_k,h^T q_h) . x_l + const, and sum_l p_l v_l = W_v,h (sum_l p_l x_l) + b_v,h, so per set
+        Q~ = kappa * W_k,h^T q_h   [n_cols = queries x heads, d]      S = xn Q~^T  [L, n_cols]
+        P  = softmax over l        Z = P^T xn  [n_cols, d]            o_h = W_v,h Z_h + b_v,h
+    - batched tcgen05 GEMMs over sets (S, Z) and over heads (Q~, o), 8x fewer flops than the [L, d] x [d, 2d] projection at 8
+    queries, and the tokens are the only large tensor read.  -> o [n_q, d] in set-major order, and what backward needs."""
+    dev = xn.device
+    hd, n_cols, n_q = d // heads, q_per_set * heads, n_sets * q_per_set
+    w_k, w_v = w_kv[:d], w_kv[d:]
+    qp_sm = _to_set_major(qp, order, n_sets, q_per_set).contiguous()
+    qt = torch.empty(n_q, heads, d, dtype=cd, device=dev)                       # Q~, rows (set, query), then head
+    _bgemm(qp_sm, w_k, qt, n_q, d, hd, d, d, heads * d, heads, hd, hd * d, d, True, False, alpha=hd ** -0.5)
+    scores = torch.empty(n_sets, L, n_cols, dtype=torch.float32, device=dev)
+    _bgemm(xn, qt, scores, L, n_cols, d, d, d, n_cols, n_sets, L * d, n_cols * d, L * n_cols, True, True)
+    pd = torch.empty(n_sets, L, 2 * n_cols, dtype=cd, device=dev)               # [P | dS]: the second half is filled by backward
+    _colsoftmax_fwd(scores, pd, n_sets, L, n_cols, 2 * n_cols)
+    z = torch.empty(n_q, heads, d, dtype=cd, device=dev)
+    _bgemm(pd, xn, z, n_cols, d, L, 2 * n_cols, d, d, n_sets, L * 2 * n_cols, L * d, n_cols * d, False, False)
+    o_sm = torch.empty(n_q, d, dtype=cd, device=dev)
+    _bgemm(z, w_v, o_sm, n_q, hd, d, heads * d, d, d, heads, d, hd * d, hd, True, True, bias=b_in[2 * d:], sbias=hd)
+    return o_sm, qp_sm, qt, pd, z
+
+
+def _folded_bwd(g_o_sm, xn, qp_sm, qt, pd, z, w_kv, g_in_w, g_in_b, n_sets, L, d, heads, q_per_set, cd):
+    """-> (g_xn [n_sets * L, d], dq_sm [n_q, d] set-major); accumulates dW_k, dW_v into g_in_w[d:3d] and db_v into g_in_b[2d:]
+    (db_k is exactly zero: a shift of every key's score by the same amount leaves the softmax unchanged)."""
+    dev = xn.device
+    hd, n_cols, n_q = d // heads, q_per_set * heads, n_sets * q_per_set
+    w_k, w_v = w_kv[:d], w_kv[d:]
+    kappa = hd ** -0.5
+    splits = _wgrad_splits(n_q, heads * ((d + 255) // 256))
+    # o_h = W_v,h Z_h + b_v,h
+    _bgemm(g_o_sm, z, g_in_w[2 * d:], hd, d, n_q, d, heads * d, d, heads, hd, d, hd * d, False, False, splits=splits)
+    _colsum(g_o_sm, d, g_in_b[2 * d:])
+    dz = torch.empty(n_q, heads, d, dtype=cd, device=dev)
+    _bgemm(g_o_sm, w_v, dz, n_q, d, hd, d, d, heads * d, heads, hd, hd * d, d, True, False)
+    # Z = P^T xn
+    d_p = torch.empty(n_sets, L, n_cols, dtype=torch.float32, device=dev)
+    _bgemm(xn, dz, d_p, L, n_cols, d, d, d, n_cols, n_sets, L * d, n_cols * d, L * n_cols, True, True)
+    ds = pd[:, :, n_cols:]
+    _colsoftmax_bwd(pd, d_p, ds, n_sets, L, n_cols, 2 * n_cols)
+    # d xn = P dZ + dS Q~   (two products into one output)
+    g_xn = torch.empty(n_sets * L, d, dtype=cd, device=dev)
+    _bgemm(pd, dz, g_xn, L, d, n_cols, 2 * n_cols, d, d, n_sets, L * 2 * n_cols, n_cols * d, L * d, True, False)
+    _bgemm(ds, qt, g_xn, L, d, n_cols, 2 * n_cols, d, d, n_sets, L * 2 * n_cols, n_cols * d, L * d, True, False, accumulate=True)
+    # S = xn Q~^T,  Q~ = kappa W_k,h^T q_h
+    dqt = torch.empty(n_q, heads, d, dtype=cd, device=dev)
+    _bgemm(ds, xn, dqt, n_cols, d, L, 2 * n_cols, d, d, n_sets, L * 2 * n_cols, L * d, n_cols * d, False, False)
+    dq_sm = torch.empty(n_q, d, dtype=cd, device=dev)
+    _bgemm(dqt, w_k, dq_sm, n_q, hd, d, heads * d, d, d, heads, d, hd * d, hd, True, True, alpha=kappa)
+    _bgemm(qp_sm, dqt, g_in_w[d:2 * d], hd, d, n_q, d, heads * d, d, heads, hd, d, hd * d, False, False, splits=splits, alpha=kappa)
+    return g_xn, dq_sm
 
 
 def _linear(x, w, bias, out_dtype):
@@ -106,6 +231,31 @@ def _ln_bwd(dy, x2d, w, mean, rstd, dx, accumulate, dw=None, db=None):
                                          rows, dim, dev.index, _stream(dev))
     _lib.check(st, "layernorm_bwd")
     return dw, db
+
+
+def _addnorm_fwd(q_in, pooled):
+    """normalize(q_in + pooled) row-wise (model.py:379-380) -> (out in q_in's dtype, 1 / norm fp32)"""
+    n_q, d = q_in.shape
+    dev = q_in.device
+    out = torch.empty_like(q_in)
+    inv_norm = torch.empty(n_q, dtype=torch.float32, device=dev)
+    st = _lib.lib().cosmos_addnorm_fwd(q_in.data_ptr(), _code(q_in), pooled.data_ptr(), out.data_ptr(), inv_norm.data_ptr(), n_q, d,
+                                       dev.index, _stream(dev))
+    _lib.check(st, "addnorm_fwd")
+    return out, inv_norm
+
+
+def _addnorm_bwd(g_out, out, inv_norm, cd):
+    """-> (gradient of the sum in fp32, the same in the compute dtype)"""
+    n_q, d = out.shape
+    dev = out.device
+    g_z32 = torch.empty(n_q, d, dtype=torch.float32, device=dev)
+    g_p = torch.empty(n_q, d, dtype=cd, device=dev)
+    g_out = g_out.to(out.dtype)
+    st = _lib.lib().cosmos_addnorm_bwd(g_out.data_ptr(), out.data_ptr(), _code(out), inv_norm.data_ptr(), g_z32.data_ptr(),
+                                       g_p.data_ptr(), _code(g_p), n_q, d, dev.index, _stream(dev))
+    _lib.check(st, "addnorm_bwd")
+    return g_z32, g_p
 
 
 class _MapTokens(torch.autograd.Function):
@@ -175,34 +325,42 @@ class _CrossPool(torch.autograd.Function):
         lnq_w32, lnq_b32, lnk_w32, lnk_b32 = f32(lnq_w), f32(lnq_b), f32(lnk_w), f32(lnk_b)
 
         xn, mean_k, rstd_k = _ln_fwd(tokens2d, lnk_w32, lnk_b32, cd, eps_k)        # once per unique token set
-        kv = _linear(xn, w_kv, b_in[d:], cd)                                       # [n_sets*L, 2d]
         fn, mean_q, rstd_q = _ln_fwd(q_in, lnq_w32, lnq_b32, cd, eps_q)
         qp = _linear(fn, w_q, b_in[:d], cd)                                        # [n_q, d]
-        o = torch.empty(n_q, d, dtype=cd, device=dev)
-        lse = torch.empty(n_q, heads, dtype=torch.float32, device=dev)
-        st = _lib.lib().cosmos_attn_core_fwd(qp.data_ptr(), kv.data_ptr(), o.data_ptr(), lse.data_ptr(), _code(qp), n_sets, L, d,
-                                             heads, q_per_set, qs, qq, dev.index, _stream(dev))
-        _lib.check(st, "attn_core_fwd")
+        folded = _fold_ok(n_sets, q_per_set, qs, qq, heads, d)
+        if folded:
+            order = _row_order(n_sets, q_per_set, qs, qq)
+            o_sm, qp_sm, qt, pd, z = _folded_fwd(xn, qp, w_kv, b_in, n_sets, L, d, heads, q_per_set, order, cd)
+            o = _from_set_major(o_sm, order, n_sets, q_per_set).contiguous()
+            kv = lse = torch.empty(0, device=dev)
+            fold_saved = (qp_sm, qt, pd, z)
+        else:
+            order = None
+            kv = _linear(xn, w_kv, b_in[d:], cd)                                   # [n_sets*L, 2d]
+            o = torch.empty(n_q, d, dtype=cd, device=dev)
+            lse = torch.empty(n_q, heads, dtype=torch.float32, device=dev)
+            st = _lib.lib().cosmos_attn_core_fwd(qp.data_ptr(), kv.data_ptr(), o.data_ptr(), lse.data_ptr(), _code(qp), n_sets, L, d,
+                                                 heads, q_per_set, qs, qq, dev.index, _stream(dev))
+            _lib.check(st, "attn_core_fwd")
+            fold_saved = tuple(torch.empty(0, device=dev) for _ in range(4))
+        ctx.fold = (folded, order)
         pooled = _linear(o, w_o, f32(out_b), torch.float32)                        # [n_q, d] fp32
         ctx.cfg = (n_sets, L, d, heads, q_per_set, qs, qq, fuse_norm, cd)
         ctx.dtypes = (tokens.dtype, queries.dtype, lnq_w.dtype, lnk_w.dtype, in_w.dtype, in_b.dtype, out_w.dtype, out_b.dtype)
         if fuse_norm:
-            out = torch.empty_like(q_in)
-            inv_norm = torch.empty(n_q, dtype=torch.float32, device=dev)
-            st = _lib.lib().cosmos_addnorm_fwd(q_in.data_ptr(), _code(q_in), pooled.data_ptr(), out.data_ptr(),
-                                               inv_norm.data_ptr(), n_q, d, dev.index, _stream(dev))
-            _lib.check(st, "addnorm_fwd")
+            out, inv_norm = _addnorm_fwd(q_in, pooled)
         else:
             out = pooled.to(queries.dtype)
             inv_norm = torch.empty(0, device=dev)
         ctx.save_for_backward(tokens2d, q_in, xn, mean_k, rstd_k, fn, mean_q, rstd_q, kv, qp, o, lse, w_q, w_kv, w_o,
-                              lnq_w32, lnk_w32, out, inv_norm)
+                              lnq_w32, lnk_w32, out, inv_norm, *fold_saved)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         (tokens2d, q_in, xn, mean_k, rstd_k, fn, mean_q, rstd_q, kv, qp, o, lse, w_q, w_kv, w_o, lnq_w32, lnk_w32, out,
-         inv_norm) = ctx.saved_tensors
+         inv_norm, qp_sm, qt, pd, z) = ctx.saved_tensors
+        folded, order = ctx.fold
         n_sets, L, d, heads, q_per_set, qs, qq, fuse_norm, cd = ctx.cfg
         dt_tok, dt_q, dt_lnq, dt_lnk, dt_inw, dt_inb, dt_ow, dt_ob = ctx.dtypes
         dev = tokens2d.device
@@ -217,11 +375,7 @@ class _CrossPool(torch.autograd.Function):
         g_in_b, g_bo = vec[:3 * d], vec[3 * d:4 * d]
         g_lnq_w, g_lnq_b, g_lnk_w, g_lnk_b = vec[4 * d:5 * d], vec[5 * d:6 * d], vec[6 * d:7 * d], vec[7 * d:8 * d]
         if fuse_norm:
-            g_z32 = torch.empty(n_q, d, dtype=torch.float32, device=dev)
-            g_p = torch.empty(n_q, d, dtype=cd, device=dev)
-            st = lib.cosmos_addnorm_bwd(g_out.to(out.dtype).data_ptr(), out.data_ptr(), _code(out), inv_norm.data_ptr(),
-                                        g_z32.data_ptr(), g_p.data_ptr(), _code(g_p), n_q, d, dev.index, _stream(dev))
-            _lib.check(st, "addnorm_bwd")
+            g_z32, g_p = _addnorm_bwd(g_out, out, inv_norm, cd)
             g_queries = g_z32                                  # residual branch; the LN_q path is accumulated below
             _colsum(g_z32, d, g_bo)
         else:
@@ -232,20 +386,26 @@ class _CrossPool(torch.autograd.Function):
         _wgrad(g_p, o, g_wo)                                   # [d, d]
         g_o = _dgrad(g_p, w_o, cd)                             # [n_q, d]
         # attention core
-        dq = torch.empty(n_q, d, dtype=cd, device=dev)
-        dkv = torch.empty_like(kv)
-        st = lib.cosmos_attn_core_bwd(qp.data_ptr(), kv.data_ptr(), g_o.data_ptr(), lse.data_ptr(), dq.data_ptr(), dkv.data_ptr(),
-                                      _code(qp), n_sets, L, d, heads, q_per_set, qs, qq, dev.index, _stream(dev))
-        _lib.check(st, "attn_core_bwd")
+        if folded:
+            g_o_sm = _to_set_major(g_o, order, n_sets, q_per_set).contiguous()
+            g_xn, dq_sm = _folded_bwd(g_o_sm, xn, qp_sm, qt, pd, z, w_kv, g_in_w, g_in_b, n_sets, L, d, heads, q_per_set, cd)
+            dq = _from_set_major(dq_sm, order, n_sets, q_per_set).contiguous()
+        else:
+            dq = torch.empty(n_q, d, dtype=cd, device=dev)
+            dkv = torch.empty_like(kv)
+            st = lib.cosmos_attn_core_bwd(qp.data_ptr(), kv.data_ptr(), g_o.data_ptr(), lse.data_ptr(), dq.data_ptr(), dkv.data_ptr(),
+                                          _code(qp), n_sets, L, d, heads, q_per_set, qs, qq, dev.index, _stream(dev))
+            _lib.check(st, "attn_core_bwd")
         # query in-projection + LayerNorm_q
         _wgrad(dq, fn, g_in_w[:d])
         _colsum(dq, d, g_in_b[:d])
         g_fn = _dgrad(dq, w_q, cd)
         _ln_bwd(g_fn, q_in, lnq_w32, mean_q, rstd_q, g_queries, True, g_lnq_w, g_lnq_b)
         # key/value in-projection + LayerNorm_k (once per unique token set)
-        _wgrad(dkv, xn, g_in_w[d:])
-        _colsum(dkv, 2 * d, g_in_b[d:])
-        g_xn = _dgrad(dkv, w_kv, cd)
+        if not folded:
+            _wgrad(dkv, xn, g_in_w[d:])
+            _colsum(dkv, 2 * d, g_in_b[d:])
+            g_xn = _dgrad(dkv, w_kv, cd)
         g_tokens = torch.empty(n_sets * L, d, dtype=dt_tok, device=dev)
         _ln_bwd(g_xn, tokens2d, lnk_w32, mean_k, rstd_k, g_tokens, False, g_lnk_w, g_lnk_b)
         return (g_tokens.view(n_sets, L, d), g_queries.to(dt_q), g_lnq_w.to(dt_lnq), g_lnq_b.to(dt_lnq), g_lnk_w.to(dt_lnk),

@@ -174,6 +174,29 @@ int cosmos_gemm(const void* a, const void* b, void* d, const float* bias, int32_
                 int64_t lda, int64_t ldb, int64_t ldd, int32_t a_kmajor, int32_t b_kmajor, int32_t in_dtype,
                 int32_t out_dtype, int32_t splits, float alpha, int device, void* stream);
 
+/* The same GEMM for `batch` independent problems of one shape: problem t reads a + t * stride_a, b + t * stride_b (elements;
+ * multiples of 8, and they may be SMALLER than the row strides: the per-head column blocks of one matrix are a batch), adds
+ * bias + t * stride_bias and writes d + t * stride_d.  Tiles past M, N or K of one problem read zeros, never a neighbour's
+ * rows (each problem is its own slice of a 3-D tensor map).  accumulate != 0: D += ... (splits must be 1).
+ * Used by the folded attention of the pooler (cosmos_b200/pooler.py): with one query per (sample, crop) the key projection
+ * of nn.MultiheadAttention (transformer.py:214, 225-229) folds into the queries, q~ = W_k,h^T q_h, so that per sample
+ * scores = LN(x) q~^T and pooled_h = W_v,h (P^T LN(x)): four small GEMMs per sample instead of the [L, d] x [d, 2d] key /
+ * value projection, and no key / value tensor in memory.                                                                   */
+int cosmos_gemm_batched(const void* a, const void* b, void* d, const float* bias, int32_t M, int32_t N, int32_t K, int64_t lda,
+                        int64_t ldb, int64_t ldd, int32_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_d,
+                        int64_t stride_bias, int32_t a_kmajor, int32_t b_kmajor, int32_t in_dtype, int32_t out_dtype, int32_t splits,
+                        int32_t accumulate, float alpha, int device, void* stream);
+
+/* Softmax over the KEYS of the folded attention (F.multi_head_attention_forward's softmax(dim=-1) of [queries, keys] scores,
+ * stored here keys-major): s fp32 [n_sets][L][n_cols] (row stride lds, set stride s_stride) -> p 16-bit, same indexing with
+ * its own strides; p[set][:, c] = softmax over l of s[set][:, c].                                                          */
+int cosmos_colsoftmax_fwd(const float* s, int64_t s_stride, int32_t lds, void* p, int64_t p_stride, int32_t ldp, int32_t p_dtype,
+                          int32_t n_sets, int32_t L, int32_t n_cols, int device, void* stream);
+/* Its backward: ds = p * (dp - sum_l p * dp) per column; dp fp32, p and ds 16-bit (dtype).                                 */
+int cosmos_colsoftmax_bwd(const void* p, int64_t p_stride, int32_t ldp, const float* dp, int64_t dp_stride, int32_t lddp, void* ds,
+                          int64_t ds_stride, int32_t ldds, int32_t dtype, int32_t n_sets, int32_t L, int32_t n_cols, int device,
+                          void* stream);
+
 /* LayerNorm over the last dim (eps: the module's own, nn.LayerNorm default 1e-5): y = (x - mean) * rstd * w + b, one row per warp.
  * x: [rows, dim] of x_dtype; y: [rows, dim] bf16/f16 (y_dtype); mean, rstd: fp32 [rows] (saved for backward). */
 int cosmos_layernorm_fwd(const void* x, int32_t x_dtype, const float* w, const float* b, void* y, int32_t y_dtype,

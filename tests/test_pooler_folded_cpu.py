@@ -1,0 +1,80 @@
+"""CPU: the algebra and the stride bookkeeping of the pooler's folded attention (cosmos_b200/pooler.py:_folded_fwd/_folded_bwd)
+against the oracle's written-out AttentionalCrossPooler (src/open_clip/transformer.py:210-230, src/open_clip/model.py:366-387),
+with the kernel entry points replaced by the documented-contract emulation tests/emulation_pooler.py.  The kernels themselves
+are covered by tests/test_gpu_pooler.py."""
+import pytest
+import torch
+
+from tests import emulation_pooler
+from oracle import cosmos_oracle as O
+
+
+def cosine(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float(a @ b / (a.norm() * b.norm()))
+
+
+@pytest.mark.parametrize("d,L,B,n,heads,seed", [(64, 13, 5, 4, 4, 1), (128, 70, 3, 8, 8, 2), (96, 9, 2, 2, 12, 3)])
+def test_folded_crossmodal_matches_oracle(monkeypatch, d, L, B, n, heads, seed):
+    from cosmos_b200 import pooler
+    emulation_pooler.install(monkeypatch)
+    assert pooler._fold_ok(B, n, 1, B, heads, d)
+    params, tokens, feats, w = O.make_pooler_case(d, L, B, n, seed)
+    r16 = lambda t: t.bfloat16().float()
+    p32 = {k: (r16(v) if v.dim() == 2 else v.clone()).requires_grad_(True) for k, v in params.items()}
+    t32, f32 = r16(tokens).requires_grad_(True), r16(feats).requires_grad_(True)
+    ref = O.cosmos_crossmodal(f32, t32, p32, heads, B)
+    (ref * w).sum().backward()
+    mod = pooler.AttentionalCrossPooler(d, d, heads)
+    mod.load_state_dict({k: (r16(v) if v.dim() == 2 else v) for k, v in params.items()})
+    tok = tokens.bfloat16().requires_grad_(True)
+    f = feats.bfloat16().requires_grad_(True)
+    xm = pooler.crossmodal_features(mod, tok, f, B)                   # crop-major query rows (model.py:373-376)
+    (xm.float() * w).sum().backward()
+    assert float((xm.detach().float() - ref.detach()).norm() / ref.detach().norm()) < 1e-2
+    assert cosine(f.grad, f32.grad) >= 0.9995 and cosine(tok.grad, t32.grad) >= 0.9995
+    for k, p in mod.named_parameters():
+        g, gr = p.grad, p32[k].grad
+        if k == "attn.in_proj_bias":          # the key third is exactly zero (softmax shift invariance): the folded route says so
+            assert float(g[d:2 * d].abs().max()) == 0.0
+            sel = torch.cat([torch.arange(0, d), torch.arange(2 * d, 3 * d)])
+            g, gr = g[sel], gr[sel]
+        assert cosine(g, gr) >= 0.999, (k, cosine(g, gr))
+        assert abs(float(g.float().norm() / gr.norm()) - 1) < 2e-2, k
+
+
+def test_folded_module_forward_set_major_matches_oracle(monkeypatch):
+    """forward(x, q) (transformer.py:225-230): queries of a sample are consecutive rows - no reordering copies."""
+    from cosmos_b200 import pooler
+    emulation_pooler.install(monkeypatch)
+    d, L, B, Lq, heads = 64, 11, 3, 6, 8
+    params, tokens, _, _ = O.make_pooler_case(d, L, B, 1, 7)
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(B, Lq, d, generator=g)
+    w = torch.randn(B, Lq, d, generator=g)
+    r16 = lambda t: t.bfloat16().float()
+    p32 = {k: (r16(v) if v.dim() == 2 else v.clone()).requires_grad_(True) for k, v in params.items()}
+    t32, q32 = r16(tokens).requires_grad_(True), r16(q).requires_grad_(True)
+    ref = O.cross_pool(t32, q32, p32, heads)
+    (ref * w).sum().backward()
+    mod = pooler.AttentionalCrossPooler(d, d, heads)
+    mod.load_state_dict({k: (r16(v) if v.dim() == 2 else v) for k, v in params.items()})
+    assert pooler._fold_ok(B, Lq, Lq, 1, heads, d) and pooler._row_order(B, Lq, Lq, 1) == "set"
+    tok, qq = tokens.bfloat16().requires_grad_(True), q.bfloat16().requires_grad_(True)
+    out = mod(tok, qq)
+    (out.float() * w).sum().backward()
+    assert float((out.detach().float() - ref.detach()).norm() / ref.detach().norm()) < 1e-2
+    assert cosine(qq.grad, q32.grad) >= 0.9995 and cosine(tok.grad, t32.grad) >= 0.9995
+    for k, p in mod.named_parameters():
+        if k == "attn.in_proj_bias":
+            continue
+        assert cosine(p.grad, p32[k].grad) >= 0.999, k
+
+
+def test_fold_decision():
+    from cosmos_b200 import pooler
+    assert pooler._fold_ok(1024, 8, 1, 1024, 8, 512)             # COSMOS: 8 crops x 8 heads = 64 score columns
+    assert pooler._fold_ok(4, 2, 1, 4, 12, 768)
+    assert not pooler._fold_ok(1024, 77, 77, 1, 12, 768)         # BASELINE config 4 literal: 924 columns -> key / value route
+    assert not pooler._fold_ok(4, 20, 20, 1, 12, 768)
+    assert not pooler._fold_ok(8, 4, 2, 3, 8, 512)               # an unknown row pattern
