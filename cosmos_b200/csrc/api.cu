@@ -560,8 +560,11 @@ int cosmos_gemm(const void* a, const void* b, void* d, const float* bias, int32_
 int cosmos_gemm_batched(const void* a, const void* b, void* d, const float* bias, int32_t M, int32_t N, int32_t K, int64_t lda,
                         int64_t ldb, int64_t ldd, int32_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_d,
                         int64_t stride_bias, int32_t a_kmajor, int32_t b_kmajor, int32_t in_dtype, int32_t out_dtype, int32_t splits,
-                        int32_t accumulate, float alpha, int device, void* stream) {
-  if (!a || !b || !d || M <= 0 || N <= 0 || K <= 0 || splits <= 0 || batch <= 0) return COSMOS_ERR_INVALID_ARGUMENT;
+                        int32_t accumulate, float alpha, const void* a2, const void* b2, int32_t K2, int64_t lda2, int64_t ldb2,
+                        int64_t stride_a2, int64_t stride_b2, int device, void* stream) {
+  if (!a || !b || !d || M <= 0 || N <= 0 || K <= 0 || splits <= 0 || batch <= 0 || K2 < 0) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (K2 > 0 && (!a2 || !b2 || (lda2 & 7) || (ldb2 & 7) || (stride_a2 & 7) || (stride_b2 & 7) || !aligned16(a2) || !aligned16(b2)))
+    return COSMOS_ERR_INVALID_ARGUMENT;
   if (!dtype16(in_dtype) || !dtype_any(out_dtype)) return COSMOS_ERR_UNSUPPORTED;
   if ((lda & 7) || (ldb & 7) || (stride_a & 7) || (stride_b & 7) || !aligned16(a) || !aligned16(b) || !aligned16(d))
     return COSMOS_ERR_INVALID_ARGUMENT;
@@ -574,6 +577,7 @@ int cosmos_gemm_batched(const void* a, const void* b, void* d, const float* bias
   ga.a_kmajor = a_kmajor; ga.b_kmajor = b_kmajor; ga.in_dtype = in_dtype; ga.out_dtype = out_dtype;
   ga.splits = splits; ga.alpha = alpha;
   ga.batch = batch; ga.sa = stride_a; ga.sb = stride_b; ga.sd = stride_d; ga.sbias = stride_bias; ga.accumulate = accumulate;
+  ga.a2 = a2; ga.b2 = b2; ga.K2 = K2; ga.lda2 = lda2; ga.ldb2 = ldb2; ga.sa2 = stride_a2; ga.sb2 = stride_b2;
   cudaError_t e = cudaSuccess;
   int ctas = sm_count_of(device);
   if (const int c = gemm_cta_cap(); c > 0 && c < ctas) ctas = c;

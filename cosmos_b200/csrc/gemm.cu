@@ -34,7 +34,8 @@ struct Misc {
 // TMEM let the epilogue of one tile overlap the MMAs of the next.
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA2,
+            const __grid_constant__ CUtensorMap tmB2, GemmParams p) {
   constexpr int kStages = BN == 256 ? 4 : 6;
   constexpr int kBBytes = BN * 64 * 2;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -46,7 +47,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_n = (p.N + BN - 1) / BN;
   const int tiles_m = (p.M + BM - 1) / BM;
-  const int k_slabs = (p.K + BK - 1) / BK;
+  // D = A B^T + A2 B2^T: the K slabs of an optional second operand pair (K2 > 0; same storage orders) follow those of the first
+  const int k_slabs1 = (p.K + BK - 1) / BK;
+  const int k_slabs = k_slabs1 + (p.K2 + BK - 1) / BK;
   const int per_split = (k_slabs + p.splits - 1) / p.splits;
   const int per_batch = tiles_m * tiles_n * p.splits;
   const int n_items = per_batch * p.batch;
@@ -65,6 +68,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.K2 > 0) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
   }
   if (warp == 2) tmem_alloc<2 * BN>(&misc->tmem_slot);
   tc_fence_before();
@@ -95,19 +102,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint8_t* a = sA + stage * kABytes;
         uint8_t* b = sB + stage * kBBytes;
         if (elect_one()) {
+        const bool second = s >= k_slabs1;
+        const CUtensorMap* mA = second ? &tmA2 : &tmA;
+        const CUtensorMap* mB = second ? &tmB2 : &tmB;
+        const int k0 = (second ? s - k_slabs1 : s) * BK;
         mbar_expect_tx(&misc->full[stage], kABytes + kBBytes);
         if (p.a_kmajor) {
-          tma_load_3d(a, &tmA, &misc->full[stage], s * BK, m0, bt);           // box 64 k x 128 rows
+          tma_load_3d(a, mA, &misc->full[stage], k0, m0, bt);           // box 64 k x 128 rows
         } else {
-          tma_load_3d(a, &tmA, &misc->full[stage], m0, s * BK, bt);           // box 64 m x 64 k-rows per 64-wide chunk
-          tma_load_3d(a + 8192, &tmA, &misc->full[stage], m0 + 64, s * BK, bt);
+          tma_load_3d(a, mA, &misc->full[stage], m0, k0, bt);           // box 64 m x 64 k-rows per 64-wide chunk
+          tma_load_3d(a + 8192, mA, &misc->full[stage], m0 + 64, k0, bt);
         }
         if (p.b_kmajor) {
 #pragma unroll
-          for (int c = 0; c < BN / 128; ++c) tma_load_3d(b + c * 16384, &tmB, &misc->full[stage], s * BK, n0 + c * 128, bt);
+          for (int c = 0; c < BN / 128; ++c) tma_load_3d(b + c * 16384, mB, &misc->full[stage], k0, n0 + c * 128, bt);
         } else {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c) tma_load_3d(b + c * 8192, &tmB, &misc->full[stage], n0 + c * 64, s * BK, bt);
+          for (int c = 0; c < BN / 64; ++c) tma_load_3d(b + c * 8192, mB, &misc->full[stage], n0 + c * 64, k0, bt);
         }
         }
         __syncwarp();
@@ -175,6 +186,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int k = 0; k < 32; ++k)
                 if (n0 + c + k < p.N) o[k] += src[k];
+            } else if (n0 + c + 32 <= p.N && (p.ldd & 7) == 0 && (p.sd & 7) == 0) {
+              const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.d) + off);
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const uint4 u = src[k4];
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  if (p.out_dtype == COSMOS_DTYPE_BF16) {
+                    o[k4 * 8 + 2 * j] += __uint_as_float(w[j] << 16);
+                    o[k4 * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+                  } else {
+                    o[k4 * 8 + 2 * j] += __half2float(__ushort_as_half(static_cast<unsigned short>(w[j] & 0xffff)));
+                    o[k4 * 8 + 2 * j + 1] += __half2float(__ushort_as_half(static_cast<unsigned short>(w[j] >> 16)));
+                  }
+                }
+              }
             } else {
               const uint16_t* src = reinterpret_cast<const uint16_t*>(p.d) + off;
 #pragma unroll
@@ -257,7 +285,8 @@ static int make_operand_map(CUtensorMap* map, const void* ptr, int is_bf16, int 
 }
 
 template <int BN>
-static cudaError_t launch_gemm_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, int bf, int sm_count, cudaStream_t stream) {
+static cudaError_t launch_gemm_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
+                                  GemmParams p, int bf, int sm_count, cudaStream_t stream) {
   constexpr int kStages = BN == 256 ? 4 : 6;
   p.idesc = make_idesc(bf, p.a_kmajor ? 0 : 1, p.b_kmajor ? 0 : 1, BM, BN);
   const int smem_bytes = kStages * (kABytes + BN * 64 * 2) + 1024;
@@ -265,7 +294,7 @@ static cudaError_t launch_gemm_bn(const CUtensorMap& tmA, const CUtensorMap& tmB
   if (e != cudaSuccess) return e;
   const int items = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.splits * p.batch;
   const int grid = items < sm_count ? items : sm_count;
-  gemm_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  gemm_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmA2, tmB2, p);
   return cudaGetLastError();
 }
 
@@ -277,14 +306,21 @@ int launch_gemm(const GemmArgs& a, int sm_count, cudaStream_t stream, cudaError_
   int r1 = make_operand_map(&tmA, a.a, bf, a.a_kmajor, a.M, a.K, a.lda, a.batch, a.sa);
   int r2 = make_operand_map(&tmB, a.b, bf, a.b_kmajor, a.N, a.K, a.ldb, a.batch, a.sb);
   if (r1 != 0 || r2 != 0) return 100000 + (r1 != 0 ? r1 : r2);
+  CUtensorMap tmA2 = tmA, tmB2 = tmB;
+  if (a.K2 > 0) {
+    r1 = make_operand_map(&tmA2, a.a2, bf, a.a_kmajor, a.M, a.K2, a.lda2, a.batch, a.sa2);
+    r2 = make_operand_map(&tmB2, a.b2, bf, a.b_kmajor, a.N, a.K2, a.ldb2, a.batch, a.sb2);
+    if (r1 != 0 || r2 != 0) return 100000 + (r1 != 0 ? r1 : r2);
+  }
   GemmParams p;
   p.M = a.M; p.N = a.N; p.K = a.K; p.ldd = static_cast<int>(a.ldd);
   p.a_kmajor = a.a_kmajor; p.b_kmajor = a.b_kmajor; p.splits = a.splits;
   p.out_dtype = a.splits > 1 ? COSMOS_DTYPE_F32 : a.out_dtype;
   p.alpha = a.alpha; p.bias = a.bias; p.d = a.d;
-  p.batch = a.batch; p.accumulate = a.accumulate; p.sd = a.sd; p.sbias = a.sbias;
+  p.batch = a.batch; p.accumulate = a.accumulate; p.sd = a.sd; p.sbias = a.sbias; p.K2 = a.K2;
   p.idesc = 0;
-  *err = wide ? launch_gemm_bn<256>(tmA, tmB, p, bf, sm_count, stream) : launch_gemm_bn<128>(tmA, tmB, p, bf, sm_count, stream);
+  *err = wide ? launch_gemm_bn<256>(tmA, tmB, tmA2, tmB2, p, bf, sm_count, stream)
+              : launch_gemm_bn<128>(tmA, tmB, tmA2, tmB2, p, bf, sm_count, stream);
   return *err == cudaSuccess ? 0 : -1;
 }
 

@@ -34,6 +34,7 @@ struct GemmParams {
   void* d;
   int batch, accumulate;
   long long sd, sbias;        // batch strides (elements) of D and of the bias
+  int K2;                     // contraction length of the optional second operand pair (0: none)
 };
 struct GemmArgs {
   const void* a; const void* b; void* d; const float* bias;
@@ -45,6 +46,10 @@ struct GemmArgs {
   int batch = 1;              // independent problems of the same shape: the third dimension of the operand tensor maps
   int64_t sa = 0, sb = 0, sd = 0, sbias = 0;    // their strides (elements); any multiple of 8 for a / b, also below the row stride
   int accumulate = 0;         // D += ... instead of D = ... (read-modify-write in the epilogue; splits == 1)
+  // optional second operand pair, same storage orders and batch count: D = alpha * (A B^T + A2 B2^T)
+  const void* a2 = nullptr; const void* b2 = nullptr;
+  int K2 = 0;
+  int64_t lda2 = 0, ldb2 = 0, sa2 = 0, sb2 = 0;
 };
 // returns 0, -1 (CUDA error in *err) or 100000 + CUresult (tensor map)
 int launch_gemm(const GemmArgs& a, int sm_count, cudaStream_t stream, cudaError_t* err);

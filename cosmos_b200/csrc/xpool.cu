@@ -35,8 +35,22 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 
-// One row in registers, element c = k * 32 + lane.  The dtype switch sits OUTSIDE the unrolled loops so that the
-// loads of a row are independent instructions the memory system can overlap.
+// One row in registers.  Two element-to-lane maps.  Scalar: column c = k * 32 + lane.  Vector (kVec, dim a multiple of 256):
+// register k = 8 j + e holds column (32 j + lane) * 8 + e - groups of 8 consecutive elements, so a 16-bit row moves as one
+// 16-byte vector per lane and group and every warp access is 512 contiguous bytes.  Measured on the [200704, 512] token
+// LayerNorm (tools/ln_ab.py, same box, L2 flushed): forward 171 -> 149 us with the vector map, backward 297 us against an
+// erratic 240 - 680 us with the scalar map; four rows per warp in flight made both slower (197 / 587 us: fewer warps per SM
+// cost more than the longer bursts gained).  row_col() gives the column of register k (or -1).  The dtype switch
+// sits OUTSIDE the unrolled loops so that the loads of a row are independent instructions the memory system can overlap.
+template <bool kVec>
+__device__ __forceinline__ int row_per(int dim) { return (kVec && (dim & 255) == 0) ? dim >> 5 : 0; }
+template <bool kVec>
+__device__ __forceinline__ int row_col(int k, int lane, int dim) {
+  const int per = row_per<kVec>(dim);
+  if (per) return k < per ? (((k >> 3) * 32 + lane) << 3) + (k & 7) : -1;
+  const int c = k * 32 + lane;
+  return c < dim ? c : -1;
+}
 template <class T>
 __device__ __forceinline__ float cvt_in(T v);
 template <>
@@ -54,33 +68,65 @@ __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { retur
 template <>
 __device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
 
-template <class T, int V>
+template <bool kVec = false, class T, int V>
 __device__ __forceinline__ void load_row_t(const T* __restrict__ p, int dim, int lane, float (&v)[V]) {
+  const int per = row_per<kVec>(dim);
+  if (kVec && per && per <= V && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    constexpr int E = 16 / sizeof(T);        // elements per 16-byte vector: 8 (one per group) or 4 (two per group)
+#pragma unroll
+    for (int k0 = 0; k0 < V; k0 += E) {
+      if (k0 < per) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p + ((((k0 >> 3) * 32 + lane) << 3) + (k0 & 7)));
+        const T* e = reinterpret_cast<const T*>(&u);
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[k0 + j] = cvt_in<T>(e[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[k0 + j] = 0.f;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < V; ++k) {
-    const int c = k * 32 + lane;
-    v[k] = c < dim ? cvt_in<T>(p[c]) : 0.f;
+    const int c = row_col<kVec>(k, lane, dim);
+    v[k] = c >= 0 ? cvt_in<T>(p[c]) : 0.f;
   }
 }
-template <int V>
+template <bool kVec = false, int V>
 __device__ __forceinline__ void load_row(const void* base, int dtype, int64_t row, int dim, int lane, float (&v)[V]) {
-  if (dtype == COSMOS_DTYPE_F32) load_row_t(reinterpret_cast<const float*>(base) + row * dim, dim, lane, v);
-  else if (dtype == COSMOS_DTYPE_BF16) load_row_t(reinterpret_cast<const __nv_bfloat16*>(base) + row * dim, dim, lane, v);
-  else load_row_t(reinterpret_cast<const __half*>(base) + row * dim, dim, lane, v);
+  if (dtype == COSMOS_DTYPE_F32) load_row_t<kVec>(reinterpret_cast<const float*>(base) + row * dim, dim, lane, v);
+  else if (dtype == COSMOS_DTYPE_BF16) load_row_t<kVec>(reinterpret_cast<const __nv_bfloat16*>(base) + row * dim, dim, lane, v);
+  else load_row_t<kVec>(reinterpret_cast<const __half*>(base) + row * dim, dim, lane, v);
 }
-template <class T, int V>
+template <bool kVec = false, class T, int V>
 __device__ __forceinline__ void store_row_t(T* __restrict__ p, int dim, int lane, const float (&v)[V]) {
+  const int per = row_per<kVec>(dim);
+  if (kVec && per && per <= V && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    constexpr int E = 16 / sizeof(T);
+#pragma unroll
+    for (int k0 = 0; k0 < V; k0 += E) {
+      if (k0 < per) {
+        uint4 u;
+        T* e = reinterpret_cast<T*>(&u);
+#pragma unroll
+        for (int j = 0; j < E; ++j) e[j] = cvt_out<T>(v[k0 + j]);
+        *reinterpret_cast<uint4*>(p + ((((k0 >> 3) * 32 + lane) << 3) + (k0 & 7))) = u;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < V; ++k) {
-    const int c = k * 32 + lane;
-    if (c < dim) p[c] = cvt_out<T>(v[k]);
+    const int c = row_col<kVec>(k, lane, dim);
+    if (c >= 0) p[c] = cvt_out<T>(v[k]);
   }
 }
-template <int V>
+template <bool kVec = false, int V>
 __device__ __forceinline__ void store_row(void* base, int dtype, int64_t row, int dim, int lane, const float (&v)[V]) {
-  if (dtype == COSMOS_DTYPE_F32) store_row_t(reinterpret_cast<float*>(base) + row * dim, dim, lane, v);
-  else if (dtype == COSMOS_DTYPE_BF16) store_row_t(reinterpret_cast<__nv_bfloat16*>(base) + row * dim, dim, lane, v);
-  else store_row_t(reinterpret_cast<__half*>(base) + row * dim, dim, lane, v);
+  if (dtype == COSMOS_DTYPE_F32) store_row_t<kVec>(reinterpret_cast<float*>(base) + row * dim, dim, lane, v);
+  else if (dtype == COSMOS_DTYPE_BF16) store_row_t<kVec>(reinterpret_cast<__nv_bfloat16*>(base) + row * dim, dim, lane, v);
+  else store_row_t<kVec>(reinterpret_cast<__half*>(base) + row * dim, dim, lane, v);
 }
 
 }  // namespace
@@ -96,9 +142,9 @@ layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __res
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   float v[V], wv[V], bv[V];
-  load_row(x, x_dtype, row, dim, lane, v);
-  load_row_t(w, dim, lane, wv);
-  load_row_t(b, dim, lane, bv);
+  load_row<true>(x, x_dtype, row, dim, lane, v);
+  load_row_t<true>(w, dim, lane, wv);
+  load_row_t<true>(b, dim, lane, bv);
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < V; ++k) s += v[k];
@@ -106,19 +152,23 @@ layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __res
   float q = 0.f;
 #pragma unroll
   for (int k = 0; k < V; ++k) {
-    const int c = k * 32 + lane;
-    const float d = c < dim ? v[k] - mu : 0.f;
+    const float d = row_col<true>(k, lane, dim) >= 0 ? v[k] - mu : 0.f;
     q += d * d;
   }
   const float rs = rsqrtf(warp_sum(q) / dim + eps);
 #pragma unroll
   for (int k = 0; k < V; ++k) v[k] = (v[k] - mu) * rs * wv[k] + bv[k];
-  store_row(y, y_dtype, row, dim, lane, v);
+  store_row<true>(y, y_dtype, row, dim, lane, v);
   if (lane == 0) {
     mean[row] = mu;
     rstd[row] = rs;
   }
 }
+
+#ifndef COSMOS_LN_BWD_VEC
+#define COSMOS_LN_BWD_VEC 1
+#endif
+constexpr bool kLnBwdVec = COSMOS_LN_BWD_VEC != 0;      // which row map the backward uses (A/B builds flip it)
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w;  dw += dy * xhat, db += dy (block partials -> atomics)
 template <int V>
@@ -134,18 +184,17 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
   float aw[V], ab[V], wv[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) aw[k] = ab[k] = 0.f;
-  load_row_t(w, dim, lane, wv);
+  load_row_t<kLnBwdVec>(w, dim, lane, wv);
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
   for (int64_t row = r0 + wid; row < min(rows, r0 + rows_per_block); row += 8) {
     const float mu = mean[row], rs = rstd[row];
     float g[V], xh[V];
-    load_row(dy, dy_dtype, row, dim, lane, g);
-    load_row(x, x_dtype, row, dim, lane, xh);
+    load_row<kLnBwdVec>(dy, dy_dtype, row, dim, lane, g);
+    load_row<kLnBwdVec>(x, x_dtype, row, dim, lane, xh);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      const int c = k * 32 + lane;
-      xh[k] = c < dim ? (xh[k] - mu) * rs : 0.f;
+      xh[k] = row_col<kLnBwdVec>(k, lane, dim) >= 0 ? (xh[k] - mu) * rs : 0.f;
       aw[k] = fmaf(g[k], xh[k], aw[k]);
       ab[k] += g[k];
       g[k] *= wv[k];
@@ -154,17 +203,21 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
     }
     s1 = warp_sum(s1) / dim;
     s2 = warp_sum(s2) / dim;
-    float o[V];
-    if (accumulate) load_row(dx, dx_dtype, row, dim, lane, o);
+    // (in place: the result overwrites g, a previous dx to add to is loaded into xh - one row array less alive)
 #pragma unroll
-    for (int k = 0; k < V; ++k) o[k] = (accumulate ? o[k] : 0.f) + rs * (g[k] - s1 - xh[k] * s2);
-    store_row(dx, dx_dtype, row, dim, lane, o);
+    for (int k = 0; k < V; ++k) g[k] = rs * (g[k] - s1 - xh[k] * s2);
+    if (accumulate) {
+      load_row<kLnBwdVec>(dx, dx_dtype, row, dim, lane, xh);
+#pragma unroll
+      for (int k = 0; k < V; ++k) g[k] += xh[k];
+    }
+    store_row<kLnBwdVec>(dx, dx_dtype, row, dim, lane, g);
   }
   if (dw != nullptr) {
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-      const int c = k * 32 + lane;
-      if (c < dim) {
+      const int c = row_col<kLnBwdVec>(k, lane, dim);
+      if (c >= 0) {
         atomicAdd(&red[c], aw[k]);
         atomicAdd(&red[dim + c], ab[k]);
       }

@@ -50,14 +50,17 @@ def _gemm(a, b, out, M, N, K, lda, ldb, a_kmajor, b_kmajor, bias=None, splits=1,
 
 
 def _bgemm(a, b, out, M, N, K, lda, ldb, ldd, batch, sa, sb, sd, a_kmajor, b_kmajor, bias=None, sbias=0, splits=1, accumulate=False,
-           alpha=1.0):
+           alpha=1.0, second=None):
     """`batch` problems D_t = alpha * opA_t opB_t^T (+ bias_t) through cosmos_gemm_batched; a, b, out, bias are tensors (views) whose
     first element is the first problem's, every stride is in elements.  a_kmajor: A_t stored [M, K] (row stride lda), else
-    [K, M]; likewise B_t [N, K] / [K, N]."""
+    [K, M]; likewise B_t [N, K] / [K, N].  second = (a2, b2, K2, lda2, ldb2, sa2, sb2): D_t = alpha * (A_t B_t^T + A2_t B2_t^T)."""
     dev = a.device
+    a2, b2, K2, lda2, ldb2, sa2, sb2 = second if second is not None else (None, None, 0, 0, 0, 0, 0)
     st = _lib.lib().cosmos_gemm_batched(a.data_ptr(), b.data_ptr(), out.data_ptr(), bias.data_ptr() if bias is not None else None,
                                         M, N, K, lda, ldb, ldd, batch, sa, sb, sd, sbias, int(a_kmajor), int(b_kmajor), _code(a),
-                                        _code(out), splits, int(accumulate), float(alpha), dev.index, _stream(dev))
+                                        _code(out), splits, int(accumulate), float(alpha),
+                                        a2.data_ptr() if a2 is not None else None, b2.data_ptr() if b2 is not None else None, K2, lda2,
+                                        ldb2, sa2, sb2, dev.index, _stream(dev))
     _lib.check(st, "gemm_batched")
     return out
 
@@ -157,10 +160,10 @@ def _folded_bwd(g_o_sm, xn, qp_sm, qt, pd, z, w_kv, g_in_w, g_in_b, n_sets, L, d
     _bgemm(xn, dz, d_p, L, n_cols, d, d, d, n_cols, n_sets, L * d, n_cols * d, L * n_cols, True, True)
     ds = pd[:, :, n_cols:]
     _colsoftmax_bwd(pd, d_p, ds, n_sets, L, n_cols, 2 * n_cols)
-    # d xn = P dZ + dS Q~   (two products into one output)
+    # d xn = P dZ + dS Q~   (two operand pairs, one pass over the output)
     g_xn = torch.empty(n_sets * L, d, dtype=cd, device=dev)
-    _bgemm(pd, dz, g_xn, L, d, n_cols, 2 * n_cols, d, d, n_sets, L * 2 * n_cols, n_cols * d, L * d, True, False)
-    _bgemm(ds, qt, g_xn, L, d, n_cols, 2 * n_cols, d, d, n_sets, L * 2 * n_cols, n_cols * d, L * d, True, False, accumulate=True)
+    _bgemm(pd, dz, g_xn, L, d, n_cols, 2 * n_cols, d, d, n_sets, L * 2 * n_cols, n_cols * d, L * d, True, False,
+           second=(ds, qt, n_cols, 2 * n_cols, d, L * 2 * n_cols, n_cols * d))
     # S = xn Q~^T,  Q~ = kappa W_k,h^T q_h
     dqt = torch.empty(n_q, heads, d, dtype=cd, device=dev)
     _bgemm(ds, xn, dqt, n_cols, d, L, 2 * n_cols, d, d, n_sets, L * 2 * n_cols, L * d, n_cols * d, False, False)

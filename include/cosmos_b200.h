@@ -178,6 +178,8 @@ int cosmos_gemm(const void* a, const void* b, void* d, const float* bias, int32_
  * multiples of 8, and they may be SMALLER than the row strides: the per-head column blocks of one matrix are a batch), adds
  * bias + t * stride_bias and writes d + t * stride_d.  Tiles past M, N or K of one problem read zeros, never a neighbour's
  * rows (each problem is its own slice of a 3-D tensor map).  accumulate != 0: D += ... (splits must be 1).
+ * K2 > 0: a second operand pair of the same storage orders, D = alpha * (A B^T + A2 B2^T) in one pass over the output (the
+ * token gradient of the folded attention is P dZ + dS Q~).
  * Used by the folded attention of the pooler (cosmos_b200/pooler.py): with one query per (sample, crop) the key projection
  * of nn.MultiheadAttention (transformer.py:214, 225-229) folds into the queries, q~ = W_k,h^T q_h, so that per sample
  * scores = LN(x) q~^T and pooled_h = W_v,h (P^T LN(x)): four small GEMMs per sample instead of the [L, d] x [d, 2d] key /
@@ -185,7 +187,8 @@ int cosmos_gemm(const void* a, const void* b, void* d, const float* bias, int32_
 int cosmos_gemm_batched(const void* a, const void* b, void* d, const float* bias, int32_t M, int32_t N, int32_t K, int64_t lda,
                         int64_t ldb, int64_t ldd, int32_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_d,
                         int64_t stride_bias, int32_t a_kmajor, int32_t b_kmajor, int32_t in_dtype, int32_t out_dtype, int32_t splits,
-                        int32_t accumulate, float alpha, int device, void* stream);
+                        int32_t accumulate, float alpha, const void* a2, const void* b2, int32_t K2, int64_t lda2, int64_t ldb2,
+                        int64_t stride_a2, int64_t stride_b2, int device, void* stream);
 
 /* Softmax over the KEYS of the folded attention (F.multi_head_attention_forward's softmax(dim=-1) of [queries, keys] scores,
  * stored here keys-major): s fp32 [n_sets][L][n_cols] (row stride lds, set stride s_stride) -> p 16-bit, same indexing with

@@ -14,10 +14,14 @@ def _mat(t, rows, cols, ld, batch, bs, kmajor):
 
 
 def emu_bgemm(a, b, out, M, N, K, lda, ldb, ldd, batch, sa, sb, sd, a_kmajor, b_kmajor, bias=None, sbias=0, splits=1, accumulate=False,
-              alpha=1.0):
+              alpha=1.0, second=None):
     A = _mat(a, M, K, lda, batch, sa, a_kmajor).double()
     B = _mat(b, N, K, ldb, batch, sb, b_kmajor).double()
-    res = alpha * (A @ B.transpose(1, 2))
+    res = A @ B.transpose(1, 2)
+    if second is not None:
+        a2, b2, K2, lda2, ldb2, sa2, sb2 = second
+        res = res + _mat(a2, M, K2, lda2, batch, sa2, a_kmajor).double() @ _mat(b2, N, K2, ldb2, batch, sb2, b_kmajor).double().transpose(1, 2)
+    res = alpha * res
     if bias is not None:
         res = res + bias.as_strided((batch, 1, N), (sbias, 0, 1)).double()
     D = out.as_strided((batch, M, N), (sd, ldd, 1))
