@@ -230,6 +230,78 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
   }
 }
 
+// ---- forward, second generation for dims that are multiples of 256 (the vector row map): CTAs stride over the rows, a warp
+// has TWO rows in flight, and the LayerNorm weights live in shared memory (register order: a lane's four consecutive values
+// are one conflict-free LDS.128) so that the second row does not cost occupancy.  tools/ln_ab.py, [200704, 512] bf16, same
+// box: 149.5 -> 135 us (3.0 TB/s).  Measured and rejected: loading the NEXT row before reducing the current one (178 us: the
+// second register set halves the resident warps), four rows per warp (197 us); for the backward, two rows per warp (389 us)
+// and next-row prefetch (299 us, the same as without) - it stays on the first-generation kernel with the vector map.
+__device__ __forceinline__ int vec_slot(int k, int lane) { return (((k >> 2) * 32 + lane) << 2) + (k & 3); }   // of register k
+
+template <int V>
+__global__ void __launch_bounds__(256)
+layernorm_fwd2_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ w, const float* __restrict__ b,
+                      void* __restrict__ y, int y_dtype, float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int dim, float eps) {
+  extern __shared__ __align__(16) float swb[];            // [V * 32] w, [V * 32] b in register order
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int per = dim >> 5;
+  for (int i = threadIdx.x; i < V * 32; i += blockDim.x) {
+    const int k = ((i >> 7) << 2) + (i & 3), ln = (i >> 2) & 31;       // inverse of vec_slot
+    const int c = row_col<true>(k, ln, dim);
+    swb[i] = c >= 0 ? w[c] : 0.f;
+    swb[V * 32 + i] = c >= 0 ? b[c] : 0.f;
+  }
+  __syncthreads();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * 16;
+  for (int64_t r0 = (static_cast<int64_t>(blockIdx.x) * 8 + wid) * 2; r0 < rows; r0 += stride) {
+    const bool two = r0 + 1 < rows;
+    float v[2][V];
+    load_row<true>(x, x_dtype, r0, dim, lane, v[0]);
+    if (two) {
+      load_row<true>(x, x_dtype, r0 + 1, dim, lane, v[1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[1][k] = 0.f;
+    }
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      s0 += v[0][k];
+      s1 += v[1][k];
+    }
+    const float mu0 = warp_sum(s0) / dim, mu1 = warp_sum(s1) / dim;
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float d0 = k < per ? v[0][k] - mu0 : 0.f, d1 = k < per ? v[1][k] - mu1 : 0.f;
+      q0 += d0 * d0;
+      q1 += d1 * d1;
+    }
+    const float rs0 = rsqrtf(warp_sum(q0) / dim + eps), rs1 = rsqrtf(warp_sum(q1) / dim + eps);
+#pragma unroll
+    for (int k4 = 0; k4 < V; k4 += 4) {
+      const float4 ww = *reinterpret_cast<const float4*>(swb + vec_slot(k4, lane));
+      const float4 bb = *reinterpret_cast<const float4*>(swb + V * 32 + vec_slot(k4, lane));
+      const float wv[4] = {ww.x, ww.y, ww.z, ww.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[0][k4 + j] = (v[0][k4 + j] - mu0) * rs0 * wv[j] + bv[j];
+        v[1][k4 + j] = (v[1][k4 + j] - mu1) * rs1 * wv[j] + bv[j];
+      }
+    }
+    store_row<true>(y, y_dtype, r0, dim, lane, v[0]);
+    if (two) store_row<true>(y, y_dtype, r0 + 1, dim, lane, v[1]);
+    if (lane == 0) {
+      mean[r0] = mu0;
+      rstd[r0] = rs0;
+      if (two) {
+        mean[r0 + 1] = mu1;
+        rstd[r0 + 1] = rs1;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // attention core: one CTA per (key/value set, head); K_h and V_h of the set stay in shared memory while the
 // set's few queries are processed.  Rows padded to hd + 2 elements so that "one thread = one key" reads do
@@ -606,6 +678,15 @@ colsum_kernel(const void* __restrict__ src, int dtype, float* __restrict__ dst, 
 cudaError_t launch_layernorm_fwd(const void* x, int x_dtype, const float* w, const float* b, void* y, int y_dtype, float* mean,
                                  float* rstd, int64_t rows, int dim, float eps, cudaStream_t s) {
   if (rows == 0) return cudaSuccess;
+  if ((dim & 255) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    // strided CTAs, two rows per warp in flight, weights in shared memory (dims 256 / 512 / 768 / 1024)
+    const int64_t want = (rows + 15) / 16;
+    const unsigned grid2 = static_cast<unsigned>(want < 148 * 8 ? want : 148 * 8);
+    if (dim <= 256) layernorm_fwd2_kernel<8><<<grid2, 256, 2 * 8 * 32 * 4, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim, eps);
+    else if (dim <= 512) layernorm_fwd2_kernel<16><<<grid2, 256, 2 * 16 * 32 * 4, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim, eps);
+    else layernorm_fwd2_kernel<32><<<grid2, 256, 2 * 32 * 32 * 4, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim, eps);
+    return cudaGetLastError();
+  }
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   if (dim <= 256) layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim, eps);
   else if (dim <= 512) layernorm_fwd_kernel<16><<<grid, 256, 0, s>>>(x, x_dtype, w, b, y, y_dtype, mean, rstd, rows, dim, eps);
