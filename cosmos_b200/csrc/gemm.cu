@@ -6,7 +6,7 @@
 // Tile 128 x 128 x 64, 6-stage TMA ring, one CTA per output tile and K split (gridDim.z); K splits
 // accumulate with fp32 red.global.add into a zero-initialised D (weight gradients contract over the very
 // long row dimension, so the output has few tiles and needs the split for parallelism).
-// Warp roles as in the InfoNCE kernels: warp 0 TMA, warp 1 MMA issue, warp 2 TMEM, warps 4-7 epilogue.
+// Warp roles as in the InfoNCE kernels: warp 0 TMA, warp 1 MMA issue, warp 2 TMEM, warps 4-11 epilogue.
 #include "common.cuh"
 #include "internal.h"
 #include "tma_host.h"
@@ -17,7 +17,8 @@ namespace {
 
 constexpr int BM = 128, BK = 64;
 constexpr int kABytes = 128 * 64 * 2;    // 16 KB of A per stage
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;             // two per TMEM lane quarter, each draining half of the tile's columns
+constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kMaxStages = 6;
 
 struct Misc {
@@ -61,7 +62,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&misc->acc_full[s], 1);
-      mbar_init(&misc->acc_empty[s], 4);
+      mbar_init(&misc->acc_empty[s], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -156,6 +157,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     const uint32_t q = warp & 3;
+    // The folded attention's GEMMs have one or two K slabs per tile: four epilogue warps then set the pace (a 128 x 256 tile
+    // is 64 KB of output per 4 MMAs).  Eight warps: warp / 4 selects the half of the tile's columns.
+    const int c_begin = static_cast<int>((warp - 4) >> 2) * (BN / 2), c_end = c_begin + BN / 2;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       int bt, m0, n0, ks0, ks1;
@@ -167,7 +171,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool add_bias = p.bias != nullptr && (item % p.splits) == 0;
       const float* bias = p.bias != nullptr ? p.bias + static_cast<size_t>(bt) * p.sbias : nullptr;
       const bool has_k = ks1 > ks0;
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = c_begin; c < c_end; c += 32) {
         if (n0 + c >= p.N) break;
         uint32_t v[32];
         tmem_ld32(tmem + ((q * 32u) << 16) + as * BN + c, v);
