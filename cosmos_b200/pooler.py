@@ -17,8 +17,9 @@ reference executes them on 8x duplicated rows), and it fuses the residual add + 
 All contractions run on tcgen05 tensor cores (csrc/gemm.cu).  With the few queries per sample COSMOS uses (one per crop:
 8 x 8 heads = 64 score columns) the attention is FOLDED: the key projection moves into the queries and the value
 projection behind the pooling (`_folded_fwd`), so scores, pooling and all their gradients are batched GEMMs over the
-samples and no key / value tensor exists; more than 128 score columns per sample (the module's general forward(x, q) with
-many queries) keep the key / value projection GEMM and the CUDA-core attention kernel.  LayerNorm, the column softmax and
+samples and no key / value tensor exists; where folding would cost more than twice the flops of the key / value projection
+(the module's general forward(x, q) with hundreds of queries per sample) that projection GEMM and the CUDA-core attention
+kernel remain.  LayerNorm, the column softmax and
 add+normalise are HBM-bound CUDA kernels (csrc/xpool.cu).  There is no PyTorch fallback.
 """
 from __future__ import annotations
@@ -65,18 +66,20 @@ def _bgemm(a, b, out, M, N, K, lda, ldb, ldd, batch, sa, sb, sd, a_kmajor, b_kma
     return out
 
 
-def _colsoftmax_fwd(scores, p_out, n_sets, L, n_cols, ldp):
-    """softmax over the L keys of every column of scores [n_sets, L, n_cols] fp32 -> p_out (16-bit view, row stride ldp)."""
+def _colsoftmax_fwd(scores, p_out, n_sets, L, n_cols, lds, ldp):
+    """softmax over the L keys of every column of scores [n_sets, L, n_cols] fp32 (row stride lds) -> p_out (16-bit view, row
+    stride ldp)."""
     dev = scores.device
-    st = _lib.lib().cosmos_colsoftmax_fwd(scores.data_ptr(), L * n_cols, n_cols, p_out.data_ptr(), L * ldp, ldp, _code(p_out), n_sets, L,
+    st = _lib.lib().cosmos_colsoftmax_fwd(scores.data_ptr(), L * lds, lds, p_out.data_ptr(), L * ldp, ldp, _code(p_out), n_sets, L,
                                           n_cols, dev.index, _stream(dev))
     _lib.check(st, "colsoftmax_fwd")
 
 
-def _colsoftmax_bwd(p_in, d_p, ds_out, n_sets, L, n_cols, ldp):
-    """ds = p * (dp - sum_l p dp) per column; p_in / ds_out 16-bit views with row stride ldp, d_p [n_sets, L, n_cols] fp32."""
+def _colsoftmax_bwd(p_in, d_p, ds_out, n_sets, L, n_cols, lds, ldp):
+    """ds = p * (dp - sum_l p dp) per column; p_in / ds_out 16-bit views with row stride ldp, d_p [n_sets, L, n_cols] fp32 with
+    row stride lds."""
     dev = d_p.device
-    st = _lib.lib().cosmos_colsoftmax_bwd(p_in.data_ptr(), L * ldp, ldp, d_p.data_ptr(), L * n_cols, n_cols, ds_out.data_ptr(), L * ldp,
+    st = _lib.lib().cosmos_colsoftmax_bwd(p_in.data_ptr(), L * ldp, ldp, d_p.data_ptr(), L * lds, lds, ds_out.data_ptr(), L * ldp,
                                           ldp, _code(p_in), n_sets, L, n_cols, dev.index, _stream(dev))
     _lib.check(st, "colsoftmax_bwd")
 
@@ -108,14 +111,20 @@ def _from_set_major(t, order, n_sets, q_per_set):
 
 
 # Folded attention (few queries per token set): COSMOS_B200_POOLER=unfolded keeps the key / value projection route (diagnostics)
-_FOLD_MAX_COLS = 0 if os.environ.get("COSMOS_B200_POOLER", "") == "unfolded" else 128
+# COSMOS_B200_POOLER_FOLD_MAX: largest number of score columns (queries x heads) per sample that is folded (diagnostics;
+# default: the flop comparison in _fold_ok)
+_FOLD_MAX_COLS = 0 if os.environ.get("COSMOS_B200_POOLER", "") == "unfolded" else int(os.environ.get("COSMOS_B200_POOLER_FOLD_MAX", "-1"))
 
 
 def _fold_ok(n_sets, q_per_set, qs, qq, heads, d):
     hd = d // heads
     n_cols = q_per_set * heads
-    return (n_cols <= _FOLD_MAX_COLS and n_cols % 8 == 0 and hd % 8 == 0 and hd * heads == d
-            and _row_order(n_sets, q_per_set, qs, qq) is not None)
+    # Folded, the two large products cost 4 L n_cols d flop per sample, all on tensor cores; the key / value route 4 L d (d +
+    # queries), of which the 4 L d queries of the attention core run on CUDA cores.  Measured at batch 1024, width 768, 12
+    # heads: 77 queries x 197 keys (924 columns, 1.1x the flops) 9.0 vs 16.2 ms; 197 x 77 (2364 columns, 2.4x) 16.9 vs 18.2 ms
+    # with 15 GB of folded queries - so: fold up to twice the flops.
+    limit = _FOLD_MAX_COLS if _FOLD_MAX_COLS >= 0 else max(128, 2 * (d + q_per_set))
+    return (n_cols <= limit and hd % 8 == 0 and hd * heads == d and _row_order(n_sets, q_per_set, qs, qq) is not None)
 
 
 def _folded_fwd(xn, qp, w_kv, b_in, n_sets, L, d, heads, q_per_set, order, cd):
@@ -131,12 +140,13 @@ def _folded_fwd(xn, qp, w_kv, b_in, n_sets, L, d, heads, q_per_set, order, cd):
     qp_sm = _to_set_major(qp, order, n_sets, q_per_set).contiguous()
     qt = torch.empty(n_q, heads, d, dtype=cd, device=dev)                       # Q~, rows (set, query), then head
     _bgemm(qp_sm, w_k, qt, n_q, d, hd, d, d, heads * d, heads, hd, hd * d, d, True, False, alpha=hd ** -0.5)
-    scores = torch.empty(n_sets, L, n_cols, dtype=torch.float32, device=dev)
-    _bgemm(xn, qt, scores, L, n_cols, d, d, d, n_cols, n_sets, L * d, n_cols * d, L * n_cols, True, True)
-    pd = torch.empty(n_sets, L, 2 * n_cols, dtype=cd, device=dev)               # [P | dS]: the second half is filled by backward
-    _colsoftmax_fwd(scores, pd, n_sets, L, n_cols, 2 * n_cols)
+    ncp = (n_cols + 7) // 8 * 8                                                 # row pitch of the score blocks (16-byte rows and halves)
+    scores = torch.empty(n_sets, L, ncp, dtype=torch.float32, device=dev)
+    _bgemm(xn, qt, scores, L, n_cols, d, d, d, ncp, n_sets, L * d, n_cols * d, L * ncp, True, True)
+    pd = torch.empty(n_sets, L, 2 * ncp, dtype=cd, device=dev)                  # [P | dS]: the second half is filled by backward
+    _colsoftmax_fwd(scores, pd, n_sets, L, n_cols, ncp, 2 * ncp)
     z = torch.empty(n_q, heads, d, dtype=cd, device=dev)
-    _bgemm(pd, xn, z, n_cols, d, L, 2 * n_cols, d, d, n_sets, L * 2 * n_cols, L * d, n_cols * d, False, False)
+    _bgemm(pd, xn, z, n_cols, d, L, 2 * ncp, d, d, n_sets, L * 2 * ncp, L * d, n_cols * d, False, False)
     o_sm = torch.empty(n_q, d, dtype=cd, device=dev)
     _bgemm(z, w_v, o_sm, n_q, hd, d, heads * d, d, d, heads, d, hd * d, hd, True, True, bias=b_in[2 * d:], sbias=hd)
     return o_sm, qp_sm, qt, pd, z
@@ -156,17 +166,18 @@ def _folded_bwd(g_o_sm, xn, qp_sm, qt, pd, z, w_kv, g_in_w, g_in_b, n_sets, L, d
     dz = torch.empty(n_q, heads, d, dtype=cd, device=dev)
     _bgemm(g_o_sm, w_v, dz, n_q, d, hd, d, d, heads * d, heads, hd, hd * d, d, True, False)
     # Z = P^T xn
-    d_p = torch.empty(n_sets, L, n_cols, dtype=torch.float32, device=dev)
-    _bgemm(xn, dz, d_p, L, n_cols, d, d, d, n_cols, n_sets, L * d, n_cols * d, L * n_cols, True, True)
-    ds = pd[:, :, n_cols:]
-    _colsoftmax_bwd(pd, d_p, ds, n_sets, L, n_cols, 2 * n_cols)
+    ncp = pd.shape[2] // 2
+    d_p = torch.empty(n_sets, L, ncp, dtype=torch.float32, device=dev)
+    _bgemm(xn, dz, d_p, L, n_cols, d, d, d, ncp, n_sets, L * d, n_cols * d, L * ncp, True, True)
+    ds = pd[:, :, ncp:]
+    _colsoftmax_bwd(pd, d_p, ds, n_sets, L, n_cols, ncp, 2 * ncp)
     # d xn = P dZ + dS Q~   (two operand pairs, one pass over the output)
     g_xn = torch.empty(n_sets * L, d, dtype=cd, device=dev)
-    _bgemm(pd, dz, g_xn, L, d, n_cols, 2 * n_cols, d, d, n_sets, L * 2 * n_cols, n_cols * d, L * d, True, False,
-           second=(ds, qt, n_cols, 2 * n_cols, d, L * 2 * n_cols, n_cols * d))
+    _bgemm(pd, dz, g_xn, L, d, n_cols, 2 * ncp, d, d, n_sets, L * 2 * ncp, n_cols * d, L * d, True, False,
+           second=(ds, qt, n_cols, 2 * ncp, d, L * 2 * ncp, n_cols * d))
     # S = xn Q~^T,  Q~ = kappa W_k,h^T q_h
     dqt = torch.empty(n_q, heads, d, dtype=cd, device=dev)
-    _bgemm(ds, xn, dqt, n_cols, d, L, 2 * n_cols, d, d, n_sets, L * 2 * n_cols, L * d, n_cols * d, False, False)
+    _bgemm(ds, xn, dqt, n_cols, d, L, 2 * ncp, d, d, n_sets, L * 2 * ncp, L * d, n_cols * d, False, False)
     dq_sm = torch.empty(n_q, d, dtype=cd, device=dev)
     _bgemm(dqt, w_k, dq_sm, n_q, hd, d, heads * d, d, d, heads, d, hd * d, hd, True, True, alpha=kappa)
     _bgemm(qp_sm, dqt, g_in_w[d:2 * d], hd, d, n_q, d, heads * d, d, heads, hd, d, hd * d, False, False, splits=splits, alpha=kappa)

@@ -68,14 +68,15 @@ def emu_ln_bwd(dy, x2d, w, mean, rstd, dx, accumulate, dw=None, db=None):
     return dw, db
 
 
-def emu_colsoftmax_fwd(scores, p_out, n_sets, L, n_cols, ldp):
-    P = torch.softmax(scores.double(), dim=1)
+def emu_colsoftmax_fwd(scores, p_out, n_sets, L, n_cols, lds, ldp):
+    S = scores.as_strided((n_sets, L, n_cols), (L * lds, lds, 1))
+    P = torch.softmax(S.double(), dim=1)
     p_out.as_strided((n_sets, L, n_cols), (L * ldp, ldp, 1)).copy_(P.to(p_out.dtype))
 
 
-def emu_colsoftmax_bwd(p_in, d_p, ds_out, n_sets, L, n_cols, ldp):
+def emu_colsoftmax_bwd(p_in, d_p, ds_out, n_sets, L, n_cols, lds, ldp):
     P = p_in.as_strided((n_sets, L, n_cols), (L * ldp, ldp, 1)).double()
-    dP = d_p.double()
+    dP = d_p.as_strided((n_sets, L, n_cols), (L * lds, lds, 1)).double()
     dS = P * (dP - (P * dP).sum(1, keepdim=True))
     ds_out.as_strided((n_sets, L, n_cols), (L * ldp, ldp, 1)).copy_(dS.to(ds_out.dtype))
 

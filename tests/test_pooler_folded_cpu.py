@@ -14,7 +14,7 @@ def cosine(a, b):
     return float(a @ b / (a.norm() * b.norm()))
 
 
-@pytest.mark.parametrize("d,L,B,n,heads,seed", [(64, 13, 5, 4, 4, 1), (128, 70, 3, 8, 8, 2), (96, 9, 2, 2, 12, 3)])
+@pytest.mark.parametrize("d,L,B,n,heads,seed", [(64, 13, 5, 4, 4, 1), (128, 70, 3, 8, 8, 2), (96, 9, 2, 2, 12, 3), (64, 10, 3, 3, 4, 4)])
 def test_folded_crossmodal_matches_oracle(monkeypatch, d, L, B, n, heads, seed):
     from cosmos_b200 import pooler
     emulation_pooler.install(monkeypatch)
@@ -75,6 +75,7 @@ def test_fold_decision():
     from cosmos_b200 import pooler
     assert pooler._fold_ok(1024, 8, 1, 1024, 8, 512)             # COSMOS: 8 crops x 8 heads = 64 score columns
     assert pooler._fold_ok(4, 2, 1, 4, 12, 768)
-    assert not pooler._fold_ok(1024, 77, 77, 1, 12, 768)         # BASELINE config 4 literal: 924 columns -> key / value route
-    assert not pooler._fold_ok(4, 20, 20, 1, 12, 768)
+    assert pooler._fold_ok(1024, 77, 77, 1, 12, 768)             # BASELINE config 4 literal, 77 queries: 924 columns, 1.1x the flops
+    assert not pooler._fold_ok(1024, 197, 197, 1, 12, 768)       # 197 queries: 2364 columns, 2.4x the flops -> key / value route
+    assert pooler._fold_ok(4, 20, 20, 1, 12, 768)
     assert not pooler._fold_ok(8, 4, 2, 3, 8, 512)               # an unknown row pattern
