@@ -90,7 +90,20 @@ _INFONCE_SIGS = {
 }
 
 
+class GemmDesc(C.Structure):
+    """cosmos_gemm_desc (include/cosmos_b200.h)"""
+    _fields_ = ([(n, C.c_void_p) for n in ("a", "b", "d", "bias", "a2", "b2")] +
+                [(n, C.c_int32) for n in ("M", "N", "K", "K2")] +
+                [(n, C.c_int64) for n in ("lda", "ldb", "ldd", "lda2", "ldb2")] +
+                [(n, C.c_int32) for n in ("batch", "batch_in")] +
+                [(n, C.c_int64) for n in ("stride_a", "stride_b", "stride_d", "stride_bias", "stride_a2", "stride_b2",
+                                          "stride_a_in", "stride_b_in", "stride_d_in", "stride_bias_in", "stride_a2_in", "stride_b2_in")] +
+                [(n, C.c_int32) for n in ("a_kmajor", "b_kmajor", "in_dtype", "out_dtype", "splits", "accumulate")] +
+                [("alpha", C.c_float), ("reserved", C.c_int32)])
+
+
 _POOL_SIGS = {
+    "cosmos_gemm_ex": [vp_, i32_, vp_],
     "cosmos_gemm": [vp_, vp_, vp_, vp_, i32_, i32_, i32_, i64_, i64_, i64_, i32_, i32_, i32_, i32_, i32_, f32_, i32_, vp_],
     "cosmos_gemm_batched": [vp_, vp_, vp_, vp_, i32_, i32_, i32_, i64_, i64_, i64_, i32_, i64_, i64_, i64_, i64_, i32_, i32_, i32_,
                             i32_, i32_, i32_, f32_, vp_, vp_, i32_, i64_, i64_, i64_, i64_, i32_, vp_],

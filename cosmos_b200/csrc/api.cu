@@ -557,27 +557,31 @@ int cosmos_gemm(const void* a, const void* b, void* d, const float* bias, int32_
   return COSMOS_ERR_CUDA;
 }
 
-int cosmos_gemm_batched(const void* a, const void* b, void* d, const float* bias, int32_t M, int32_t N, int32_t K, int64_t lda,
-                        int64_t ldb, int64_t ldd, int32_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_d,
-                        int64_t stride_bias, int32_t a_kmajor, int32_t b_kmajor, int32_t in_dtype, int32_t out_dtype, int32_t splits,
-                        int32_t accumulate, float alpha, const void* a2, const void* b2, int32_t K2, int64_t lda2, int64_t ldb2,
-                        int64_t stride_a2, int64_t stride_b2, int device, void* stream) {
-  if (!a || !b || !d || M <= 0 || N <= 0 || K <= 0 || splits <= 0 || batch <= 0 || K2 < 0) return COSMOS_ERR_INVALID_ARGUMENT;
-  if (K2 > 0 && (!a2 || !b2 || (lda2 & 7) || (ldb2 & 7) || (stride_a2 & 7) || (stride_b2 & 7) || !aligned16(a2) || !aligned16(b2)))
+int cosmos_gemm_ex(const cosmos_gemm_desc* q, int device, void* stream) {
+  if (!q) return COSMOS_ERR_INVALID_ARGUMENT;
+  const int batch_in = q->batch_in > 0 ? q->batch_in : 1;
+  if (!q->a || !q->b || !q->d || q->M <= 0 || q->N <= 0 || q->K <= 0 || q->splits <= 0 || q->batch <= 0 || q->K2 < 0)
     return COSMOS_ERR_INVALID_ARGUMENT;
-  if (!dtype16(in_dtype) || !dtype_any(out_dtype)) return COSMOS_ERR_UNSUPPORTED;
-  if ((lda & 7) || (ldb & 7) || (stride_a & 7) || (stride_b & 7) || !aligned16(a) || !aligned16(b) || !aligned16(d))
+  if (!dtype16(q->in_dtype) || !dtype_any(q->out_dtype)) return COSMOS_ERR_UNSUPPORTED;
+  if ((q->lda & 7) || (q->ldb & 7) || (q->stride_a & 7) || (q->stride_b & 7) || (q->stride_a_in & 7) || (q->stride_b_in & 7) ||
+      !aligned16(q->a) || !aligned16(q->b) || !aligned16(q->d))
     return COSMOS_ERR_INVALID_ARGUMENT;
-  if (accumulate && splits != 1) return COSMOS_ERR_INVALID_ARGUMENT;
+  if (q->K2 > 0 && (!q->a2 || !q->b2 || (q->lda2 & 7) || (q->ldb2 & 7) || (q->stride_a2 & 7) || (q->stride_b2 & 7) ||
+                    (q->stride_a2_in & 7) || (q->stride_b2_in & 7) || !aligned16(q->a2) || !aligned16(q->b2)))
+    return COSMOS_ERR_INVALID_ARGUMENT;
+  if (q->accumulate && q->splits != 1) return COSMOS_ERR_INVALID_ARGUMENT;
   DeviceGuard g(device);
   if (!g.ok) return COSMOS_ERR_CUDA;
   cb::GemmArgs ga;
-  ga.a = a; ga.b = b; ga.d = d; ga.bias = bias;
-  ga.M = M; ga.N = N; ga.K = K; ga.lda = lda; ga.ldb = ldb; ga.ldd = ldd;
-  ga.a_kmajor = a_kmajor; ga.b_kmajor = b_kmajor; ga.in_dtype = in_dtype; ga.out_dtype = out_dtype;
-  ga.splits = splits; ga.alpha = alpha;
-  ga.batch = batch; ga.sa = stride_a; ga.sb = stride_b; ga.sd = stride_d; ga.sbias = stride_bias; ga.accumulate = accumulate;
-  ga.a2 = a2; ga.b2 = b2; ga.K2 = K2; ga.lda2 = lda2; ga.ldb2 = ldb2; ga.sa2 = stride_a2; ga.sb2 = stride_b2;
+  ga.a = q->a; ga.b = q->b; ga.d = q->d; ga.bias = q->bias;
+  ga.M = q->M; ga.N = q->N; ga.K = q->K; ga.lda = q->lda; ga.ldb = q->ldb; ga.ldd = q->ldd;
+  ga.a_kmajor = q->a_kmajor; ga.b_kmajor = q->b_kmajor; ga.in_dtype = q->in_dtype; ga.out_dtype = q->out_dtype;
+  ga.splits = q->splits; ga.alpha = q->alpha;
+  ga.batch = q->batch; ga.sa = q->stride_a; ga.sb = q->stride_b; ga.sd = q->stride_d; ga.sbias = q->stride_bias;
+  ga.accumulate = q->accumulate;
+  ga.a2 = q->a2; ga.b2 = q->b2; ga.K2 = q->K2; ga.lda2 = q->lda2; ga.ldb2 = q->ldb2; ga.sa2 = q->stride_a2; ga.sb2 = q->stride_b2;
+  ga.batch_in = batch_in; ga.sa_in = q->stride_a_in; ga.sb_in = q->stride_b_in; ga.sd_in = q->stride_d_in;
+  ga.sbias_in = q->stride_bias_in; ga.sa2_in = q->stride_a2_in; ga.sb2_in = q->stride_b2_in;
   cudaError_t e = cudaSuccess;
   int ctas = sm_count_of(device);
   if (const int c = gemm_cta_cap(); c > 0 && c < ctas) ctas = c;
@@ -585,6 +589,23 @@ int cosmos_gemm_batched(const void* a, const void* b, void* d, const float* bias
   if (r == 0) return COSMOS_OK;
   if (r > 0) g_last_cuda = r; else cu_fail(e);
   return COSMOS_ERR_CUDA;
+}
+
+int cosmos_gemm_batched(const void* a, const void* b, void* d, const float* bias, int32_t M, int32_t N, int32_t K, int64_t lda,
+                        int64_t ldb, int64_t ldd, int32_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_d,
+                        int64_t stride_bias, int32_t a_kmajor, int32_t b_kmajor, int32_t in_dtype, int32_t out_dtype, int32_t splits,
+                        int32_t accumulate, float alpha, const void* a2, const void* b2, int32_t K2, int64_t lda2, int64_t ldb2,
+                        int64_t stride_a2, int64_t stride_b2, int device, void* stream) {
+  cosmos_gemm_desc q = {};
+  q.a = a; q.b = b; q.d = d; q.bias = bias; q.a2 = a2; q.b2 = b2;
+  q.M = M; q.N = N; q.K = K; q.K2 = K2;
+  q.lda = lda; q.ldb = ldb; q.ldd = ldd; q.lda2 = lda2; q.ldb2 = ldb2;
+  q.batch = batch; q.batch_in = 1;
+  q.stride_a = stride_a; q.stride_b = stride_b; q.stride_d = stride_d; q.stride_bias = stride_bias;
+  q.stride_a2 = stride_a2; q.stride_b2 = stride_b2;
+  q.a_kmajor = a_kmajor; q.b_kmajor = b_kmajor; q.in_dtype = in_dtype; q.out_dtype = out_dtype; q.splits = splits;
+  q.accumulate = accumulate; q.alpha = alpha;
+  return cosmos_gemm_ex(&q, device, stream);
 }
 
 int cosmos_colsoftmax_fwd(const float* s, int64_t s_stride, int32_t lds, void* p, int64_t p_stride, int32_t ldp, int32_t p_dtype,

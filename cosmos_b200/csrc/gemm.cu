@@ -53,7 +53,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int k_slabs = k_slabs1 + (p.K2 + BK - 1) / BK;
   const int per_split = (k_slabs + p.splits - 1) / p.splits;
   const int per_batch = tiles_m * tiles_n * p.splits;
-  const int n_items = per_batch * p.batch;
+  const int n_items = per_batch * p.batch * p.batch2;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -80,9 +80,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem = misc->tmem_slot;
 
-  auto decode = [&](int item, int& bt, int& m0, int& n0, int& ks0, int& ks1) {
-    bt = item / per_batch;          // batch slowest: CTAs running together work on neighbouring problems
-    item -= bt * per_batch;
+  auto decode = [&](int item, int& bt, int& bi, int& m0, int& n0, int& ks0, int& ks1) {
+    const int t = item / per_batch;          // batch slowest: CTAs running together work on neighbouring problems
+    item -= t * per_batch;
+    bt = t / p.batch2;                       // outer (samples), inner (heads)
+    bi = t - bt * p.batch2;
     const int split = item % p.splits;
     const int tile = item / p.splits;
     n0 = (tile % tiles_n) * BN;     // n fastest: CTAs running together share the A rows
@@ -96,8 +98,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0) {
     uint32_t stage = 0, phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      int bt, m0, n0, ks0, ks1;
-      decode(item, bt, m0, n0, ks0, ks1);
+      int bt, bi, m0, n0, ks0, ks1;
+      decode(item, bt, bi, m0, n0, ks0, ks1);
       for (int s = ks0; s < ks1; ++s) {
         mbar_wait(&misc->empty[stage], phase ^ 1);
         uint8_t* a = sA + stage * kABytes;
@@ -109,17 +111,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int k0 = (second ? s - k_slabs1 : s) * BK;
         mbar_expect_tx(&misc->full[stage], kABytes + kBBytes);
         if (p.a_kmajor) {
-          tma_load_3d(a, mA, &misc->full[stage], k0, m0, bt);           // box 64 k x 128 rows
+          tma_load_4d(a, mA, &misc->full[stage], k0, m0, bi, bt);           // box 64 k x 128 rows
         } else {
-          tma_load_3d(a, mA, &misc->full[stage], m0, k0, bt);           // box 64 m x 64 k-rows per 64-wide chunk
-          tma_load_3d(a + 8192, mA, &misc->full[stage], m0 + 64, k0, bt);
+          tma_load_4d(a, mA, &misc->full[stage], m0, k0, bi, bt);           // box 64 m x 64 k-rows per 64-wide chunk
+          tma_load_4d(a + 8192, mA, &misc->full[stage], m0 + 64, k0, bi, bt);
         }
         if (p.b_kmajor) {
 #pragma unroll
-          for (int c = 0; c < BN / 128; ++c) tma_load_3d(b + c * 16384, mB, &misc->full[stage], k0, n0 + c * 128, bt);
+          for (int c = 0; c < BN / 128; ++c) tma_load_4d(b + c * 16384, mB, &misc->full[stage], k0, n0 + c * 128, bi, bt);
         } else {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c) tma_load_3d(b + c * 8192, mB, &misc->full[stage], n0 + c * 64, k0, bt);
+          for (int c = 0; c < BN / 64; ++c) tma_load_4d(b + c * 8192, mB, &misc->full[stage], n0 + c * 64, k0, bi, bt);
         }
         }
         __syncwarp();
@@ -130,8 +132,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t stage = 0, phase = 0;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      int bt, m0, n0, ks0, ks1;
-      decode(item, bt, m0, n0, ks0, ks1);
+      int bt, bi, m0, n0, ks0, ks1;
+      decode(item, bt, bi, m0, n0, ks0, ks1);
       const uint32_t as = it & 1;
       mbar_wait(&misc->acc_empty[as], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -162,14 +164,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int c_begin = static_cast<int>((warp - 4) >> 2) * (BN / 2), c_end = c_begin + BN / 2;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      int bt, m0, n0, ks0, ks1;
-      decode(item, bt, m0, n0, ks0, ks1);
+      int bt, bi, m0, n0, ks0, ks1;
+      decode(item, bt, bi, m0, n0, ks0, ks1);
       const uint32_t as = it & 1;
       const int row = m0 + q * 32 + lane;
       mbar_wait(&misc->acc_full[as], (it >> 1) & 1);
       tc_fence_after();
       const bool add_bias = p.bias != nullptr && (item % p.splits) == 0;
-      const float* bias = p.bias != nullptr ? p.bias + static_cast<size_t>(bt) * p.sbias : nullptr;
+      const float* bias = p.bias != nullptr ? p.bias + static_cast<size_t>(bt) * p.sbias + static_cast<size_t>(bi) * p.sbias2 : nullptr;
       const bool has_k = ks1 > ks0;
       for (int c = c_begin; c < c_end; c += 32) {
         if (n0 + c >= p.N) break;
@@ -183,14 +185,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int col = n0 + c + k;
             o[k] = (has_k ? __uint_as_float(v[k]) * p.alpha : 0.f) + ((add_bias && col < p.N) ? __ldg(bias + col) : 0.f);
           }
-          const size_t off = static_cast<size_t>(bt) * p.sd + static_cast<size_t>(row) * p.ldd + n0 + c;
+          const size_t off = static_cast<size_t>(bt) * p.sd + static_cast<size_t>(bi) * p.sd2 + static_cast<size_t>(row) * p.ldd + n0 + c;
           if (p.accumulate) {             // D += ...: the caller's second product into the same output (splits == 1)
             if (p.out_dtype == COSMOS_DTYPE_F32) {
               const float* src = reinterpret_cast<const float*>(p.d) + off;
 #pragma unroll
               for (int k = 0; k < 32; ++k)
                 if (n0 + c + k < p.N) o[k] += src[k];
-            } else if (n0 + c + 32 <= p.N && (p.ldd & 7) == 0 && (p.sd & 7) == 0) {
+            } else if (n0 + c + 32 <= p.N && (p.ldd & 7) == 0 && (p.sd & 7) == 0 && (p.sd2 & 7) == 0) {
               const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.d) + off);
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4) {
@@ -223,7 +225,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (n0 + c + k < p.N) atomicAdd(dst + k, o[k]);
           } else if (p.out_dtype == COSMOS_DTYPE_F32) {
             float* dst = reinterpret_cast<float*>(p.d) + off;
-            if (n0 + c + 32 <= p.N && (p.ldd & 3) == 0) {
+            if (n0 + c + 32 <= p.N && (p.ldd & 3) == 0 && (p.sd & 3) == 0 && (p.sd2 & 3) == 0) {
 #pragma unroll
               for (int k = 0; k < 8; ++k)
                 reinterpret_cast<float4*>(dst)[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
@@ -235,7 +237,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
             const int fmt = p.out_dtype == COSMOS_DTYPE_BF16 ? 1 : 0;
             uint16_t* dst = reinterpret_cast<uint16_t*>(p.d) + off;
-            if (n0 + c + 32 <= p.N && (p.ldd & 7) == 0) {
+            if (n0 + c + 32 <= p.N && (p.ldd & 7) == 0 && (p.sd & 7) == 0 && (p.sd2 & 7) == 0) {
               uint32_t w[16];
 #pragma unroll
               for (int k = 0; k < 16; ++k) w[k] = pack2(o[2 * k], o[2 * k + 1], fmt);
@@ -265,24 +267,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 // 2-D operand map: K-major [rows, K] -> box {64 k, 128 rows}; MN-major [K, rows] -> box {64 rows, 64 k}.
 static int make_operand_map(CUtensorMap* map, const void* ptr, int is_bf16, int kmajor, int64_t rows, int64_t K, int64_t ld,
-                            int batch, int64_t bstride) {
+                            int batch, int64_t bstride, int batch_in, int64_t bstride_in) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) return -1;
-  cuuint64_t gdim[3], gstride[2];
-  cuuint32_t box[3], estr[3] = {1, 1, 1};
+  // rank 4: {contiguous dim, rows, inner batch, outer batch}
+  cuuint64_t gdim[4], gstride[3];
+  cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
   if (kmajor) {
-    gdim[0] = K; gdim[1] = rows; gdim[2] = batch;
-    box[0] = 64; box[1] = 128; box[2] = 1;
+    gdim[0] = K; gdim[1] = rows;
+    box[0] = 64; box[1] = 128;
   } else {
-    gdim[0] = rows; gdim[1] = K; gdim[2] = batch;
-    box[0] = 64; box[1] = 64; box[2] = 1;
+    gdim[0] = rows; gdim[1] = K;
+    box[0] = 64; box[1] = 64;
   }
+  gdim[2] = batch_in; gdim[3] = batch;
+  box[2] = 1; box[3] = 1;
   // (the batch stride may be smaller than the row stride - per-head column blocks of one matrix: strides only have to be
   //  multiples of 16 bytes; every dimension is bounded on its own, so tiles past M, N or K of one problem read zeros and
   //  never its neighbour's rows)
   gstride[0] = static_cast<cuuint64_t>(ld) * 2;
-  gstride[1] = batch > 1 ? static_cast<cuuint64_t>(bstride) * 2 : gstride[0] * gdim[1];
-  CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), gdim,
+  const cuuint64_t whole = gstride[0] * gdim[1];
+  gstride[1] = batch_in > 1 ? static_cast<cuuint64_t>(bstride_in) * 2 : whole;
+  gstride[2] = batch > 1 ? static_cast<cuuint64_t>(bstride) * 2 : whole;
+  CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gdim,
                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
@@ -296,7 +303,7 @@ static cudaError_t launch_gemm_bn(const CUtensorMap& tmA, const CUtensorMap& tmB
   const int smem_bytes = kStages * (kABytes + BN * 64 * 2) + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return e;
-  const int items = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.splits * p.batch;
+  const int items = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN) * p.splits * p.batch * p.batch2;
   const int grid = items < sm_count ? items : sm_count;
   gemm_kernel<BN><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmA2, tmB2, p);
   return cudaGetLastError();
@@ -307,13 +314,13 @@ int launch_gemm(const GemmArgs& a, int sm_count, cudaStream_t stream, cudaError_
   CUtensorMap tmA, tmB;
   const int bf = a.in_dtype == COSMOS_DTYPE_BF16;
   const bool wide = a.N >= 256;       // 128 x 256 tiles when the output is wide enough
-  int r1 = make_operand_map(&tmA, a.a, bf, a.a_kmajor, a.M, a.K, a.lda, a.batch, a.sa);
-  int r2 = make_operand_map(&tmB, a.b, bf, a.b_kmajor, a.N, a.K, a.ldb, a.batch, a.sb);
+  int r1 = make_operand_map(&tmA, a.a, bf, a.a_kmajor, a.M, a.K, a.lda, a.batch, a.sa, a.batch_in, a.sa_in);
+  int r2 = make_operand_map(&tmB, a.b, bf, a.b_kmajor, a.N, a.K, a.ldb, a.batch, a.sb, a.batch_in, a.sb_in);
   if (r1 != 0 || r2 != 0) return 100000 + (r1 != 0 ? r1 : r2);
   CUtensorMap tmA2 = tmA, tmB2 = tmB;
   if (a.K2 > 0) {
-    r1 = make_operand_map(&tmA2, a.a2, bf, a.a_kmajor, a.M, a.K2, a.lda2, a.batch, a.sa2);
-    r2 = make_operand_map(&tmB2, a.b2, bf, a.b_kmajor, a.N, a.K2, a.ldb2, a.batch, a.sb2);
+    r1 = make_operand_map(&tmA2, a.a2, bf, a.a_kmajor, a.M, a.K2, a.lda2, a.batch, a.sa2, a.batch_in, a.sa2_in);
+    r2 = make_operand_map(&tmB2, a.b2, bf, a.b_kmajor, a.N, a.K2, a.ldb2, a.batch, a.sb2, a.batch_in, a.sb2_in);
     if (r1 != 0 || r2 != 0) return 100000 + (r1 != 0 ? r1 : r2);
   }
   GemmParams p;
@@ -322,6 +329,7 @@ int launch_gemm(const GemmArgs& a, int sm_count, cudaStream_t stream, cudaError_
   p.out_dtype = a.splits > 1 ? COSMOS_DTYPE_F32 : a.out_dtype;
   p.alpha = a.alpha; p.bias = a.bias; p.d = a.d;
   p.batch = a.batch; p.accumulate = a.accumulate; p.sd = a.sd; p.sbias = a.sbias; p.K2 = a.K2;
+  p.batch2 = a.batch_in; p.sd2 = a.sd_in; p.sbias2 = a.sbias_in;
   p.idesc = 0;
   *err = wide ? launch_gemm_bn<256>(tmA, tmB, tmA2, tmB2, p, bf, sm_count, stream)
               : launch_gemm_bn<128>(tmA, tmB, tmA2, tmB2, p, bf, sm_count, stream);

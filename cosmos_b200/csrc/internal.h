@@ -35,6 +35,8 @@ struct GemmParams {
   int batch, accumulate;
   long long sd, sbias;        // batch strides (elements) of D and of the bias
   int K2;                     // contraction length of the optional second operand pair (0: none)
+  int batch2;                 // inner batch dimension (problem t = t1 * batch2 + t2)
+  long long sd2, sbias2;      // its strides for D and the bias
 };
 struct GemmArgs {
   const void* a; const void* b; void* d; const float* bias;
@@ -50,6 +52,9 @@ struct GemmArgs {
   const void* a2 = nullptr; const void* b2 = nullptr;
   int K2 = 0;
   int64_t lda2 = 0, ldb2 = 0, sa2 = 0, sb2 = 0;
+  // inner batch dimension: problem (t1, t2), t2 < batch_in, at a + t1 * sa + t2 * sa_in, ... (heads inside samples)
+  int batch_in = 1;
+  int64_t sa_in = 0, sb_in = 0, sd_in = 0, sbias_in = 0, sa2_in = 0, sb2_in = 0;
 };
 // returns 0, -1 (CUDA error in *err) or 100000 + CUresult (tensor map)
 int launch_gemm(const GemmArgs& a, int sm_count, cudaStream_t stream, cudaError_t* err);

@@ -17,13 +17,15 @@ reference executes them on 8x duplicated rows), and it fuses the residual add + 
 All contractions run on tcgen05 tensor cores (csrc/gemm.cu).  With the few queries per sample COSMOS uses (one per crop:
 8 x 8 heads = 64 score columns) the attention is FOLDED: the key projection moves into the queries and the value
 projection behind the pooling (`_folded_fwd`), so scores, pooling and all their gradients are batched GEMMs over the
-samples and no key / value tensor exists; where folding would cost more than twice the flops of the key / value projection
-(the module's general forward(x, q) with hundreds of queries per sample) that projection GEMM and the CUDA-core attention
-kernel remain.  LayerNorm, the column softmax and
+samples and no key / value tensor exists.  Where folding would not at least halve the flops (the module's general
+forward(x, q) with many queries per sample) the key / value projection GEMM stays and the attention core itself runs as
+batched GEMMs with samples as the outer and heads as the inner batch dimension (`_core_fwd`); the CUDA-core attention
+kernel is only left for head dims that are not a multiple of 8.  LayerNorm, the column softmax and
 add+normalise are HBM-bound CUDA kernels (csrc/xpool.cu).  There is no PyTorch fallback.
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 from typing import Optional
 
@@ -51,18 +53,29 @@ def _gemm(a, b, out, M, N, K, lda, ldb, a_kmajor, b_kmajor, bias=None, splits=1,
 
 
 def _bgemm(a, b, out, M, N, K, lda, ldb, ldd, batch, sa, sb, sd, a_kmajor, b_kmajor, bias=None, sbias=0, splits=1, accumulate=False,
-           alpha=1.0, second=None):
-    """`batch` problems D_t = alpha * opA_t opB_t^T (+ bias_t) through cosmos_gemm_batched; a, b, out, bias are tensors (views) whose
+           alpha=1.0, second=None, inner=None):
+    """`batch` problems D_t = alpha * opA_t opB_t^T (+ bias_t) through cosmos_gemm_ex; a, b, out, bias are tensors (views) whose
     first element is the first problem's, every stride is in elements.  a_kmajor: A_t stored [M, K] (row stride lda), else
-    [K, M]; likewise B_t [N, K] / [K, N].  second = (a2, b2, K2, lda2, ldb2, sa2, sb2): D_t = alpha * (A_t B_t^T + A2_t B2_t^T)."""
+    [K, M]; likewise B_t [N, K] / [K, N].  second = (a2, b2, K2, lda2, ldb2, sa2, sb2): D_t = alpha * (A_t B_t^T + A2_t B2_t^T).
+    inner = (batch_in, sa_in, sb_in, sd_in): an inner batch dimension, problem (t1, t2) at a + t1 * sa + t2 * sa_in, ..."""
     dev = a.device
-    a2, b2, K2, lda2, ldb2, sa2, sb2 = second if second is not None else (None, None, 0, 0, 0, 0, 0)
-    st = _lib.lib().cosmos_gemm_batched(a.data_ptr(), b.data_ptr(), out.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                        M, N, K, lda, ldb, ldd, batch, sa, sb, sd, sbias, int(a_kmajor), int(b_kmajor), _code(a),
-                                        _code(out), splits, int(accumulate), float(alpha),
-                                        a2.data_ptr() if a2 is not None else None, b2.data_ptr() if b2 is not None else None, K2, lda2,
-                                        ldb2, sa2, sb2, dev.index, _stream(dev))
-    _lib.check(st, "gemm_batched")
+    g = _lib.GemmDesc()
+    g.a, g.b, g.d = a.data_ptr(), b.data_ptr(), out.data_ptr()
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldb, g.ldd = lda, ldb, ldd
+    g.batch, g.batch_in = batch, 1
+    g.stride_a, g.stride_b, g.stride_d, g.stride_bias = sa, sb, sd, sbias
+    if second is not None:
+        a2, b2, g.K2, g.lda2, g.ldb2, g.stride_a2, g.stride_b2 = second
+        g.a2, g.b2 = a2.data_ptr(), b2.data_ptr()
+    if inner is not None:
+        g.batch_in, g.stride_a_in, g.stride_b_in, g.stride_d_in = inner
+    g.a_kmajor, g.b_kmajor = int(a_kmajor), int(b_kmajor)
+    g.in_dtype, g.out_dtype = _code(a), _code(out)
+    g.splits, g.accumulate, g.alpha = splits, int(accumulate), float(alpha)
+    st = _lib.lib().cosmos_gemm_ex(C.byref(g), dev.index, _stream(dev))
+    _lib.check(st, "gemm_ex")
     return out
 
 
@@ -119,11 +132,11 @@ _FOLD_MAX_COLS = 0 if os.environ.get("COSMOS_B200_POOLER", "") == "unfolded" els
 def _fold_ok(n_sets, q_per_set, qs, qq, heads, d):
     hd = d // heads
     n_cols = q_per_set * heads
-    # Folded, the two large products cost 4 L n_cols d flop per sample, all on tensor cores; the key / value route 4 L d (d +
-    # queries), of which the 4 L d queries of the attention core run on CUDA cores.  Measured at batch 1024, width 768, 12
-    # heads: 77 queries x 197 keys (924 columns, 1.1x the flops) 9.0 vs 16.2 ms; 197 x 77 (2364 columns, 2.4x) 16.9 vs 18.2 ms
-    # with 15 GB of folded queries - so: fold up to twice the flops.
-    limit = _FOLD_MAX_COLS if _FOLD_MAX_COLS >= 0 else max(128, 2 * (d + q_per_set))
+    # Folded, the two large products cost 4 L n_cols d flop per sample against 4 L d (d + queries) on the key / value route
+    # (both all on tensor cores: the attention core of that route is batched GEMMs too, _core_fwd).  Measured at batch 1024:
+    # 8 queries x 8 heads, width 512 (64 columns, 0.12x the flops): 1.50 vs 2.68 ms; 77 queries x 12 heads, width 768 (924
+    # columns, 1.1x the flops, 1.5 GB of folded queries): 9.0 vs 7.2 ms - so: fold up to half the flops.
+    limit = _FOLD_MAX_COLS if _FOLD_MAX_COLS >= 0 else max(128, (d + q_per_set) // 2)
     return (n_cols <= limit and hd % 8 == 0 and hd * heads == d and _row_order(n_sets, q_per_set, qs, qq) is not None)
 
 
@@ -182,6 +195,58 @@ def _folded_bwd(g_o_sm, xn, qp_sm, qt, pd, z, w_kv, g_in_w, g_in_b, n_sets, L, d
     _bgemm(dqt, w_k, dq_sm, n_q, hd, d, heads * d, d, d, heads, d, hd * d, hd, True, True, alpha=kappa)
     _bgemm(qp_sm, dqt, g_in_w[d:2 * d], hd, d, n_q, d, heads * d, d, heads, hd, d, hd * d, False, False, splits=splits, alpha=kappa)
     return g_xn, dq_sm
+
+
+def _core_ok(n_sets, q_per_set, qs, qq, heads, d):
+    """The attention core of the key / value route as batched GEMMs (any number of queries)."""
+    hd = d // heads
+    return (os.environ.get("COSMOS_B200_POOLER_CORE", "") != "cuda_cores" and hd % 8 == 0 and hd * heads == d
+            and _row_order(n_sets, q_per_set, qs, qq) is not None)
+
+
+def _core_fwd(qp_sm, kv, n_sets, L, d, heads, q_per_set, cd):
+    """softmax(q_h k_h^T / sqrt(hd)) v_h per (sample, head) - F.multi_head_attention_forward's core - on tensor cores: per
+    (sample, head) problem  S^T = kappa K_h Q_h^T  [L, queries]  (keys-major, so that the softmax over the keys is the column
+    softmax of the folded route),  O_h = P^T V_h  [queries, hd].  Samples are the outer, heads the inner batch dimension of the
+    operand tensor maps (head h of a [rows, d] matrix is the column block h * hd).  qp_sm [n_q, d] set-major, kv [n_sets * L, 2d]
+    -> o_sm [n_q, d] and pd = [P | room for dS] [n_sets * heads, L, 2 * pitch]."""
+    dev = kv.device
+    hd, q = d // heads, q_per_set
+    qpad = (q + 7) // 8 * 8
+    scores = torch.empty(n_sets * heads, L, qpad, dtype=torch.float32, device=dev)
+    _bgemm(kv, qp_sm, scores, L, q, hd, 2 * d, d, qpad, n_sets, L * 2 * d, q * d, heads * L * qpad, True, True, alpha=hd ** -0.5,
+           inner=(heads, hd, hd, L * qpad))
+    pd = torch.empty(n_sets * heads, L, 2 * qpad, dtype=cd, device=dev)
+    _colsoftmax_fwd(scores, pd, n_sets * heads, L, q, qpad, 2 * qpad)
+    o_sm = torch.empty(n_sets * q, d, dtype=cd, device=dev)
+    _bgemm(pd, kv[:, d:], o_sm, q, hd, L, 2 * qpad, 2 * d, d, n_sets, heads * L * 2 * qpad, L * 2 * d, q * d, False, False,
+           inner=(heads, L * 2 * qpad, hd, hd))
+    return o_sm, pd
+
+
+def _core_bwd(g_o_sm, qp_sm, kv, pd, n_sets, L, d, heads, q_per_set, cd):
+    """-> (dq_sm [n_q, d] set-major, dkv [n_sets * L, 2d])"""
+    dev = kv.device
+    hd, q = d // heads, q_per_set
+    qpad = pd.shape[2] // 2
+    kappa = hd ** -0.5
+    v = kv[:, d:]
+    d_p = torch.empty(n_sets * heads, L, qpad, dtype=torch.float32, device=dev)          # dP^T = V_h dO_h^T
+    _bgemm(v, g_o_sm, d_p, L, q, hd, 2 * d, d, qpad, n_sets, L * 2 * d, q * d, heads * L * qpad, True, True,
+           inner=(heads, hd, hd, L * qpad))
+    ds = pd[:, :, qpad:]
+    _colsoftmax_bwd(pd, d_p, ds, n_sets * heads, L, q, qpad, 2 * qpad)
+    dkv = torch.empty_like(kv)
+    # dV_h = P dO_h,  dK_h = kappa dS Q_h   ([L, queries] x [queries, hd]: the second operands are read as stored, [K, N])
+    _bgemm(pd, g_o_sm, dkv[:, d:], L, hd, q, 2 * qpad, d, 2 * d, n_sets, heads * L * 2 * qpad, q * d, L * 2 * d, True, False,
+           inner=(heads, L * 2 * qpad, hd, hd))
+    _bgemm(ds, qp_sm, dkv, L, hd, q, 2 * qpad, d, 2 * d, n_sets, heads * L * 2 * qpad, q * d, L * 2 * d, True, False, alpha=kappa,
+           inner=(heads, L * 2 * qpad, hd, hd))
+    # dQ_h = kappa dS^T K_h
+    dq_sm = torch.empty(n_sets * q, d, dtype=cd, device=dev)
+    _bgemm(ds, kv, dq_sm, q, hd, L, 2 * qpad, 2 * d, d, n_sets, heads * L * 2 * qpad, L * 2 * d, q * d, False, False, alpha=kappa,
+           inner=(heads, L * 2 * qpad, hd, hd))
+    return dq_sm, dkv
 
 
 def _linear(x, w, bias, out_dtype):
@@ -349,14 +414,23 @@ class _CrossPool(torch.autograd.Function):
             kv = lse = torch.empty(0, device=dev)
             fold_saved = (qp_sm, qt, pd, z)
         else:
-            order = None
             kv = _linear(xn, w_kv, b_in[d:], cd)                                   # [n_sets*L, 2d]
-            o = torch.empty(n_q, d, dtype=cd, device=dev)
-            lse = torch.empty(n_q, heads, dtype=torch.float32, device=dev)
-            st = _lib.lib().cosmos_attn_core_fwd(qp.data_ptr(), kv.data_ptr(), o.data_ptr(), lse.data_ptr(), _code(qp), n_sets, L, d,
-                                                 heads, q_per_set, qs, qq, dev.index, _stream(dev))
-            _lib.check(st, "attn_core_fwd")
-            fold_saved = tuple(torch.empty(0, device=dev) for _ in range(4))
+            empty = torch.empty(0, device=dev)
+            if _core_ok(n_sets, q_per_set, qs, qq, heads, d):                      # attention core as batched GEMMs
+                order = _row_order(n_sets, q_per_set, qs, qq)
+                qp_sm = _to_set_major(qp, order, n_sets, q_per_set).contiguous()
+                o_sm, pd = _core_fwd(qp_sm, kv, n_sets, L, d, heads, q_per_set, cd)
+                o = _from_set_major(o_sm, order, n_sets, q_per_set).contiguous()
+                lse = empty
+                fold_saved = (qp_sm, empty, pd, empty)
+            else:                                                                  # CUDA-core attention kernel (head dims not a multiple of 8, unknown row patterns)
+                order = None
+                o = torch.empty(n_q, d, dtype=cd, device=dev)
+                lse = torch.empty(n_q, heads, dtype=torch.float32, device=dev)
+                st = _lib.lib().cosmos_attn_core_fwd(qp.data_ptr(), kv.data_ptr(), o.data_ptr(), lse.data_ptr(), _code(qp), n_sets, L,
+                                                     d, heads, q_per_set, qs, qq, dev.index, _stream(dev))
+                _lib.check(st, "attn_core_fwd")
+                fold_saved = (empty, empty, empty, empty)
         ctx.fold = (folded, order)
         pooled = _linear(o, w_o, f32(out_b), torch.float32)                        # [n_q, d] fp32
         ctx.cfg = (n_sets, L, d, heads, q_per_set, qs, qq, fuse_norm, cd)
@@ -403,6 +477,10 @@ class _CrossPool(torch.autograd.Function):
         if folded:
             g_o_sm = _to_set_major(g_o, order, n_sets, q_per_set).contiguous()
             g_xn, dq_sm = _folded_bwd(g_o_sm, xn, qp_sm, qt, pd, z, w_kv, g_in_w, g_in_b, n_sets, L, d, heads, q_per_set, cd)
+            dq = _from_set_major(dq_sm, order, n_sets, q_per_set).contiguous()
+        elif order is not None:
+            g_o_sm = _to_set_major(g_o, order, n_sets, q_per_set).contiguous()
+            dq_sm, dkv = _core_bwd(g_o_sm, qp_sm, kv, pd, n_sets, L, d, heads, q_per_set, cd)
             dq = _from_set_major(dq_sm, order, n_sets, q_per_set).contiguous()
         else:
             dq = torch.empty(n_q, d, dtype=cd, device=dev)

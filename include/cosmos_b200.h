@@ -190,6 +190,24 @@ int cosmos_gemm_batched(const void* a, const void* b, void* d, const float* bias
                         int32_t accumulate, float alpha, const void* a2, const void* b2, int32_t K2, int64_t lda2, int64_t ldb2,
                         int64_t stride_a2, int64_t stride_b2, int device, void* stream);
 
+/* The general form: every field of the batched GEMM plus an INNER batch dimension - problem (t1, t2), t1 < batch, t2 < batch_in,
+ * reads a + t1 * stride_a + t2 * stride_a_in, ... (heads inside samples: the attention core of nn.MultiheadAttention as
+ * batched GEMMs, scores^T = K_h Q_h^T and O_h = P^T V_h per (sample, head), F.multi_head_attention_forward).  Plain C struct,
+ * zero-initialise and fill; batch_in = 0 is read as 1.                                                                      */
+typedef struct cosmos_gemm_desc {
+  const void* a; const void* b; void* d; const float* bias;
+  const void* a2; const void* b2;                 /* optional second operand pair (K2 > 0), same storage orders */
+  int32_t M, N, K, K2;
+  int64_t lda, ldb, ldd, lda2, ldb2;
+  int32_t batch, batch_in;
+  int64_t stride_a, stride_b, stride_d, stride_bias, stride_a2, stride_b2;                             /* outer batch */
+  int64_t stride_a_in, stride_b_in, stride_d_in, stride_bias_in, stride_a2_in, stride_b2_in;           /* inner batch */
+  int32_t a_kmajor, b_kmajor, in_dtype, out_dtype, splits, accumulate;
+  float alpha;
+  int32_t reserved;
+} cosmos_gemm_desc;
+int cosmos_gemm_ex(const cosmos_gemm_desc* g, int device, void* stream);
+
 /* Softmax over the KEYS of the folded attention (F.multi_head_attention_forward's softmax(dim=-1) of [queries, keys] scores,
  * stored here keys-major): s fp32 [n_sets][L][n_cols] (row stride lds, set stride s_stride) -> p 16-bit, same indexing with
  * its own strides; p[set][:, c] = softmax over l of s[set][:, c].                                                          */

@@ -6,25 +6,26 @@ exercised exactly as the tensor maps would read it.  Never imported by the packa
 import torch
 
 
-def _mat(t, rows, cols, ld, batch, bs, kmajor):
-    """the [batch, rows, cols] matrices an operand pointer describes: stored [rows, cols] (kmajor) or [cols, rows]"""
+def _mat(t, rows, cols, ld, batch, bs, kmajor, batch_in=1, bs_in=0):
+    """the [batch, batch_in, rows, cols] matrices an operand pointer describes: stored [rows, cols] (kmajor) or [cols, rows]"""
     if kmajor:
-        return t.as_strided((batch, rows, cols), (bs, ld, 1))
-    return t.as_strided((batch, cols, rows), (bs, ld, 1)).transpose(1, 2)
+        return t.as_strided((batch, batch_in, rows, cols), (bs, bs_in, ld, 1))
+    return t.as_strided((batch, batch_in, cols, rows), (bs, bs_in, ld, 1)).transpose(2, 3)
 
 
 def emu_bgemm(a, b, out, M, N, K, lda, ldb, ldd, batch, sa, sb, sd, a_kmajor, b_kmajor, bias=None, sbias=0, splits=1, accumulate=False,
-              alpha=1.0, second=None):
-    A = _mat(a, M, K, lda, batch, sa, a_kmajor).double()
-    B = _mat(b, N, K, ldb, batch, sb, b_kmajor).double()
-    res = A @ B.transpose(1, 2)
+              alpha=1.0, second=None, inner=None):
+    bi, sa_in, sb_in, sd_in = inner if inner is not None else (1, 0, 0, 0)
+    A = _mat(a, M, K, lda, batch, sa, a_kmajor, bi, sa_in).double()
+    B = _mat(b, N, K, ldb, batch, sb, b_kmajor, bi, sb_in).double()
+    res = A @ B.transpose(2, 3)
     if second is not None:
         a2, b2, K2, lda2, ldb2, sa2, sb2 = second
-        res = res + _mat(a2, M, K2, lda2, batch, sa2, a_kmajor).double() @ _mat(b2, N, K2, ldb2, batch, sb2, b_kmajor).double().transpose(1, 2)
+        res = res + _mat(a2, M, K2, lda2, batch, sa2, a_kmajor).double() @ _mat(b2, N, K2, ldb2, batch, sb2, b_kmajor).double().transpose(2, 3)
     res = alpha * res
     if bias is not None:
-        res = res + bias.as_strided((batch, 1, N), (sbias, 0, 1)).double()
-    D = out.as_strided((batch, M, N), (sd, ldd, 1))
+        res = res + bias.as_strided((batch, 1, 1, N), (sbias, 0, 0, 1)).double()
+    D = out.as_strided((batch, bi, M, N), (sd, sd_in, ldd, 1))
     if splits > 1 or accumulate:
         D.copy_((D.double() + res).to(out.dtype))
     else:

@@ -133,16 +133,19 @@ def test_pooler_bf16_inputs_and_dedup_equivalence():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("route", ["folded", "key_value"])
+@pytest.mark.parametrize("route", ["folded", "key_value", "key_value_cuda_cores"])
 def test_pooler_module_many_queries(monkeypatch, route):
     """forward(x, q) with more queries per sample than one pass of the attention kernel handles (20 > 8) and width 768 / 12
     heads (the literal BASELINE config-4 geometry, scaled down), against the oracle - through the folded attention (240 score
     columns per sample) and through the key / value projection + attention-kernel route."""
     from cosmos_b200 import pooler
     from cosmos_b200.pooler import AttentionalCrossPooler
-    if route == "key_value":
+    if route != "folded":
         monkeypatch.setattr(pooler, "_FOLD_MAX_COLS", 0)
+    if route == "key_value_cuda_cores":      # the attention kernel instead of the batched-GEMM core
+        monkeypatch.setenv("COSMOS_B200_POOLER_CORE", "cuda_cores")
     assert pooler._fold_ok(3, 20, 20, 1, 12, 768) == (route == "folded")
+    assert pooler._core_ok(3, 20, 20, 1, 12, 768) == (route != "key_value_cuda_cores")
     d, h, L, B, Lq = 768, 12, 37, 3, 20
     params, tokens, _, _ = O.make_pooler_case(d, L, B, 1, seed=11)
     g = torch.Generator().manual_seed(12)
@@ -232,7 +235,7 @@ def test_custom_norm_layer_eps_is_honoured():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("route", ["folded", "key_value"])
+@pytest.mark.parametrize("route", ["folded", "key_value", "key_value_cuda_cores"])
 @pytest.mark.parametrize("d,L,B,n,heads,seed", [(512, 77, 16, 8, 8, 1), (512, 196, 16, 8, 8, 2), (512, 49, 5, 8, 8, 3), (768, 197, 4, 2, 12, 4)])
 def test_pooler_meets_north_star_tolerance_on_16bit_values(monkeypatch, d, L, B, n, heads, seed, route):
     """The north_star tolerance (gradient cosine >= 0.9999) for the pooler, measured the way it is defined for the loss: against
@@ -243,8 +246,10 @@ def test_pooler_meets_north_star_tolerance_on_16bit_values(monkeypatch, d, L, B,
     against the reference in fp32 on UN-rounded inputs and weights: there the rounding of the inputs dominates."""
     from cosmos_b200 import pooler
     from cosmos_b200.pooler import AttentionalCrossPooler, crossmodal_features
-    if route == "key_value":          # both routes of the attention meet the tolerance
+    if route != "folded":             # every route of the attention meets the tolerance
         monkeypatch.setattr(pooler, "_FOLD_MAX_COLS", 0)
+    if route == "key_value_cuda_cores":
+        monkeypatch.setenv("COSMOS_B200_POOLER_CORE", "cuda_cores")
     params, tokens, feats, w = O.make_pooler_case(d, L, B, n, seed)
     r16 = lambda t: t.bfloat16().float()
     p32 = {k: (r16(v) if v.dim() == 2 else v.clone()).requires_grad_(True) for k, v in params.items()}

@@ -75,7 +75,40 @@ def test_fold_decision():
     from cosmos_b200 import pooler
     assert pooler._fold_ok(1024, 8, 1, 1024, 8, 512)             # COSMOS: 8 crops x 8 heads = 64 score columns
     assert pooler._fold_ok(4, 2, 1, 4, 12, 768)
-    assert pooler._fold_ok(1024, 77, 77, 1, 12, 768)             # BASELINE config 4 literal, 77 queries: 924 columns, 1.1x the flops
-    assert not pooler._fold_ok(1024, 197, 197, 1, 12, 768)       # 197 queries: 2364 columns, 2.4x the flops -> key / value route
+    assert not pooler._fold_ok(1024, 77, 77, 1, 12, 768)         # BASELINE config 4 literal, 77 queries: 924 columns, 1.1x the flops
+    assert not pooler._fold_ok(1024, 197, 197, 1, 12, 768)       # 197 queries: 2364 columns -> key / value route with the GEMM core
+    assert pooler._core_ok(1024, 197, 197, 1, 12, 768) and not pooler._core_ok(8, 4, 4, 1, 8, 96)      # head dim 12
     assert pooler._fold_ok(4, 20, 20, 1, 12, 768)
     assert not pooler._fold_ok(8, 4, 2, 3, 8, 512)               # an unknown row pattern
+
+
+@pytest.mark.parametrize("d,L,B,Lq,heads", [(64, 11, 3, 6, 8), (96, 7, 2, 13, 12)])
+def test_key_value_route_with_gemm_core_matches_oracle(monkeypatch, d, L, B, Lq, heads):
+    """The attention core of the key / value route as batched GEMMs with samples as the outer and heads as the inner batch
+    dimension (cosmos_b200/pooler.py:_core_fwd/_core_bwd), forced by switching the fold off."""
+    from cosmos_b200 import pooler
+    emulation_pooler.install(monkeypatch)
+    monkeypatch.setattr(pooler, "_FOLD_MAX_COLS", 0)
+    assert not pooler._fold_ok(B, Lq, Lq, 1, heads, d) and pooler._core_ok(B, Lq, Lq, 1, heads, d)
+    params, tokens, _, _ = O.make_pooler_case(d, L, B, 1, 17)
+    g = torch.Generator().manual_seed(6)
+    q = torch.randn(B, Lq, d, generator=g)
+    w = torch.randn(B, Lq, d, generator=g)
+    r16 = lambda t: t.bfloat16().float()
+    p32 = {k: (r16(v) if v.dim() == 2 else v.clone()).requires_grad_(True) for k, v in params.items()}
+    t32, q32 = r16(tokens).requires_grad_(True), r16(q).requires_grad_(True)
+    ref = O.cross_pool(t32, q32, p32, heads)
+    (ref * w).sum().backward()
+    mod = pooler.AttentionalCrossPooler(d, d, heads)
+    mod.load_state_dict({k: (r16(v) if v.dim() == 2 else v) for k, v in params.items()})
+    tok, qq = tokens.bfloat16().requires_grad_(True), q.bfloat16().requires_grad_(True)
+    out = mod(tok, qq)
+    (out.float() * w).sum().backward()
+    assert float((out.detach().float() - ref.detach()).norm() / ref.detach().norm()) < 1e-2
+    assert cosine(qq.grad, q32.grad) >= 0.9995 and cosine(tok.grad, t32.grad) >= 0.9995
+    for k, p in mod.named_parameters():
+        gg, gr = p.grad, p32[k].grad
+        if k == "attn.in_proj_bias":
+            sel = torch.cat([torch.arange(0, d), torch.arange(2 * d, 3 * d)])
+            gg, gr = gg[sel], gr[sel]
+        assert cosine(gg, gr) >= 0.999, (k, cosine(gg, gr))
