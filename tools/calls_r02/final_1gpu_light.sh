@@ -1,6 +1,6 @@
 #!/bin/bash
 # last single-GPU call of round 2 (the InfoNCE kernels are those of the r02g captures): GPU tests, smoke, the full bench line
-TAG=r02i
+TAG=r02j
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$TAG.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu_$TAG.log
