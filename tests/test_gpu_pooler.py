@@ -46,6 +46,69 @@ def test_tcgen05_gemm(M, N, K, akm, bkm, splits, out):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", ["heads_as_batch", "samples_x_heads", "ragged_mn_major", "two_pairs", "accumulate", "split_k_batched"])
+def test_batched_gemm_against_the_stride_emulation(case):
+    """cosmos_gemm_ex on views of larger buffers - batch strides below the row stride (per-head column blocks), an inner batch
+    dimension, tiles past M / N / K of one problem, a second operand pair, D += ..., split-K over a batch - against
+    tests/emulation_pooler.emu_bgemm, which builds the same matrices with as_strided from the same (pointer, strides)."""
+    from cosmos_b200 import pooler as P
+    from tests import emulation_pooler as E
+    g = torch.Generator().manual_seed(sum(map(ord, case)))
+    rnd = lambda *s: (torch.randn(*s, generator=g) / 4).bfloat16()
+    kw, out_dtype, zero = {}, torch.bfloat16, False
+    if case == "heads_as_batch":          # A = rows x (heads * hd) matrix, head h its column block; B = per-head [hd, N] blocks
+        heads, hd, rows, N = 8, 64, 333, 512
+        a, b = rnd(rows, heads * hd), rnd(heads * hd, N)
+        out = torch.empty(rows, heads, N, dtype=out_dtype)
+        args = (rows, N, hd, heads * hd, N, heads * N, heads, hd, hd * N, N, True, False)
+        kw = dict(alpha=0.125)
+    elif case == "samples_x_heads":       # scores^T = K_h Q_h^T per (sample, head)
+        B_, heads, hd, L, q = 5, 12, 64, 77, 21
+        d = heads * hd
+        a, b = rnd(B_ * L, 2 * d), rnd(B_ * q, d)
+        out = torch.zeros(B_ * heads, L, 24, dtype=torch.float32)         # 21 columns at a pitch of 24: the pad is not written
+        out_dtype = torch.float32
+        args = (L, q, hd, 2 * d, d, 24, B_, L * 2 * d, q * d, heads * L * 24, True, True)
+        kw = dict(inner=(heads, hd, hd, L * 24), alpha=0.3)
+    elif case == "ragged_mn_major":       # Z = P^T x per set: M = 12 columns of a 2 x 16 pitch, K = 197 keys, both operands [K, rows]
+        sets, L, nc, pitch, d = 7, 197, 12, 16, 256
+        a, b = rnd(sets, L, 2 * pitch), rnd(sets * L, d)
+        out = torch.empty(sets, nc, d, dtype=out_dtype)
+        args = (nc, d, L, 2 * pitch, d, d, sets, L * 2 * pitch, L * d, nc * d, False, False)
+    elif case == "two_pairs":             # d xn = P dZ + dS Q~
+        sets, L, nc, pitch, d = 4, 150, 40, 40, 512
+        a, b = rnd(sets, L, 2 * pitch), rnd(sets, nc, d)
+        b2 = rnd(sets, nc, d)
+        out = torch.empty(sets * L, d, dtype=out_dtype)
+        args = (L, d, nc, 2 * pitch, d, d, sets, L * 2 * pitch, nc * d, L * d, True, False)
+        kw = dict(second=(a[:, :, pitch:], b2, nc, 2 * pitch, d, L * 2 * pitch, nc * d))
+    elif case == "accumulate":
+        sets, M, N, K = 3, 130, 200, 70
+        a, b = rnd(sets, M, K + 2)[:, :, :K], rnd(sets, N, 72)
+        a = rnd(sets, M, 72)
+        out = rnd(sets, M, N)
+        args = (M, N, 70, 72, 72, N, sets, M * 72, N * 72, M * N, True, True)
+        kw = dict(accumulate=True)
+    else:                                 # per-head weight gradients: [hd, d] = g[:, head]^T z[:, head, :], split over the rows
+        heads, hd, rows, d = 8, 64, 3000, 256
+        a, b = rnd(rows, heads * hd), rnd(rows, heads, d)
+        out = torch.zeros(heads * hd, d, dtype=torch.float32)
+        out_dtype = torch.float32
+        args = (hd, d, rows, heads * hd, heads * d, d, heads, hd, d, hd * d, False, False)
+        kw = dict(splits=5, alpha=0.5)
+    want = out.clone()
+    kw_cpu = dict(kw)
+    E.emu_bgemm(a, b, want, *args, **kw_cpu)
+    a_d, b_d, out_d = a.cuda(), b.cuda(), out.cuda()
+    if "second" in kw:                    # the same views on the device copies
+        a2, b2_, *rest = kw["second"]
+        kw = dict(kw, second=(a_d[:, :, a.shape[2] // 2:], b2_.cuda(), *rest))
+    P._bgemm(a_d, b_d, out_d, *args, **kw)
+    tol = 2e-5 if out_dtype == torch.float32 else 8e-3
+    assert relerr(out_d.cpu().float(), want.float()) < tol, (case, relerr(out_d.cpu().float(), want.float()))
+
+
+@pytest.mark.gpu
 def test_layernorm_and_addnorm_blocks():
     from cosmos_b200 import pooler as P
     g = torch.Generator().manual_seed(2)
