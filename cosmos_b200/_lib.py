@@ -107,7 +107,7 @@ _POOL_SIGS = {
     "cosmos_gemm": [vp_, vp_, vp_, vp_, i32_, i32_, i32_, i64_, i64_, i64_, i32_, i32_, i32_, i32_, i32_, f32_, i32_, vp_],
     "cosmos_gemm_batched": [vp_, vp_, vp_, vp_, i32_, i32_, i32_, i64_, i64_, i64_, i32_, i64_, i64_, i64_, i64_, i32_, i32_, i32_,
                             i32_, i32_, i32_, f32_, vp_, vp_, i32_, i64_, i64_, i64_, i64_, i32_, vp_],
-    "cosmos_colsoftmax_fwd": [vp_, i64_, i32_, vp_, i64_, i32_, i32_, i32_, i32_, i32_, i32_, vp_],
+    "cosmos_colsoftmax_fwd": [vp_, i64_, i32_, vp_, i64_, i32_, i32_, i32_, i32_, i32_, i32_, i32_, vp_],
     "cosmos_colsoftmax_bwd": [vp_, i64_, i32_, vp_, i64_, i32_, vp_, i64_, i32_, i32_, i32_, i32_, i32_, i32_, vp_],
     "cosmos_layernorm_fwd": [vp_, i32_, vp_, vp_, vp_, i32_, vp_, vp_, i64_, i32_, f32_, i32_, vp_],
     "cosmos_layernorm_bwd": [vp_, i32_, vp_, i32_, vp_, vp_, vp_, vp_, i32_, i32_, vp_, vp_, i64_, i32_, i32_, vp_],

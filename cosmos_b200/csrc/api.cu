@@ -609,12 +609,13 @@ int cosmos_gemm_batched(const void* a, const void* b, void* d, const float* bias
 }
 
 int cosmos_colsoftmax_fwd(const float* s, int64_t s_stride, int32_t lds, void* p, int64_t p_stride, int32_t ldp, int32_t p_dtype,
-                          int32_t n_sets, int32_t L, int32_t n_cols, int device, void* stream) {
+                          int32_t n_sets, int32_t L, int32_t n_cols, int32_t zero_key, int device, void* stream) {
   if (!s || !p || n_sets < 0 || L <= 0 || n_cols <= 0 || lds < n_cols || ldp < n_cols) return COSMOS_ERR_INVALID_ARGUMENT;
   if (!dtype16(p_dtype)) return COSMOS_ERR_UNSUPPORTED;
   DeviceGuard g(device);
   if (!g.ok) return COSMOS_ERR_CUDA;
-  return cu_fail(cb::launch_colsoftmax_fwd(s, s_stride, lds, p, p_stride, ldp, p_dtype, n_sets, L, n_cols, static_cast<cudaStream_t>(stream)))
+  return cu_fail(cb::launch_colsoftmax_fwd(s, s_stride, lds, p, p_stride, ldp, p_dtype, n_sets, L, n_cols, zero_key != 0,
+                                           static_cast<cudaStream_t>(stream)))
              ? COSMOS_ERR_CUDA : COSMOS_OK;
 }
 

@@ -76,7 +76,7 @@ cudaError_t launch_addnorm_bwd(const void* g_out, const void* out, int f_dtype, 
                                int g_dtype, int64_t rows, int dim, cudaStream_t s);
 cudaError_t launch_colsum(const void* src, int dtype, float* dst, int64_t rows, int n, int64_t ld, cudaStream_t s);
 cudaError_t launch_colsoftmax_fwd(const float* S, int64_t s_bs, int lds, void* P, int64_t p_bs, int ldp, int dtype, int n_sets, int L,
-                                  int Nc, cudaStream_t s);
+                                  int Nc, int zero_key, cudaStream_t s);
 cudaError_t launch_colsoftmax_bwd(const void* P, int64_t p_bs, int ldp, const float* dP, int64_t d_bs, int ldd, void* dS, int64_t ds_bs,
                                   int ldds, int dtype, int n_sets, int L, int Nc, cudaStream_t s);
 

@@ -793,7 +793,8 @@ cudaError_t launch_addnorm_bwd(const void* g_out, const void* out, int f_dtype, 
 // The block (L x Nc fp32, 50 KB at 196 x 64) is read twice; the second read hits L2.
 template <class T>
 __global__ void __launch_bounds__(256)
-colsoftmax_fwd_kernel(const float* __restrict__ S, long long s_bs, int lds, T* __restrict__ P, long long p_bs, int ldp, int L, int Nc) {
+colsoftmax_fwd_kernel(const float* __restrict__ S, long long s_bs, int lds, T* __restrict__ P, long long p_bs, int ldp, int L, int Nc,
+                      int zero_key) {
   __shared__ float sm_m[4][64], sm_s[4][64];
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   const float* s0 = S + static_cast<size_t>(blockIdx.x) * s_bs;
@@ -816,7 +817,8 @@ colsoftmax_fwd_kernel(const float* __restrict__ S, long long s_bs, int lds, T* _
     sm_s[ty][tx] = sum;
     __syncthreads();
     float M = fmaxf(fmaxf(sm_m[0][tx], sm_m[1][tx]), fmaxf(sm_m[2][tx], sm_m[3][tx]));
-    float tot = 0.f;
+    if (zero_key) M = fmaxf(M, 0.f);       // add_zero_attn: one more key with score 0 (and value 0: it only enters the denominator)
+    float tot = zero_key ? __expf(-M) : 0.f;
 #pragma unroll
     for (int g = 0; g < 4; ++g)
       if (sm_m[g][tx] != -INFINITY) tot += sm_s[g][tx] * __expf(sm_m[g][tx] - M);
@@ -855,12 +857,12 @@ colsoftmax_bwd_kernel(const T* __restrict__ P, long long p_bs, int ldp, const fl
 }
 
 cudaError_t launch_colsoftmax_fwd(const float* S, int64_t s_bs, int lds, void* P, int64_t p_bs, int ldp, int dtype, int n_sets, int L,
-                                  int Nc, cudaStream_t s) {
+                                  int Nc, int zero_key, cudaStream_t s) {
   if (n_sets == 0) return cudaSuccess;
   if (dtype == COSMOS_DTYPE_BF16)
-    colsoftmax_fwd_kernel<__nv_bfloat16><<<n_sets, 256, 0, s>>>(S, s_bs, lds, static_cast<__nv_bfloat16*>(P), p_bs, ldp, L, Nc);
+    colsoftmax_fwd_kernel<__nv_bfloat16><<<n_sets, 256, 0, s>>>(S, s_bs, lds, static_cast<__nv_bfloat16*>(P), p_bs, ldp, L, Nc, zero_key);
   else
-    colsoftmax_fwd_kernel<__half><<<n_sets, 256, 0, s>>>(S, s_bs, lds, static_cast<__half*>(P), p_bs, ldp, L, Nc);
+    colsoftmax_fwd_kernel<__half><<<n_sets, 256, 0, s>>>(S, s_bs, lds, static_cast<__half*>(P), p_bs, ldp, L, Nc, zero_key);
   return cudaGetLastError();
 }
 

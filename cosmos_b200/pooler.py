@@ -79,12 +79,12 @@ def _bgemm(a, b, out, M, N, K, lda, ldb, ldd, batch, sa, sb, sd, a_kmajor, b_kma
     return out
 
 
-def _colsoftmax_fwd(scores, p_out, n_sets, L, n_cols, lds, ldp):
+def _colsoftmax_fwd(scores, p_out, n_sets, L, n_cols, lds, ldp, zero_key=False):
     """softmax over the L keys of every column of scores [n_sets, L, n_cols] fp32 (row stride lds) -> p_out (16-bit view, row
-    stride ldp)."""
+    stride ldp).  zero_key: one more key with score 0 and value 0 (add_zero_attn)."""
     dev = scores.device
     st = _lib.lib().cosmos_colsoftmax_fwd(scores.data_ptr(), L * lds, lds, p_out.data_ptr(), L * ldp, ldp, _code(p_out), n_sets, L,
-                                          n_cols, dev.index, _stream(dev))
+                                          n_cols, int(zero_key), dev.index, _stream(dev))
     _lib.check(st, "colsoftmax_fwd")
 
 
@@ -204,7 +204,7 @@ def _core_ok(n_sets, q_per_set, qs, qq, heads, d):
             and _row_order(n_sets, q_per_set, qs, qq) is not None)
 
 
-def _core_fwd(qp_sm, kv, n_sets, L, d, heads, q_per_set, cd):
+def _core_fwd(qp_sm, kv, n_sets, L, d, heads, q_per_set, cd, zero_key=False):
     """softmax(q_h k_h^T / sqrt(hd)) v_h per (sample, head) - F.multi_head_attention_forward's core - on tensor cores: per
     (sample, head) problem  S^T = kappa K_h Q_h^T  [L, queries]  (keys-major, so that the softmax over the keys is the column
     softmax of the folded route),  O_h = P^T V_h  [queries, hd].  Samples are the outer, heads the inner batch dimension of the
@@ -217,7 +217,7 @@ def _core_fwd(qp_sm, kv, n_sets, L, d, heads, q_per_set, cd):
     _bgemm(kv, qp_sm, scores, L, q, hd, 2 * d, d, qpad, n_sets, L * 2 * d, q * d, heads * L * qpad, True, True, alpha=hd ** -0.5,
            inner=(heads, hd, hd, L * qpad))
     pd = torch.empty(n_sets * heads, L, 2 * qpad, dtype=cd, device=dev)
-    _colsoftmax_fwd(scores, pd, n_sets * heads, L, q, qpad, 2 * qpad)
+    _colsoftmax_fwd(scores, pd, n_sets * heads, L, q, qpad, 2 * qpad, zero_key)
     o_sm = torch.empty(n_sets * q, d, dtype=cd, device=dev)
     _bgemm(pd, kv[:, d:], o_sm, q, hd, L, 2 * qpad, 2 * d, d, n_sets, heads * L * 2 * qpad, L * 2 * d, q * d, False, False,
            inner=(heads, L * 2 * qpad, hd, hd))
@@ -383,7 +383,7 @@ class _CrossPool(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, tokens, queries, lnq_w, lnq_b, lnk_w, lnk_b, in_w, in_b, out_w, out_b, heads, q_per_set, qs, qq, fuse_norm,
-                eps_q=1e-5, eps_k=1e-5):
+                eps_q=1e-5, eps_k=1e-5, zero_key=False):
         for t in (tokens, queries, lnq_w, lnq_b, lnk_w, lnk_b, in_w, in_b, out_w, out_b):
             _lib.require_cuda(t, "pooler tensor")
         n_sets, L, C = tokens.shape
@@ -406,7 +406,11 @@ class _CrossPool(torch.autograd.Function):
         xn, mean_k, rstd_k = _ln_fwd(tokens2d, lnk_w32, lnk_b32, cd, eps_k)        # once per unique token set
         fn, mean_q, rstd_q = _ln_fwd(q_in, lnq_w32, lnq_b32, cd, eps_q)
         qp = _linear(fn, w_q, b_in[:d], cd)                                        # [n_q, d]
-        folded = _fold_ok(n_sets, q_per_set, qs, qq, heads, d)
+        # add_zero_attn: the extra all-zero key is appended AFTER the key projection, so its score relative to the real keys
+        # involves the key bias the fold drops - it takes the key / value route with the batched-GEMM core
+        folded = _fold_ok(n_sets, q_per_set, qs, qq, heads, d) and not zero_key
+        if zero_key and not _core_ok(n_sets, q_per_set, qs, qq, heads, d):
+            raise NotImplementedError("cosmos_b200.pooler: add_zero_attn needs head dims that are a multiple of 8")
         if folded:
             order = _row_order(n_sets, q_per_set, qs, qq)
             o_sm, qp_sm, qt, pd, z = _folded_fwd(xn, qp, w_kv, b_in, n_sets, L, d, heads, q_per_set, order, cd)
@@ -419,7 +423,7 @@ class _CrossPool(torch.autograd.Function):
             if _core_ok(n_sets, q_per_set, qs, qq, heads, d):                      # attention core as batched GEMMs
                 order = _row_order(n_sets, q_per_set, qs, qq)
                 qp_sm = _to_set_major(qp, order, n_sets, q_per_set).contiguous()
-                o_sm, pd = _core_fwd(qp_sm, kv, n_sets, L, d, heads, q_per_set, cd)
+                o_sm, pd = _core_fwd(qp_sm, kv, n_sets, L, d, heads, q_per_set, cd, zero_key)
                 o = _from_set_major(o_sm, order, n_sets, q_per_set).contiguous()
                 lse = empty
                 fold_saved = (qp_sm, empty, pd, empty)
@@ -502,7 +506,7 @@ class _CrossPool(torch.autograd.Function):
         _ln_bwd(g_xn, tokens2d, lnk_w32, mean_k, rstd_k, g_tokens, False, g_lnk_w, g_lnk_b)
         return (g_tokens.view(n_sets, L, d), g_queries.to(dt_q), g_lnq_w.to(dt_lnq), g_lnq_b.to(dt_lnq), g_lnk_w.to(dt_lnk),
                 g_lnk_b.to(dt_lnk), g_in_w.to(dt_inw), g_in_b.to(dt_inb), g_wo.to(dt_ow), g_bo.to(dt_ob), None, None, None, None,
-                None, None, None)
+                None, None, None, None)
 
 
 class AttentionalCrossPooler(nn.Module):
@@ -511,12 +515,11 @@ class AttentionalCrossPooler(nn.Module):
 
     def __init__(self, d_model: int, context_dim: int, n_head: int = 8, norm_layer=nn.LayerNorm, add_zero_attn: bool = False):
         super().__init__()
-        if add_zero_attn:
-            raise NotImplementedError("cosmos_b200.pooler: add_zero_attn=True is not used by the COSMOS recipes and is unsupported")
         if context_dim != d_model:
             raise NotImplementedError("cosmos_b200.pooler: context_dim must equal d_model (COSMOS maps tokens to embed_dim first)")
         # parameter containers with the reference's names; their own forward() is never called
-        self.attn = nn.MultiheadAttention(d_model, n_head, kdim=context_dim, vdim=context_dim, add_zero_attn=False)
+        self.attn = nn.MultiheadAttention(d_model, n_head, kdim=context_dim, vdim=context_dim, add_zero_attn=add_zero_attn)
+        self.add_zero_attn = bool(add_zero_attn)
         self.ln_q = norm_layer(d_model)
         self.ln_k = norm_layer(context_dim)
         self.n_head = n_head
@@ -532,7 +535,7 @@ class AttentionalCrossPooler(nn.Module):
     def forward(self, x: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
         """x: [N, L, C] keys/values, q: [N, Lq, d] queries -> [N, Lq, d] (transformer.py:225-230)."""
         N, Lq, d = q.shape
-        out = _CrossPool.apply(x, q.reshape(N * Lq, d), *self._params(), self.n_head, Lq, Lq, 1, False, *self._eps())
+        out = _CrossPool.apply(x, q.reshape(N * Lq, d), *self._params(), self.n_head, Lq, Lq, 1, False, *self._eps(), self.add_zero_attn)
         return out.view(N, Lq, d)
 
 
@@ -542,4 +545,5 @@ def crossmodal_features(pooler: AttentionalCrossPooler, tokens: torch.Tensor, fe
     n = features.shape[0] // batch_size
     if n * batch_size != features.shape[0]:
         raise RuntimeError("cosmos_b200.pooler: features rows must be a multiple of batch_size")
-    return _CrossPool.apply(tokens[:batch_size], features, *pooler._params(), pooler.n_head, n, 1, batch_size, True, *pooler._eps())
+    return _CrossPool.apply(tokens[:batch_size], features, *pooler._params(), pooler.n_head, n, 1, batch_size, True, *pooler._eps(),
+                            pooler.add_zero_attn)

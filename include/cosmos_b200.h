@@ -210,10 +210,12 @@ int cosmos_gemm_ex(const cosmos_gemm_desc* g, int device, void* stream);
 
 /* Softmax over the KEYS of the folded attention (F.multi_head_attention_forward's softmax(dim=-1) of [queries, keys] scores,
  * stored here keys-major): s fp32 [n_sets][L][n_cols] (row stride lds, set stride s_stride) -> p 16-bit, same indexing with
- * its own strides; p[set][:, c] = softmax over l of s[set][:, c].                                                          */
+ * its own strides; p[set][:, c] = softmax over l of s[set][:, c].  zero_key != 0: add_zero_attn (transformer.py:221) - one more
+ * key with score 0 and value 0 per column; it only enters the denominator.                                                 */
 int cosmos_colsoftmax_fwd(const float* s, int64_t s_stride, int32_t lds, void* p, int64_t p_stride, int32_t ldp, int32_t p_dtype,
-                          int32_t n_sets, int32_t L, int32_t n_cols, int device, void* stream);
-/* Its backward: ds = p * (dp - sum_l p * dp) per column; dp fp32, p and ds 16-bit (dtype).                                 */
+                          int32_t n_sets, int32_t L, int32_t n_cols, int32_t zero_key, int device, void* stream);
+/* Its backward: ds = p * (dp - sum_l p * dp) per column; dp fp32, p and ds 16-bit (dtype).  (Unchanged by a zero key: its
+ * value is zero, so its dp is zero and it drops out of the sum.)                                                           */
 int cosmos_colsoftmax_bwd(const void* p, int64_t p_stride, int32_t ldp, const float* dp, int64_t dp_stride, int32_t lddp, void* ds,
                           int64_t ds_stride, int32_t ldds, int32_t dtype, int32_t n_sets, int32_t L, int32_t n_cols, int device,
                           void* stream);

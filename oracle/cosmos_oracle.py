@@ -192,7 +192,8 @@ def layer_norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1
     return (x - mu) / torch.sqrt(var + eps) * w + b
 
 
-def cross_pool(tokens: torch.Tensor, query: torch.Tensor, p: Dict[str, torch.Tensor], n_head: int) -> torch.Tensor:
+def cross_pool(tokens: torch.Tensor, query: torch.Tensor, p: Dict[str, torch.Tensor], n_head: int,
+               add_zero_attn: bool = False) -> torch.Tensor:
     """AttentionalCrossPooler.forward (transformer.py:225-230) written out.
 
     tokens [B, L, C] are the keys/values, query [B, Lq, d] the queries,
@@ -213,6 +214,9 @@ def cross_pool(tokens: torch.Tensor, query: torch.Tensor, p: Dict[str, torch.Ten
     q = q.view(B, Lq, n_head, hd).transpose(1, 2)          # B h Lq hd
     k = k.view(B, L, n_head, hd).transpose(1, 2)
     v = v.view(B, L, n_head, hd).transpose(1, 2)
+    if add_zero_attn:      # transformer.py:221 -> F.multi_head_attention_forward: one all-zero key / value per head, after the projection
+        k = torch.cat([k, k.new_zeros(B, n_head, 1, hd)], dim=2)
+        v = torch.cat([v, v.new_zeros(B, n_head, 1, hd)], dim=2)
     att = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
     o = (att @ v).transpose(1, 2).reshape(B, Lq, d)
     return o @ p["attn.out_proj.weight"].T + p["attn.out_proj.bias"]

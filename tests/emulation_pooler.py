@@ -69,9 +69,11 @@ def emu_ln_bwd(dy, x2d, w, mean, rstd, dx, accumulate, dw=None, db=None):
     return dw, db
 
 
-def emu_colsoftmax_fwd(scores, p_out, n_sets, L, n_cols, lds, ldp):
-    S = scores.as_strided((n_sets, L, n_cols), (L * lds, lds, 1))
-    P = torch.softmax(S.double(), dim=1)
+def emu_colsoftmax_fwd(scores, p_out, n_sets, L, n_cols, lds, ldp, zero_key=False):
+    S = scores.as_strided((n_sets, L, n_cols), (L * lds, lds, 1)).double()
+    if zero_key:
+        S = torch.cat([S, S.new_zeros(n_sets, 1, n_cols)], dim=1)
+    P = torch.softmax(S, dim=1)[:, :L]
     p_out.as_strided((n_sets, L, n_cols), (L * ldp, ldp, 1)).copy_(P.to(p_out.dtype))
 
 

@@ -335,3 +335,39 @@ def test_pooler_meets_north_star_tolerance_on_16bit_values(monkeypatch, d, L, B,
             g, gr = g[sel], gr[sel]
         assert cosine(g, gr) >= 0.9999, (k, cosine(g, gr))
         assert abs(float(g.float().norm().cpu() / gr.norm()) - 1) < 2e-3, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,L,B,n,heads,seed", [(512, 77, 8, 8, 8, 5), (768, 50, 3, 20, 12, 6)])
+def test_add_zero_attn(d, L, B, n, heads, seed):
+    """AttentionalCrossPooler(add_zero_attn=True) (src/open_clip/transformer.py:214-221): one more all-zero key / value per head
+    after the projection.  Key / value route with the batched-GEMM core; the column softmax counts the zero key in its
+    denominator.  Against the oracle (pinned against nn.MultiheadAttention on the CPU, tests/test_pooler_folded_cpu.py)."""
+    from cosmos_b200.pooler import AttentionalCrossPooler, crossmodal_features
+    params, tokens, feats, w = O.make_pooler_case(d, L, B, n, seed)
+    r16 = lambda t: t.bfloat16().float()
+    p32 = {k: (r16(v) if v.dim() == 2 else v.clone()).requires_grad_(True) for k, v in params.items()}
+    t32, f32 = r16(tokens).requires_grad_(True), r16(feats).requires_grad_(True)
+    rep = t32[:B].repeat(n, 1, 1)
+    ref = torch.nn.functional.normalize(f32 + O.cross_pool(rep, f32.unsqueeze(1), p32, heads, add_zero_attn=True).squeeze(1), dim=-1)
+    (ref * w).sum().backward()
+    mod = AttentionalCrossPooler(d, d, heads, add_zero_attn=True).cuda()
+    mod.load_state_dict({k: (r16(v) if v.dim() == 2 else v) for k, v in params.items()})
+    tok = tokens.bfloat16().cuda().requires_grad_(True)
+    f = feats.bfloat16().cuda().requires_grad_(True)
+    xm = crossmodal_features(mod, tok, f, B)
+    (xm.float() * w.cuda()).sum().backward()
+    assert relerr(xm.detach().float(), ref.detach()) < 5e-3
+    assert cosine(f.grad.float(), f32.grad) >= 0.9999 and cosine(tok.grad.float(), t32.grad) >= 0.9999
+    for k, p in mod.named_parameters():
+        assert cosine(p.grad, p32[k].grad) >= 0.9995, (k, cosine(p.grad, p32[k].grad))
+    # and it is not the plain module: on the pooled vectors themselves (module forward, no residual / normalise) the zero key
+    # takes ~1 / (L + 1) of every softmax, far above the bf16 resolution of the output
+    with torch.no_grad():
+        q = feats.view(n, B, d).transpose(0, 1).contiguous()
+        got = mod(tokens[:B].bfloat16().cuda(), q.bfloat16().cuda()).float()
+        d32 = {k: v.detach() for k, v in p32.items()}
+        want = O.cross_pool(r16(tokens[:B]), r16(q), d32, heads, add_zero_attn=True)
+        plain = O.cross_pool(r16(tokens[:B]), r16(q), d32, heads)
+    assert relerr(got, want) < 1e-2
+    assert cosine(got.cpu() - plain, want - plain) > 0.7        # the measured deviation from the plain module is the zero key's

@@ -175,8 +175,7 @@ def test_pooler_module_is_checkpoint_compatible():
     mod = AttentionalCrossPooler(64, 64, 4)
     assert {k: tuple(v.shape) for k, v in mod.state_dict().items()} == {k: tuple(v.shape) for k, v in params.items()}
     mod.load_state_dict(params)
-    with pytest.raises(NotImplementedError):
-        AttentionalCrossPooler(64, 64, 4, add_zero_attn=True)
+    assert AttentionalCrossPooler(64, 64, 4, add_zero_attn=True).add_zero_attn          # supported (key / value route)
     with pytest.raises(NotImplementedError):
         AttentionalCrossPooler(64, 32, 4)
     with pytest.raises(RuntimeError, match="no CPU fallback"):

@@ -112,3 +112,61 @@ def test_key_value_route_with_gemm_core_matches_oracle(monkeypatch, d, L, B, Lq,
             sel = torch.cat([torch.arange(0, d), torch.arange(2 * d, 3 * d)])
             gg, gr = gg[sel], gr[sel]
         assert cosine(gg, gr) >= 0.999, (k, cosine(gg, gr))
+
+
+def test_oracle_add_zero_attn_matches_torch_multihead_attention():
+    """Pins the oracle's add_zero_attn branch (the reference module is LayerNorm x2 + nn.MultiheadAttention(add_zero_attn=...),
+    src/open_clip/transformer.py:219-229) against torch's own implementation."""
+    import torch.nn as nn
+    d, L, B, Lq, heads = 32, 9, 3, 4, 4
+    params, tokens, _, _ = O.make_pooler_case(d, L, B, 1, 23)
+    g = torch.Generator().manual_seed(9)
+    q = torch.randn(B, Lq, d, generator=g)
+    attn = nn.MultiheadAttention(d, heads, kdim=d, vdim=d, add_zero_attn=True)
+    ln_q, ln_k = nn.LayerNorm(d), nn.LayerNorm(d)
+    with torch.no_grad():
+        attn.in_proj_weight.copy_(params["attn.in_proj_weight"]); attn.in_proj_bias.copy_(params["attn.in_proj_bias"])
+        attn.out_proj.weight.copy_(params["attn.out_proj.weight"]); attn.out_proj.bias.copy_(params["attn.out_proj.bias"])
+        ln_q.weight.copy_(params["ln_q.weight"]); ln_q.bias.copy_(params["ln_q.bias"])
+        ln_k.weight.copy_(params["ln_k.weight"]); ln_k.bias.copy_(params["ln_k.bias"])
+        x = ln_k(tokens).permute(1, 0, 2)
+        want = attn(ln_q(q).permute(1, 0, 2), x, x, need_weights=False)[0].permute(1, 0, 2)      # transformer.py:225-229
+    got = O.cross_pool(tokens, q, params, heads, add_zero_attn=True)
+    assert torch.allclose(got, want, atol=2e-5, rtol=1e-4)
+    assert not torch.allclose(O.cross_pool(tokens, q, params, heads), want, atol=1e-3)
+
+
+@pytest.mark.parametrize("crop_major", [False, True])
+def test_add_zero_attn_route_matches_oracle(monkeypatch, crop_major):
+    """add_zero_attn=True: the key / value route with the batched-GEMM core and one more (zero) key in the softmax."""
+    from cosmos_b200 import pooler
+    emulation_pooler.install(monkeypatch)
+    d, L, B, n, heads = 64, 7, 3, 4, 8
+    params, tokens, feats, w = O.make_pooler_case(d, L, B, n, 31)
+    r16 = lambda t: t.bfloat16().float()
+    p32 = {k: (r16(v) if v.dim() == 2 else v.clone()).requires_grad_(True) for k, v in params.items()}
+    mod = pooler.AttentionalCrossPooler(d, d, heads, add_zero_attn=True)
+    mod.load_state_dict({k: (r16(v) if v.dim() == 2 else v) for k, v in params.items()})
+    t32 = r16(tokens).requires_grad_(True)
+    tok = tokens.bfloat16().requires_grad_(True)
+    if crop_major:          # the call site of model.py:375-380 (one query per crop, crop-major rows, fused add + normalise)
+        f32 = r16(feats).requires_grad_(True)
+        rep = t32[:B].repeat(n, 1, 1)
+        ref = torch.nn.functional.normalize(f32 + O.cross_pool(rep, f32.unsqueeze(1), p32, heads, add_zero_attn=True).squeeze(1), dim=-1)
+        f = feats.bfloat16().requires_grad_(True)
+        out = pooler.crossmodal_features(mod, tok, f, B)
+        qg, qr = f, f32
+    else:
+        q = feats.view(n, B, d).transpose(0, 1).contiguous()
+        q32 = r16(q).requires_grad_(True)
+        ref = O.cross_pool(t32, q32, p32, heads, add_zero_attn=True)
+        qq = q.bfloat16().requires_grad_(True)
+        out = mod(tok, qq)
+        w = w.view(n, B, d).transpose(0, 1).contiguous()
+        qg, qr = qq, q32
+    (ref * w).sum().backward()
+    (out.float() * w).sum().backward()
+    assert float((out.detach().float() - ref.detach()).norm() / ref.detach().norm()) < 1e-2
+    assert cosine(qg.grad, qr.grad) >= 0.9995 and cosine(tok.grad, t32.grad) >= 0.9995
+    for k, p in mod.named_parameters():
+        assert cosine(p.grad, p32[k].grad) >= 0.999, (k, cosine(p.grad, p32[k].grad))      # incl. the key bias: not zero any more
