@@ -93,3 +93,74 @@ def test_fullsize_closed_form_logits():
     torch.testing.assert_close(own, torch.full_like(own, (s / N) * (m * math.exp(s) / Z - 1.0)), rtol=2e-2, atol=0)
     off = g.sum(dim=1) - own
     torch.testing.assert_close(off, torch.full_like(off, (s / N) * (D - 1) * m / Z), rtol=2e-2, atol=0)
+
+
+@pytest.mark.gpu
+def test_fullsize_headline_grouping_against_fp32_eager():
+    """The headline configuration itself (BASELINE.json: global batch 32768, dim 512, 8 + 8 student, 8 + 8 cross-modal and 2 + 2
+    teacher feature tensors per sample = 64 distillation + 16 CLIP pairs, bf16) through COSMOSLoss on the stored-exponential route,
+    against the oracle's formulas (oracle.symmetric_infonce over src/open_clip/loss.py:116-117 logits, composition of
+    loss.py:176-207) evaluated in fp32 on the same GPU, one 32768 x 32768 logit matrix at a time (the oracle's own loop keeps
+    all 80 alive in one autograd graph; pair by pair with an immediate backward is the same sum).  north_star tolerance:
+    loss relative error <= 1e-4, gradient cosine >= 0.9999 for every feature tensor, d logit_scale within 3e-3."""
+    from cosmos_b200 import COSMOSLoss
+    from oracle import cosmos_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(2024)
+    z = torch.randn(N, D, device="cuda", generator=g)
+
+    def view(noise):
+        return torch.nn.functional.normalize(z + noise * torch.randn(N, D, device="cuda", generator=g), dim=-1).bfloat16()
+
+    counts = {"s_image": 8, "s_text": 8, "s_img_x": 8, "s_txt_x": 8, "t_image": 2, "t_text": 2}
+    feats = {k: [view(1.0 + 0.25 * i) for i in range(n)] for k, n in counts.items()}
+    teacher = ("t_image", "t_text")
+    x = {k: [t.clone().requires_grad_(k not in teacher) for t in v] for k, v in feats.items()}
+    ls = torch.tensor(14.2857, device="cuda", requires_grad=True)
+    ds = torch.tensor(30.0, device="cuda", requires_grad=True)
+    out = COSMOSLoss(local_loss=False, gather_with_grad=False, cache_labels=True, rank=0, world_size=1)(
+        x["s_image"], x["s_text"], ls, t_image_features=x["t_image"], t_text_features=x["t_text"], output_dict=True,
+        distill_logit_scale=ds, s_img_crossmodal_features=x["s_img_x"], s_txt_crossmodal_features=x["s_txt_x"])
+    (out["distill_loss"] + out["clip_loss"]).backward()
+    torch.cuda.synchronize()
+
+    r = {k: [t.float().requires_grad_(k not in teacher) for t in v] for k, v in feats.items()}
+    rls = torch.tensor(14.2857, device="cuda", requires_grad=True)
+    rds = torch.tensor(30.0, device="cuda", requires_grad=True)
+    ref = {"distill_loss": 0.0, "clip_loss": 0.0}
+
+    def group(name, a_list, b_list, scale, weight):
+        for a in a_list:
+            for b in b_list:
+                logits = scale * a @ b.T                                  # loss.py:116: the other direction is its transpose
+                term = weight * O.symmetric_infonce(logits, logits.T) / (len(a_list) * len(b_list))
+                term.backward()
+                ref[name] += float(term.detach())
+                del logits, term
+
+    group("distill_loss", r["s_img_x"], r["t_image"], rds, 0.25)          # loss.py:193-203: mean of the four groups
+    group("distill_loss", r["s_img_x"], r["t_text"], rds, 0.25)
+    group("distill_loss", r["s_txt_x"], r["t_image"], rds, 0.25)
+    group("distill_loss", r["s_txt_x"], r["t_text"], rds, 0.25)
+    group("clip_loss", r["s_image"][:2], r["s_text"], rls, 1.0)           # loss.py:205-206: the first two image crops only
+    torch.cuda.synchronize()
+
+    worst = {"loss_rel": 0.0, "grad_cos_min": 1.0, "grad_norm_rel": 0.0}
+    for k in ref:
+        worst["loss_rel"] = max(worst["loss_rel"], abs(float(out[k].detach()) - ref[k]) / abs(ref[k]))
+        assert abs(float(out[k].detach()) - ref[k]) <= 1e-4 * abs(ref[k]), (k, float(out[k].detach()), ref[k])
+    for k in ("s_image", "s_text", "s_img_x", "s_txt_x"):
+        for i, (t, rt) in enumerate(zip(x[k], r[k])):
+            if rt.grad is None:                                            # student image crops 2.. take no part in any term
+                assert t.grad is None or float(t.grad.abs().max()) == 0.0, (k, i)
+                continue
+            c, nr = _cos(t.grad, rt.grad), abs(float(t.grad.double().norm() / rt.grad.double().norm()) - 1.0)
+            worst["grad_cos_min"], worst["grad_norm_rel"] = min(worst["grad_cos_min"], c), max(worst["grad_norm_rel"], nr)
+            assert c >= 0.9999, (k, i, c)
+            assert nr <= 5e-3, (k, i, nr)
+    worst["dscale_rel"] = max(abs(float(ls.grad) - float(rls.grad)) / abs(float(rls.grad)),
+                              abs(float(ds.grad) - float(rds.grad)) / abs(float(rds.grad)))
+    print("fullsize headline parity (N = 32768, 80 pairs, bf16 vs fp32 eager):", worst, "losses", ref)      # pytest -s
+    assert abs(float(ls.grad) - float(rls.grad)) <= 3e-3 * abs(float(rls.grad))
+    assert abs(float(ds.grad) - float(rds.grad)) <= 3e-3 * abs(float(rds.grad))
