@@ -379,6 +379,39 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 - two fp32 operations per lane and issue slot, each rounded exactly like the
+// scalar instruction; a pair of equal scalars becomes the instruction's broadcast operand, no packing is executed)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_pack_bits(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// ----------------------------------------------------------------------------------------------
 // warp-level transpose-reduce: every lane holds v[0..31] (one row, 32 columns); on return lane L
 // holds op over the 32 lanes of column L.  31 shuffles instead of 32 * 5.
 // ----------------------------------------------------------------------------------------------
@@ -434,6 +467,30 @@ __device__ __forceinline__ float warp_transpose_reduce(const float (&v)[32], uin
   const float keep = up ? d[1] : d[0];
   const float send = up ? d[0] : d[1];
   return op(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+}
+
+// The same reduction for sums with the additions of two columns packed into one FADD2 (the identical additions in the identical
+// order: bit-equal to warp_transpose_reduce(v, lane, OpAdd()), 16 instead of 31 add instructions).
+template <int kN>
+__device__ __forceinline__ void transpose_add_stage(const float (&in)[2 * kN], float (&out)[kN], bool up, int sft) {
+#pragma unroll
+  for (int j = 0; j < kN; j += 2) {
+    const float k0 = up ? in[j + kN] : in[j], k1 = up ? in[j + 1 + kN] : in[j + 1];
+    const float s0 = up ? in[j] : in[j + kN], s1 = up ? in[j + 1] : in[j + 1 + kN];
+    const float r0 = __shfl_xor_sync(0xffffffffu, s0, sft), r1 = __shfl_xor_sync(0xffffffffu, s1, sft);
+    f2_unpack(f2_add(f2_pack(k0, k1), f2_pack(r0, r1)), out[j], out[j + 1]);
+  }
+}
+__device__ __forceinline__ float warp_transpose_sum(const float (&v)[32], uint32_t lane) {
+  float a[16], b[8], c[4], d[2];
+  transpose_add_stage<16>(v, a, lane & 16, 16);
+  transpose_add_stage<8>(a, b, lane & 8, 8);
+  transpose_add_stage<4>(b, c, lane & 4, 4);
+  transpose_add_stage<2>(c, d, lane & 2, 2);
+  const bool up = lane & 1;
+  const float keep = up ? d[1] : d[0];
+  const float send = up ? d[0] : d[1];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
 }  // namespace cb

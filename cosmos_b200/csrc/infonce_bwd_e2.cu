@@ -276,10 +276,10 @@ infonce_bwd_e2_kernel(const __grid_constant__ CUtensorMap tmY64, BwdEParams p) {
           const uint4 w = e_cur[p4];
           const float4 k0 = *reinterpret_cast<const float4*>(&kc_w[p4 * 8]);
           const float4 k1 = *reinterpret_cast<const float4*>(&kc_w[p4 * 8 + 4]);
-          const uint32_t f01 = pack2(fmaf(A2, k0.x, A1), fmaf(A2, k0.y, A1), 1);
-          const uint32_t f23 = pack2(fmaf(A2, k0.z, A1), fmaf(A2, k0.w, A1), 1);
-          const uint32_t f45 = pack2(fmaf(A2, k1.x, A1), fmaf(A2, k1.y, A1), 1);
-          const uint32_t f67 = pack2(fmaf(A2, k1.z, A1), fmaf(A2, k1.w, A1), 1);
+          const uint32_t f01 = factor_pair(k0.x, k0.y, A2, A1);
+          const uint32_t f23 = factor_pair(k0.z, k0.w, A2, A1);
+          const uint32_t f45 = factor_pair(k1.x, k1.y, A2, A1);
+          const uint32_t f67 = factor_pair(k1.z, k1.w, A2, A1);
           const uint4 outv = make_uint4(mul_bf16x2(w.x, f01), mul_bf16x2(w.y, f23), mul_bf16x2(w.z, f45), mul_bf16x2(w.w, f67));
           sts128(stage + p4 * 2048, outv);          // a warp's store of one piece: 512 contiguous bytes, no bank conflicts
           if (g_row != nullptr && row_valid && col0 + p4 * 8 < p.n_cols) *reinterpret_cast<uint4*>(g_row + p4 * 8) = outv;

@@ -40,6 +40,19 @@ __device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
   asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
   return d;
 }
+// the factors of two neighbouring columns, f = A2 * kc + A1 in fp32 (ONE FFMA2: both lanes rounded like fmaf), as a bf16 pair
+#ifndef COSMOS_BWD_F2
+#define COSMOS_BWD_F2 1
+#endif
+__device__ __forceinline__ uint32_t factor_pair(float kc0, float kc1, float A2, float A1) {
+#if COSMOS_BWD_F2
+  float f0, f1;
+  f2_unpack(f2_fma(f2_pack(kc0, kc1), f2_pack(A2, A2), f2_pack(A1, A1)), f0, f1);
+  return pack2(f0, f1, 1);
+#else
+  return pack2(fmaf(A2, kc0, A1), fmaf(A2, kc1, A1), 1);
+#endif
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }

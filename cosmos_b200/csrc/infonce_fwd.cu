@@ -26,6 +26,10 @@
 #include "common.cuh"
 #include "infonce.h"
 
+#ifndef COSMOS_FWD_F2
+#define COSMOS_FWD_F2 1      // packed fp32 pairs in the epilogue's fast path (0: the scalar instruction stream of round 2's first half)
+#endif
+
 namespace cb {
 
 namespace {
@@ -41,8 +45,8 @@ constexpr int kThreads = 128 + 32 * kEpiWarps;   // 4 warps per scheduler hide w
 constexpr int kEpiThreads = 32 * kEpiWarps;
 
 // E tile images (include/cosmos_b200.h): per 128-column step [4 slabs of 32 rows][16 pieces of 8 columns][32 rows][8] bf16;
-// offset (16-byte units) of global piece gp = step * 16 + piece inside a row tile's images, without the slab / row part
-__device__ __forceinline__ size_t e_piece_offset(int gp) { return static_cast<size_t>(gp >> 4) * 2048 + (gp & 15) * 32; }
+// offset (16-byte units) of global piece gp = step * 16 + piece inside a row tile's images, without the slab / row part:
+// (gp >> 4) * 2048 + (gp & 15) * 32
 
 struct Misc {
   uint64_t x_full;
@@ -266,6 +270,8 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const int col0 = tc * BN + h * 64 + chunk * 32;
         if (col0 >= p.n_cols) break;
         if ((p.dbg & 1) && chunk > 0) break;
+        // the chunk's four 16-byte pieces of this row lie 512 bytes apart (col0 is a multiple of 32: one address per chunk)
+        uint4* e_chunk = e_tile + static_cast<size_t>(col0 >> 7) * 2048 + ((col0 >> 5) & 3) * 128;
         uint32_t v[32];
         tmem_ld32(tmem + ((q * 32u) << 16) + as * BN + h * 64 + chunk * 32, v);
         tmem_ld_wait();
@@ -295,9 +301,48 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           if (mw != NEG_INF) {                             // warp-uniform: at least one row of this warp is real
             const float f = row_valid ? ex2(m_run - mw) : 0.f;
             const float neg_m = -m_run;
-            float ssum = 0.f;
+#if COSMOS_FWD_F2
+            // two columns per instruction (FFMA2 / FADD2 / FMUL2): the epilogue is bound by its issue slots, and the argument of
+            // the exponential, the row sum and the re-based copy for the column sum are 96 of its ~420 instructions per chunk
+            const uint64_t k2p = f2_pack(k2, k2), nmp = f2_pack(neg_m, neg_m), fp = f2_pack(f, f);
+            uint64_t ss2 = f2_pack(0.f, 0.f);
+            auto pair_of = [&](int k, float& e0, float& e1) {
+              float a0, a1;
+              f2_unpack(f2_fma(f2_pack_bits(v[k], v[k + 1]), k2p, nmp), a0, a1);
+              e0 = ex2(a0);
+              e1 = ex2(a1);
+              const uint64_t ep = f2_pack(e0, e1);
+              ss2 = f2_add(ss2, ep);
+              f2_unpack(f2_mul(ep, fp), t[k], t[k + 1]);
+            };
             if (keep_e) {
               // 16-byte pieces leave as soon as their 8 exponentials exist: no extra live registers across the reduce below
+#pragma unroll
+              for (int k8 = 0; k8 < 4; ++k8) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int k2i = 0; k2i < 4; ++k2i) {
+                  float e0, e1;
+                  pair_of(k8 * 8 + k2i * 2, e0, e1);
+                  pk[k2i] = pack2(e0, e1, 1);
+                }
+                e_chunk[k8 * 32] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+              off_row[static_cast<size_t>(col0 >> 5) * p.n_rows] = m_run;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; k += 2) {
+                float e0, e1;
+                pair_of(k, e0, e1);
+              }
+            }
+            float ss_lo, ss_hi;
+            f2_unpack(ss2, ss_lo, ss_hi);
+            l_run += ss_lo + ss_hi;
+            const float csum = warp_transpose_sum(t, lane);
+#else
+            float ssum = 0.f;
+            if (keep_e) {
 #pragma unroll
               for (int k8 = 0; k8 < 4; ++k8) {
                 uint32_t pk[4];
@@ -312,7 +357,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                   t[k + 1] = e1 * f;
                   pk[k2i] = pack2(e0, e1, 1);
                 }
-                e_tile[e_piece_offset((col0 >> 3) + k8)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                e_chunk[k8 * 32] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
               off_row[static_cast<size_t>(col0 >> 5) * p.n_rows] = m_run;
             } else {
@@ -325,6 +370,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             }
             l_run += ssum;
             const float csum = warp_transpose_reduce(t, lane, OpAdd());
+#endif
             // Every significant term of a column is a normal fp32 number iff the column sum is not tiny relative
             // to 2^M_w (DESIGN.md "one-exp statistics"); otherwise redo this block with true column maxima.
             if (__all_sync(0xffffffffu, csum >= 8.0779e-28f)) {   // 2^-90
@@ -373,7 +419,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 s += e1;
                 pk[k2i] = pack2(e0, e1, 1);
               }
-              e_tile[e_piece_offset((col0 >> 3) + k8)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              e_chunk[k8 * 32] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
             off_row[static_cast<size_t>(col0 >> 5) * p.n_rows] = m_run;
           } else {
@@ -384,7 +430,7 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         } else if (keep_e) {
           // every logit of this row so far is -inf (scale * x.y = -inf cannot happen with finite inputs; kept for safety)
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8) e_tile[e_piece_offset((col0 >> 3) + k8)] = make_uint4(0u, 0u, 0u, 0u);
+          for (int k8 = 0; k8 < 4; ++k8) e_chunk[k8 * 32] = make_uint4(0u, 0u, 0u, 0u);
           off_row[static_cast<size_t>(col0 >> 5) * p.n_rows] = 0.f;
         }
         // columns: reduce over the warp's 32 rows

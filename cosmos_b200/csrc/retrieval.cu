@@ -105,11 +105,13 @@ retrieval_count_kernel(const T* __restrict__ q, const T* __restrict__ g, int M, 
   const int tx = tid & 15, ty = tid >> 4;
   const int row0 = blockIdx.y * kRB, col0 = blockIdx.x * kRB;
 
-  float acc[8][8];
+  // two neighbouring columns per accumulator register pair: ONE FFMA2 (sm_100's packed fp32 pair, each half rounded like fmaf)
+  // per two scores - the plain three-register FFMA issues every other cycle, which held this kernel at half of the fp32 peak
+  uint64_t acc2[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc2[i][j] = f2_pack(0.f, 0.f);
 
   float vq[8], vg[8];
   load_stage(q, ldq, row0, M, 0, D, tid, vq);
@@ -131,14 +133,21 @@ retrieval_count_kernel(const T* __restrict__ q, const T* __restrict__ g, int M, 
       const float4 b0 = *reinterpret_cast<const float4*>(sG + kk * kRLd + tx * 4);
       const float4 b1 = *reinterpret_cast<const float4*>(sG + kk * kRLd + 64 + tx * 4);
       const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const uint64_t b2[4] = {f2_pack(b0.x, b0.y), f2_pack(b0.z, b0.w), f2_pack(b1.x, b1.y), f2_pack(b1.z, b1.w)};
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const uint64_t ai = f2_pack(a[i], a[i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc2[i][j] = f2_fma(ai, b2[j], acc2[i][j]);
+      }
     }
     __syncthreads();
   }
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f2_unpack(acc2[i][j], acc[i][2 * j], acc[i][2 * j + 1]);
 
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
