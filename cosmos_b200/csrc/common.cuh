@@ -378,6 +378,14 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
   return r;
 }
 
+// warp-wide maximum in ONE instruction (sm_100a: CREDUX.MAX.F32; -inf for a warp of -inf) instead of five shuffle + max rounds
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }   // one FMNMX3
+
 // ----------------------------------------------------------------------------------------------
 // packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 - two fp32 operations per lane and issue slot, each rounded exactly like the
 // scalar instruction; a pair of equal scalars becomes the instruction's broadcast operand, no packing is executed)

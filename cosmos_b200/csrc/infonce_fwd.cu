@@ -26,10 +26,6 @@
 #include "common.cuh"
 #include "infonce.h"
 
-#ifndef COSMOS_FWD_F2
-#define COSMOS_FWD_F2 1      // packed fp32 pairs in the epilogue's fast path (0: the scalar instruction stream of round 2's first half)
-#endif
-
 namespace cb {
 
 namespace {
@@ -272,8 +268,9 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if ((p.dbg & 1) && chunk > 0) break;
         // the chunk's four 16-byte pieces of this row lie 512 bytes apart (col0 is a multiple of 32: one address per chunk)
         uint4* e_chunk = e_tile + static_cast<size_t>(col0 >> 7) * 2048 + ((col0 >> 5) & 3) * 128;
+        const uint32_t t_chunk = tmem + ((q * 32u) << 16) + as * BN + h * 64 + chunk * 32;
         uint32_t v[32];
-        tmem_ld32(tmem + ((q * 32u) << 16) + as * BN + h * 64 + chunk * 32, v);
+        tmem_ld32(t_chunk, v);
         tmem_ld_wait();
         if (row_valid && label >= col0 && label < col0 + 32) {
           const int idx = label - col0;
@@ -286,110 +283,82 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (!need_exact) {
           // ---- one exponential per logit: rows use their own running max m_r as offset; the column sums reuse the
           // same exponentials, re-based to the warp's largest running max M_w by one multiply with f_r = 2^(m_r - M_w).
-          float cmr = __uint_as_float(v[0]);
+          // The epilogue is bound by the LATENCY of its dependent chains, not by issue slots (ncu, round 2: issue 56 - 65 %
+          // busy at 70 % tensor pipe), so: the row maximum is a depth-4 tree of three-input maxima, the warp maximum is ONE
+          // instruction (CREDUX.MAX.F32), and the exponentials - which need only m_r - are issued before M_w is consumed.
+          // Packed pairs (FFMA2 / FADD2 / FMUL2) cut 80 of the ~420 instructions per chunk on top.
+          float m1[11];
 #pragma unroll
-          for (int k = 1; k < 32; ++k) cmr = fmaxf(cmr, __uint_as_float(v[k]));
-          const float cm = cmr * k2;                       // k2 > 0 on this path
+          for (int k = 0; k < 10; ++k)
+            m1[k] = max3(__uint_as_float(v[3 * k]), __uint_as_float(v[3 * k + 1]), __uint_as_float(v[3 * k + 2]));
+          m1[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+          const float m2a = max3(m1[0], m1[1], m1[2]), m2b = max3(m1[3], m1[4], m1[5]), m2c = max3(m1[6], m1[7], m1[8]);
+          const float cm = fmaxf(max3(m2a, m2b, m2c), fmaxf(m1[9], m1[10])) * k2;          // k2 > 0 on this path
           const float m_before = m_run, l_before = l_run;
           if (cm > m_run) {
             l_run *= ex2(m_run - cm);
             m_run = cm;
           }
-          float mw = row_valid ? m_run : NEG_INF;
+          const float mw = warp_max_f32(row_valid ? m_run : NEG_INF);
+          // rows past the batch hold zero logits (TMA zero fill): finite everywhere, their results are dropped below
+          const float neg_m = -m_run;
+          const uint64_t k2p = f2_pack(k2, k2), nmp = f2_pack(neg_m, neg_m);
+          uint64_t ss2 = f2_pack(0.f, 0.f);
+          auto pair_of = [&](int k) {                  // t[k], t[k + 1] <- 2^(s2 - m_r), and their sum
+            float a0, a1;
+            f2_unpack(f2_fma(f2_pack_bits(v[k], v[k + 1]), k2p, nmp), a0, a1);
+            t[k] = ex2(a0);
+            t[k + 1] = ex2(a1);
+            ss2 = f2_add(ss2, f2_pack(t[k], t[k + 1]));
+          };
+          if (keep_e) {
+            // 16-byte pieces leave as soon as their 8 exponentials exist
 #pragma unroll
-          for (int sft = 16; sft > 0; sft >>= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, sft));
-          if (mw != NEG_INF) {                             // warp-uniform: at least one row of this warp is real
-            const float f = row_valid ? ex2(m_run - mw) : 0.f;
-            const float neg_m = -m_run;
-#if COSMOS_FWD_F2
-            // two columns per instruction (FFMA2 / FADD2 / FMUL2): the epilogue is bound by its issue slots, and the argument of
-            // the exponential, the row sum and the re-based copy for the column sum are 96 of its ~420 instructions per chunk
-            const uint64_t k2p = f2_pack(k2, k2), nmp = f2_pack(neg_m, neg_m), fp = f2_pack(f, f);
-            uint64_t ss2 = f2_pack(0.f, 0.f);
-            auto pair_of = [&](int k, float& e0, float& e1) {
-              float a0, a1;
-              f2_unpack(f2_fma(f2_pack_bits(v[k], v[k + 1]), k2p, nmp), a0, a1);
-              e0 = ex2(a0);
-              e1 = ex2(a1);
-              const uint64_t ep = f2_pack(e0, e1);
-              ss2 = f2_add(ss2, ep);
-              f2_unpack(f2_mul(ep, fp), t[k], t[k + 1]);
-            };
-            if (keep_e) {
-              // 16-byte pieces leave as soon as their 8 exponentials exist: no extra live registers across the reduce below
+            for (int k8 = 0; k8 < 4; ++k8) {
+              uint32_t pk[4];
 #pragma unroll
-              for (int k8 = 0; k8 < 4; ++k8) {
-                uint32_t pk[4];
-#pragma unroll
-                for (int k2i = 0; k2i < 4; ++k2i) {
-                  float e0, e1;
-                  pair_of(k8 * 8 + k2i * 2, e0, e1);
-                  pk[k2i] = pack2(e0, e1, 1);
-                }
-                e_chunk[k8 * 32] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              for (int k2i = 0; k2i < 4; ++k2i) {
+                const int k = k8 * 8 + k2i * 2;
+                pair_of(k);
+                pk[k2i] = pack2(t[k], t[k + 1], 1);
               }
-              off_row[static_cast<size_t>(col0 >> 5) * p.n_rows] = m_run;
-            } else {
-#pragma unroll
-              for (int k = 0; k < 32; k += 2) {
-                float e0, e1;
-                pair_of(k, e0, e1);
-              }
+              e_chunk[k8 * 32] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
-            float ss_lo, ss_hi;
-            f2_unpack(ss2, ss_lo, ss_hi);
-            l_run += ss_lo + ss_hi;
-            const float csum = warp_transpose_sum(t, lane);
-#else
-            float ssum = 0.f;
-            if (keep_e) {
-#pragma unroll
-              for (int k8 = 0; k8 < 4; ++k8) {
-                uint32_t pk[4];
-#pragma unroll
-                for (int k2i = 0; k2i < 4; ++k2i) {
-                  const int k = k8 * 8 + k2i * 2;
-                  const float e0 = ex2(fmaf(__uint_as_float(v[k]), k2, neg_m));
-                  const float e1 = ex2(fmaf(__uint_as_float(v[k + 1]), k2, neg_m));
-                  ssum += e0;
-                  ssum += e1;
-                  t[k] = e0 * f;
-                  t[k + 1] = e1 * f;
-                  pk[k2i] = pack2(e0, e1, 1);
-                }
-                e_chunk[k8 * 32] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              }
-              off_row[static_cast<size_t>(col0 >> 5) * p.n_rows] = m_run;
-            } else {
-#pragma unroll
-              for (int k = 0; k < 32; ++k) {
-                const float e = ex2(fmaf(__uint_as_float(v[k]), k2, neg_m));
-                ssum += e;
-                t[k] = e * f;
-              }
-            }
-            l_run += ssum;
-            const float csum = warp_transpose_reduce(t, lane, OpAdd());
-#endif
-            // Every significant term of a column is a normal fp32 number iff the column sum is not tiny relative
-            // to 2^M_w (DESIGN.md "one-exp statistics"); otherwise redo this block with true column maxima.
-            if (__all_sync(0xffffffffu, csum >= 8.0779e-28f)) {   // 2^-90
-              publish(col0, mw, csum);
-              continue;
-            }
-            need_exact = true;
-            // undo this block's row update: the exact path below redoes it from scratch - from the accumulator, which is still
-            // in tensor memory: reading it again (rare) instead of keeping its 32 registers alive across the column reduce
-            // above takes the spills out of the common path (ncu, round 2: ~10 local-memory accesses per chunk, and the
-            // instructions behind them held ~15 % of the kernel's stall samples)
-            m_run = m_before;
-            l_run = l_before;
-            tmem_ld32(tmem + ((q * 32u) << 16) + as * BN + h * 64 + chunk * 32, v);
-            tmem_ld_wait();
+            off_row[static_cast<size_t>(col0 >> 5) * p.n_rows] = m_run;
           } else {
+#pragma unroll
+            for (int k = 0; k < 32; k += 2) pair_of(k);
+          }
+          float ss_lo, ss_hi;
+          f2_unpack(ss2, ss_lo, ss_hi);
+          l_run += ss_lo + ss_hi;
+          if (mw == NEG_INF) {                             // warp-uniform: no row of this warp is real
             publish(col0, NEG_INF, 0.f);
             continue;
           }
+          const float f = row_valid ? ex2(m_run - mw) : 0.f;
+          const uint64_t fp = f2_pack(f, f);
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) f2_unpack(f2_mul(f2_pack(t[k], t[k + 1]), fp), t[k], t[k + 1]);
+          // (Measured and rejected: requesting the NEXT chunk's accumulator - tcgen05.ld into the registers that are free after
+          // two rounds of this reduce - so that the tensor-memory read overlaps the rest: the 32 registers stay live across the
+          // loop edge, ptxas spills ~20 values, forward with E stores 16.1 -> 20.3 ms.  profiles/fwd_abc_r02.txt)
+          const float csum = warp_transpose_sum(t, lane);
+          // Every significant term of a column is a normal fp32 number iff the column sum is not tiny relative
+          // to 2^M_w (DESIGN.md "one-exp statistics"); otherwise redo this block with true column maxima.
+          if (__all_sync(0xffffffffu, csum >= 8.0779e-28f)) {   // 2^-90
+            publish(col0, mw, csum);
+            continue;
+          }
+          need_exact = true;
+          // undo this block's row update: the exact path below redoes it from scratch - from the accumulator, which is still
+          // in tensor memory: reading it again (rare) instead of keeping its 32 registers alive across the column reduce
+          // above takes the spills out of the common path (ncu, round 2: ~10 local-memory accesses per chunk, and the
+          // instructions behind them held ~15 % of the kernel's stall samples)
+          m_run = m_before;
+          l_run = l_before;
+          tmem_ld32(t_chunk, v);
+          tmem_ld_wait();
         }
 #pragma unroll
         for (int k = 0; k < 32; ++k) t[k] = __uint_as_float(v[k]) * k2;

@@ -4,7 +4,7 @@
 TAG=${1:-r02}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit,driver_version --format=csv > gpurun_out/gpu_$TAG.txt 2>&1
-timeout 600 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$TAG.log 2>&1
+timeout 600 python -m pytest tests -m gpu -q -rP > gpurun_out/pytest_gpu_$TAG.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu_$TAG.log
 timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1
 echo "smoke exit $?" >> gpurun_out/smoke_$TAG.log
