@@ -32,7 +32,7 @@ DIM = 512
 N_IMG, N_TXT = 8, 8
 KEYS = (("s_image", N_IMG), ("s_text", N_TXT), ("s_img_x", N_IMG), ("s_txt_x", N_TXT), ("t_image", 2), ("t_text", 2))
 LOGIT_SCALE = 14.2857
-PROFILE_TAG = "r02g"    # profiles/ncu_<kernel>_<tag>.txt: the committed ncu summaries this round's roofline.traffic comes from
+PROFILE_TAG = "r02m"    # profiles/ncu_<kernel>_<tag>.txt: the committed ncu summaries this round's roofline.traffic comes from
 
 
 def algorithmic_flops(n_global: int, dim: int = DIM) -> float:

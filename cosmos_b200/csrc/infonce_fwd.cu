@@ -261,6 +261,8 @@ infonce_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         mbar_wait(&misc->acc_full[as], (tc >> 1) & 1);
       }
       tc_fence_after();
+      // (Measured, no effect: starting the four column groups of a scheduler 400 / 800 cycles apart at the first tile, so that
+      // they would not queue for the same pipe phase by phase - forward launch 17.90 / 17.90 / 17.90 ms.  profiles/stagger_r02.txt)
 #pragma unroll 1   // measured: unrolling by 2 lowers throughput (register pressure in the 8 epilogue warps)
       for (int chunk = 0; chunk < 2; ++chunk) {
         const int col0 = tc * BN + h * 64 + chunk * 32;
