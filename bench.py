@@ -325,6 +325,47 @@ class LossHead:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def graph_ms_per_step(self, steps: int):
+        """The same device-resident step captured ONCE with torch.cuda.graph and replayed: what the kernels take when the host
+        that launches them is out of the picture (small configurations are ~130 launches of 3 - 700 us, and a busy or slow
+        host core shows up directly in their eager-launch time).  Same L2 policy as `timed`; one process only."""
+        if self.world > 1:
+            return None
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.step(False)
+        torch.cuda.current_stream().wait_stream(side)
+        for t in list(self.dev_bufs[0].values()) + [self.logit_scale, self.distill_scale]:
+            t.grad = None
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.step(False)
+        graph.replay()
+        torch.cuda.synchronize()
+        total_ms = 0.0
+        if self.h2d_bytes > self.L2_BYTES:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            total_ms = e0.elapsed_time(e1)
+        else:
+            for _ in range(steps):
+                self.flush.fill_(1)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                graph.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                total_ms += e0.elapsed_time(e1)
+        loss = [float(out["distill_loss"].detach()), float(out["clip_loss"].detach())]
+        del graph
+        return {"ms_per_step": total_ms / steps, "loss": loss}
+
     def measure(self, steps, warmup, e2e=True):
         """-> dict(ms_per_step, e2e_ms_per_step, launches, kernels, loss): warm-up, device-resident leg, host-buffer leg."""
         inst = self.inst
@@ -531,14 +572,29 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _graph_leg(head, steps):
+    """LossHead.graph_ms_per_step, never fatal for the bench line: -> dict with ms_per_step (nan + error text on failure)."""
+    try:
+        return head.graph_ms_per_step(steps)
+    except Exception as e:      # noqa: BLE001 - an extra leg must not take the headline down with it
+        torch.cuda.synchronize()
+        return {"ms_per_step": float("nan"), "loss": None, "error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+
 def bench_other_batch(n_global, dev, inst, flush, steps=10):
     """BASELINE config 2 (global batch 4096, dim 512, bf16, one B200) through the same LossHead as the headline line."""
     head = LossHead(n_global, dev, 0, 1, inst, flush)
     m = head.measure(steps, 3)
+    g = _graph_leg(head, steps)
     burst, sustained, _, src = peaks()
     tf = algorithmic_flops(n_global) / (m["ms_per_step"] * 1e-3) / 1e12
     return {"workload": "COSMOS ViT-B/16 loss head fwd+bwd, global batch %d, dim 512, bf16, 1 B200" % n_global,
             "ms_per_step": m["ms_per_step"], "value": n_global / (m["ms_per_step"] * 1e-3), "unit": "samples/s",
+            "cuda_graph": {"ms_per_step": g["ms_per_step"], "value": n_global / (g["ms_per_step"] * 1e-3), "unit": "samples/s",
+                           "frac_of_sustained_peak": algorithmic_flops(n_global) / (g["ms_per_step"] * 1e-3) / 1e12 / sustained,
+                           "loss": g["loss"], **({"error": g["error"]} if "error" in g else {}),
+                           "note": "the same public-API step (COSMOSLoss forward + backward) captured once with torch.cuda.graph "
+                                   "and replayed: kernel time without the host's launch path"},
             "e2e": {"value": n_global / (m["e2e_ms_per_step"] * 1e-3), "unit": "samples/s", "ms_per_step": m["e2e_ms_per_step"],
                     "h2d_bytes_per_step": head.h2d_bytes, "d2h_bytes_per_step": 8},
             "algorithmic_tflops": tf, "frac_of_sustained_peak": tf / sustained, "frac_of_burst_peak": tf / burst, "peak_source": src,
@@ -550,6 +606,7 @@ def bench_same_size(dev, inst, flush, seconds, n_global=1024):
     B200 through the public API (device-resident and from pinned host buffers) and on the host cores through the oracle port."""
     head = LossHead(n_global, dev, 0, 1, inst, flush)
     m = head.measure(20, 3)
+    g = _graph_leg(head, 20)
     del head
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -565,6 +622,7 @@ def bench_same_size(dev, inst, flush, seconds, n_global=1024):
     return {"workload": "COSMOS loss head fwd+bwd, global batch %d, dim 512, 80 pairs: the same configuration on both arms "
                         "(GPU: bf16 kernels; CPU: fp32 oracle port, %d torch threads)" % (n_global, cores),
             "gpu_ms_per_step": m["ms_per_step"], "gpu_samples_per_s": gpu, "gpu_e2e_ms_per_step": m["e2e_ms_per_step"],
+            "gpu_cuda_graph_ms_per_step": g["ms_per_step"],
             "gpu_e2e_samples_per_s": e2e, "cpu_port_ms_per_step": cpu_ms, "cpu_port_samples_per_s": cpu, "cpu_cores": cores,
             "cpu_steps": n, "same_config": True, "ratio": gpu / cpu, "e2e_ratio": e2e / cpu}
 
@@ -603,6 +661,26 @@ def _event_ms(fn, reps, flush=None):
         ms.append(e0.elapsed_time(e1))
     ms.sort()
     return ms[len(ms) // 2], ms[0]
+
+
+def _graph_event_ms(fn, reps, flush=None):
+    """`fn` (launches only, no host reads) captured once with torch.cuda.graph, then the replay event-timed like _event_ms:
+    -> (median, best) ms, or (nan, nan) when the capture fails (an extra number must not take the line down)."""
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fn()
+        graph.replay()
+        torch.cuda.synchronize()
+        return _event_ms(graph.replay, reps, flush)
+    except Exception:      # noqa: BLE001
+        torch.cuda.synchronize()
+        return float("nan"), float("nan")
 
 
 def bench_ema(dev, flush):
@@ -652,6 +730,7 @@ def bench_xattn(dev, flush):
         for _ in range(3):
             step()
         med, best = _event_ms(step, 10, flush)
+        g_med, g_best = _graph_event_ms(step, 10, flush)       # the same step replayed from a CUDA graph (no host launch path)
         # algorithmic flops: K/V projection once per unique sample + 8 queries, x3 for fwd+bwd
         fwd = 2.0 * B * L * d * 2 * d + 2.0 * n * B * d * d * 2 + 4.0 * n * B * L * d
         p16 = {k: v.to(dev) for k, v in params.items()}
@@ -671,7 +750,8 @@ def bench_xattn(dev, flush):
         # per sample.  The K/V projection the kernels still materialise is why they sit far below it.
         alg_bytes = 2.0 * (3 * B * L * d + 5 * n * B * d)
         gbs = alg_bytes / (med * 1e-3) / 1e9
-        out[name] = {"ms": med, "ms_best": best, "algorithmic_tflops": tf, "frac_of_bf16_peak": tf / burst,
+        out[name] = {"ms": med, "ms_best": best, "cuda_graph_ms": g_med, "cuda_graph_ms_best": g_best,
+                     "algorithmic_tflops": tf, "frac_of_bf16_peak": tf / burst,
                      "hbm_roofline": {"bound": "hbm", "algorithmic_bytes": alg_bytes, "achieved": gbs, "peak": hbm, "unit": "GB/s",
                                       "frac": gbs / hbm, "peak_source": src},
                      "eager_restatement_ms": ref_med, "batch": B, "queries_per_sample": n, "tokens": L, "dim": d}
@@ -695,9 +775,10 @@ def bench_xattn(dev, flush):
         for _ in range(3):
             step2()
         med, best = _event_ms(step2, 5, flush)
+        g_med, g_best = _graph_event_ms(step2, 5, flush)
         fwd = 2.0 * B2 * (Lq + 2 * Lk) * d2 * d2 + 4.0 * B2 * Lq * Lk * d2 + 2.0 * B2 * Lq * d2 * d2
         tf2 = 3.0 * fwd / (med * 1e-3) / 1e12
-        out[name] = {"ms": med, "ms_best": best, "algorithmic_tflops": tf2,
+        out[name] = {"ms": med, "ms_best": best, "cuda_graph_ms": g_med, "cuda_graph_ms_best": g_best, "algorithmic_tflops": tf2,
                      "tensor_roofline": {"bound": "tensor", "achieved": tf2, "peak": peaks()[0], "unit": "TFLOP/s", "frac": tf2 / peaks()[0]},
                      "batch": B2, "queries": Lq, "tokens": Lk, "dim": d2, "heads": h2}
     return out
