@@ -168,6 +168,27 @@ def case_pooler(T):
     torch.save(cases, os.path.join(HERE, "pooler.pt"))
 
 
+def case_pooler_zero_attn(T):
+    """AttentionalCrossPooler(add_zero_attn=True) (transformer.py:214-221; off in every COSMOS recipe, supported by the drop-in):
+    outputs and every gradient at small shapes, through the module's own forward and through the model.py:378-380 lines."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle.cosmos_oracle import make_pooler_case
+    cases = []
+    for idx, (d, h, L_k, B, n) in enumerate([(64, 4, 7, 3, 2), (128, 8, 13, 2, 4)]):
+        params, tokens, feats, w = make_pooler_case(d, L_k, B, n, seed=70 + idx)
+        mod = T.AttentionalCrossPooler(d, d, h, add_zero_attn=True)
+        mod.load_state_dict(params)
+        tokens.requires_grad_(True)
+        feats.requires_grad_(True)
+        pooled = mod(tokens[:B].repeat(n, 1, 1), feats.unsqueeze(1))
+        xmodal = torch.nn.functional.normalize(feats + pooled.squeeze(), dim=-1)
+        (xmodal * w).sum().backward()
+        cases.append(dict(d=d, heads=h, L=L_k, batch_size=B, n=n, seed=70 + idx, pooled=pooled.detach().clone(),
+                          xmodal=xmodal.detach().clone(), g_feats=feats.grad.clone(), g_tokens=tokens.grad.clone(),
+                          g_params={k: v.grad.clone() for k, v in mod.named_parameters()}))
+    torch.save(cases, os.path.join(HERE, "pooler_zero_attn.pt"))
+
+
 def case_ema():
     g = torch.Generator().manual_seed(9)
     shapes = [(1,), (), (7,), (33, 5), (4096,), (1000, 3)]
@@ -384,6 +405,7 @@ if __name__ == "__main__":
     case_gather(3, 29614, "gather_w3.pt")
     case_dropin()
     case_pooler(T)
+    case_pooler_zero_attn(T)
     case_ema()
     case_retrieval()
     case_clamp()

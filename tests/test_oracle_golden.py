@@ -147,6 +147,30 @@ def test_pooler_matches_reference(golden_dir):
             _close(v.grad.reshape(-1)[:64], rec["g_param_head"][k], rtol=2e-3, atol=2e-5)
 
 
+def test_pooler_add_zero_attn_matches_reference(golden_dir):
+    """add_zero_attn=True (transformer.py:214-221): the oracle's branch against the unmodified reference module - outputs and
+    every gradient, key bias included (with the extra zero key its gradient is no longer zero)."""
+    for rec in _load(golden_dir, "pooler_zero_attn.pt"):
+        params, tokens, feats, w = O.make_pooler_case(rec["d"], rec["L"], rec["batch_size"], rec["n"], rec["seed"])
+        params = {k: v.requires_grad_(True) for k, v in params.items()}
+        tokens.requires_grad_(True)
+        feats.requires_grad_(True)
+        B, n = rec["batch_size"], rec["n"]
+        pooled = O.cross_pool(tokens[:B].repeat(n, 1, 1), feats.unsqueeze(1), params, rec["heads"], add_zero_attn=True)
+        _close(pooled, rec["pooled"], rtol=1e-4, atol=2e-5)
+        xmodal = torch.nn.functional.normalize(feats + pooled.squeeze(1), dim=-1)           # model.py:379-380
+        _close(xmodal, rec["xmodal"], rtol=1e-4, atol=1e-5)
+        (xmodal * w).sum().backward()
+        _close(feats.grad, rec["g_feats"], rtol=1e-3, atol=1e-5)
+        _close(tokens.grad, rec["g_tokens"], rtol=1e-3, atol=1e-5)
+        for k, v in params.items():
+            _close(v.grad, rec["g_params"][k], rtol=2e-3, atol=2e-5)
+        d = rec["d"]
+        assert float(rec["g_params"]["attn.in_proj_bias"][d:2 * d].abs().max()) > 0        # the key bias matters here
+        plain = O.cross_pool(tokens[:B].repeat(n, 1, 1), feats.unsqueeze(1), params, rec["heads"])
+        assert not torch.allclose(plain, rec["pooled"], rtol=1e-3, atol=1e-4)
+
+
 def test_ema_matches_reference(golden_dir):
     rec = _load(golden_dir, "ema.pt")
     for m, want in rec["outs"].items():
