@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("COSMOS_B200_LIB") or os.path.join(HERE, "libcosmos_b200.so")     # (override: A/B of two builds)
 
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 CLAMP_MAX = 8   # COSMOS_CLAMP_MAX
 
 _DEBUG_SYNC = os.environ.get("COSMOS_B200_DEBUG_SYNC", "0") == "1"

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define COSMOS_B200_ABI_VERSION 2
+#define COSMOS_B200_ABI_VERSION 3
 
 /* status codes */
 #define COSMOS_OK 0

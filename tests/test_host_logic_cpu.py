@@ -193,7 +193,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert len(names) >= 18
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.cosmos_abi_version() == 2
+    assert lib.cosmos_abi_version() == 3
     assert lib.cosmos_status_string(0) == b"ok"
     # host-only helpers behave
     numel = (ctypes.c_int64 * 3)(8192, 1, 8193)
