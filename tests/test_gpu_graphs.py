@@ -61,7 +61,7 @@ def test_loss_head_step_replays_from_a_cuda_graph(route, monkeypatch):
                 static[k].copy_(fresh[k])
         graph.replay()
         torch.cuda.synchronize()
-        got_total = float(static_total)
+        got_total = float(static_total.detach())
         got = [t.grad.detach().clone() for t in leaves]
         eager = {k: v.clone().requires_grad_(k in grads_of) for k, v in fresh.items()}
         els = torch.tensor(14.2857, device="cuda", requires_grad=True)

@@ -17,6 +17,7 @@ def _worker(rank, world, port, tmpdir, keep_g=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
+    torch.set_num_threads(max(1, (os.cpu_count() or world) // world))      # the CPU oracle of every rank runs at the same time
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from cosmos_b200 import COSMOSLoss, infonce
