@@ -557,15 +557,23 @@ def run_ours(args):
     del head
     torch.cuda.empty_cache()
     if rank == 0:
+        def extra(fn, *a, **kw):
+            """The other rows of the line: a failure in one of them is reported in its place, the headline still prints."""
+            try:
+                return fn(*a, **kw)
+            except Exception as e:      # noqa: BLE001
+                sys.stderr.write("bench.py: %s failed: %s: %s\n" % (fn.__name__, type(e).__name__, e))
+                return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
         if world == 1 and not args.no_extras:
-            line["config2_global_batch_4096"] = bench_other_batch(4096, dev, inst, flush, steps=10)
-            line["same_size_cpu_vs_gpu"] = bench_same_size(dev, inst, flush, args.cpu_seconds)
-            line["ema"] = bench_ema(dev, flush)
-            line["xattn"] = bench_xattn(dev, flush)
-            line["retrieval"] = bench_retrieval(dev, flush)
-            line["eager_gpu_baseline"] = bench_eager_gpu(dev)
+            line["config2_global_batch_4096"] = extra(bench_other_batch, 4096, dev, inst, flush, steps=10)
+            line["same_size_cpu_vs_gpu"] = extra(bench_same_size, dev, inst, flush, args.cpu_seconds)
+            line["ema"] = extra(bench_ema, dev, flush)
+            line["xattn"] = extra(bench_xattn, dev, flush)
+            line["retrieval"] = extra(bench_retrieval, dev, flush)
+            line["eager_gpu_baseline"] = extra(bench_eager_gpu, dev)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+            line["cpu_baseline"] = extra(cpu_baseline, args.cpu_seconds)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -573,12 +581,12 @@ def run_ours(args):
 
 
 def _graph_leg(head, steps):
-    """LossHead.graph_ms_per_step, never fatal for the bench line: -> dict with ms_per_step (nan + error text on failure)."""
+    """LossHead.graph_ms_per_step, never fatal for the bench line: -> dict with ms_per_step (None + error text on failure)."""
     try:
         return head.graph_ms_per_step(steps)
     except Exception as e:      # noqa: BLE001 - an extra leg must not take the headline down with it
         torch.cuda.synchronize()
-        return {"ms_per_step": float("nan"), "loss": None, "error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+        return {"ms_per_step": None, "loss": None, "error": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
 
 def bench_other_batch(n_global, dev, inst, flush, steps=10):
@@ -590,11 +598,12 @@ def bench_other_batch(n_global, dev, inst, flush, steps=10):
     tf = algorithmic_flops(n_global) / (m["ms_per_step"] * 1e-3) / 1e12
     return {"workload": "COSMOS ViT-B/16 loss head fwd+bwd, global batch %d, dim 512, bf16, 1 B200" % n_global,
             "ms_per_step": m["ms_per_step"], "value": n_global / (m["ms_per_step"] * 1e-3), "unit": "samples/s",
-            "cuda_graph": {"ms_per_step": g["ms_per_step"], "value": n_global / (g["ms_per_step"] * 1e-3), "unit": "samples/s",
-                           "frac_of_sustained_peak": algorithmic_flops(n_global) / (g["ms_per_step"] * 1e-3) / 1e12 / sustained,
-                           "loss": g["loss"], **({"error": g["error"]} if "error" in g else {}),
-                           "note": "the same public-API step (COSMOSLoss forward + backward) captured once with torch.cuda.graph "
-                                   "and replayed: kernel time without the host's launch path"},
+            "cuda_graph": {"error": g["error"]} if "error" in g else {
+                "ms_per_step": g["ms_per_step"], "value": n_global / (g["ms_per_step"] * 1e-3), "unit": "samples/s",
+                "frac_of_sustained_peak": algorithmic_flops(n_global) / (g["ms_per_step"] * 1e-3) / 1e12 / sustained,
+                "loss": g["loss"],
+                "note": "the same public-API step (COSMOSLoss forward + backward) captured once with torch.cuda.graph "
+                        "and replayed: kernel time without the host's launch path"},
             "e2e": {"value": n_global / (m["e2e_ms_per_step"] * 1e-3), "unit": "samples/s", "ms_per_step": m["e2e_ms_per_step"],
                     "h2d_bytes_per_step": head.h2d_bytes, "d2h_bytes_per_step": 8},
             "algorithmic_tflops": tf, "frac_of_sustained_peak": tf / sustained, "frac_of_burst_peak": tf / burst, "peak_source": src,
@@ -665,7 +674,7 @@ def _event_ms(fn, reps, flush=None):
 
 def _graph_event_ms(fn, reps, flush=None):
     """`fn` (launches only, no host reads) captured once with torch.cuda.graph, then the replay event-timed like _event_ms:
-    -> (median, best) ms, or (nan, nan) when the capture fails (an extra number must not take the line down)."""
+    -> (median, best) ms, or (None, None) when the capture fails (an extra number must not take the line down)."""
     try:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -680,7 +689,7 @@ def _graph_event_ms(fn, reps, flush=None):
         return _event_ms(graph.replay, reps, flush)
     except Exception:      # noqa: BLE001
         torch.cuda.synchronize()
-        return float("nan"), float("nan")
+        return None, None
 
 
 def bench_ema(dev, flush):
