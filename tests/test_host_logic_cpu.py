@@ -195,6 +195,14 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(lib, n), n
     assert lib.cosmos_abi_version() == 3
     assert lib.cosmos_status_string(0) == b"ok"
+    # and the other way round: the library (built with -fvisibility=hidden) exports nothing but what the header declares
+    import shutil
+    import subprocess
+    if shutil.which("nm"):
+        out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+        exported = {ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-2] in ("T", "t", "W", "w", "D", "B")}
+        exported = {n for n in exported if not n.startswith(("_init", "_fini", "_edata", "_end", "__bss_start"))}
+        assert exported == names, (sorted(exported - names), sorted(names - exported))
     # host-only helpers behave
     numel = (ctypes.c_int64 * 3)(8192, 1, 8193)
     assert lib.cosmos_ema_table_entries(3, numel) == 1 + 1 + 2
